@@ -1,0 +1,155 @@
+/* sigtk_b200.h -- C-ABI of the B200-native sigtk raw-signal hot path.
+ *
+ * Plain C99, no CUDA or torch types in any signature.  Built for sm_100a only;
+ * there is NO CPU fallback: every entry point returns SGPU_E_CUDA (or the
+ * library fails to load) when no CUDA device is usable.
+ *
+ * What it replaces in the reference (file:line under hasindu2008/sigtk):
+ *   - float *signal_in_picoamps(slow5_rec_t*)            src/sigtk.h:124, src/misc.c:15-32
+ *   - event_table getevents(size_t, float*, int8_t rna)  src/sigtk.h:134, src/events.c:553-573
+ *   - meanf/stdvf/medianf/meani16/stdvi16/mediani16      src/stat.h:17-73 (as used by stat_func,
+ *                                                        src/cfunc.c:126-159)
+ * The reference calls those once per record from a callback
+ * `void (*func)(slow5_rec_t*, opt_t)` (src/cmain.c:95-126).  Here the unit of
+ * work is a BATCH of records: the host appends decoded records to a pinned
+ * slot, submits it, and reads per-read results back in record order.
+ *
+ * Ownership: the library owns all device and pinned memory for the lifetime
+ * of the context; the host fills / reads slot buffers in place.  Nothing is
+ * malloc'd per read.  A context is used by one host thread at a time.
+ *
+ * Errors: every function returns 0 or a negative SGPU_E_* code and never
+ * calls exit(); sgpu_strerror() gives text, sgpu_last_error(ctx) the CUDA
+ * detail.
+ */
+#ifndef SIGTK_B200_H
+#define SIGTK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGPU_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define SGPU_OK            0
+#define SGPU_E_INVAL      -1  /* bad argument */
+#define SGPU_E_CUDA       -2  /* CUDA runtime / driver / kernel error (see sgpu_last_error) */
+#define SGPU_E_NOMEM      -3  /* host or device allocation failed */
+#define SGPU_E_FULL       -4  /* slot cannot take this read: submit it and retry */
+#define SGPU_E_TOOBIG     -5  /* a single read exceeds the context's max_samples */
+#define SGPU_E_STATE      -6  /* call out of order (e.g. wait on a slot that was not submitted) */
+#define SGPU_E_EVCAP      -7  /* event capacity exceeded (never for n/3+2 sizing; reported, not truncated) */
+#define SGPU_E_SCRATCH    -8  /* sequential-order scratch too small for the reads that need it */
+
+/* ---- what to compute (bitmask) ------------------------------------------ */
+#define SGPU_WANT_EVENTS   1u /* event table: getevents(), events.c:553-573 */
+#define SGPU_WANT_PA       2u /* materialise pA floats: signal_in_picoamps(), misc.c:15-32 */
+#define SGPU_WANT_STAT     4u /* the six numbers of stat_func, cfunc.c:126-159 */
+
+/* ---- context flags ------------------------------------------------------ */
+#define SGPU_F_DEFAULT       0u
+#define SGPU_F_FORCE_GENERIC 1u /* run every read through the sequential-order (reference-order) kernels */
+#define SGPU_F_NO_HOST_SLOTS 2u /* device-resident use only: do not allocate pinned slots */
+
+typedef struct sgpu_ctx sgpu_ctx_t;
+
+/* Reads are laid out back to back in one flat int16 array; read r occupies
+ * samples[read_off[r] .. read_off[r]+read_len[r]) and every read_off[r] is a
+ * multiple of SGPU_ALIGN samples (16 bytes) so that 128-bit / bulk loads are
+ * aligned.  The per-read scalars are the reference's narrowed floats:
+ *   offset_f   = (float)rec->offset                        (misc.c:19)
+ *   raw_unit_f = (float)rec->range / (float)rec->digitisation  (misc.c:17-18,26)
+ * computed on the host in C exactly as the reference does. */
+#define SGPU_ALIGN 8
+
+typedef struct {
+    int16_t  *samples;     /* [capacity max_samples] */
+    uint64_t *read_off;    /* [n_reads+1]; read_off[n_reads] = end of used span (aligned) */
+    uint32_t *read_len;    /* [n_reads] */
+    float    *offset_f;    /* [n_reads] */
+    float    *raw_unit_f;  /* [n_reads] */
+    uint32_t  n_reads;
+    uint32_t  rna;         /* 0: DNA detector parameters (events.c:43-47), 1: RNA (50-54) */
+} sgpu_batch_t;
+
+/* Per-batch results.  Host pointers (pinned) from sgpu_wait(), device
+ * pointers from sgpu_run_device().  Event k of read r is
+ *   k in [ev_off[r], ev_off[r+1]),  start = ev_start[k] (sample index in the read),
+ *   end = next event's start, or read_len[r] for the read's last event
+ *   (event_t, sigtk.h:55-62: length = (float)(end-start)). */
+typedef struct {
+    uint64_t *ev_off;      /* [n_reads+1] */
+    uint32_t *ev_start;    /* [n_events] */
+    float    *ev_mean;     /* [n_events] */
+    float    *ev_stdv;     /* [n_events] */
+    float    *pa;          /* same layout as samples; NULL unless SGPU_WANT_PA */
+    float    *stat;        /* [n_reads][6]: raw_mean, pa_mean, raw_std, pa_std, raw_median, pa_median */
+    uint32_t *seq_order;   /* [n_reads] 1 if the read went through the sequential-order kernels
+                              (exact-sum witness failed, or forced); such reads are still bit-exact */
+    uint32_t *fixups;      /* [n_reads] number of detector chunks re-run after a boundary-state mismatch */
+    uint64_t  n_events;    /* total events in the batch (host result only; 0 from sgpu_run_device) */
+} sgpu_result_t;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int  sgpu_device_count(void);
+int  sgpu_create(sgpu_ctx_t **out, int device, uint64_t max_samples, uint32_t max_reads,
+                 uint32_t n_slots, uint32_t flags);
+void sgpu_destroy(sgpu_ctx_t *ctx);
+const char *sgpu_strerror(int code);
+const char *sgpu_last_error(const sgpu_ctx_t *ctx);
+int  sgpu_abi_version(void);
+
+/* ---- host path: pinned slots, async H2D -> kernels -> D2H ---------------- */
+/* Pinned input buffers of a slot (valid until destroy). */
+int  sgpu_slot_batch(sgpu_ctx_t *ctx, uint32_t slot, sgpu_batch_t **out);
+/* Start a new batch in the slot. */
+int  sgpu_slot_reset(sgpu_ctx_t *ctx, uint32_t slot, uint32_t rna);
+/* Append one decoded record (the fields of slow5_rec_t the path uses,
+ * slow5.h:274-286).  Returns the read's index in the batch, SGPU_E_FULL when
+ * it does not fit (submit and retry), SGPU_E_TOOBIG when it can never fit. */
+int64_t sgpu_slot_add_read(sgpu_ctx_t *ctx, uint32_t slot, const int16_t *raw, uint64_t len_raw_signal,
+                           double digitisation, double offset, double range);
+/* Asynchronous: copies the slot to the device, runs the kernels, copies the
+ * results back, all on the slot's stream. */
+int  sgpu_submit(sgpu_ctx_t *ctx, uint32_t slot, uint32_t want);
+/* Blocks until the slot's work is done; fills *out with pinned host pointers. */
+int  sgpu_wait(sgpu_ctx_t *ctx, uint32_t slot, sgpu_result_t *out);
+
+/* ---- device-resident path (benchmarks, callers that already hold the data in HBM) ---- */
+typedef struct {
+    const int16_t  *samples;    /* device */
+    const uint64_t *read_off;   /* device [n_reads+1] */
+    const uint32_t *read_len;   /* device [n_reads] */
+    const float    *offset_f;   /* device [n_reads] */
+    const float    *raw_unit_f; /* device [n_reads] */
+    uint32_t n_reads;
+    uint32_t rna;
+    uint64_t span;              /* = read_off[n_reads] (known to the host) */
+} sgpu_dev_batch_t;
+
+/* Runs the kernels on `stream` (a cudaStream_t passed as void*, NULL = the
+ * legacy default stream) without any host<->device copies or synchronisation.
+ * *out receives DEVICE pointers owned by the context (valid until the next
+ * run on this context). */
+int  sgpu_run_device(sgpu_ctx_t *ctx, const sgpu_dev_batch_t *batch, uint32_t want,
+                     void *stream, sgpu_result_t *out);
+
+/* Counters of the last completed run (host path: after sgpu_wait; device path:
+ * after the caller synchronised the stream). Synchronises the device. */
+typedef struct {
+    uint64_t n_events;
+    uint64_t n_seq_order_reads;   /* reads routed to the sequential-order kernels */
+    uint64_t n_fixups;            /* detector chunks re-run after boundary-state mismatch */
+    uint64_t n_kernel_launches;   /* kernels launched by the last run */
+    int32_t  status;              /* 0 or SGPU_E_EVCAP / SGPU_E_SCRATCH reported by the device */
+} sgpu_counters_t;
+int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGTK_B200_H */

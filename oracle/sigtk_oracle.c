@@ -1,0 +1,300 @@
+/* sigtk_oracle.c -- TEST INFRASTRUCTURE ONLY (CPU restatement, never shipped
+ * in the product path; the product fails loudly without its CUDA library).
+ *
+ * Restates, with every rounding step written as an explicit cast, the
+ * arithmetic of the reference's per-read hot path.  Build with
+ * -std=c99 -ffp-contract=off (no FMA contraction, FLT_EVAL_METHOD 0), the
+ * same floating-point environment as the reference (Makefile:5).
+ *
+ * PARITY PINNED by tests/test_oracle.py against
+ *   - /root/reference/test/event_dna.exp  (committed as tests/golden/event_dna.exp)
+ *   - outputs of the compiled, unmodified reference (oracle/_ref) on
+ *     test/sp1_dna.blow5 and on seeded synthetic DNA / RNA reads,
+ *     committed under tests/golden/ with the generating script.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "sigtk_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* events.c:43-54 */
+void orc_params(int rna, orc_params_t *p) {
+    if (rna) {
+        p->w_short = 7;  p->w_long = 14;
+        p->thr_short = 2.5f; p->thr_long = 9.0f; p->peak_height = 1.0f;
+    } else {
+        p->w_short = 3;  p->w_long = 6;
+        p->thr_short = 1.4f; p->thr_long = 9.0f; p->peak_height = 0.2f;
+    }
+}
+
+/* misc.c:15-32: the three per-read doubles are narrowed to float first
+ * (17-19), raw_unit is a float division (26), then float add, float mul (28). */
+void orc_pa(const int16_t *raw, uint64_t n, double digitisation, double offset,
+            double range, float *pa) {
+    const float range_f = (float)range;
+    const float dig_f = (float)digitisation;
+    const float off_f = (float)offset;
+    const float unit = range_f / dig_f;
+    for (uint64_t j = 0; j < n; j++) {
+        const float shifted = (float)raw[j] + off_f;
+        pa[j] = shifted * unit;
+    }
+}
+
+/* events.c:293-303: sequential double accumulation; the square is a FLOAT
+ * product widened afterwards. */
+void orc_prefix(const float *pa, uint64_t n, double *S, double *Q) {
+    double s = 0.0, q = 0.0;
+    S[0] = 0.0;
+    Q[0] = 0.0;
+    for (uint64_t i = 0; i < n; i++) {
+        const float sq = pa[i] * pa[i];
+        s = s + (double)pa[i];
+        q = q + (double)sq;
+        S[i + 1] = s;
+        Q[i + 1] = q;
+    }
+}
+
+/* events.c:315-364 */
+void orc_tstat(const double *S, const double *Q, uint64_t n, uint32_t w, float *t) {
+    memset(t, 0, n * sizeof(float));
+    if (n < 2ull * w || w < 2) return;           /* 328-330 */
+    const float wf = (float)w;
+    const double wd = (double)wf;
+    for (uint64_t i = w; i + w <= n; i++) {      /* 338: w <= i <= n-w */
+        /* left window [i-w, i): kept in double (339-344; i==w subtracts S[0]==0) */
+        const double sum1 = (i > w) ? S[i] - S[i - w] : S[i];
+        const double ssq1 = (i > w) ? Q[i] - Q[i - w] : Q[i];
+        /* right window [i, i+w): narrowed to float at once (345-346) */
+        const float sum2 = (float)(S[i + w] - S[i]);
+        const float ssq2 = (float)(Q[i + w] - Q[i]);
+        const float mean1 = (float)(sum1 / wd);  /* double division, then narrow */
+        const float mean2 = sum2 / wf;           /* float division */
+        const float m1sq = mean1 * mean1;        /* float products */
+        const float m2sq = mean2 * mean2;
+        const float v2 = ssq2 / wf;              /* float division */
+        double acc = ssq1 / wd;                  /* 349-350, left to right in double */
+        acc = acc - (double)m1sq;
+        acc = acc + (double)v2;
+        acc = acc - (double)m2sq;
+        float cv = (float)acc;
+        cv = fmaxf(cv, FLT_MIN);                 /* 353 */
+        const float delta = mean2 - mean1;
+        const float scaled = cv / wf;            /* float division inside sqrt() */
+        const double num = fabs((double)delta);
+        const double den = sqrt((double)scaled);
+        t[i] = (float)(num / den);               /* 360 */
+    }
+}
+
+/* events.c:516-536 */
+void orc_det_init(orc_det_t *s, orc_det_t *l) {
+    s->masked_to = 0; s->peak_pos = -1; s->peak_value = FLT_MAX; s->valid = 0;
+    *l = *s;
+}
+
+/* cold start with `at` the first index that is processed */
+void orc_det_cold(orc_det_t *s, orc_det_t *l, uint64_t at) {
+    orc_det_init(s, l);
+    if (at > 0) { s->masked_to = at - 1; l->masked_to = at - 1; }
+}
+
+/* CASE 1 (391-404): no maximum recorded yet. Track the running minimum until
+ * the signal has risen by more than `height` above it. */
+static void seek_rise(orc_det_t *d, uint64_t i, float cur, float height) {
+    if (cur < d->peak_value) {
+        d->peak_value = cur;
+    } else if (cur - d->peak_value > height) {
+        d->peak_value = cur;
+        d->peak_pos = (int64_t)i;
+    }
+}
+
+uint64_t orc_detect(const float *t1, const float *t2, uint64_t from, uint64_t to,
+                    const orc_params_t *p, orc_det_t *s, orc_det_t *l,
+                    uint64_t *peaks, uint64_t cap) {
+    uint64_t np = 0;
+    orc_det_t *det[2] = {s, l};
+    const float *sig[2] = {t1, t2};
+    const float thr[2] = {p->thr_short, p->thr_long};
+    const uint32_t win[2] = {p->w_short, p->w_long};
+    for (uint64_t i = from; i < to; i++) {
+        for (int k = 0; k < 2; k++) {            /* short first, then long (385-386) */
+            orc_det_t *d = det[k];
+            if (d->masked_to >= i) continue;     /* 387 */
+            const float cur = sig[k][i];
+            if (d->peak_pos < 0) {
+                seek_rise(d, i, cur, p->peak_height);
+                continue;                        /* a 1->2 transition acts from the next i */
+            }
+            /* CASE 2, 405-437 */
+            if (cur > d->peak_value) {
+                d->peak_value = cur;
+                d->peak_pos = (int64_t)i;
+            }
+            if (k == 0 && d->peak_value > thr[0]) {   /* 414-422: dominate the long detector */
+                l->masked_to = (uint64_t)d->peak_pos + win[0];
+                l->peak_pos = -1;
+                l->peak_value = FLT_MAX;
+                l->valid = 0;
+            }
+            if (d->peak_value - cur > p->peak_height && d->peak_value > thr[k]) d->valid = 1;
+            if (d->valid && (i - (uint64_t)d->peak_pos) > win[k] / 2) {
+                if (np < cap) peaks[np] = (uint64_t)d->peak_pos;
+                np++;
+                d->peak_pos = -1;
+                d->peak_value = cur;
+                d->valid = 0;
+            }
+        }
+    }
+    return np;
+}
+
+/* events.c:457-473 */
+static void make_event(uint64_t a, uint64_t b, const double *S, const double *Q,
+                       uint64_t *start, float *length, float *mean, float *stdv) {
+    const float len = (float)(b - a);
+    const float dsum = (float)(S[b] - S[a]);     /* narrowed BEFORE the float division */
+    const float m = dsum / len;
+    const float dsq = (float)(Q[b] - Q[a]);
+    const float ex2 = dsq / len;
+    const float mm = m * m;
+    const float var = ex2 - mm;
+    *start = a;
+    *length = len;
+    *mean = m;
+    *stdv = sqrtf(fmaxf(var, 0.0f));
+}
+
+/* events.c:475-504 */
+uint64_t orc_events(const uint64_t *peaks, uint64_t n_peaks, const double *S,
+                    const double *Q, uint64_t n, uint64_t *start, float *length,
+                    float *mean, float *stdv) {
+    uint64_t ne = 0, a = 0;
+    for (uint64_t k = 0; k < n_peaks; k++) {
+        const uint64_t p = peaks[k];
+        if (!(p > 0 && p < n)) continue;         /* 481-485 */
+        make_event(a, p, S, Q, &start[ne], &length[ne], &mean[ne], &stdv[ne]);
+        ne++;
+        a = p;
+    }
+    make_event(a, n, S, Q, &start[ne], &length[ne], &mean[ne], &stdv[ne]);
+    return ne + 1;
+}
+
+int64_t orc_getevents(uint64_t n, const float *pa, int rna, uint64_t cap,
+                      uint64_t *start, float *length, float *mean, float *stdv) {
+    orc_params_t p;
+    orc_params(rna, &p);
+    double *S = (double *)malloc((n + 1) * sizeof(double));
+    double *Q = (double *)malloc((n + 1) * sizeof(double));
+    float *t1 = (float *)malloc((n ? n : 1) * sizeof(float));
+    float *t2 = (float *)malloc((n ? n : 1) * sizeof(float));
+    uint64_t *peaks = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+    orc_prefix(pa, n, S, Q);
+    orc_tstat(S, Q, n, p.w_short, t1);
+    orc_tstat(S, Q, n, p.w_long, t2);
+    orc_det_t s, l;
+    orc_det_init(&s, &l);
+    const uint64_t np = orc_detect(t1, t2, 0, n, &p, &s, &l, peaks, n);
+    int64_t ne;
+    if (np + 1 > cap) {
+        ne = -(int64_t)(np + 1);
+    } else {
+        ne = (int64_t)orc_events(peaks, np, S, Q, n, start, length, mean, stdv);
+    }
+    free(peaks); free(t2); free(t1); free(Q); free(S);
+    return ne;
+}
+
+int64_t orc_event_read(const int16_t *raw, uint64_t n, double digitisation,
+                       double offset, double range, int rna, uint64_t cap,
+                       uint64_t *start, float *length, float *mean, float *stdv) {
+    float *pa = (float *)malloc((n ? n : 1) * sizeof(float));
+    orc_pa(raw, n, digitisation, offset, range, pa);
+    const int64_t ne = orc_getevents(n, pa, rna, cap, start, length, mean, stdv);
+    free(pa);
+    return ne;
+}
+
+static int cmp_float(const void *a, const void *b) {
+    const float x = *(const float *)a, y = *(const float *)b;
+    return (x > y) - (x < y);
+}
+
+/* cfunc.c:126-159 + stat.h:17-73 (sequential float accumulators; the median
+ * is the element of rank n/2, ksort.h:233-259) */
+void orc_stat(const int16_t *raw, uint64_t n, double digitisation, double offset,
+              double range, float *out6) {
+    const int ni = (int)n;
+    const float nf = (float)ni;
+    float *pa = (float *)malloc((n ? n : 1) * sizeof(float));
+    orc_pa(raw, n, digitisation, offset, range, pa);
+
+    float acc_r = 0.0f, acc_p = 0.0f;
+    for (int i = 0; i < ni; i++) {
+        acc_r = acc_r + (float)raw[i];
+        acc_p = acc_p + pa[i];
+    }
+    const float mean_r = acc_r / nf, mean_p = acc_p / nf;
+
+    float dev_r = 0.0f, dev_p = 0.0f;
+    for (int i = 0; i < ni; i++) {
+        const float dr = (float)raw[i] - mean_r;
+        const float dp = pa[i] - mean_p;
+        dev_r = dev_r + dr * dr;
+        dev_p = dev_p + dp * dp;
+    }
+    const float std_r = sqrtf(dev_r / nf), std_p = sqrtf(dev_p / nf);
+
+    /* rank n/2 of the raw values by counting */
+    uint32_t *hist = (uint32_t *)calloc(65536, sizeof(uint32_t));
+    for (int i = 0; i < ni; i++) hist[(uint16_t)(raw[i] + 32768)]++;
+    uint64_t rank = (uint64_t)(ni / 2), seen = 0;
+    int med_r = 0;
+    for (int v = 0; v < 65536; v++) {
+        seen += hist[v];
+        if (seen > rank) { med_r = v - 32768; break; }
+    }
+    free(hist);
+    qsort(pa, n, sizeof(float), cmp_float);
+    const float med_p = ni > 0 ? pa[ni / 2] : 0.0f;
+    free(pa);
+
+    out6[0] = mean_r; out6[1] = mean_p; out6[2] = std_r; out6[3] = std_p;
+    out6[4] = (float)med_r; out6[5] = med_p;
+}
+
+double orc_time_events(const int16_t *samples, const uint64_t *read_off,
+                       uint64_t n_reads, const double *digitisation,
+                       const double *offset, const double *range, int rna,
+                       uint64_t *total_events) {
+    uint64_t maxn = 1, nev = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const uint64_t n = read_off[r + 1] - read_off[r];
+        if (n > maxn) maxn = n;
+    }
+    uint64_t *st = (uint64_t *)malloc(maxn * sizeof(uint64_t));
+    float *ln = (float *)malloc(maxn * sizeof(float));
+    float *mn = (float *)malloc(maxn * sizeof(float));
+    float *sd = (float *)malloc(maxn * sizeof(float));
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (uint64_t r = 0; r < n_reads; r++) {
+        const uint64_t n = read_off[r + 1] - read_off[r];
+        const int64_t ne = orc_event_read(samples + read_off[r], n, digitisation[r],
+                                          offset[r], range[r], rna, maxn, st, ln, mn, sd);
+        if (ne > 0) nev += (uint64_t)ne;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    free(sd); free(mn); free(ln); free(st);
+    if (total_events) *total_events = nev;
+    return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+}

@@ -1,0 +1,176 @@
+"""Host-side mirror of the reference's operator interface for the raw-signal path.
+
+The reference works one record at a time through
+``float *signal_in_picoamps(slow5_rec_t*)`` (src/sigtk.h:124) and
+``event_table getevents(size_t, float*, int8_t rna)`` (src/sigtk.h:134) and
+prints ``event_t {start, length, mean, stdv}`` (src/sigtk.h:55-62).  Here the
+unit of work is a batch of records; results come back per read in record
+order.  All compute happens in ``libsigtk_b200.so`` (hand-written CUDA for
+sm_100a) through the C-ABI in ``include/sigtk_b200.h``; this module only moves
+numpy buffers in and out of the pinned slots.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import (ALIGN, F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, WANT_EVENTS, WANT_PA, WANT_STAT,
+                   SgpuError)
+
+Read = Tuple[np.ndarray, float, float, float]  # raw int16, digitisation, offset, range
+
+
+@dataclass
+class EventTable:
+    """event_table of one read (src/sigtk.h:65-70) as arrays."""
+    start: np.ndarray   # uint64
+    length: np.ndarray  # float32, (float)(end - start)
+    mean: np.ndarray    # float32
+    stdv: np.ndarray    # float32
+
+    @property
+    def n(self) -> int:
+        return int(self.start.shape[0])
+
+
+@dataclass
+class BatchResult:
+    n_reads: int
+    read_len: np.ndarray
+    ev_off: Optional[np.ndarray] = None
+    ev_start: Optional[np.ndarray] = None
+    ev_mean: Optional[np.ndarray] = None
+    ev_stdv: Optional[np.ndarray] = None
+    pa: Optional[List[np.ndarray]] = None
+    stat: Optional[np.ndarray] = None
+    seq_order: Optional[np.ndarray] = None
+    fixups: Optional[np.ndarray] = None
+
+    def events(self, r: int) -> EventTable:
+        a, b = int(self.ev_off[r]), int(self.ev_off[r + 1])
+        start = self.ev_start[a:b].astype(np.uint64)
+        end = np.empty_like(start)
+        end[:-1] = start[1:]
+        end[-1] = self.read_len[r]
+        length = (end - start).astype(np.float32)
+        return EventTable(start, length, self.ev_mean[a:b].copy(), self.ev_stdv[a:b].copy())
+
+
+def _np_from(ptr: int, dtype, count: int) -> np.ndarray:
+    if count == 0:
+        return np.empty(0, dtype=dtype)
+    buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+
+class Context:
+    """One GPU context (sgpu_ctx_t)."""
+
+    def __init__(self, device: int = 0, max_samples: int = 1 << 24, max_reads: int = 1 << 16,
+                 n_slots: int = 2, flags: int = F_DEFAULT):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.max_samples, self.max_reads, self.n_slots = max_samples, max_reads, n_slots
+        rc = self._lib.sgpu_create(C.byref(self._h), device, max_samples, max_reads, n_slots, flags)
+        if rc != 0:
+            raise SgpuError(rc, self._lib.sgpu_strerror(rc).decode())
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.sgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc < 0:
+            raise SgpuError(rc, f"{self._lib.sgpu_strerror(rc).decode()} | {self._lib.sgpu_last_error(self._h).decode()}")
+
+    # ---- host path -------------------------------------------------------
+    def fill(self, slot: int, reads: Sequence[Read], rna: int) -> None:
+        self._check(self._lib.sgpu_slot_reset(self._h, slot, int(rna)))
+        for raw, dig, off, rng in reads:
+            raw = np.ascontiguousarray(raw, dtype=np.int16)
+            rc = self._lib.sgpu_slot_add_read(self._h, slot, raw.ctypes.data, raw.shape[0], float(dig), float(off),
+                                              float(rng))
+            self._check(int(rc))
+
+    def submit(self, slot: int, want: int) -> None:
+        self._check(self._lib.sgpu_submit(self._h, slot, want))
+
+    def wait(self, slot: int, want: int) -> BatchResult:
+        res = _lib.Result()
+        self._check(self._lib.sgpu_wait(self._h, slot, C.byref(res)))
+        pb = C.POINTER(_lib.Batch)()
+        self._check(self._lib.sgpu_slot_batch(self._h, slot, C.byref(pb)))
+        b = pb.contents
+        n = int(b.n_reads)
+        read_len = np.ctypeslib.as_array(b.read_len, shape=(max(n, 1),))[:n].copy()
+        read_off = np.ctypeslib.as_array(b.read_off, shape=(n + 1,)).copy()
+        out = BatchResult(n_reads=n, read_len=read_len)
+        if want & WANT_EVENTS:
+            ne = int(res.n_events)
+            out.ev_off = _np_from(res.ev_off, np.uint64, n + 1)
+            out.ev_start = _np_from(res.ev_start, np.uint32, ne)
+            out.ev_mean = _np_from(res.ev_mean, np.float32, ne)
+            out.ev_stdv = _np_from(res.ev_stdv, np.float32, ne)
+            out.seq_order = _np_from(res.seq_order, np.uint32, n)
+            out.fixups = _np_from(res.fixups, np.uint32, n)
+        if want & WANT_STAT:
+            out.stat = _np_from(res.stat, np.float32, n * 6).reshape(n, 6)
+        if want & WANT_PA:
+            span = int(read_off[n]) if n else 0
+            flat = _np_from(res.pa, np.float32, span)
+            out.pa = [flat[int(read_off[r]): int(read_off[r]) + int(read_len[r])].copy() for r in range(n)]
+        return out
+
+    def run(self, reads: Sequence[Read], rna: int = 0, want: int = WANT_EVENTS, slot: int = 0) -> BatchResult:
+        """fill + submit + wait on one slot (the call a host program makes per batch)."""
+        self.fill(slot, reads, rna)
+        self.submit(slot, want)
+        return self.wait(slot, want)
+
+    # ---- device-resident path ---------------------------------------------
+    def run_device(self, samples_ptr: int, read_off_ptr: int, read_len_ptr: int, offset_ptr: int, unit_ptr: int,
+                   n_reads: int, span: int, rna: int, want: int, stream: int = 0) -> _lib.Result:
+        db = _lib.DevBatch(samples_ptr, read_off_ptr, read_len_ptr, offset_ptr, unit_ptr, n_reads, int(rna), span)
+        res = _lib.Result()
+        self._check(self._lib.sgpu_run_device(self._h, C.byref(db), want, C.c_void_p(stream), C.byref(res)))
+        return res
+
+    def counters(self) -> dict:
+        c = _lib.Counters()
+        self._check(self._lib.sgpu_counters(self._h, C.byref(c)))
+        return {"n_events": int(c.n_events), "n_seq_order_reads": int(c.n_seq_order_reads),
+                "n_fixups": int(c.n_fixups), "n_kernel_launches": int(c.n_kernel_launches), "status": int(c.status)}
+
+
+# ---- per-record conveniences mirroring the reference's function names --------
+def signal_in_picoamps(ctx: Context, raw: np.ndarray, digitisation: float, offset: float, range_: float) -> np.ndarray:
+    """misc.c:15-32 for one record."""
+    return ctx.run([(raw, digitisation, offset, range_)], 0, WANT_PA).pa[0]
+
+
+def getevents(ctx: Context, raw: np.ndarray, digitisation: float, offset: float, range_: float,
+              rna: int = 0) -> EventTable:
+    """events.c:553-573 for one record (pA conversion is fused, so this takes the raw samples)."""
+    return ctx.run([(raw, digitisation, offset, range_)], rna, WANT_EVENTS).events(0)
+
+
+def stat(ctx: Context, raw: np.ndarray, digitisation: float, offset: float, range_: float) -> np.ndarray:
+    """The six numbers of stat_func (cfunc.c:126-159) for one record."""
+    return ctx.run([(raw, digitisation, offset, range_)], 0, WANT_STAT).stat[0]

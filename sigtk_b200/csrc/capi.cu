@@ -1,0 +1,485 @@
+// capi.cu -- the C-ABI of the sigtk B200 hot path (include/sigtk_b200.h).
+//
+// Context = one device, its workspace in HBM, and n_slots pinned host slots.
+// Host path per slot:  H2D (slot stream) -> kernels (context compute stream) -> D2H (slot stream),
+// chained with events so that copies of one slot overlap the kernels of another while the
+// kernels themselves are serialised (they share one scratch area).
+#include "../../include/sigtk_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "kernels.cuh"
+
+using namespace sgpu;
+
+namespace {
+
+struct DevOut {  // device-side outputs of one batch
+    uint64_t* ev_off = nullptr;
+    uint32_t* ev_start = nullptr;
+    float* ev_mean = nullptr;
+    float* ev_stdv = nullptr;
+    float* pa = nullptr;
+    float* stat = nullptr;
+};
+
+struct Slot {
+    // pinned host input
+    sgpu_batch_t batch{};
+    uint64_t used = 0;
+    // device input
+    int16_t* d_samples = nullptr;
+    uint64_t* d_read_off = nullptr;
+    uint32_t* d_read_len = nullptr;
+    float* d_offset = nullptr;
+    float* d_unit = nullptr;
+    DevOut dout;
+    uint32_t* d_seq = nullptr;
+    uint32_t* d_fix = nullptr;
+    // pinned host output
+    uint64_t* h_ev_off = nullptr;
+    uint32_t* h_ev_start = nullptr;
+    float* h_ev_mean = nullptr;
+    float* h_ev_stdv = nullptr;
+    float* h_pa = nullptr;
+    float* h_stat = nullptr;
+    uint32_t* h_seq = nullptr;
+    uint32_t* h_fix = nullptr;
+    unsigned long long* h_counters = nullptr;  // [4]
+    int* h_status = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t in_ready = nullptr, kernels_done = nullptr, small_back = nullptr;
+    bool submitted = false;
+    uint32_t want = 0;
+};
+
+}  // namespace
+
+struct sgpu_ctx {
+    int device = 0;
+    int sm_count = 148;
+    uint64_t max_samples = 0;
+    uint32_t max_reads = 0;
+    uint32_t n_slots = 0;
+    uint32_t flags = 0;
+    uint64_t ev_cap = 0;
+    Scratch sc{};
+    DevOut dev_out;              // outputs of the device-resident path
+    uint32_t* dev_seq = nullptr; // aliases sc.seq_flag / sc.fixups for the device path
+    Slot* slots = nullptr;
+    cudaStream_t compute = nullptr;
+    uint64_t last_launches = 0;
+    char err[512] = {0};
+};
+
+namespace {
+
+bool cuda_fail(sgpu_ctx* c, cudaError_t e, const char* what, int line) {
+    if (e == cudaSuccess) return false;
+    if (c) snprintf(c->err, sizeof c->err, "%s: %s (%s) at capi.cu:%d", what, cudaGetErrorName(e),
+                    cudaGetErrorString(e), line);
+    return true;
+}
+#define CU(call)                                                         \
+    do {                                                                 \
+        if (cuda_fail(ctx, (call), #call, __LINE__)) return SGPU_E_CUDA; \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T** p, uint64_t count) {
+    return cudaMalloc(reinterpret_cast<void**>(p), (size_t)(count ? count : 1) * sizeof(T));
+}
+template <typename T>
+cudaError_t pin_alloc(T** p, uint64_t count) {
+    return cudaHostAlloc(reinterpret_cast<void**>(p), (size_t)(count ? count : 1) * sizeof(T), cudaHostAllocDefault);
+}
+
+uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t n, uint32_t v) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+int alloc_dev_out(sgpu_ctx* ctx, DevOut& o) {
+    CU(dev_alloc(&o.ev_off, (uint64_t)ctx->max_reads + 1));
+    CU(dev_alloc(&o.ev_start, ctx->ev_cap));
+    CU(dev_alloc(&o.ev_mean, ctx->ev_cap));
+    CU(dev_alloc(&o.ev_stdv, ctx->ev_cap));
+    CU(dev_alloc(&o.stat, (uint64_t)ctx->max_reads * 6));
+    o.pa = nullptr;  // allocated on first use (4 B/sample)
+    return SGPU_OK;
+}
+
+void free_dev_out(DevOut& o) {
+    cudaFree(o.ev_off); cudaFree(o.ev_start); cudaFree(o.ev_mean); cudaFree(o.ev_stdv);
+    cudaFree(o.pa); cudaFree(o.stat);
+    o = DevOut{};
+}
+
+// The kernel sequence of one batch. No host synchronisation, no host<->device copies.
+int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uint32_t* d_seq, uint32_t* d_fix,
+                 cudaStream_t st) {
+    Scratch& sc = ctx->sc;
+    uint64_t launches = 0;
+    if (b.n_reads > ctx->max_reads || b.span > ctx->max_samples) return SGPU_E_INVAL;
+    CU(cudaMemsetAsync(sc.status, 0, sizeof(int), st));
+    CU(cudaMemsetAsync(sc.counters, 0, 4 * sizeof(unsigned long long), st));
+    if (b.n_reads == 0) {
+        CU(cudaMemsetAsync(o.ev_off, 0, sizeof(uint64_t), st));
+        ctx->last_launches = 0;
+        return SGPU_OK;
+    }
+    if (want & SGPU_WANT_PA) {
+        if (!o.pa) CU(dev_alloc(&o.pa, align_up(ctx->max_samples, SGPU_ALIGN)));
+        launches += launch_pa(b, o.pa, ctx->sm_count, st);
+    }
+    if (want & SGPU_WANT_STAT) launches += launch_stat(b, o.stat, ctx->sm_count, st);
+    if (want & SGPU_WANT_EVENTS) {
+        const uint64_t words = (b.span >> 5) + 2;
+        if (words > sc.bitmap_words) return SGPU_E_INVAL;
+        CU(cudaMemsetAsync(sc.bitmap, 0, words * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(d_fix, 0, (size_t)b.n_reads * sizeof(uint32_t), st));
+        // round 1: every read goes through the sequential-order kernels
+        if (b.span > sc.gen_cap) return SGPU_E_SCRATCH;
+        WorkList wl{nullptr, b.read_off, nullptr, b.n_reads};
+        launches += launch_generic_detect(b, wl, b.span, sc, /*clear_first=*/0, ctx->sm_count, st);
+        fill_u32_kernel<<<(b.n_reads + 255) / 256, 256, 0, st>>>(d_seq, b.n_reads, 1u);
+        launches += 1;
+        launches += launch_count_scan(b, sc, o.ev_off, reinterpret_cast<uint64_t*>(sc.counters), ctx->sm_count, st);
+        launches += launch_generic_emit(b, wl, sc, o.ev_off, ctx->ev_cap, o.ev_start, o.ev_mean, o.ev_stdv, sc.status,
+                                        ctx->sm_count, st);
+        set_u64_kernel<<<1, 1, 0, st>>>(sc.counters + 1, (unsigned long long)b.n_reads);
+        launches += 1;
+    }
+    CU(cudaGetLastError());
+    ctx->last_launches = launches;
+    return SGPU_OK;
+}
+
+int map_dev_status(int s) {
+    if (s == SGPU_DEV_E_EVCAP) return SGPU_E_EVCAP;
+    if (s == SGPU_DEV_E_SCRATCH) return SGPU_E_SCRATCH;
+    return SGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sgpu_abi_version(void) { return SGPU_ABI_VERSION; }
+
+int sgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* sgpu_strerror(int code) {
+    switch (code) {
+        case SGPU_OK: return "success";
+        case SGPU_E_INVAL: return "invalid argument";
+        case SGPU_E_CUDA: return "CUDA error (no usable B200 / kernel failure); there is no CPU fallback";
+        case SGPU_E_NOMEM: return "out of memory";
+        case SGPU_E_FULL: return "slot full";
+        case SGPU_E_TOOBIG: return "read larger than the context's max_samples";
+        case SGPU_E_STATE: return "call out of order";
+        case SGPU_E_EVCAP: return "event capacity exceeded";
+        case SGPU_E_SCRATCH: return "sequential-order scratch too small";
+        default: return "unknown error";
+    }
+}
+
+const char* sgpu_last_error(const sgpu_ctx_t* ctx) { return ctx ? ctx->err : "no context"; }
+
+int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max_reads, uint32_t n_slots,
+                uint32_t flags) {
+    if (!out || max_samples == 0 || max_reads == 0) return SGPU_E_INVAL;
+    *out = nullptr;
+    if (flags & SGPU_F_NO_HOST_SLOTS) n_slots = 0; else if (n_slots == 0) n_slots = 2;
+    sgpu_ctx* ctx = new (std::nothrow) sgpu_ctx();
+    if (!ctx) return SGPU_E_NOMEM;
+    int rc = SGPU_OK;
+    auto fail = [&](int code) { sgpu_destroy(ctx); return code; };
+    {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || device < 0 || device >= ndev) {
+            fprintf(stderr, "[sigtk_b200] no usable CUDA device %d (%s); this library has no CPU fallback\n", device,
+                    e == cudaSuccess ? "index out of range" : cudaGetErrorString(e));
+            delete ctx;
+            return SGPU_E_CUDA;
+        }
+    }
+#define CUC(call)                                                               \
+    do {                                                                        \
+        if (cuda_fail(ctx, (call), #call, __LINE__)) {                          \
+            fprintf(stderr, "[sigtk_b200] %s\n", ctx->err);                     \
+            return fail(SGPU_E_CUDA);                                           \
+        }                                                                       \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    max_samples = align_up(max_samples, 64);
+    ctx->max_samples = max_samples;
+    ctx->max_reads = max_reads;
+    ctx->n_slots = n_slots;
+    ctx->flags = flags;
+    // consecutive peaks are >= 3 samples apart (DNA; 5 for RNA) => <= n/3 + 2 events per read
+    ctx->ev_cap = max_samples / 3 + 2ull * max_reads + 16;
+    Scratch& sc = ctx->sc;
+    // round 1: all reads use the sequential-order scratch
+    sc.gen_cap = max_samples;
+    if (const char* e = getenv("SGPU_GEN_CAP")) { uint64_t v = strtoull(e, nullptr, 10); if (v) sc.gen_cap = v; }
+    CUC(dev_alloc(&sc.Sinc, sc.gen_cap));
+    CUC(dev_alloc(&sc.Qinc, sc.gen_cap));
+    CUC(dev_alloc(&sc.t1, sc.gen_cap));
+    CUC(dev_alloc(&sc.t2, sc.gen_cap));
+    sc.bitmap_words = (max_samples >> 5) + 4;
+    CUC(dev_alloc(&sc.bitmap, sc.bitmap_words));
+    CUC(dev_alloc(&sc.ev_cnt, max_reads));
+    CUC(dev_alloc(&sc.seq_flag, max_reads));
+    CUC(dev_alloc(&sc.fixups, max_reads));
+    CUC(dev_alloc(&sc.seq_list, max_reads));
+    CUC(dev_alloc(&sc.seq_sbase, (uint64_t)max_reads + 1));
+    CUC(dev_alloc(&sc.seq_count, 1));
+    CUC(dev_alloc(&sc.scan_status, scan_tiles_for(max_reads) + 1));
+    CUC(dev_alloc(&sc.scan_ticket, 1));
+    CUC(dev_alloc(&sc.status, 1));
+    CUC(dev_alloc(&sc.counters, 4));
+    CUC(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    rc = alloc_dev_out(ctx, ctx->dev_out);
+    if (rc) return fail(rc);
+    if (n_slots) {
+        ctx->slots = new (std::nothrow) Slot[n_slots];
+        if (!ctx->slots) return fail(SGPU_E_NOMEM);
+        for (uint32_t s = 0; s < n_slots; s++) {
+            Slot& sl = ctx->slots[s];
+            CUC(pin_alloc(&sl.batch.samples, max_samples));
+            CUC(pin_alloc(&sl.batch.read_off, (uint64_t)max_reads + 1));
+            CUC(pin_alloc(&sl.batch.read_len, max_reads));
+            CUC(pin_alloc(&sl.batch.offset_f, max_reads));
+            CUC(pin_alloc(&sl.batch.raw_unit_f, max_reads));
+            CUC(dev_alloc(&sl.d_samples, max_samples));
+            CUC(dev_alloc(&sl.d_read_off, (uint64_t)max_reads + 1));
+            CUC(dev_alloc(&sl.d_read_len, max_reads));
+            CUC(dev_alloc(&sl.d_offset, max_reads));
+            CUC(dev_alloc(&sl.d_unit, max_reads));
+            CUC(dev_alloc(&sl.d_seq, max_reads));
+            CUC(dev_alloc(&sl.d_fix, max_reads));
+            // every slot gets its own outputs (its D2H overlaps the next slot's kernels)
+            rc = alloc_dev_out(ctx, sl.dout);
+            if (rc) return fail(rc);
+            CUC(pin_alloc(&sl.h_ev_off, (uint64_t)max_reads + 1));
+            CUC(pin_alloc(&sl.h_ev_start, ctx->ev_cap));
+            CUC(pin_alloc(&sl.h_ev_mean, ctx->ev_cap));
+            CUC(pin_alloc(&sl.h_ev_stdv, ctx->ev_cap));
+            CUC(pin_alloc(&sl.h_stat, (uint64_t)max_reads * 6));
+            CUC(pin_alloc(&sl.h_seq, max_reads));
+            CUC(pin_alloc(&sl.h_fix, max_reads));
+            CUC(pin_alloc(&sl.h_counters, 4));
+            CUC(pin_alloc(&sl.h_status, 1));
+            CUC(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            CUC(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+            CUC(cudaEventCreateWithFlags(&sl.kernels_done, cudaEventDisableTiming));
+            CUC(cudaEventCreateWithFlags(&sl.small_back, cudaEventDisableTiming));
+            sl.batch.n_reads = 0;
+            sl.batch.read_off[0] = 0;
+        }
+    }
+#undef CUC
+    *out = ctx;
+    return SGPU_OK;
+}
+
+void sgpu_destroy(sgpu_ctx_t* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    Scratch& sc = ctx->sc;
+    cudaFree(sc.Sinc); cudaFree(sc.Qinc); cudaFree(sc.t1); cudaFree(sc.t2); cudaFree(sc.bitmap);
+    cudaFree(sc.ev_cnt); cudaFree(sc.seq_flag); cudaFree(sc.fixups); cudaFree(sc.seq_list); cudaFree(sc.seq_sbase);
+    cudaFree(sc.seq_count); cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status);
+    cudaFree(sc.counters);
+    free_dev_out(ctx->dev_out);
+    if (ctx->slots) {
+        for (uint32_t s = 0; s < ctx->n_slots; s++) {
+            Slot& sl = ctx->slots[s];
+            cudaFreeHost(sl.batch.samples); cudaFreeHost(sl.batch.read_off); cudaFreeHost(sl.batch.read_len);
+            cudaFreeHost(sl.batch.offset_f); cudaFreeHost(sl.batch.raw_unit_f);
+            cudaFree(sl.d_samples); cudaFree(sl.d_read_off); cudaFree(sl.d_read_len); cudaFree(sl.d_offset);
+            cudaFree(sl.d_unit); cudaFree(sl.d_seq); cudaFree(sl.d_fix);
+            free_dev_out(sl.dout);
+            cudaFreeHost(sl.h_ev_off); cudaFreeHost(sl.h_ev_start); cudaFreeHost(sl.h_ev_mean);
+            cudaFreeHost(sl.h_ev_stdv); cudaFreeHost(sl.h_pa); cudaFreeHost(sl.h_stat); cudaFreeHost(sl.h_seq);
+            cudaFreeHost(sl.h_fix); cudaFreeHost(sl.h_counters); cudaFreeHost(sl.h_status);
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+            if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+            if (sl.kernels_done) cudaEventDestroy(sl.kernels_done);
+            if (sl.small_back) cudaEventDestroy(sl.small_back);
+        }
+        delete[] ctx->slots;
+    }
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    delete ctx;
+}
+
+int sgpu_slot_batch(sgpu_ctx_t* ctx, uint32_t slot, sgpu_batch_t** out) {
+    if (!ctx || !out || slot >= ctx->n_slots) return SGPU_E_INVAL;
+    *out = &ctx->slots[slot].batch;
+    return SGPU_OK;
+}
+
+int sgpu_slot_reset(sgpu_ctx_t* ctx, uint32_t slot, uint32_t rna) {
+    if (!ctx || slot >= ctx->n_slots) return SGPU_E_INVAL;
+    Slot& sl = ctx->slots[slot];
+    if (sl.submitted) return SGPU_E_STATE;
+    sl.batch.n_reads = 0;
+    sl.batch.rna = rna ? 1u : 0u;
+    sl.batch.read_off[0] = 0;
+    sl.used = 0;
+    return SGPU_OK;
+}
+
+int64_t sgpu_slot_add_read(sgpu_ctx_t* ctx, uint32_t slot, const int16_t* raw, uint64_t n, double digitisation,
+                           double offset, double range) {
+    if (!ctx || slot >= ctx->n_slots || (!raw && n)) return SGPU_E_INVAL;
+    Slot& sl = ctx->slots[slot];
+    if (sl.submitted) return SGPU_E_STATE;
+    if (n >= (1ull << 31)) return SGPU_E_TOOBIG;  // the reference itself narrows to int32_t (misc.c:20)
+    const uint64_t need = align_up(n, SGPU_ALIGN);
+    if (need > ctx->max_samples) return SGPU_E_TOOBIG;
+    sgpu_batch_t& b = sl.batch;
+    if (b.n_reads >= ctx->max_reads || sl.used + need > ctx->max_samples) return SGPU_E_FULL;
+    const uint32_t r = b.n_reads;
+    memcpy(b.samples + sl.used, raw, (size_t)n * sizeof(int16_t));
+    b.read_off[r] = sl.used;
+    b.read_len[r] = (uint32_t)n;
+    // misc.c:17-19,26: narrow the three doubles to float first, then ONE float division
+    const float range_f = (float)range, dig_f = (float)digitisation, off_f = (float)offset;
+    volatile float unit = range_f / dig_f;
+    b.offset_f[r] = off_f;
+    b.raw_unit_f[r] = unit;
+    sl.used += need;
+    b.n_reads = r + 1;
+    b.read_off[r + 1] = sl.used;
+    return (int64_t)r;
+}
+
+int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
+    if (!ctx || slot >= ctx->n_slots || (want & ~7u) || want == 0) return SGPU_E_INVAL;
+    Slot& sl = ctx->slots[slot];
+    if (sl.submitted) return SGPU_E_STATE;
+    CU(cudaSetDevice(ctx->device));
+    const sgpu_batch_t& hb = sl.batch;
+    const uint32_t nr = hb.n_reads;
+    cudaStream_t st = sl.stream;
+    CU(cudaMemcpyAsync(sl.d_samples, hb.samples, (size_t)sl.used * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sl.d_read_off, hb.read_off, ((size_t)nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sl.d_read_len, hb.read_len, (size_t)nr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sl.d_offset, hb.offset_f, (size_t)nr * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sl.d_unit, hb.raw_unit_f, (size_t)nr * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(sl.in_ready, st));
+    CU(cudaStreamWaitEvent(ctx->compute, sl.in_ready, 0));
+    DevBatch b{sl.d_samples, sl.d_read_off, sl.d_read_len, sl.d_offset, sl.d_unit, nr, (int)hb.rna, sl.used};
+    if ((want & SGPU_WANT_PA) && !sl.h_pa) CU(pin_alloc(&sl.h_pa, ctx->max_samples));
+    const int rc = run_pipeline(ctx, b, want, sl.dout, sl.d_seq, sl.d_fix, ctx->compute);
+    if (rc) return rc;
+    // small results come back right away; the big arrays are sized by n_events in sgpu_wait
+    CU(cudaMemcpyAsync(sl.h_counters, ctx->sc.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                       ctx->compute));
+    CU(cudaMemcpyAsync(sl.h_status, ctx->sc.status, sizeof(int), cudaMemcpyDeviceToHost, ctx->compute));
+    CU(cudaEventRecord(sl.kernels_done, ctx->compute));
+    CU(cudaStreamWaitEvent(st, sl.kernels_done, 0));
+    if (want & SGPU_WANT_EVENTS) {
+        CU(cudaMemcpyAsync(sl.h_ev_off, sl.dout.ev_off, ((size_t)nr + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sl.h_seq, sl.d_seq, (size_t)nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sl.h_fix, sl.d_fix, (size_t)nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    if (want & SGPU_WANT_STAT)
+        CU(cudaMemcpyAsync(sl.h_stat, sl.dout.stat, (size_t)nr * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (want & SGPU_WANT_PA)
+        CU(cudaMemcpyAsync(sl.h_pa, sl.dout.pa, (size_t)sl.used * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(sl.small_back, st));
+    sl.want = want;
+    sl.submitted = true;
+    return SGPU_OK;
+}
+
+int sgpu_wait(sgpu_ctx_t* ctx, uint32_t slot, sgpu_result_t* out) {
+    if (!ctx || slot >= ctx->n_slots || !out) return SGPU_E_INVAL;
+    Slot& sl = ctx->slots[slot];
+    if (!sl.submitted) return SGPU_E_STATE;
+    CU(cudaSetDevice(ctx->device));
+    sl.submitted = false;
+    CU(cudaEventSynchronize(sl.small_back));
+    memset(out, 0, sizeof *out);
+    const int dev_rc = map_dev_status(*sl.h_status);
+    if (dev_rc) return dev_rc;
+    const uint32_t nr = sl.batch.n_reads;
+    if (sl.want & SGPU_WANT_EVENTS) {
+        const uint64_t ne = nr ? sl.h_ev_off[nr] : 0;
+        if (ne > ctx->ev_cap) return SGPU_E_EVCAP;
+        cudaStream_t st = sl.stream;
+        CU(cudaMemcpyAsync(sl.h_ev_start, sl.dout.ev_start, (size_t)ne * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sl.h_ev_mean, sl.dout.ev_mean, (size_t)ne * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sl.h_ev_stdv, sl.dout.ev_stdv, (size_t)ne * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        out->ev_off = sl.h_ev_off;
+        out->ev_start = sl.h_ev_start;
+        out->ev_mean = sl.h_ev_mean;
+        out->ev_stdv = sl.h_ev_stdv;
+        out->seq_order = sl.h_seq;
+        out->fixups = sl.h_fix;
+        out->n_events = ne;
+    }
+    if (sl.want & SGPU_WANT_STAT) out->stat = sl.h_stat;
+    if (sl.want & SGPU_WANT_PA) out->pa = sl.h_pa;
+    return SGPU_OK;
+}
+
+int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t want, void* stream,
+                    sgpu_result_t* out) {
+    if (!ctx || !batch || !out || (want & ~7u) || want == 0) return SGPU_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    DevBatch b{batch->samples, batch->read_off, batch->read_len, batch->offset_f, batch->raw_unit_f,
+               batch->n_reads, (int)batch->rna, batch->span};
+    const int rc = run_pipeline(ctx, b, want, ctx->dev_out, ctx->sc.seq_flag, ctx->sc.fixups,
+                                reinterpret_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->ev_off = ctx->dev_out.ev_off;
+    out->ev_start = ctx->dev_out.ev_start;
+    out->ev_mean = ctx->dev_out.ev_mean;
+    out->ev_stdv = ctx->dev_out.ev_stdv;
+    out->pa = (want & SGPU_WANT_PA) ? ctx->dev_out.pa : nullptr;
+    out->stat = ctx->dev_out.stat;
+    out->seq_order = ctx->sc.seq_flag;
+    out->fixups = ctx->sc.fixups;
+    return SGPU_OK;
+}
+
+int sgpu_counters(sgpu_ctx_t* ctx, sgpu_counters_t* out) {
+    if (!ctx || !out) return SGPU_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long c[4];
+    int status = 0;
+    CU(cudaMemcpy(c, ctx->sc.counters, sizeof c, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&status, ctx->sc.status, sizeof status, cudaMemcpyDeviceToHost));
+    out->n_events = c[0];
+    out->n_seq_order_reads = c[1];
+    out->n_fixups = c[2];
+    out->n_kernel_launches = ctx->last_launches;
+    out->status = map_dev_status(status);
+    return SGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// generic.cu -- the sequential-order ("reference-order") kernels.
+//
+// These kernels evaluate the reference's per-read pipeline in exactly the
+// reference's operation order, so their results are bit-identical to
+// src/events.c for ANY input (including reads whose FP64 prefix sums are not
+// exactly representable and therefore depend on the summation order):
+//
+//   gen_prefix_kernel   compute_sum_sumsq          events.c:293-303  (one thread walks one read)
+//   gen_tstat_kernel    compute_tstat (both w)     events.c:315-364  (one thread per sample)
+//   gen_detect_kernel   short_long_peak_detector   events.c:371-443  (one thread walks one read)
+//   gen_emit_kernel     create_events/create_event events.c:457-504  (one thread walks one read)
+//
+// They serve (a) reads that fail the exact-sum witness of the fast path,
+// (b) SGPU_F_FORCE_GENERIC, and (c) as the on-device cross-check of the fast
+// path in the tests.  They keep S, Q (16 B/sample) and t1, t2 (8 B/sample) in
+// an HBM scratch area, so they are NOT the roofline path.
+#include "kernels.cuh"
+
+namespace sgpu {
+
+// ---------------------------------------------------------------------------
+// compute_sum_sumsq: Sinc[base+i] = S[i+1], Qinc[base+i] = Q[i+1]  (S[0]=Q[0]=0 implied)
+__global__ void __launch_bounds__(128) gen_prefix_kernel(DevBatch b, WorkList wl, double* __restrict__ Sinc,
+                                                         double* __restrict__ Qinc) {
+    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
+        const uint32_t r = wl.list ? wl.list[j] : j;
+        const uint64_t base = wl.sbase[j];
+        const int16_t* __restrict__ raw = b.samples + b.read_off[r];
+        const uint32_t n = b.read_len[r];
+        const float off = b.offset[r], unit = b.unit[r];
+        double s = 0.0, q = 0.0;
+        for (uint32_t i = 0; i < n; i++) {
+            const float x = pa_of(raw[i], off, unit);
+            const float xx = __fmul_rn(x, x);  // float product, widened afterwards (events.c:301)
+            s = __dadd_rn(s, (double)x);
+            q = __dadd_rn(q, (double)xx);
+            Sinc[base + i] = s;
+            Qinc[base + i] = q;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double prefix_at(const double* __restrict__ inc, uint64_t base, uint32_t k) {
+    return k ? inc[base + k - 1] : 0.0;
+}
+
+__device__ __forceinline__ float tstat_at(const double* __restrict__ Sinc, const double* __restrict__ Qinc,
+                                          uint64_t base, uint32_t n, uint32_t i, uint32_t w) {
+    // events.c:328-338: zero unless w <= i <= n-w (and n >= 2w, w >= 2)
+    if (n < 2u * w || w < 2u || i < w || i + w > n) return 0.0f;
+    const double s_i = prefix_at(Sinc, base, i), q_i = prefix_at(Qinc, base, i);
+    // i == w subtracts S[0] == 0.0, identical to the reference's "if (i > w)" branch
+    const double sum1 = __dsub_rn(s_i, prefix_at(Sinc, base, i - w));
+    const double ssq1 = __dsub_rn(q_i, prefix_at(Qinc, base, i - w));
+    const double sum2 = __dsub_rn(prefix_at(Sinc, base, i + w), s_i);
+    const double ssq2 = __dsub_rn(prefix_at(Qinc, base, i + w), q_i);
+    return tstat_reference_chain(sum1, ssq1, sum2, ssq2, (float)w);
+}
+
+__global__ void __launch_bounds__(256) gen_tstat_kernel(DevBatch b, WorkList wl, const double* __restrict__ Sinc,
+                                                        const double* __restrict__ Qinc, float* __restrict__ t1,
+                                                        float* __restrict__ t2) {
+    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
+    if (n_list == 0) return;
+    const uint64_t total = wl.sbase[n_list];
+    const DetParams p = det_params(b.rna);
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total;
+         u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = find_read(wl.sbase, n_list, u);
+        const uint32_t r = wl.list ? wl.list[j] : j;
+        const uint64_t base = wl.sbase[j];
+        const uint32_t n = b.read_len[r];
+        const uint64_t i64 = u - base;
+        if (i64 >= n) continue;  // alignment gap
+        const uint32_t i = (uint32_t)i64;
+        t1[u] = tstat_at(Sinc, Qinc, base, n, i, (uint32_t)p.w1);
+        t2[u] = tstat_at(Sinc, Qinc, base, n, i, (uint32_t)p.w2);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Clear the peak bits of one read (edge words are shared with neighbouring reads).
+__device__ void clear_read_bits(uint32_t* __restrict__ bitmap, uint64_t p0, uint64_t p1) {
+    if (p1 <= p0) return;
+    const uint64_t w0 = p0 >> 5, w1 = (p1 - 1) >> 5;
+    const uint32_t m0 = 0xffffffffu << (p0 & 31);
+    const uint32_t m1 = 0xffffffffu >> (31 - ((p1 - 1) & 31));
+    if (w0 == w1) { atomicAnd(&bitmap[w0], ~(m0 & m1)); return; }
+    atomicAnd(&bitmap[w0], ~m0);
+    for (uint64_t w = w0 + 1; w < w1; w++) bitmap[w] = 0u;
+    atomicAnd(&bitmap[w1], ~m1);
+}
+
+// One step of one detector (events.c:387-437). Returns the emitted peak position or -1.
+// `is_short` selects the masking of the long detector (414-422).
+__device__ __forceinline__ int32_t det_step(DetState& d, DetState* other_long, bool is_short, uint32_t i,
+                                            float cur, float thr, int w, float height) {
+    if (d.masked_to >= i) return -1;
+    if (d.peak_pos < 0) {  // CASE 1
+        if (cur < d.peak_value) {
+            d.peak_value = cur;
+        } else if (__fsub_rn(cur, d.peak_value) > height) {
+            d.peak_value = cur;
+            d.peak_pos = (int32_t)i;
+        }
+        return -1;
+    }
+    // CASE 2
+    if (cur > d.peak_value) { d.peak_value = cur; d.peak_pos = (int32_t)i; }
+    if (is_short && d.peak_value > thr) {
+        other_long->masked_to = (uint32_t)d.peak_pos + (uint32_t)w;
+        other_long->peak_pos = -1;
+        other_long->peak_value = FLT_MAX;
+        other_long->valid = 0;
+    }
+    if (__fsub_rn(d.peak_value, cur) > height && d.peak_value > thr) d.valid = 1;
+    if (d.valid && (i - (uint32_t)d.peak_pos) > (uint32_t)(w / 2)) {
+        const int32_t out = d.peak_pos;
+        d.peak_pos = -1;
+        d.peak_value = cur;
+        d.valid = 0;
+        return out;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(128) gen_detect_kernel(DevBatch b, WorkList wl, const float* __restrict__ t1,
+                                                         const float* __restrict__ t2, uint32_t* __restrict__ bitmap,
+                                                         int clear_first) {
+    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
+    const DetParams p = det_params(b.rna);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
+        const uint32_t r = wl.list ? wl.list[j] : j;
+        const uint64_t base = wl.sbase[j];
+        const uint64_t foff = b.read_off[r];
+        const uint32_t n = b.read_len[r];
+        if (clear_first) clear_read_bits(bitmap, foff, foff + n);
+        DetState s, l;
+        det_reset(s);
+        det_reset(l);
+        for (uint32_t i = 0; i < n; i++) {
+            const int32_t ps = det_step(s, &l, true, i, t1[base + i], p.thr1, p.w1, p.height);
+            if (ps > 0) { const uint64_t f = foff + (uint32_t)ps; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
+            const int32_t pl = det_step(l, nullptr, false, i, t2[base + i], p.thr2, p.w2, p.height);
+            if (pl > 0) { const uint64_t f = foff + (uint32_t)pl; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// number of events of every read = 1 + number of peak bits in (0, n)  (events.c:479-485)
+// one warp per read, lanes stride over the bitmap words
+__global__ void __launch_bounds__(256) count_events_kernel(DevBatch b, const uint32_t* __restrict__ bitmap,
+                                                           uint32_t* __restrict__ ev_cnt) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < b.n_reads; r += n_warps) {
+        const uint64_t p0 = b.read_off[r];
+        const uint32_t n = b.read_len[r];
+        uint32_t cnt = 0;
+        if (n > 0) {
+            const uint64_t p1 = p0 + n;
+            const uint64_t w0 = p0 >> 5, w1 = (p1 - 1) >> 5;
+            for (uint64_t w = w0 + lane; w <= w1; w += 32) {
+                uint32_t v = bitmap[w];
+                if (w == w0) v &= 0xffffffffu << (p0 & 31);
+                if (w == w1) v &= 0xffffffffu >> (31 - ((p1 - 1) & 31));
+                cnt += __popc(v);
+            }
+        }
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) ev_cnt[r] = cnt + 1u;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Exclusive scan ev_cnt[u32] -> ev_off[u64] (n+1 entries), single pass with
+// decoupled look-back (tile status = 2 flag bits | 62-bit value).
+static constexpr int SCAN_THREADS = 256;
+static constexpr int SCAN_ITEMS = 8;
+static constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+static constexpr uint64_t ST_AGG = 1ull << 62, ST_INC = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_counts_kernel(const uint32_t* __restrict__ cnt, uint32_t n,
+                                                                   uint64_t* __restrict__ off,
+                                                                   unsigned long long* __restrict__ status,
+                                                                   uint32_t* __restrict__ ticket,
+                                                                   uint64_t* __restrict__ total_out) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint64_t s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint64_t v[SCAN_ITEMS];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? cnt[base + k] : 0u;
+        sum += v[k];
+    }
+    // CTA-wide exclusive scan of the per-thread sums
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    uint64_t warp_excl = 0, cta_total = 0;
+    for (int k = 0; k < SCAN_THREADS / 32; k++) {
+        if (k < (int)wid) warp_excl += s_warp[k];
+        cta_total += s_warp[k];
+    }
+    uint64_t excl = warp_excl + inc - sum;
+    if (threadIdx.x == 0) {
+        uint64_t prefix = 0;
+        if (tile == 0) {
+            __threadfence();
+            atomicExch(&status[0], ST_INC | cta_total);
+        } else {
+            atomicExch(&status[tile], ST_AGG | cta_total);
+            int64_t look = (int64_t)tile - 1;
+            while (look >= 0) {
+                unsigned long long st;
+                do { st = atomicAdd(&status[look], 0ull); } while ((st >> 62) == 0);
+                prefix += st & ST_MASK;
+                if ((st >> 62) == 2) break;
+                look--;
+            }
+            atomicExch(&status[tile], ST_INC | (prefix + cta_total));
+        }
+        s_prefix = prefix;
+    }
+    __syncthreads();
+    excl += s_prefix;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) off[base + k] = excl;
+        excl += v[k];
+        if (base + k == n - 1) { off[n] = excl; if (total_out) *total_out = excl; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// create_events / create_event (events.c:457-504) from the sequential-order prefix sums.
+__global__ void __launch_bounds__(128) gen_emit_kernel(DevBatch b, WorkList wl, const double* __restrict__ Sinc,
+                                                       const double* __restrict__ Qinc,
+                                                       const uint32_t* __restrict__ bitmap,
+                                                       const uint64_t* __restrict__ ev_off, uint64_t ev_cap,
+                                                       uint32_t* __restrict__ ev_start, float* __restrict__ ev_mean,
+                                                       float* __restrict__ ev_stdv, int* __restrict__ status) {
+    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
+        const uint32_t r = wl.list ? wl.list[j] : j;
+        const uint64_t base = wl.sbase[j];
+        const uint64_t p0 = b.read_off[r];
+        const uint32_t n = b.read_len[r];
+        uint64_t k = ev_off[r];
+        if (ev_off[r + 1] > ev_cap) { atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
+        uint32_t a = 0;  // start of the open event
+        if (n > 0) {
+            const uint64_t p1 = p0 + n;
+            for (uint64_t w = p0 >> 5; w <= ((p1 - 1) >> 5); w++) {
+                uint32_t v = bitmap[w];
+                while (v) {
+                    const int bit = __ffs(v) - 1;
+                    v &= v - 1;
+                    const uint64_t f = (w << 5) + bit;
+                    if (f <= p0 || f >= p1) continue;  // peaks[i] > 0 && peaks[i] < nsample (events.c:482)
+                    const uint32_t e = (uint32_t)(f - p0);
+                    float m, sd;
+                    event_stats(__dsub_rn(prefix_at(Sinc, base, e), prefix_at(Sinc, base, a)),
+                                __dsub_rn(prefix_at(Qinc, base, e), prefix_at(Qinc, base, a)), e - a, &m, &sd);
+                    ev_start[k] = a; ev_mean[k] = m; ev_stdv[k] = sd;
+                    k++;
+                    a = e;
+                }
+            }
+        }
+        float m, sd;  // last event ends at nsample (events.c:499-501)
+        event_stats(__dsub_rn(prefix_at(Sinc, base, n), prefix_at(Sinc, base, a)),
+                    __dsub_rn(prefix_at(Qinc, base, n), prefix_at(Qinc, base, a)), n - a, &m, &sd);
+        ev_start[k] = a; ev_mean[k] = m; ev_stdv[k] = sd;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// signal_in_picoamps (misc.c:15-32) for a whole batch: one thread converts one
+// 16-byte group of 8 samples (groups never straddle reads: read starts are 8-aligned).
+__global__ void __launch_bounds__(256) pa_kernel(DevBatch b, float* __restrict__ pa) {
+    const uint64_t n_groups = b.span >> 3;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p = g << 3;
+        const uint32_t r = find_read(b.read_off, b.n_reads, p);
+        if (p - b.read_off[r] >= b.read_len[r]) continue;  // alignment gap
+        const float off = b.offset[r], unit = b.unit[r];
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(b.samples + p));
+        const int v[4] = {raw.x, raw.y, raw.z, raw.w};
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            o[2 * k] = pa_of((int16_t)(v[k] & 0xffff), off, unit);
+            o[2 * k + 1] = pa_of((int16_t)(v[k] >> 16), off, unit);
+        }
+        float4* dst = reinterpret_cast<float4*>(pa + p);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+static inline int grid_for(uint64_t work, int block, int max_blocks) {
+    uint64_t g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (uint64_t)max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+int launch_generic_detect(const DevBatch& b, const WorkList& wl, uint64_t scratch_span_hint, Scratch& sc,
+                          int clear_first, int sm_count, cudaStream_t st) {
+    const uint32_t n = wl.n_fixed;  // upper bound on the list length
+    gen_prefix_kernel<<<grid_for(n, 128, sm_count * 16), 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc);
+    gen_tstat_kernel<<<grid_for(scratch_span_hint, 256, sm_count * 8), 256, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.t1,
+                                                                                   sc.t2);
+    gen_detect_kernel<<<grid_for(n, 128, sm_count * 16), 128, 0, st>>>(b, wl, sc.t1, sc.t2, sc.bitmap, clear_first);
+    return 3;
+}
+
+int launch_count_scan(const DevBatch& b, Scratch& sc, uint64_t* ev_off, uint64_t* total_out, int sm_count,
+                      cudaStream_t st) {
+    count_events_kernel<<<grid_for((uint64_t)b.n_reads * 32, 256, sm_count * 8), 256, 0, st>>>(b, sc.bitmap,
+                                                                                             sc.ev_cnt);
+    const uint32_t tiles = (b.n_reads + SCAN_TILE - 1) / SCAN_TILE;
+    cudaMemsetAsync(sc.scan_status, 0, (size_t)(tiles + 1) * sizeof(unsigned long long), st);
+    cudaMemsetAsync(sc.scan_ticket, 0, sizeof(uint32_t), st);
+    scan_counts_kernel<<<tiles ? tiles : 1, SCAN_THREADS, 0, st>>>(sc.ev_cnt, b.n_reads, ev_off, sc.scan_status,
+                                                                  sc.scan_ticket, total_out);
+    return 2;
+}
+
+int launch_generic_emit(const DevBatch& b, const WorkList& wl, Scratch& sc, const uint64_t* ev_off, uint64_t ev_cap,
+                        uint32_t* ev_start, float* ev_mean, float* ev_stdv, int* status, int sm_count,
+                        cudaStream_t st) {
+    gen_emit_kernel<<<grid_for(wl.n_fixed, 128, sm_count * 16), 128, 0, st>>>(
+        b, wl, sc.Sinc, sc.Qinc, sc.bitmap, ev_off, ev_cap, ev_start, ev_mean, ev_stdv, status);
+    return 1;
+}
+
+int launch_pa(const DevBatch& b, float* pa, int sm_count, cudaStream_t st) {
+    pa_kernel<<<grid_for(b.span >> 3, 256, sm_count * 16), 256, 0, st>>>(b, pa);
+    return 1;
+}
+
+uint32_t scan_tiles_for(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE + 1; }
+
+}  // namespace sgpu

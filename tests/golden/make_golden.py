@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/ from the UNMODIFIED reference (run in the build container only).
+
+Needs /root/reference (read-only) and `make -C oracle ref` (oracle/_ref/{sigtk,blow5_dump,blow5_write}).
+Nothing here runs on the GPU box; the fixtures it writes are committed.
+
+  sp1_dna.blow5, event_dna.exp      the reference's own test input + golden file (scripts/test.sh:70-72)
+  sp1_dna.npz                       flat dump of sp1_dna.blow5 (what the hot path consumes)
+  ref_sp1_{event_c,stat}.txt        full stdout of the compiled reference (BASELINE config C1)
+  ref_sp1_{event,pa}_first10.txt.gz stdout for the first 10 read ids; sha256 of the full stdout in sha256.json
+  synth_rna.blow5 / .npz            12 seeded synthetic RNA reads, experiment_type=rna (BASELINE config C2;
+                                    the real test/sequin_rna.blow5 is a missing large blob)
+  ref_rna_{event,event_c,stat}.txt* stdout of the compiled reference on synth_rna.blow5
+"""
+import gzip
+import hashlib
+import json
+import os
+import shutil
+import struct
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from sigtk_b200 import synth  # noqa: E402
+
+REF = "/root/reference"
+BIN = os.path.join(ROOT, "oracle", "_ref")
+SIGTK = os.path.join(BIN, "sigtk")
+
+
+def run(args):
+    return subprocess.run(args, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+
+
+def parse_dump(blob):
+    ids, lens, dig, off, rng, chunks = [], [], [], [], [], []
+    p = 0
+    while p < len(blob):
+        (idl,) = struct.unpack_from("<I", blob, p); p += 4
+        ids.append(blob[p:p + idl].decode()); p += idl
+        n, d, o, r = struct.unpack_from("<Qddd", blob, p); p += 32
+        chunks.append(np.frombuffer(blob, dtype="<i2", count=n, offset=p)); p += 2 * n
+        lens.append(n); dig.append(d); off.append(o); rng.append(r)
+    read_off = np.zeros(len(ids) + 1, dtype=np.uint64)
+    read_off[1:] = np.cumsum(lens)
+    return dict(read_ids=np.array(ids), samples=np.concatenate(chunks).astype(np.int16), read_off=read_off,
+                digitisation=np.array(dig), offset=np.array(off), range=np.array(rng))
+
+
+def dump_to_npz(blow5, npz):
+    d = parse_dump(run([os.path.join(BIN, "blow5_dump"), blow5]))
+    np.savez_compressed(npz, **d)
+    return d
+
+
+def write_blow5(reads, ids, path, exp_type):
+    blob = bytearray()
+    for (raw, dig, off, rng), rid in zip(reads, ids):
+        b = rid.encode()
+        blob += struct.pack("<I", len(b)) + b + struct.pack("<Qddd", raw.shape[0], dig, off, rng) + raw.tobytes()
+    if os.path.exists(path):
+        os.remove(path)
+    subprocess.run([os.path.join(BIN, "blow5_write"), path, exp_type], input=bytes(blob), check=True)
+
+
+def main():
+    sha = {}
+    shutil.copyfile(os.path.join(REF, "test", "sp1_dna.blow5"), os.path.join(HERE, "sp1_dna.blow5"))
+    shutil.copyfile(os.path.join(REF, "test", "event_dna.exp"), os.path.join(HERE, "event_dna.exp"))
+    os.chmod(os.path.join(HERE, "sp1_dna.blow5"), 0o644)
+    os.chmod(os.path.join(HERE, "event_dna.exp"), 0o644)
+    sp1 = os.path.join(HERE, "sp1_dna.blow5")
+    d = dump_to_npz(sp1, os.path.join(HERE, "sp1_dna.npz"))
+    first10 = list(d["read_ids"][:10])
+    for mode, args in (("event_c", ["event", "-c"]), ("stat", ["stat"])):
+        out = run([SIGTK] + args + [sp1])
+        open(os.path.join(HERE, f"ref_sp1_{mode}.txt"), "wb").write(out)
+        sha[f"sp1_{mode}"] = hashlib.sha256(out).hexdigest()
+    for mode in ("event", "pa"):
+        full = run([SIGTK, mode, sp1])
+        sha[f"sp1_{mode}"] = hashlib.sha256(full).hexdigest()
+        part = run([SIGTK, mode, sp1] + first10)
+        with gzip.GzipFile(os.path.join(HERE, f"ref_sp1_{mode}_first10.txt.gz"), "wb", mtime=0) as f:
+            f.write(part)
+
+    # synthetic RNA (config C2): experiment_type=rna makes the reference pick the RNA parameters
+    reads = synth.make_reads(12, mean=25000.0, sigma=0.5, seed=11, rna=True)
+    ids = [f"synth-rna-{i:04d}" for i in range(len(reads))]
+    rna = os.path.join(HERE, "synth_rna.blow5")
+    write_blow5(reads, ids, rna, "rna")
+    dump_to_npz(rna, os.path.join(HERE, "synth_rna.npz"))
+    for mode, args in (("event_c", ["event", "-c"]), ("stat", ["stat"])):
+        out = run([SIGTK] + args + [rna])
+        open(os.path.join(HERE, f"ref_rna_{mode}.txt"), "wb").write(out)
+        sha[f"rna_{mode}"] = hashlib.sha256(out).hexdigest()
+    full = run([SIGTK, "event", rna])
+    sha["rna_event"] = hashlib.sha256(full).hexdigest()
+    with gzip.GzipFile(os.path.join(HERE, "ref_rna_event.txt.gz"), "wb", mtime=0) as f:
+        f.write(full)
+    full = run([SIGTK, "pa", rna])
+    sha["rna_pa"] = hashlib.sha256(full).hexdigest()
+    json.dump(sha, open(os.path.join(HERE, "sha256.json"), "w"), indent=1, sort_keys=True)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+"""Pins the CPU oracle (oracle/sigtk_oracle.c) to the reference:
+   - the reference's own golden file test/event_dna.exp (scripts/test.sh:70-72),
+   - stdout of the compiled, unmodified reference (fixtures in tests/golden/, made by make_golden.py),
+   - the compiled reference functions themselves (oracle/_ref) on seeded synthetic reads, when present.
+CPU only."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import _fmt
+from _oracle import Oracle, Reference, have_ref
+from sigtk_b200 import synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def sp1():
+    return _fmt.load_npz(os.path.join(G, "sp1_dna.npz"))
+
+
+@pytest.fixture(scope="module")
+def rna():
+    return _fmt.load_npz(os.path.join(G, "synth_rna.npz"))
+
+
+def test_event_dna_exp(orc, sp1):
+    """the reference's own golden: long-form events of read 05d90f17-... (header line of the .exp is stale)"""
+    exp = open(os.path.join(G, "event_dna.exp")).read().split("\n", 1)[1]
+    rid, rd = next(x for x in sp1 if x[0] == "05d90f17-f4a6-4349-924c-3ffd3457a99d")
+    got = _fmt.event_long(rid, *orc.events(*rd))
+    assert got == exp
+    assert got.count("\n") == 915 + 1
+
+
+def test_sp1_event_compact_all_reads(orc, sp1):
+    exp = open(os.path.join(G, "ref_sp1_event_c.txt")).read()
+    got = _fmt.EVENT_HDR_COMPACT
+    total = 0
+    for rid, rd in sp1:
+        st, ln, _, _ = orc.events(*rd)
+        total += len(st)
+        got += _fmt.event_compact(rid, len(rd[0]), st, ln)
+    assert got == exp
+    assert total == 92935
+
+
+def test_sp1_event_long_first10(orc, sp1):
+    exp = gzip.open(os.path.join(G, "ref_sp1_event_first10.txt.gz"), "rt").read()
+    got = _fmt.EVENT_HDR_LONG + "".join(_fmt.event_long(rid, *orc.events(*rd)) for rid, rd in sp1[:10])
+    assert got == exp
+
+
+def test_sp1_pa_first10(orc, sp1):
+    exp = gzip.open(os.path.join(G, "ref_sp1_pa_first10.txt.gz"), "rt").read()
+    got = _fmt.PA_HDR + "".join(_fmt.pa_line(rid, orc.pa(*rd)) for rid, rd in sp1[:10])
+    assert got == exp
+
+
+def test_sp1_stat(orc, sp1):
+    exp = open(os.path.join(G, "ref_sp1_stat.txt")).read()
+    got = _fmt.STAT_HDR + "".join(_fmt.stat_line(rid, len(rd[0]), orc.stat(*rd)) for rid, rd in sp1)
+    assert got == exp
+
+
+def test_rna_event_long_and_compact(orc, rna):
+    exp = gzip.open(os.path.join(G, "ref_rna_event.txt.gz"), "rt").read()
+    got = _fmt.EVENT_HDR_LONG + "".join(_fmt.event_long(rid, *orc.events(*rd, rna=1)) for rid, rd in rna)
+    assert got == exp
+    exp = open(os.path.join(G, "ref_rna_event_c.txt")).read()
+    got = _fmt.EVENT_HDR_COMPACT
+    for rid, rd in rna:
+        st, ln, _, _ = orc.events(*rd, rna=1)
+        got += _fmt.event_compact(rid, len(rd[0]), st, ln)
+    assert got == exp
+
+
+def test_rna_stat(orc, rna):
+    exp = open(os.path.join(G, "ref_rna_stat.txt")).read()
+    got = _fmt.STAT_HDR + "".join(_fmt.stat_line(rid, len(rd[0]), orc.stat(*rd)) for rid, rd in rna)
+    assert got == exp
+
+
+def _bits(a):
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("rna_flag,seed", [(0, 1), (0, 2), (1, 3)])
+def test_oracle_equals_compiled_reference(orc, rna_flag, seed):
+    ref = Reference()
+    for rd in synth.make_reads(8, mean=15000.0, seed=seed, rna=bool(rna_flag)):
+        a, b = orc.events(*rd, rna=rna_flag), ref.events(*rd, rna=rna_flag)
+        for x, y in zip(a, b):
+            assert np.array_equal(_bits(x), _bits(y))
+        assert np.array_equal(_bits(orc.pa(*rd)), _bits(ref.pa(*rd)))
+        assert np.array_equal(_bits(orc.stat(*rd)), _bits(ref.stat(*rd)))
+
+
+def test_stagewise_consistency(orc):
+    """the staged entry points compose to the same events as the one-shot call"""
+    rd = synth.make_read(3, 12000)
+    pa = orc.pa(*rd)
+    S, Q = orc.prefix(pa)
+    p = orc.params(0)
+    t1, t2 = orc.tstat(S, Q, p.w_short), orc.tstat(S, Q, p.w_long)
+    peaks, _, _ = orc.detect(t1, t2, 0)
+    st, _, _, _ = orc.events(*rd)
+    assert np.array_equal(np.concatenate([[0], peaks]).astype(np.uint64), st)
+    assert np.all(np.diff(peaks.astype(np.int64)) >= 3)  # min peak gap floor(w1/2)+2
+
+
+def test_detector_cold_start_adversarial(orc):
+    """a sub-threshold peak held across a flat stretch makes cold-start states differ forever
+    while the emitted peaks agree."""
+    n = 1200
+    t1 = np.zeros(n, dtype=np.float32)
+    t1[10], t1[900] = 0.5, 3.0
+    t2 = np.zeros(n, dtype=np.float32)
+    peaks_true, s_true, _ = orc.detect(t1, t2, 0, 0, 500)
+    peaks_cold, s_cold, _ = orc.detect(t1, t2, 0, 400, 500, cold=True)
+    assert s_true[1:3] == (10, 0.5) and s_cold[1] == -1
+    full, _, _ = orc.detect(t1, t2, 0)
+    assert list(full) == [900]
+
+
+def test_degenerate_inputs_defined(orc):
+    """where the reference aborts (n<200, constant signal, zero peaks) the oracle defines one event [0,n)"""
+    raw = np.full(50, 500, dtype=np.int16)
+    st, ln, mn, sd = orc.events(raw, 8192.0, 10.0, 1400.0)
+    assert list(st) == [0] and list(ln) == [50.0]
+    st, ln, _, _ = orc.events(np.array([7], dtype=np.int16), 8192.0, 10.0, 1400.0)
+    assert list(st) == [0] and list(ln) == [1.0]
