@@ -149,6 +149,10 @@ typedef struct {
 } sgpu_counters_t;
 int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
 
+/* Copies `bytes` from a device pointer returned by sgpu_run_device() to host memory (synchronous;
+ * for callers of the device-resident path that have no CUDA runtime of their own). */
+int  sgpu_memcpy_d2h(sgpu_ctx_t *ctx, void *dst_host, const void *src_device, uint64_t bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ E_FULL, E_TOOBIG = -4, -5
 EXPORTS = (
     "sgpu_abi_version", "sgpu_device_count", "sgpu_create", "sgpu_destroy", "sgpu_strerror",
     "sgpu_last_error", "sgpu_slot_batch", "sgpu_slot_reset", "sgpu_slot_add_read", "sgpu_submit",
-    "sgpu_wait", "sgpu_run_device", "sgpu_counters",
+    "sgpu_wait", "sgpu_run_device", "sgpu_counters", "sgpu_memcpy_d2h",
 )
 
 
@@ -101,5 +101,7 @@ def load() -> C.CDLL:
     lib.sgpu_run_device.restype = i32
     lib.sgpu_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.sgpu_counters.restype = i32
+    lib.sgpu_memcpy_d2h.argtypes = [vp, vp, vp, u64]
+    lib.sgpu_memcpy_d2h.restype = i32
     _lib = lib
     return lib

@@ -152,6 +152,12 @@ class Context:
         self._check(self._lib.sgpu_run_device(self._h, C.byref(db), want, C.c_void_p(stream), C.byref(res)))
         return res
 
+    def d2h(self, dev_ptr: int, dtype, count: int) -> np.ndarray:
+        """copy `count` items of a device result array (a pointer from run_device) to a new numpy array"""
+        out = np.empty(count, dtype=dtype)
+        self._check(self._lib.sgpu_memcpy_d2h(self._h, out.ctypes.data, C.c_void_p(dev_ptr), out.nbytes))
+        return out
+
     def counters(self) -> dict:
         c = _lib.Counters()
         self._check(self._lib.sgpu_counters(self._h, C.byref(c)))

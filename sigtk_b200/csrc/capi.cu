@@ -482,4 +482,12 @@ int sgpu_counters(sgpu_ctx_t* ctx, sgpu_counters_t* out) {
     return SGPU_OK;
 }
 
+int sgpu_memcpy_d2h(sgpu_ctx_t* ctx, void* dst, const void* src, uint64_t bytes) {
+    if (!ctx || (!dst && bytes) || (!src && bytes)) return SGPU_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    if (bytes) CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return SGPU_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,54 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/sigtk_b200.h declares, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from sigtk_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "sigtk_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(sgpu_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sigtk_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+    assert lib.sgpu_abi_version() == 1
+
+
+def test_strerror_and_argument_checks():
+    lib = _lib.load()
+    assert lib.sgpu_strerror(0) == b"success"
+    assert b"no CPU fallback" in lib.sgpu_strerror(-2)
+    h = C.c_void_p()
+    assert lib.sgpu_create(C.byref(h), 0, 0, 0, 2, 0) == -1  # INVAL before any CUDA call
+    assert lib.sgpu_submit(None, 0, 1) == -1
+    assert lib.sgpu_wait(None, 0, None) == -1
+
+
+def test_no_cpu_fallback_without_a_device():
+    lib = _lib.load()
+    if lib.sgpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    h = C.c_void_p()
+    assert lib.sgpu_create(C.byref(h), 0, 1 << 20, 16, 2, 0) == -2  # SGPU_E_CUDA, loudly
+    assert not h.value
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sigtk_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("test infrastructure", ""), f"{f} mentions the oracle"

@@ -1,0 +1,281 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, include/sigtk_b200.h) against the CPU oracle and
+against the committed stdout of the compiled reference. Bit-exact for boundaries, pA, means, stdv and stat."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import _fmt
+from _oracle import Oracle
+import sigtk_b200 as sg
+from sigtk_b200 import synth
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALL = sg.WANT_EVENTS | sg.WANT_PA | sg.WANT_STAT
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sg.Context(device=0, max_samples=1 << 23, max_reads=4096)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_generic():
+    c = sg.Context(device=0, max_samples=1 << 23, max_reads=4096, flags=sg.F_FORCE_GENERIC)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def sp1():
+    return _fmt.load_npz(os.path.join(G, "sp1_dna.npz"))
+
+
+@pytest.fixture(scope="module")
+def rna():
+    return _fmt.load_npz(os.path.join(G, "synth_rna.npz"))
+
+
+def bits(a):
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def check_against_oracle(orc, res, reads, rna_flag, want=ALL):
+    for r, rd in enumerate(reads):
+        if want & sg.WANT_EVENTS:
+            st, ln, mn, sd = orc.events(*rd, rna=rna_flag)
+            ev = res.events(r)
+            assert np.array_equal(ev.start, st), f"read {r}: boundaries differ"
+            assert np.array_equal(bits(ev.length), bits(ln)), f"read {r}"
+            assert np.array_equal(bits(ev.mean), bits(mn)), f"read {r}: event_mean differs"
+            assert np.array_equal(bits(ev.stdv), bits(sd)), f"read {r}: event_std differs"
+        if want & sg.WANT_PA:
+            assert np.array_equal(bits(res.pa[r]), bits(orc.pa(*rd))), f"read {r}: pA differs"
+        if want & sg.WANT_STAT:
+            assert np.array_equal(bits(res.stat[r]), bits(orc.stat(*rd))), f"read {r}: stat differs"
+
+
+# ---- BASELINE config C1: sp1_dna.blow5 ------------------------------------------------------------
+def test_sp1_compact_text_equals_reference_stdout(ctx, sp1):
+    res = ctx.run([rd for _, rd in sp1], rna=0, want=sg.WANT_EVENTS)
+    got = _fmt.EVENT_HDR_COMPACT
+    for r, (rid, rd) in enumerate(sp1):
+        ev = res.events(r)
+        got += _fmt.event_compact(rid, len(rd[0]), ev.start, ev.length)
+    assert got == open(os.path.join(G, "ref_sp1_event_c.txt")).read()
+    assert int(res.ev_off[-1]) == 92935
+    assert ctx.counters()["n_events"] == 92935
+
+
+def test_sp1_event_dna_exp(ctx, sp1):
+    """the reference's own golden file (scripts/test.sh:70-72); its header line is stale"""
+    exp = open(os.path.join(G, "event_dna.exp")).read().split("\n", 1)[1]
+    rid, rd = next(x for x in sp1 if x[0] == "05d90f17-f4a6-4349-924c-3ffd3457a99d")
+    ev = sg.getevents(ctx, *rd)
+    assert _fmt.event_long(rid, ev.start, ev.length, ev.mean, ev.stdv) == exp
+
+
+def test_sp1_long_pa_stat_text(ctx, sp1):
+    res = ctx.run([rd for _, rd in sp1], rna=0, want=ALL)
+    got = _fmt.EVENT_HDR_LONG
+    for r, (rid, _) in enumerate(sp1[:10]):
+        ev = res.events(r)
+        got += _fmt.event_long(rid, ev.start, ev.length, ev.mean, ev.stdv)
+    assert got == gzip.open(os.path.join(G, "ref_sp1_event_first10.txt.gz"), "rt").read()
+    got = _fmt.PA_HDR + "".join(_fmt.pa_line(rid, res.pa[r]) for r, (rid, _) in enumerate(sp1[:10]))
+    assert got == gzip.open(os.path.join(G, "ref_sp1_pa_first10.txt.gz"), "rt").read()
+    got = _fmt.STAT_HDR + "".join(_fmt.stat_line(rid, len(rd[0]), res.stat[r]) for r, (rid, rd) in enumerate(sp1))
+    assert got == open(os.path.join(G, "ref_sp1_stat.txt")).read()
+
+
+def test_sp1_all_reads_vs_oracle(ctx, orc, sp1):
+    reads = [rd for _, rd in sp1]
+    check_against_oracle(orc, ctx.run(reads, rna=0, want=ALL), reads, 0)
+
+
+# ---- BASELINE config C2: RNA parameters, long form --------------------------------------------------
+def test_rna_text_equals_reference_stdout(ctx, rna):
+    res = ctx.run([rd for _, rd in rna], rna=1, want=sg.WANT_EVENTS | sg.WANT_STAT)
+    got_l, got_c = _fmt.EVENT_HDR_LONG, _fmt.EVENT_HDR_COMPACT
+    for r, (rid, rd) in enumerate(rna):
+        ev = res.events(r)
+        got_l += _fmt.event_long(rid, ev.start, ev.length, ev.mean, ev.stdv)
+        got_c += _fmt.event_compact(rid, len(rd[0]), ev.start, ev.length)
+    assert got_l == gzip.open(os.path.join(G, "ref_rna_event.txt.gz"), "rt").read()
+    assert got_c == open(os.path.join(G, "ref_rna_event_c.txt")).read()
+    got = _fmt.STAT_HDR + "".join(_fmt.stat_line(rid, len(rd[0]), res.stat[r]) for r, (rid, rd) in enumerate(rna))
+    assert got == open(os.path.join(G, "ref_rna_stat.txt")).read()
+
+
+# ---- seeded synthetic batches -----------------------------------------------------------------------
+@pytest.mark.parametrize("rna_flag,seed,n,mean", [(0, 21, 64, 12000.0), (1, 22, 32, 20000.0), (0, 23, 300, 3000.0)])
+def test_synthetic_batches_vs_oracle(ctx, orc, rna_flag, seed, n, mean):
+    reads = synth.make_reads(n, mean=mean, seed=seed, rna=bool(rna_flag))
+    res = ctx.run(reads, rna=rna_flag, want=ALL)
+    check_against_oracle(orc, res, reads, rna_flag)
+    assert res.fixups is not None and res.seq_order is not None
+
+
+@pytest.mark.parametrize("rna_flag", [0, 1])
+def test_fast_equals_sequential_order_path(ctx, ctx_generic, rna_flag):
+    """the fast kernels and the reference-order kernels must agree bit for bit (on-device cross-check)"""
+    reads = synth.make_reads(48, mean=30000.0, seed=77 + rna_flag, rna=bool(rna_flag))
+    a = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
+    b = ctx_generic.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
+    assert np.array_equal(a.ev_off, b.ev_off)
+    assert np.array_equal(a.ev_start, b.ev_start)
+    assert np.array_equal(bits(a.ev_mean), bits(b.ev_mean))
+    assert np.array_equal(bits(a.ev_stdv), bits(b.ev_stdv))
+    assert np.all(b.seq_order == 1)
+
+
+@pytest.mark.parametrize("rna_flag", [0, 1])
+def test_long_reads_cross_tile(ctx, orc, rna_flag):
+    """reads much longer than one tile / one CTA: cross-tile scan carry and detector chunk hand-over"""
+    reads = [synth.make_read(900 + k, n, seed=4, p_change=0.025 if rna_flag else 0.1)
+             for k, n in enumerate((1_000_003, 250_000, 2048, 777_777))]
+    res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS | sg.WANT_STAT)
+    check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS | sg.WANT_STAT)
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------
+def test_ragged_and_tiny_reads(ctx, orc):
+    """lengths around the window sizes and the alignment quantum; the reference aborts below 200 samples, the
+    oracle (and the CUDA path) define those as in DESIGN.md: same arithmetic, single event if no peak"""
+    rng = np.random.default_rng(5)
+    lens = [1, 2, 5, 6, 7, 8, 9, 11, 12, 13, 15, 16, 17, 27, 28, 29, 31, 32, 33, 63, 64, 65, 199, 200, 201, 255, 256,
+            257, 1023, 1024, 1025, 4095, 4096, 4097]
+    reads = []
+    for k, n in enumerate(lens):
+        rd = synth.make_read(k, max(n, 8), seed=9)
+        reads.append((rd[0][:n].copy(), rd[1], rd[2], rd[3]))
+    rng.shuffle(reads)
+    for rna_flag in (0, 1):
+        res = ctx.run(reads, rna=rna_flag, want=ALL)
+        check_against_oracle(orc, res, reads, rna_flag)
+
+
+def test_constant_and_extreme_signals(ctx, orc):
+    n = 5000
+    ramp = (np.arange(n) % 4000 - 2000).astype(np.int16)
+    reads = [
+        (np.full(n, 500, dtype=np.int16), 8192.0, 10.0, 1400.0),          # zero variance everywhere
+        (np.full(n, -32768, dtype=np.int16), 8192.0, 0.0, 1400.0),
+        (np.where(np.arange(n) % 2, 32767, -32768).astype(np.int16), 8192.0, 3.0, 1400.0),
+        (ramp, 8192.0, 7.0, 1400.0),
+        (np.concatenate([np.full(2500, 400, np.int16), np.full(2500, 700, np.int16)]), 8192.0, 10.0, 1400.0),
+        (synth.make_read(1, n)[0], 2048.0, -250.0, 748.5),                 # other digitisation / negative offset
+        (synth.make_read(2, n)[0], 8192.0, 12.0, -1400.0),                 # negative range => negative raw_unit
+    ]
+    for rna_flag in (0, 1):
+        res = ctx.run(reads, rna=rna_flag, want=ALL)
+        check_against_oracle(orc, res, reads, rna_flag)
+
+
+def test_flat_stretch_inside_a_read(ctx, orc):
+    """SURVEY 7.3(2) adversarial case: a long constant stretch (t-stat exactly 0) after a sub-threshold bump"""
+    rd = synth.make_read(11, 60000, seed=3)
+    raw = rd[0].copy()
+    raw[20000:45000] = raw[19999]
+    reads = [(raw, rd[1], rd[2], rd[3])]
+    for rna_flag in (0, 1):
+        res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
+        check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS)
+
+
+def test_empty_batch_and_reuse(ctx):
+    res = ctx.run([], rna=0, want=sg.WANT_EVENTS)
+    assert res.n_reads == 0
+    reads = synth.make_reads(3, mean=5000.0, seed=1)
+    a = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)
+    b = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)  # same slot again: no stale state
+    assert np.array_equal(a.ev_start, b.ev_start) and np.array_equal(a.ev_off, b.ev_off)
+
+
+def test_two_slots_in_flight(ctx, orc):
+    r0 = synth.make_reads(20, mean=8000.0, seed=31)
+    r1 = synth.make_reads(20, mean=8000.0, seed=32, rna=True)
+    ctx.fill(0, r0, 0)
+    ctx.submit(0, sg.WANT_EVENTS)
+    ctx.fill(1, r1, 1)
+    ctx.submit(1, sg.WANT_EVENTS)
+    check_against_oracle(orc, ctx.wait(0, sg.WANT_EVENTS), r0, 0, want=sg.WANT_EVENTS)
+    check_against_oracle(orc, ctx.wait(1, sg.WANT_EVENTS), r1, 1, want=sg.WANT_EVENTS)
+
+
+def test_errors(ctx):
+    with pytest.raises(sg.SgpuError) as e:
+        ctx.wait(0, sg.WANT_EVENTS)  # nothing submitted
+    assert e.value.code == -6
+    small = sg.Context(device=0, max_samples=4096, max_reads=4)
+    with pytest.raises(sg.SgpuError) as e:
+        small.fill(0, [synth.make_read(0, 5000)], 0)
+    assert e.value.code == -5  # TOOBIG
+    with pytest.raises(sg.SgpuError) as e:
+        small.fill(0, [synth.make_read(i, 1500) for i in range(3)], 0)
+    assert e.value.code == -4  # FULL
+    small.close()
+
+
+# ---- size-independent properties at larger sizes -------------------------------------------------------
+def test_properties_large_batch(ctx):
+    reads = synth.make_reads(150, mean=40000.0, seed=synth.SEED)
+    res = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)
+    off = res.ev_off.astype(np.int64)
+    assert off[0] == 0 and np.all(np.diff(off) >= 1)
+    for r in range(res.n_reads):
+        st = res.ev_start[off[r]:off[r + 1]].astype(np.int64)
+        assert st[0] == 0 and np.all(np.diff(st) >= 3) and st[-1] < res.read_len[r]
+    # concatenation invariance: every read alone gives the same events as in the batch
+    for r in (0, 17, 149):
+        ev = sg.getevents(ctx, *reads[r])
+        assert np.array_equal(ev.start, res.events(r).start)
+        assert np.array_equal(bits(ev.mean), bits(res.events(r).mean))
+    # event means re-derived from pA on the host within 1e-4 relative (north_star tolerance)
+    pa = sg.signal_in_picoamps(ctx, *reads[5]).astype(np.float64)
+    ev = res.events(5)
+    ends = np.append(ev.start[1:], len(pa)).astype(np.int64)
+    cs = np.concatenate([[0.0], np.cumsum(pa)])
+    mean = (cs[ends] - cs[ev.start.astype(np.int64)]) / (ends - ev.start.astype(np.int64))
+    assert np.allclose(ev.mean, mean, rtol=1e-4)
+
+
+def test_device_resident_path(ctx):
+    torch = pytest.importorskip("torch")
+    reads = synth.make_reads(40, mean=20000.0, seed=55)
+    host = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)
+    lens = np.array([len(r[0]) for r in reads], dtype=np.int64)
+    al = (lens + 7) // 8 * 8
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(al)
+    flat = np.zeros(int(off[-1]), dtype=np.int16)
+    for r, rd in enumerate(reads):
+        flat[off[r]:off[r] + lens[r]] = rd[0]
+    dev = torch.device("cuda:0")
+    d_s = torch.from_numpy(flat).to(dev)
+    d_off = torch.from_numpy(off).to(dev)
+    d_len = torch.from_numpy(lens.astype(np.int32)).to(dev)
+    d_o = torch.tensor([np.float32(r[2]) for r in reads], dtype=torch.float32, device=dev)
+    d_u = torch.tensor([np.float32(r[3]) / np.float32(r[1]) for r in reads], dtype=torch.float32, device=dev)
+    dctx = sg.Context(device=0, max_samples=int(off[-1]), max_reads=len(reads), flags=sg.F_NO_HOST_SLOTS)
+    st = torch.cuda.current_stream().cuda_stream
+    res = dctx.run_device(d_s.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_o.data_ptr(), d_u.data_ptr(),
+                          len(reads), int(off[-1]), 0, sg.WANT_EVENTS, st)
+    torch.cuda.synchronize()
+    c = dctx.counters()
+    assert c["status"] == 0 and c["n_events"] == int(host.ev_off[-1])
+    ne = c["n_events"]
+    h = dctx.d2h(res.ev_start, np.uint32, ne)  # raw device pointer -> host through the C-ABI
+    assert np.array_equal(h, host.ev_start)
+    assert np.array_equal(dctx.d2h(res.ev_off, np.uint64, len(reads) + 1), host.ev_off)
+    assert np.array_equal(bits(dctx.d2h(res.ev_mean, np.float32, ne)), bits(host.ev_mean))
+    dctx.close()
