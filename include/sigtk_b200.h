@@ -54,6 +54,7 @@ extern "C" {
 #define SGPU_F_DEFAULT       0u
 #define SGPU_F_FORCE_GENERIC 1u /* run every read through the sequential-order (reference-order) kernels */
 #define SGPU_F_NO_HOST_SLOTS 2u /* device-resident use only: do not allocate pinned slots */
+#define SGPU_F_STAGE_TIMERS  4u /* record CUDA events between the kernel groups of a run (sgpu_stage_times) */
 
 typedef struct sgpu_ctx sgpu_ctx_t;
 
@@ -148,6 +149,15 @@ typedef struct {
     int32_t  status;              /* 0 or SGPU_E_EVCAP / SGPU_E_SCRATCH reported by the device */
 } sgpu_counters_t;
 int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
+
+/* Device time of every kernel group of the last run, measured with CUDA events on the stream the kernels were
+ * launched on (needs SGPU_F_STAGE_TIMERS). Returns the number of entries written, or a negative code. */
+typedef struct {
+    const char *name;     /* e.g. "detect_tiles", "emit_tiles" */
+    float       ms;
+    uint32_t    launches; /* kernels in the group */
+} sgpu_stage_time_t;
+int  sgpu_stage_times(sgpu_ctx_t *ctx, sgpu_stage_time_t *out, uint32_t cap);
 
 /* Copies `bytes` from a device pointer returned by sgpu_run_device() to host memory (synchronous;
  * for callers of the device-resident path that have no CUDA runtime of their own). */

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsigtk_b200.so")
 
 WANT_EVENTS, WANT_PA, WANT_STAT = 1, 2, 4
-F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS = 0, 1, 2
+F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, F_STAGE_TIMERS = 0, 1, 2, 4
 ALIGN = 8
 
 E_FULL, E_TOOBIG = -4, -5
@@ -23,7 +23,7 @@ E_FULL, E_TOOBIG = -4, -5
 EXPORTS = (
     "sgpu_abi_version", "sgpu_device_count", "sgpu_create", "sgpu_destroy", "sgpu_strerror",
     "sgpu_last_error", "sgpu_slot_batch", "sgpu_slot_reset", "sgpu_slot_add_read", "sgpu_submit",
-    "sgpu_wait", "sgpu_run_device", "sgpu_counters", "sgpu_memcpy_d2h",
+    "sgpu_wait", "sgpu_run_device", "sgpu_counters", "sgpu_memcpy_d2h", "sgpu_stage_times",
 )
 
 
@@ -61,6 +61,10 @@ class Counters(C.Structure):  # sgpu_counters_t
         ("n_events", C.c_uint64), ("n_seq_order_reads", C.c_uint64), ("n_fixups", C.c_uint64),
         ("n_kernel_launches", C.c_uint64), ("status", C.c_int32),
     ]
+
+
+class StageTime(C.Structure):  # sgpu_stage_time_t
+    _fields_ = [("name", C.c_char_p), ("ms", C.c_float), ("launches", C.c_uint32)]
 
 
 _lib = None
@@ -101,6 +105,8 @@ def load() -> C.CDLL:
     lib.sgpu_run_device.restype = i32
     lib.sgpu_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.sgpu_counters.restype = i32
+    lib.sgpu_stage_times.argtypes = [vp, C.POINTER(StageTime), u32]
+    lib.sgpu_stage_times.restype = i32
     lib.sgpu_memcpy_d2h.argtypes = [vp, vp, vp, u64]
     lib.sgpu_memcpy_d2h.restype = i32
     _lib = lib

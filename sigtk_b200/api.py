@@ -18,8 +18,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (ALIGN, F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, WANT_EVENTS, WANT_PA, WANT_STAT,
-                   SgpuError)
+from ._lib import (ALIGN, F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, F_STAGE_TIMERS, WANT_EVENTS, WANT_PA,
+                   WANT_STAT, SgpuError)
 
 Read = Tuple[np.ndarray, float, float, float]  # raw int16, digitisation, offset, range
 
@@ -157,6 +157,13 @@ class Context:
         out = np.empty(count, dtype=dtype)
         self._check(self._lib.sgpu_memcpy_d2h(self._h, out.ctypes.data, C.c_void_p(dev_ptr), out.nbytes))
         return out
+
+    def stage_times(self) -> list:
+        """[(name, ms, launches)] of the last run (context created with F_STAGE_TIMERS)"""
+        arr = (_lib.StageTime * 16)()
+        n = self._lib.sgpu_stage_times(self._h, arr, 16)
+        self._check(n)
+        return [(arr[k].name.decode(), float(arr[k].ms), int(arr[k].launches)) for k in range(n)]
 
     def counters(self) -> dict:
         c = _lib.Counters()

@@ -68,10 +68,18 @@ struct sgpu_ctx {
     uint64_t ev_cap = 0;
     Scratch sc{};
     DevOut dev_out;              // outputs of the device-resident path
-    uint32_t* dev_seq = nullptr; // aliases sc.seq_flag / sc.fixups for the device path
+    uint32_t* dev_seq = nullptr; // seq_order / fixups of the device-resident path
+    uint32_t* dev_fix = nullptr;
     Slot* slots = nullptr;
     cudaStream_t compute = nullptr;
     uint64_t last_launches = 0;
+    // optional per-stage CUDA-event timers (SGPU_F_STAGE_TIMERS)
+    static constexpr int MAX_STAGES = 12;
+    cudaEvent_t stage_ev[MAX_STAGES + 1] = {};
+    const char* stage_name[MAX_STAGES] = {};
+    uint32_t stage_launches[MAX_STAGES] = {};
+    int n_stages = 0;
+    cudaStream_t stage_stream = nullptr;
     char err[512] = {0};
 };
 
@@ -121,43 +129,71 @@ void free_dev_out(DevOut& o) {
     o = DevOut{};
 }
 
+struct StageMarks {  // records a CUDA event between kernel groups when the context has stage timers
+    sgpu_ctx* ctx;
+    cudaStream_t st;
+    bool on;
+    uint64_t launches = 0;
+    StageMarks(sgpu_ctx* c, cudaStream_t s) : ctx(c), st(s), on((c->flags & SGPU_F_STAGE_TIMERS) != 0) {
+        c->n_stages = 0;
+        c->stage_stream = s;
+        if (on) cudaEventRecord(c->stage_ev[0], s);
+    }
+    void done(const char* name, int n) {
+        launches += (uint64_t)n;
+        if (!on || ctx->n_stages >= sgpu_ctx::MAX_STAGES) return;
+        const int k = ctx->n_stages++;
+        ctx->stage_name[k] = name;
+        ctx->stage_launches[k] = (uint32_t)n;
+        cudaEventRecord(ctx->stage_ev[k + 1], st);
+    }
+};
+
 // The kernel sequence of one batch. No host synchronisation, no host<->device copies.
 int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uint32_t* d_seq, uint32_t* d_fix,
                  cudaStream_t st) {
     Scratch& sc = ctx->sc;
-    uint64_t launches = 0;
-    if (b.n_reads > ctx->max_reads || b.span > ctx->max_samples) return SGPU_E_INVAL;
+    if (b.n_reads > ctx->max_reads || b.span > ctx->max_samples || (b.span & (SGPU_ALIGN - 1))) return SGPU_E_INVAL;
     CU(cudaMemsetAsync(sc.status, 0, sizeof(int), st));
     CU(cudaMemsetAsync(sc.counters, 0, 4 * sizeof(unsigned long long), st));
-    if (b.n_reads == 0) {
-        CU(cudaMemsetAsync(o.ev_off, 0, sizeof(uint64_t), st));
+    StageMarks marks(ctx, st);
+    if (b.n_reads == 0 || b.span == 0) {
+        CU(cudaMemsetAsync(o.ev_off, 0, ((size_t)b.n_reads + 1) * sizeof(uint64_t), st));
         ctx->last_launches = 0;
         return SGPU_OK;
     }
+    const bool force_generic = (ctx->flags & SGPU_F_FORCE_GENERIC) != 0;
+    const bool events = (want & SGPU_WANT_EVENTS) != 0;
     if (want & SGPU_WANT_PA) {
         if (!o.pa) CU(dev_alloc(&o.pa, align_up(ctx->max_samples, SGPU_ALIGN)));
-        launches += launch_pa(b, o.pa, ctx->sm_count, st);
+        // with events on the fast path the pA store is fused into detect_tiles_kernel
+        if (!events || force_generic) marks.done("pa", launch_pa(b, o.pa, ctx->sm_count, st));
     }
-    if (want & SGPU_WANT_STAT) launches += launch_stat(b, o.stat, ctx->sm_count, st);
-    if (want & SGPU_WANT_EVENTS) {
-        const uint64_t words = (b.span >> 5) + 2;
-        if (words > sc.bitmap_words) return SGPU_E_INVAL;
-        CU(cudaMemsetAsync(sc.bitmap, 0, words * sizeof(uint32_t), st));
-        CU(cudaMemsetAsync(d_fix, 0, (size_t)b.n_reads * sizeof(uint32_t), st));
-        // round 1: every read goes through the sequential-order kernels
-        if (b.span > sc.gen_cap) return SGPU_E_SCRATCH;
-        WorkList wl{nullptr, b.read_off, nullptr, b.n_reads};
-        launches += launch_generic_detect(b, wl, b.span, sc, /*clear_first=*/0, ctx->sm_count, st);
-        fill_u32_kernel<<<(b.n_reads + 255) / 256, 256, 0, st>>>(d_seq, b.n_reads, 1u);
-        launches += 1;
-        launches += launch_count_scan(b, sc, o.ev_off, reinterpret_cast<uint64_t*>(sc.counters), ctx->sm_count, st);
-        launches += launch_generic_emit(b, wl, sc, o.ev_off, ctx->ev_cap, o.ev_start, o.ev_mean, o.ev_stdv, sc.status,
-                                        ctx->sm_count, st);
-        set_u64_kernel<<<1, 1, 0, st>>>(sc.counters + 1, (unsigned long long)b.n_reads);
-        launches += 1;
+    if (want & SGPU_WANT_STAT) marks.done("stat", launch_stat(b, o.stat, ctx->sm_count, st));
+    if (events) {
+        const uint32_t n_tiles = fast_tiles_for(b.span);
+        if (n_tiles > sc.max_tiles) return SGPU_E_INVAL;
+        int n = launch_init_reads(b, sc, d_seq, d_fix, ctx->sm_count, st);
+        if (force_generic) {
+            CU(cudaMemsetAsync(sc.bitmap, 0, (size_t)n_tiles * (FAST_TILE / 32) * sizeof(uint32_t), st));
+            marks.done("init", n);
+        } else {
+            marks.done("init", n);
+            marks.done("detect_tiles", launch_fast_detect(b, sc, (want & SGPU_WANT_PA) ? o.pa : nullptr, d_seq, d_fix,
+                                                          ctx->sm_count, st));
+        }
+        n = launch_build_seq_list(b, sc, d_seq, force_generic ? 1 : 0, ctx->sm_count, st);
+        WorkList wl{sc.seq_list, sc.seq_sbase, sc.seq_count};
+        n += launch_generic_detect(b, wl, sc, ctx->sm_count, st);
+        marks.done("sequential_order_detect", n);
+        marks.done("rank_events", launch_rank_events(b, sc, o.ev_off, ctx->sm_count, st));
+        marks.done("emit_tiles", launch_fast_emit(b, sc, ctx->ev_cap, o.ev_start, o.ev_mean, o.ev_stdv, d_fix,
+                                                  ctx->sm_count, st));
+        marks.done("sequential_order_emit", launch_generic_emit(b, wl, sc, o.ev_off, ctx->ev_cap, o.ev_start, o.ev_mean,
+                                                                o.ev_stdv, ctx->sm_count, st));
     }
     CU(cudaGetLastError());
-    ctx->last_launches = launches;
+    ctx->last_launches = marks.launches;
     return SGPU_OK;
 }
 
@@ -198,7 +234,7 @@ const char* sgpu_last_error(const sgpu_ctx_t* ctx) { return ctx ? ctx->err : "no
 
 int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max_reads, uint32_t n_slots,
                 uint32_t flags) {
-    if (!out || max_samples == 0 || max_reads == 0) return SGPU_E_INVAL;
+    if (!out || max_samples == 0 || max_reads == 0 || (flags & ~7u)) return SGPU_E_INVAL;
     *out = nullptr;
     if (flags & SGPU_F_NO_HOST_SLOTS) n_slots = 0; else if (n_slots == 0) n_slots = 2;
     sgpu_ctx* ctx = new (std::nothrow) sgpu_ctx();
@@ -235,22 +271,37 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     // consecutive peaks are >= 3 samples apart (DNA; 5 for RNA) => <= n/3 + 2 events per read
     ctx->ev_cap = max_samples / 3 + 2ull * max_reads + 16;
     Scratch& sc = ctx->sc;
-    // round 1: all reads use the sequential-order scratch
-    sc.gen_cap = max_samples;
+    // scratch of the sequential-order kernels (24 B/sample): everything for small contexts or when forced,
+    // one eighth of the batch otherwise (reads that fail the fast path's checks are rare)
+    sc.gen_cap = (max_samples <= (64ull << 20) || (flags & SGPU_F_FORCE_GENERIC)) ? max_samples : max_samples / 8;
     if (const char* e = getenv("SGPU_GEN_CAP")) { uint64_t v = strtoull(e, nullptr, 10); if (v) sc.gen_cap = v; }
+    if (fast_configure() != 0) {
+        snprintf(ctx->err, sizeof ctx->err, "cudaFuncSetAttribute(max dynamic shared memory) failed");
+        fprintf(stderr, "[sigtk_b200] %s\n", ctx->err);
+        return fail(SGPU_E_CUDA);
+    }
     CUC(dev_alloc(&sc.Sinc, sc.gen_cap));
     CUC(dev_alloc(&sc.Qinc, sc.gen_cap));
     CUC(dev_alloc(&sc.t1, sc.gen_cap));
     CUC(dev_alloc(&sc.t2, sc.gen_cap));
-    sc.bitmap_words = (max_samples >> 5) + 4;
+    sc.max_tiles = fast_tiles_for(max_samples) + 1;
+    sc.bitmap_words = (uint64_t)sc.max_tiles * (FAST_TILE / 32);
     CUC(dev_alloc(&sc.bitmap, sc.bitmap_words));
-    CUC(dev_alloc(&sc.ev_cnt, max_reads));
-    CUC(dev_alloc(&sc.seq_flag, max_reads));
-    CUC(dev_alloc(&sc.fixups, max_reads));
+    CUC(dev_alloc(&sc.st_begin, (uint64_t)sc.max_tiles * 8));
+    CUC(dev_alloc(&sc.st_end, (uint64_t)sc.max_tiles * 8));
+    CUC(dev_alloc(&sc.tile_cnt, sc.max_tiles));
+    CUC(dev_alloc(&sc.tile_base, (uint64_t)sc.max_tiles + 1));
+    CUC(dev_alloc(&sc.wit_min, max_reads));
+    CUC(dev_alloc(&sc.wit_max, max_reads));
+    CUC(dev_alloc(&ctx->dev_seq, max_reads));
+    CUC(dev_alloc(&ctx->dev_fix, max_reads));
     CUC(dev_alloc(&sc.seq_list, max_reads));
     CUC(dev_alloc(&sc.seq_sbase, (uint64_t)max_reads + 1));
     CUC(dev_alloc(&sc.seq_count, 1));
-    CUC(dev_alloc(&sc.scan_status, scan_tiles_for(max_reads) + 1));
+    CUC(dev_alloc(&sc.cursor, 1));
+    CUC(dev_alloc(&sc.scan_status, scan_tiles_for(sc.max_tiles) + 1));
+    if (flags & SGPU_F_STAGE_TIMERS)
+        for (int k = 0; k <= sgpu_ctx::MAX_STAGES; k++) CUC(cudaEventCreate(&ctx->stage_ev[k]));
     CUC(dev_alloc(&sc.scan_ticket, 1));
     CUC(dev_alloc(&sc.status, 1));
     CUC(dev_alloc(&sc.counters, 4));
@@ -305,9 +356,11 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     cudaDeviceSynchronize();
     Scratch& sc = ctx->sc;
     cudaFree(sc.Sinc); cudaFree(sc.Qinc); cudaFree(sc.t1); cudaFree(sc.t2); cudaFree(sc.bitmap);
-    cudaFree(sc.ev_cnt); cudaFree(sc.seq_flag); cudaFree(sc.fixups); cudaFree(sc.seq_list); cudaFree(sc.seq_sbase);
-    cudaFree(sc.seq_count); cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status);
-    cudaFree(sc.counters);
+    cudaFree(sc.st_begin); cudaFree(sc.st_end); cudaFree(sc.tile_cnt); cudaFree(sc.tile_base);
+    cudaFree(sc.wit_min); cudaFree(sc.wit_max); cudaFree(ctx->dev_seq); cudaFree(ctx->dev_fix);
+    cudaFree(sc.seq_list); cudaFree(sc.seq_sbase); cudaFree(sc.seq_count); cudaFree(sc.cursor);
+    cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status); cudaFree(sc.counters);
+    for (int k = 0; k <= sgpu_ctx::MAX_STAGES; k++) if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
     free_dev_out(ctx->dev_out);
     if (ctx->slots) {
         for (uint32_t s = 0; s < ctx->n_slots; s++) {
@@ -451,7 +504,7 @@ int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t wan
     CU(cudaSetDevice(ctx->device));
     DevBatch b{batch->samples, batch->read_off, batch->read_len, batch->offset_f, batch->raw_unit_f,
                batch->n_reads, (int)batch->rna, batch->span};
-    const int rc = run_pipeline(ctx, b, want, ctx->dev_out, ctx->sc.seq_flag, ctx->sc.fixups,
+    const int rc = run_pipeline(ctx, b, want, ctx->dev_out, ctx->dev_seq, ctx->dev_fix,
                                 reinterpret_cast<cudaStream_t>(stream));
     if (rc) return rc;
     memset(out, 0, sizeof *out);
@@ -461,8 +514,8 @@ int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t wan
     out->ev_stdv = ctx->dev_out.ev_stdv;
     out->pa = (want & SGPU_WANT_PA) ? ctx->dev_out.pa : nullptr;
     out->stat = ctx->dev_out.stat;
-    out->seq_order = ctx->sc.seq_flag;
-    out->fixups = ctx->sc.fixups;
+    out->seq_order = ctx->dev_seq;
+    out->fixups = ctx->dev_fix;
     return SGPU_OK;
 }
 
@@ -480,6 +533,23 @@ int sgpu_counters(sgpu_ctx_t* ctx, sgpu_counters_t* out) {
     out->n_kernel_launches = ctx->last_launches;
     out->status = map_dev_status(status);
     return SGPU_OK;
+}
+
+int sgpu_stage_times(sgpu_ctx_t* ctx, sgpu_stage_time_t* out, uint32_t cap) {
+    if (!ctx || (!out && cap)) return SGPU_E_INVAL;
+    if (!(ctx->flags & SGPU_F_STAGE_TIMERS)) return SGPU_E_STATE;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->n_stages == 0) return 0;
+    CU(cudaEventSynchronize(ctx->stage_ev[ctx->n_stages]));
+    int n = 0;
+    for (int k = 0; k < ctx->n_stages && (uint32_t)k < cap; k++, n++) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, ctx->stage_ev[k], ctx->stage_ev[k + 1]));
+        out[k].name = ctx->stage_name[k];
+        out[k].ms = ms;
+        out[k].launches = ctx->stage_launches[k];
+    }
+    return n;
 }
 
 int sgpu_memcpy_d2h(sgpu_ctx_t* ctx, void* dst, const void* src, uint64_t bytes) {

@@ -85,8 +85,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // ---- shared helpers --------------------------------------------------------------------------------------------
 // List the reads that intersect flat range [lo, hi) (executed by one thread).
+// When more than SEG_MAX reads intersect the range (reads of a few dozen samples) the tile is not handled by the
+// fast path: `overflow` is raised and, if seq_flag is given, the reads beyond the list are routed to the
+// sequential-order kernels here (the caller flags the listed ones).
 __device__ int collect_segments(const DevBatch& b, long long lo, long long hi, long long region_start, Seg* segs,
-                                int* overflow) {
+                                int* overflow, uint32_t* seq_flag) {
     if (hi <= 0 || b.n_reads == 0) return 0;
     if (lo < 0) lo = 0;
     uint32_t r = find_read(b.read_off, b.n_reads, (uint64_t)lo);
@@ -96,7 +99,12 @@ __device__ int collect_segments(const DevBatch& b, long long lo, long long hi, l
         if (s >= hi) break;
         const uint32_t len = b.read_len[r];
         if (len == 0 || s + (long long)len <= lo) continue;
-        if (n == SEG_MAX) { *overflow = 1; break; }
+        if (n == SEG_MAX) {
+            *overflow = 1;
+            if (!seq_flag) break;
+            seq_flag[r] = 1u;
+            continue;
+        }
         segs[n].u0 = (int)(s - region_start);
         segs[n].len = len;
         segs[n].read = r;
@@ -250,7 +258,7 @@ struct Walker {
         for (int u = a; u < b; u++) {
             if (sidx == -2 || (u & 7) == 0) {
                 sidx = grp[u >> 3];
-                if (sidx >= 0) { su0 = segs[sidx].u0; send = su0 + (int)min(segs[sidx].len, (uint32_t)(REG + 64)); }
+                if (sidx >= 0) { su0 = segs[sidx].u0; send = (int)min((long long)su0 + (long long)segs[sidx].len, (long long)REG); }
             }
             if (sidx < 0 || u >= send) continue;           // alignment gap
             if (u == su0) { det_set(p.s, u); det_set(p.l, u); }  // first sample of a read: initial state (516-536)
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(NT) detect_tiles_kernel(DevBatch b, uint32_t n
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < n_tiles) issue_load(nxt, buf ^ 1);
             int ovf = 0;
-            sm.nseg = collect_segments(b, rs, rs + REG, rs, sm.segs, &ovf);
+            sm.nseg = collect_segments(b, rs, rs + REG, rs, sm.segs, &ovf, seq_flag);
             sm.overflow = ovf;
             sm.bad = 0;
         }
@@ -633,7 +641,7 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
         const long long ts = (long long)tile * T;
         if (tid == 0) {
             int ovf = 0;
-            sm.nseg = collect_segments(b, ts, ts + T, ts, sm.segs, &ovf);
+            sm.nseg = collect_segments(b, ts, ts + T, ts, sm.segs, &ovf, nullptr);
             sm.overflow = ovf;  // such reads were routed to the sequential-order kernels by detect_tiles_kernel
             sm.spill_u = -1;
         }
@@ -701,8 +709,9 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
                 if (end > read_end) end = read_end;
                 if (end <= T) {
                     const int eu = (int)end;
-                    const double s0 = (u == sg.u0) ? 0.0 : sm.sS[pad8(u - 1)];
-                    const double q0 = (u == sg.u0) ? 0.0 : sm.sQ[pad8(u - 1)];
+                    const bool at0 = (u == sg.u0) || (u == 0);  // nothing of this read before u inside the tile
+                    const double s0 = at0 ? 0.0 : sm.sS[pad8(u - 1)];
+                    const double q0 = at0 ? 0.0 : sm.sQ[pad8(u - 1)];
                     float mean, stdv;
                     event_stats(__dsub_rn(sm.sS[pad8(eu - 1)], s0), __dsub_rn(sm.sQ[pad8(eu - 1)], q0),
                                 (uint32_t)(eu - u), &mean, &stdv);
@@ -721,8 +730,9 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
             const int sx = sm.grp[u >> 3];
             const Seg sg = sm.segs[sx];
             const long long read_end = ts + sg.u0 + (long long)sg.len;  // flat
-            double ds = __dsub_rn(sm.sS[pad8(T - 1)], (u == sg.u0) ? 0.0 : sm.sS[pad8(u - 1)]);
-            double dq = __dsub_rn(sm.sQ[pad8(T - 1)], (u == sg.u0) ? 0.0 : sm.sQ[pad8(u - 1)]);
+            const bool at0 = (u == sg.u0) || (u == 0);
+            double ds = __dsub_rn(sm.sS[pad8(T - 1)], at0 ? 0.0 : sm.sS[pad8(u - 1)]);
+            double dq = __dsub_rn(sm.sQ[pad8(T - 1)], at0 ? 0.0 : sm.sQ[pad8(u - 1)]);
             // find the next event start at or after the tile end (bounded by the end of the read)
             long long end = read_end;
             for (long long wbase = (ts + T) >> 5; (wbase << 5) < read_end; wbase += 32) {

@@ -10,9 +10,11 @@
 //   gen_detect_kernel   short_long_peak_detector   events.c:371-443  (one thread walks one read)
 //   gen_emit_kernel     create_events/create_event events.c:457-504  (one thread walks one read)
 //
-// They serve (a) reads that fail the exact-sum witness of the fast path,
-// (b) SGPU_F_FORCE_GENERIC, and (c) as the on-device cross-check of the fast
-// path in the tests.  They keep S, Q (16 B/sample) and t1, t2 (8 B/sample) in
+// They serve (a) reads that fail the exact-sum witness or the detector
+// boundary-state check of the fast path (fast.cu), (b) SGPU_F_FORCE_GENERIC,
+// and (c) as the on-device cross-check of the fast path in the tests.  The
+// work list is built on the device (build_seq_list_kernel), so every kernel
+// here is launched with a fixed grid and returns at once when the list is empty.  They keep S, Q (16 B/sample) and t1, t2 (8 B/sample) in
 // an HBM scratch area, so they are NOT the roofline path.
 #include "kernels.cuh"
 
@@ -22,9 +24,9 @@ namespace sgpu {
 // compute_sum_sumsq: Sinc[base+i] = S[i+1], Qinc[base+i] = Q[i+1]  (S[0]=Q[0]=0 implied)
 __global__ void __launch_bounds__(128) gen_prefix_kernel(DevBatch b, WorkList wl, double* __restrict__ Sinc,
                                                          double* __restrict__ Qinc) {
-    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
+    const uint32_t n_list = *wl.count;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
-        const uint32_t r = wl.list ? wl.list[j] : j;
+        const uint32_t r = wl.list[j];
         const uint64_t base = wl.sbase[j];
         const int16_t* __restrict__ raw = b.samples + b.read_off[r];
         const uint32_t n = b.read_len[r];
@@ -62,21 +64,16 @@ __device__ __forceinline__ float tstat_at(const double* __restrict__ Sinc, const
 __global__ void __launch_bounds__(256) gen_tstat_kernel(DevBatch b, WorkList wl, const double* __restrict__ Sinc,
                                                         const double* __restrict__ Qinc, float* __restrict__ t1,
                                                         float* __restrict__ t2) {
-    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
-    if (n_list == 0) return;
-    const uint64_t total = wl.sbase[n_list];
+    const uint32_t n_list = *wl.count;
     const DetParams p = det_params(b.rna);
-    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total;
-         u += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t j = find_read(wl.sbase, n_list, u);
-        const uint32_t r = wl.list ? wl.list[j] : j;
+    for (uint32_t j = blockIdx.x; j < n_list; j += gridDim.x) {  // one CTA walks one read
+        const uint32_t r = wl.list[j];
         const uint64_t base = wl.sbase[j];
         const uint32_t n = b.read_len[r];
-        const uint64_t i64 = u - base;
-        if (i64 >= n) continue;  // alignment gap
-        const uint32_t i = (uint32_t)i64;
-        t1[u] = tstat_at(Sinc, Qinc, base, n, i, (uint32_t)p.w1);
-        t2[u] = tstat_at(Sinc, Qinc, base, n, i, (uint32_t)p.w2);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            t1[base + i] = tstat_at(Sinc, Qinc, base, n, i, (uint32_t)p.w1);
+            t2[base + i] = tstat_at(Sinc, Qinc, base, n, i, (uint32_t)p.w2);
+        }
     }
 }
 
@@ -127,16 +124,17 @@ __device__ __forceinline__ int32_t det_step(DetState& d, DetState* other_long, b
 }
 
 __global__ void __launch_bounds__(128) gen_detect_kernel(DevBatch b, WorkList wl, const float* __restrict__ t1,
-                                                         const float* __restrict__ t2, uint32_t* __restrict__ bitmap,
-                                                         int clear_first) {
-    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
+                                                         const float* __restrict__ t2, uint32_t* __restrict__ bitmap) {
+    const uint32_t n_list = *wl.count;
     const DetParams p = det_params(b.rna);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
-        const uint32_t r = wl.list ? wl.list[j] : j;
+        const uint32_t r = wl.list[j];
         const uint64_t base = wl.sbase[j];
         const uint64_t foff = b.read_off[r];
         const uint32_t n = b.read_len[r];
-        if (clear_first) clear_read_bits(bitmap, foff, foff + n);
+        if (n == 0) continue;
+        clear_read_bits(bitmap, foff, foff + n);  // drop whatever the fast path found for this read
+        atomicOr(&bitmap[foff >> 5], 1u << (foff & 31));  // event 0 starts at the first sample
         DetState s, l;
         det_reset(s);
         det_reset(l);
@@ -150,34 +148,7 @@ __global__ void __launch_bounds__(128) gen_detect_kernel(DevBatch b, WorkList wl
 }
 
 // ---------------------------------------------------------------------------
-// number of events of every read = 1 + number of peak bits in (0, n)  (events.c:479-485)
-// one warp per read, lanes stride over the bitmap words
-__global__ void __launch_bounds__(256) count_events_kernel(DevBatch b, const uint32_t* __restrict__ bitmap,
-                                                           uint32_t* __restrict__ ev_cnt) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = warp; r < b.n_reads; r += n_warps) {
-        const uint64_t p0 = b.read_off[r];
-        const uint32_t n = b.read_len[r];
-        uint32_t cnt = 0;
-        if (n > 0) {
-            const uint64_t p1 = p0 + n;
-            const uint64_t w0 = p0 >> 5, w1 = (p1 - 1) >> 5;
-            for (uint64_t w = w0 + lane; w <= w1; w += 32) {
-                uint32_t v = bitmap[w];
-                if (w == w0) v &= 0xffffffffu << (p0 & 31);
-                if (w == w1) v &= 0xffffffffu >> (31 - ((p1 - 1) & 31));
-                cnt += __popc(v);
-            }
-        }
-        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) ev_cnt[r] = cnt + 1u;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Exclusive scan ev_cnt[u32] -> ev_off[u64] (n+1 entries), single pass with
+// Exclusive scan cnt[u32] -> off[u64] (n+1 entries), single pass with
 // decoupled look-back (tile status = 2 flag bits | 62-bit value).
 static constexpr int SCAN_THREADS = 256;
 static constexpr int SCAN_ITEMS = 8;
@@ -255,14 +226,15 @@ __global__ void __launch_bounds__(128) gen_emit_kernel(DevBatch b, WorkList wl, 
                                                        const uint64_t* __restrict__ ev_off, uint64_t ev_cap,
                                                        uint32_t* __restrict__ ev_start, float* __restrict__ ev_mean,
                                                        float* __restrict__ ev_stdv, int* __restrict__ status) {
-    const uint32_t n_list = wl.count ? *wl.count : wl.n_fixed;
+    const uint32_t n_list = *wl.count;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
-        const uint32_t r = wl.list ? wl.list[j] : j;
+        const uint32_t r = wl.list[j];
         const uint64_t base = wl.sbase[j];
         const uint64_t p0 = b.read_off[r];
         const uint32_t n = b.read_len[r];
         uint64_t k = ev_off[r];
         if (ev_off[r + 1] > ev_cap) { atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
+        if (n == 0) continue;
         uint32_t a = 0;  // start of the open event
         if (n > 0) {
             const uint64_t p1 = p0 + n;
@@ -324,33 +296,26 @@ static inline int grid_for(uint64_t work, int block, int max_blocks) {
     return (int)g;
 }
 
-int launch_generic_detect(const DevBatch& b, const WorkList& wl, uint64_t scratch_span_hint, Scratch& sc,
-                          int clear_first, int sm_count, cudaStream_t st) {
-    const uint32_t n = wl.n_fixed;  // upper bound on the list length
-    gen_prefix_kernel<<<grid_for(n, 128, sm_count * 16), 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc);
-    gen_tstat_kernel<<<grid_for(scratch_span_hint, 256, sm_count * 8), 256, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.t1,
-                                                                                   sc.t2);
-    gen_detect_kernel<<<grid_for(n, 128, sm_count * 16), 128, 0, st>>>(b, wl, sc.t1, sc.t2, sc.bitmap, clear_first);
+int launch_generic_detect(const DevBatch& b, const WorkList& wl, Scratch& sc, int sm_count, cudaStream_t st) {
+    gen_prefix_kernel<<<sm_count * 4, 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc);
+    gen_tstat_kernel<<<sm_count * 8, 256, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.t1, sc.t2);
+    gen_detect_kernel<<<sm_count * 4, 128, 0, st>>>(b, wl, sc.t1, sc.t2, sc.bitmap);
     return 3;
 }
 
-int launch_count_scan(const DevBatch& b, Scratch& sc, uint64_t* ev_off, uint64_t* total_out, int sm_count,
-                      cudaStream_t st) {
-    count_events_kernel<<<grid_for((uint64_t)b.n_reads * 32, 256, sm_count * 8), 256, 0, st>>>(b, sc.bitmap,
-                                                                                             sc.ev_cnt);
-    const uint32_t tiles = (b.n_reads + SCAN_TILE - 1) / SCAN_TILE;
+int launch_scan_u32(const uint32_t* cnt, uint32_t n, uint64_t* off, uint64_t* total_out, Scratch& sc, cudaStream_t st) {
+    const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     cudaMemsetAsync(sc.scan_status, 0, (size_t)(tiles + 1) * sizeof(unsigned long long), st);
     cudaMemsetAsync(sc.scan_ticket, 0, sizeof(uint32_t), st);
-    scan_counts_kernel<<<tiles ? tiles : 1, SCAN_THREADS, 0, st>>>(sc.ev_cnt, b.n_reads, ev_off, sc.scan_status,
-                                                                  sc.scan_ticket, total_out);
-    return 2;
+    scan_counts_kernel<<<tiles ? tiles : 1, SCAN_THREADS, 0, st>>>(cnt, n, off, sc.scan_status, sc.scan_ticket,
+                                                                  total_out);
+    return 1;
 }
 
 int launch_generic_emit(const DevBatch& b, const WorkList& wl, Scratch& sc, const uint64_t* ev_off, uint64_t ev_cap,
-                        uint32_t* ev_start, float* ev_mean, float* ev_stdv, int* status, int sm_count,
-                        cudaStream_t st) {
-    gen_emit_kernel<<<grid_for(wl.n_fixed, 128, sm_count * 16), 128, 0, st>>>(
-        b, wl, sc.Sinc, sc.Qinc, sc.bitmap, ev_off, ev_cap, ev_start, ev_mean, ev_stdv, status);
+                        uint32_t* ev_start, float* ev_mean, float* ev_stdv, int sm_count, cudaStream_t st) {
+    gen_emit_kernel<<<sm_count * 4, 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.bitmap, ev_off, ev_cap, ev_start,
+                                                  ev_mean, ev_stdv, sc.status);
     return 1;
 }
 
@@ -359,6 +324,6 @@ int launch_pa(const DevBatch& b, float* pa, int sm_count, cudaStream_t st) {
     return 1;
 }
 
-uint32_t scan_tiles_for(uint32_t n_reads) { return (n_reads + SCAN_TILE - 1) / SCAN_TILE + 1; }
+uint32_t scan_tiles_for(uint32_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
 
 }  // namespace sgpu
