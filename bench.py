@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- event-detection throughput of the sigtk B200 hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads-per-step B] [--mode event+pa|event]
+
+A "step" = one pass of the hot path (pA conversion + event detection, event table out, pA materialised in the
+default `event+pa` mode) over one device-resident batch of B synthetic DNA reads drawn from the 1,000,000-read
+set of BASELINE.json configs[2] (int16, lognormal length, mean 40,000 samples, sigma 0.6).
+Reads are independent, so with N GPUs every rank processes its own batches (weak scaling, no collective on the
+data path; torch.distributed is used for the barrier and the max-over-ranks only).
+
+  value      whole-job Gsamples/s, inputs resident in HBM, CUDA-event time of the K steps, max over ranks
+  e2e        the same metric through the host C-ABI (pinned slot -> sgpu_submit -> sgpu_wait): H2D of the samples
+             and D2H of the event table (+ pA in event+pa mode) inside the timed region
+  roofline   dominant kernel (detect_tiles_kernel): algorithmic bytes of the path per launch / its CUDA-event time
+  cpu_baseline  the UNMODIFIED reference functions (oracle/_ref/libsigtk_ref.so: signal_in_picoamps + getevents)
+             on 1 host thread over a bounded sample of the same reads (N=1, rank 0 only)
+
+--impl reference times the reference's CPU path on all host threads (one reference call chain per thread over
+disjoint reads) and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from sigtk_b200 import synth  # noqa: E402
+
+N_SET = 1_000_000          # reads of the named synthetic set
+METRIC = "event_detection_throughput"
+UNIT = "Gsamples/s"
+WORKLOAD = "synthetic 1M DNA reads, int16, lognormal length mean 40k samples (sigma 0.6), {mode}"
+
+
+def alg_bytes(n_samples: int, n_reads: int, n_events: int, pa: bool) -> int:
+    """SURVEY.md 8(d) / BASELINE.md 4: algorithmic bytes of the path."""
+    return 2 * n_samples + 20 * n_reads + 12 * n_events + 8 * n_reads + (4 * n_samples if pa else 0)
+
+
+def measured_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.rows = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def device_batch(torch, dev, lens: np.ndarray, first_index: int, seed: int):
+    """One batch of synthetic reads generated on the device (signal model of sigtk_b200/synth.py).
+    -> dict(samples i16[span], read_off i64[n+1], read_len i32[n], offset f32[n], unit f32[n], span, n_samples)"""
+    n = len(lens)
+    al = (lens + 7) // 8 * 8
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(al)
+    span = int(off[-1])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    samples = torch.empty(span, dtype=torch.int16, device=dev)
+    offsets = ((first_index + np.arange(n)) % 53).astype(np.float32)
+    scale = np.float32(synth.DIGITISATION / synth.RANGE)
+    CH = 1 << 25
+    r0 = 0
+    while r0 < n:  # groups of whole reads of about CH samples
+        r1 = int(np.searchsorted(off, off[r0] + CH, side="right"))
+        r1 = min(max(r1 - 1, r0 + 1), n)
+        a, b = int(off[r0]), int(off[r1])
+        m = b - a
+        change = torch.rand(m, device=dev, generator=gen) < 0.1
+        change[0] = True
+        seg = torch.cumsum(change.to(torch.int32), 0, dtype=torch.int32) - 1
+        nlev = int(seg[-1].item()) + 1
+        levels = 60.0 + 60.0 * torch.rand(nlev, device=dev, generator=gen)
+        pa = levels[seg.long()]
+        del seg, change
+        pa += 2.0 * torch.randn(m, device=dev, generator=gen)
+        o = torch.repeat_interleave(torch.from_numpy(offsets[r0:r1]).to(dev),
+                                    torch.from_numpy(al[r0:r1]).to(dev), output_size=m)
+        raw = torch.round(pa * float(scale) - o).clamp_(-32768, 32767)
+        samples[a:b] = raw.to(torch.int16)
+        del pa, o, raw
+        r0 = r1
+    unit = (np.float32(synth.RANGE) / np.float32(synth.DIGITISATION)).astype(np.float32)
+    return {
+        "samples": samples,
+        "read_off": torch.from_numpy(off).to(dev),
+        "read_len": torch.from_numpy(lens.astype(np.int32)).to(dev),
+        "offset": torch.from_numpy(offsets).to(dev),
+        "unit": torch.full((n,), float(unit), dtype=torch.float32, device=dev),
+        "span": span, "n_samples": int(lens.sum()), "n_reads": n, "host_off": off, "host_len": lens,
+        "host_offset": offsets,
+    }
+
+
+def host_reads_of(batch, n_first: int):
+    """first reads of a device batch as the (raw, digitisation, offset, range) tuples the checkers take"""
+    off, lens = batch["host_off"], batch["host_len"]
+    n_first = min(n_first, len(lens))
+    flat = batch["samples"][: int(off[n_first])].cpu().numpy()
+    return [(flat[int(off[r]): int(off[r]) + int(lens[r])].copy(), synth.DIGITISATION, float(batch["host_offset"][r]),
+             synth.RANGE) for r in range(n_first)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def load_checker():
+    """the CPU arm: the compiled, unmodified reference if present, else the oracle port"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+    if _oracle.have_ref():
+        return _oracle.Reference(), "reference"
+    return _oracle.Oracle(), "port"
+
+
+def cpu_time_reads(chk, reads, threads: int):
+    """seconds (wall) for pA + event detection of `reads` on `threads` host threads; -> (seconds, samples, events)"""
+    if threads <= 1:
+        return chk.time_events(reads, 0)
+    shards = [reads[k::threads] for k in range(threads)]
+    shards = [s for s in shards if s]
+    out = [None] * len(shards)
+
+    def work(k):
+        out[k] = chk.time_events(shards[k], 0)  # ctypes releases the GIL during the call
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(shards))]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    return dt, sum(o[1] for o in out), sum(o[2] for o in out)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    chk, kind = load_checker()
+    threads = os.cpu_count() or 1
+    per_thread = 24
+    lens = synth.read_lengths(N_SET)
+    reads_per_step = threads * per_thread
+    pool = []
+    for j in range(3):  # three distinct samples, cycled
+        base = j * reads_per_step
+        pool.append([synth.make_read(base + i, int(lens[base + i])) for i in range(reads_per_step)])
+    for w in range(args.warmup):
+        cpu_time_reads(chk, pool[w % 3], threads)
+    t_tot, s_tot, e_tot = 0.0, 0, 0
+    for k in range(args.steps):
+        dt, ns, ne = cpu_time_reads(chk, pool[k % 3], threads)
+        t_tot += dt; s_tot += ns; e_tot += ne
+    val = s_tot / t_tot / 1e9
+    sample = f"{reads_per_step} reads (~{s_tot // max(args.steps, 1)} samples) per step, first reads of the set"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(mode=args.mode), "reads_per_step": reads_per_step},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import sigtk_b200 as sg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sigtk_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    pa_mode = args.mode == "event+pa"
+    want = sg.WANT_EVENTS | (sg.WANT_PA if pa_mode else 0)
+    B = args.reads_per_step
+    lens_all = synth.read_lengths(N_SET)
+    pool_n = max(1, min(args.pool, args.steps + args.warmup))
+    pool = []
+    for j in range(pool_n):
+        first = ((j * world + rank) * B) % (N_SET - B)
+        pool.append(device_batch(torch, dev, lens_all[first:first + B], first, synth.SEED + 7919 * (j * world + rank)))
+    torch.cuda.synchronize()
+    max_span = max(p["span"] for p in pool)
+    ctx = sg.Context(device=local, max_samples=max_span, max_reads=B, flags=sg.F_NO_HOST_SLOTS | sg.F_STAGE_TIMERS)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(p):
+        return ctx.run_device(p["samples"].data_ptr(), p["read_off"].data_ptr(), p["read_len"].data_ptr(),
+                              p["offset"].data_ptr(), p["unit"].data_ptr(), p["n_reads"], p["span"], 0, want, stream)
+
+    for w in range(args.warmup):
+        step(pool[w % pool_n])
+    torch.cuda.synchronize()
+    c0 = ctx.counters()
+    if c0["status"] != 0:
+        raise SystemExit(f"bench.py: device status {c0['status']}")
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms, stage_launches = {}, {}
+    n_samples = n_events = n_reads = launches = 0
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(args.steps):
+        p = pool[(args.warmup + k) % pool_n]
+        step(p)
+        for name, ms, nl in ctx.stage_times():  # CUDA events on the launch stream; waits for this step's last kernel
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+            stage_launches[name] = nl
+        n_samples += p["n_samples"]
+        n_reads += p["n_reads"]
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    # events per step (counters of the last run x steps would be wrong for a pool of different batches)
+    ev_per_batch = []
+    for p in pool:
+        step(p)
+        torch.cuda.synchronize()
+        c = ctx.counters()
+        ev_per_batch.append((c["n_events"], c["n_seq_order_reads"], c["n_fixups"], c["n_kernel_launches"], c["status"]))
+    for k in range(args.steps):
+        e = ev_per_batch[(args.warmup + k) % pool_n]
+        n_events += e[0]
+        launches += e[3]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_samples), float(n_events), float(n_reads)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    all_samples, all_events, all_reads = (float(x) for x in tot.tolist())
+    value = all_samples / (ms_max * 1e-3) / 1e9
+
+    # ---- end to end through the host C-ABI: pinned slots, H2D + kernels + D2H per step ----------------------------
+    e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist)
+
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    dom = "detect_tiles"
+    dom_ms = stage_ms.get(dom, 0.0) / max(args.steps, 1)
+    bytes_step = alg_bytes(n_samples, n_reads, n_events, pa_mode) / max(args.steps, 1)
+    achieved = bytes_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "detect_tiles_bytes_per_sample_pa" if pa_mode else "detect_tiles_bytes_per_sample"
+        traffic = float(tj[key]) * n_samples / max(args.steps, 1)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "detect_tiles_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": bytes_step,
+                "path_frac": bytes_step / (ms_max / max(args.steps, 1) * 1e-3) / 1e9 / peak,
+                "stage_ms_per_step": {k: v / max(args.steps, 1) for k, v in stage_ms.items()}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        chk, kind = load_checker()
+        reads = host_reads_of(pool[0], args.cpu_reads)
+        dt, ns, ne = chk.time_events(reads, 0)
+        cpu = {"value": ns / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"first {len(reads)} reads of batch 0 ({ns} samples, {ne} events, {dt:.1f} s)"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(mode=args.mode), "reads_per_step_per_gpu": B,
+                       "samples_per_step_per_gpu": n_samples // max(args.steps, 1),
+                       "events_per_sample": all_events / max(all_samples, 1.0),
+                       "l2": f"inputs {2 * max_span / 1e6:.0f} MB per step > 126 MB L2; pool of {pool_n} distinct batches",
+                       "sequential_order_reads": sum(e[1] for e in ev_per_batch),
+                       "detector_fixups": sum(e[2] for e in ev_per_batch)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist):
+    """K steps of (pinned slot -> H2D -> kernels -> D2H -> host-visible event table), two slots in flight."""
+    B = min(args.e2e_reads, batch["n_reads"])
+    off, lens = batch["host_off"], batch["host_len"]
+    reads = host_reads_of(batch, B)
+    span = int(off[B])
+    hctx = sg.Context(device=local, max_samples=span + 64, max_reads=B, n_slots=2)
+    for s in (0, 1):
+        hctx.fill(s, reads, 0)  # the batch loader's job (decode into the pinned slot): outside the timed region
+    n_samp = int(lens[:B].sum())
+
+    def wait(slot):
+        res = sg._lib.Result()
+        hctx._check(hctx._lib.sgpu_wait(hctx._h, slot, C.byref(res)))
+        return int(res.n_events)
+
+    hctx.submit(0, want); ne = wait(0)
+    hctx.submit(1, want); wait(1)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    steps = max(args.steps, 2)
+    t0 = time.perf_counter()
+    hctx.submit(0, want)
+    for k in range(1, steps):
+        hctx.submit(k & 1, want)
+        wait((k - 1) & 1)
+    wait((steps - 1) & 1)
+    dt = time.perf_counter() - t0
+    hctx.close()
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_samp * steps)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    h2d = 2 * span + 20 * B
+    d2h = 12 * ne + 8 * (B + 1) + 8 * B + (4 * span if pa_mode else 0)
+    return {"value": float(tot.item()) / float(t.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "reads_per_step_per_gpu": B, "samples_per_step_per_gpu": n_samp,
+            "timing": "host wall clock around submit/wait of K steps, 2 pinned slots in flight, max over ranks"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="event+pa", choices=["event+pa", "event"])
+    ap.add_argument("--reads-per-step", type=int, default=16384)
+    ap.add_argument("--pool", type=int, default=4, help="distinct device-resident batches cycled through")
+    ap.add_argument("--e2e-reads", type=int, default=4096)
+    ap.add_argument("--cpu-reads", type=int, default=2000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,10 +89,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // fast path: `overflow` is raised and, if seq_flag is given, the reads beyond the list are routed to the
 // sequential-order kernels here (the caller flags the listed ones).
 __device__ int collect_segments(const DevBatch& b, long long lo, long long hi, long long region_start, Seg* segs,
-                                int* overflow, uint32_t* seq_flag) {
+                                int* overflow, uint32_t* seq_flag, uint32_t r) {
     if (hi <= 0 || b.n_reads == 0) return 0;
     if (lo < 0) lo = 0;
-    uint32_t r = find_read(b.read_off, b.n_reads, (uint64_t)lo);
     int n = 0;
     for (; r < b.n_reads; r++) {
         const long long s = (long long)b.read_off[r];
@@ -247,11 +246,10 @@ struct Walker {
     const float* t2;
     const signed char* grp;
     const Seg* segs;
-    uint32_t* bits;   // core bitmap (T bits), bit = region index - HL
-    int lo, hi;       // region range of the peaks this chunk owns
+    int lo, hi;       // region range of the peaks this chunk owns (hi = lo + 64)
 
-    // run samples [a, b) through both detectors; emissions owned by the chunk are recorded when `record`
-    __device__ __forceinline__ void run(DetPair& p, int a, int b, bool record) const {
+    // run samples [a, b) through both detectors; emissions owned by the chunk set bit (pos - lo) of `mask`
+    __device__ __noinline__ void run(DetPair& p, int a, int b, unsigned long long& mask) const {
         using G = Geo<RNA>;
         const DetParams prm = det_params(RNA);
         int sidx = -2, su0 = 0, send = 0;
@@ -265,10 +263,8 @@ struct Walker {
             const float c1 = t1[pad64(u)], c2 = t2[pad64(u)];
             const int e1 = det_step<true>(p.s, p.l, u, c1, prm.thr1, G::w1, G::w1, prm.height);
             const int e2 = det_step<false>(p.l, p.l, u, c2, prm.thr2, G::w2, G::w1, prm.height);
-            if (record) {
-                if (e1 != NONE && e1 >= lo && e1 < hi) atomicOr(&bits[(e1 - G::HL) >> 5], 1u << ((e1 - G::HL) & 31));
-                if (e2 != NONE && e2 >= lo && e2 < hi) atomicOr(&bits[(e2 - G::HL) >> 5], 1u << ((e2 - G::HL) & 31));
-            }
+            if (e1 != NONE && e1 >= lo && e1 < hi) mask |= 1ull << (e1 - lo);
+            if (e2 != NONE && e2 >= lo && e2 < hi) mask |= 1ull << (e2 - lo);
         }
     }
 
@@ -278,7 +274,7 @@ struct Walker {
     }
 
     // continue past the chunk end until the owned pending peaks are resolved; false if the cap was hit
-    __device__ __forceinline__ bool run_out(DetPair p, int from) const {
+    __device__ __noinline__ bool run_out(DetPair p, int from, unsigned long long& mask) const {
         using G = Geo<RNA>;
         const DetParams prm = det_params(RNA);
         int u = from;
@@ -289,12 +285,59 @@ struct Walker {
             if (sidx < 0) return true;                              // the read ended: pending peaks are dropped
             const int su0 = segs[sidx].u0;
             if (u == su0 || (long long)u - su0 >= (long long)segs[sidx].len) return true;
-            run(p, u, u + 1, true);
+            run(p, u, u + 1, mask);
             u++;
         }
         return true;
     }
 };
+
+// Both detectors for one sample that lies inside a read and is not its first sample, without branches
+// (same transitions as det_step: events.c:387-437). Peaks the chunk owns set bit (pos - lo) of `mask`.
+template <int RNA>
+__device__ __forceinline__ void step_pair(DetPair& p, int u, float c1, float c2, int lo, unsigned long long& mask) {
+    using G = Geo<RNA>;
+    constexpr float thr1 = RNA ? 2.5f : 1.4f, thr2 = 9.0f, h = RNA ? 1.0f : 0.2f;
+    {
+        Det& d = p.s;
+        const bool act = d.mt < u, none = d.pp == NONE;
+        const bool lt = c1 < d.pv, gt = c1 > d.pv;
+        const bool rise = __fsub_rn(c1, d.pv) > h;
+        const float pv2 = gt ? c1 : d.pv;
+        const int pp2 = gt ? u : d.pp;
+        const bool big = pv2 > thr1;
+        const bool valid2 = (d.valid != 0) | (big & (__fsub_rn(pv2, c1) > h));
+        const bool emit = valid2 & ((int)((unsigned)u - (unsigned)pp2) > G::w1 / 2);
+        const bool in1 = act & none, in2 = act & !none;
+        const bool maskl = in2 & big;  // the short detector dominates the long one (414-422)
+        p.l.mt = maskl ? pp2 + G::w1 : p.l.mt;
+        p.l.pp = maskl ? NONE : p.l.pp;
+        p.l.pv = maskl ? FLT_MAX : p.l.pv;
+        p.l.valid = maskl ? 0 : p.l.valid;
+        const unsigned k = (unsigned)((in2 & emit) ? pp2 - lo : -1);
+        mask |= (k < 64u) ? (1ull << k) : 0ull;
+        d.pv = in1 ? ((lt | rise) ? c1 : d.pv) : (in2 ? (emit ? c1 : pv2) : d.pv);
+        d.pp = in1 ? ((!lt & rise) ? u : NONE) : (in2 ? (emit ? NONE : pp2) : d.pp);
+        d.valid = in2 ? ((valid2 & !emit) ? 1 : 0) : d.valid;
+    }
+    {
+        Det& d = p.l;
+        const bool act = d.mt < u, none = d.pp == NONE;
+        const bool lt = c2 < d.pv, gt = c2 > d.pv;
+        const bool rise = __fsub_rn(c2, d.pv) > h;
+        const float pv2 = gt ? c2 : d.pv;
+        const int pp2 = gt ? u : d.pp;
+        const bool big = pv2 > thr2;
+        const bool valid2 = (d.valid != 0) | (big & (__fsub_rn(pv2, c2) > h));
+        const bool emit = valid2 & ((int)((unsigned)u - (unsigned)pp2) > G::w2 / 2);
+        const bool in1 = act & none, in2 = act & !none;
+        const unsigned k = (unsigned)((in2 & emit) ? pp2 - lo : -1);
+        mask |= (k < 64u) ? (1ull << k) : 0ull;
+        d.pv = in1 ? ((lt | rise) ? c2 : d.pv) : (in2 ? (emit ? c2 : pv2) : d.pv);
+        d.pp = in1 ? ((!lt & rise) ? u : NONE) : (in2 ? (emit ? NONE : pp2) : d.pp);
+        d.valid = in2 ? ((valid2 & !emit) ? 1 : 0) : d.valid;
+    }
+}
 
 }  // namespace
 
@@ -316,11 +359,12 @@ struct DetectSmem {
 };
 
 template <int RNA>
-__global__ void __launch_bounds__(NT) detect_tiles_kernel(DevBatch b, uint32_t n_tiles, float* __restrict__ pa_out,
+__global__ void __launch_bounds__(NT, 3) detect_tiles_kernel(DevBatch b, uint32_t n_tiles, float* __restrict__ pa_out,
                                                           uint32_t* __restrict__ bitmap, int* __restrict__ st_begin,
                                                           int* __restrict__ st_end, uint32_t* __restrict__ wit_min,
                                                           uint32_t* __restrict__ wit_max,
-                                                          uint32_t* __restrict__ seq_flag) {
+                                                          uint32_t* __restrict__ seq_flag,
+                                                          const uint32_t* __restrict__ tile_read0) {
     using G = Geo<RNA>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DetectSmem& sm = *reinterpret_cast<DetectSmem*>(smem_raw);
@@ -362,7 +406,7 @@ __global__ void __launch_bounds__(NT) detect_tiles_kernel(DevBatch b, uint32_t n
             const uint32_t nxt = tile + gridDim.x;
             if (nxt < n_tiles) issue_load(nxt, buf ^ 1);
             int ovf = 0;
-            sm.nseg = collect_segments(b, rs, rs + REG, rs, sm.segs, &ovf, seq_flag);
+            sm.nseg = collect_segments(b, rs, rs + REG, rs, sm.segs, &ovf, seq_flag, tile_read0[tile]);
             sm.overflow = ovf;
             sm.bad = 0;
         }
@@ -427,17 +471,17 @@ __global__ void __launch_bounds__(NT) detect_tiles_kernel(DevBatch b, uint32_t n
                         const bool first = (i == (uint32_t)G::w1);
                         const double sl = first ? 0.0 : sm.sS[pad8(u - G::w1 - 1)];
                         const double ql = first ? 0.0 : sm.sQ[pad8(u - G::w1 - 1)];
-                        r1 = tstat_reference_chain(__dsub_rn(s_i, sl), __dsub_rn(q_i, ql),
-                                                   __dsub_rn(sm.sS[pad8(u + G::w1 - 1)], s_i),
-                                                   __dsub_rn(sm.sQ[pad8(u + G::w1 - 1)], q_i), (float)G::w1);
+                        r1 = tstat_fast<G::w1>(__dsub_rn(s_i, sl), __dsub_rn(q_i, ql),
+                                               __dsub_rn(sm.sS[pad8(u + G::w1 - 1)], s_i),
+                                               __dsub_rn(sm.sQ[pad8(u + G::w1 - 1)], q_i));
                     }
                     if (n >= 2u * G::w2 && i >= (uint32_t)G::w2 && i + G::w2 <= n) {
                         const bool first = (i == (uint32_t)G::w2);
                         const double sl = first ? 0.0 : sm.sS[pad8(u - G::w2 - 1)];
                         const double ql = first ? 0.0 : sm.sQ[pad8(u - G::w2 - 1)];
-                        r2 = tstat_reference_chain(__dsub_rn(s_i, sl), __dsub_rn(q_i, ql),
-                                                   __dsub_rn(sm.sS[pad8(u + G::w2 - 1)], s_i),
-                                                   __dsub_rn(sm.sQ[pad8(u + G::w2 - 1)], q_i), (float)G::w2);
+                        r2 = tstat_fast<G::w2>(__dsub_rn(s_i, sl), __dsub_rn(q_i, ql),
+                                               __dsub_rn(sm.sS[pad8(u + G::w2 - 1)], s_i),
+                                               __dsub_rn(sm.sQ[pad8(u + G::w2 - 1)], q_i));
                     }
                 }
             }
@@ -454,15 +498,43 @@ __global__ void __launch_bounds__(NT) detect_tiles_kernel(DevBatch b, uint32_t n
         // ---- phase D: the peak detector, one 64-sample chunk per lane of warp 0 ----------------------------------
         if (wid == 0) {
             const int cs = G::HL + lane * L, ce = cs + L;
-            Walker<RNA> wk{sm.t1, sm.t2, sm.grp, sm.segs, sm.bits, cs, ce};
+            const int wa = cs - G::W, wz = ce + G::R;   // everything this lane may look at
+            Walker<RNA> wk{sm.t1, sm.t2, sm.grp, sm.segs, cs, ce};
+            const DetParams prm = det_params(RNA);
             DetPair p;
-            det_set(p.s, cs - G::W - 1);  // cold start: cs-W is the first sample processed
-            det_set(p.l, cs - G::W - 1);
-            wk.run(p, cs - G::W, cs, false);
-            Canon begin = canon(p, cs);
-            wk.run(p, cs, ce, true);
-            Canon end = canon(p, ce);
-            bool ok = wk.run_out(p, ce);
+            det_set(p.s, wa - 1);  // cold start: wa is the first sample processed
+            det_set(p.l, wa - 1);
+            unsigned long long mask = 0ull;
+            Canon begin, end;
+            bool ok = true;
+            // common case: [wa, wz) lies inside one read and does not contain its first sample
+            bool simple = false;
+            {
+                const int sa = sm.grp[wa >> 3];
+                if (sa >= 0) simple = sm.segs[sa].u0 < wa && (long long)sm.segs[sa].u0 + (long long)sm.segs[sa].len >= wz;
+            }
+            if (simple) {
+#pragma unroll 8
+                for (int u = wa; u < cs; u++) step_pair<RNA>(p, u, sm.t1[pad64(u)], sm.t2[pad64(u)], cs, mask);
+                begin = canon(p, cs);
+#pragma unroll 8
+                for (int u = cs; u < ce; u++) step_pair<RNA>(p, u, sm.t1[pad64(u)], sm.t2[pad64(u)], cs, mask);
+                end = canon(p, ce);
+                DetPair r = p;
+                int u = ce;
+                while (wk.pending(r.s, prm.thr1) || wk.pending(r.l, prm.thr2)) {
+                    if (u >= wz) { ok = false; break; }
+                    step_pair<RNA>(r, u, sm.t1[pad64(u)], sm.t2[pad64(u)], cs, mask);
+                    u++;
+                }
+            } else {
+                unsigned long long ignore = 0ull;
+                wk.run(p, wa, cs, ignore);
+                begin = canon(p, cs);
+                wk.run(p, cs, ce, mask);
+                end = canon(p, ce);
+                ok = wk.run_out(p, ce, mask);
+            }
             const Canon tile_begin = begin;  // lane 0: speculative state at the tile start (verified across tiles)
             // compare with the previous chunk's end state; re-run mismatching chunks from the true state
             for (int round = 0; round < NCH; round++) {
@@ -482,14 +554,15 @@ __global__ void __launch_bounds__(NT) detect_tiles_kernel(DevBatch b, uint32_t n
                     p.l.pv = __int_as_float(prev.v[6]);
                     p.l.valid = prev.v[7];
                     begin = prev;
-                    sm.bits[2 * lane] = 0u;       // this chunk owns exactly these two words
-                    sm.bits[2 * lane + 1] = 0u;
-                    wk.run(p, cs, ce, true);
+                    mask = 0ull;
+                    wk.run(p, cs, ce, mask);
                     end = canon(p, ce);
-                    ok = wk.run_out(p, ce);
+                    ok = wk.run_out(p, ce, mask);
                 }
                 __syncwarp();
             }
+            sm.bits[2 * lane] = (uint32_t)mask;  // this chunk owns exactly these two words
+            sm.bits[2 * lane + 1] = (uint32_t)(mask >> 32);
             if (!ok) {  // run-out cap hit: let the sequential-order kernels do the read that contains ce-1
                 const int sidx = sm.grp[(ce - 1) >> 3];
                 if (sidx >= 0) seq_flag[sm.segs[sidx].read] = 1u;
@@ -633,7 +706,8 @@ struct EmitSmem {
 __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_tiles, const uint32_t* __restrict__ bitmap,
                                                          const uint64_t* __restrict__ tile_base, uint64_t ev_cap,
                                                          uint32_t* __restrict__ ev_start, float* __restrict__ ev_mean,
-                                                         float* __restrict__ ev_stdv, int* __restrict__ status) {
+                                                         float* __restrict__ ev_stdv, int* __restrict__ status,
+                                                         const uint32_t* __restrict__ tile_read0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -641,7 +715,7 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
         const long long ts = (long long)tile * T;
         if (tid == 0) {
             int ovf = 0;
-            sm.nseg = collect_segments(b, ts, ts + T, ts, sm.segs, &ovf, nullptr);
+            sm.nseg = collect_segments(b, ts, ts + T, ts, sm.segs, &ovf, nullptr, tile_read0[tile]);
             sm.overflow = ovf;  // such reads were routed to the sequential-order kernels by detect_tiles_kernel
             sm.spill_u = -1;
         }
@@ -778,12 +852,19 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) init_reads_kernel(uint32_t n_reads, uint32_t* __restrict__ wit_min,
+__global__ void __launch_bounds__(256) init_reads_kernel(DevBatch b, uint32_t n_tiles, uint32_t* __restrict__ wit_min,
                                                          uint32_t* __restrict__ wit_max, uint32_t* __restrict__ seq_flag,
                                                          uint32_t* __restrict__ fixups, uint32_t* __restrict__ seq_count,
-                                                         unsigned long long* __restrict__ cursor) {
+                                                         unsigned long long* __restrict__ cursor,
+                                                         uint32_t* __restrict__ tile_read0) {
+    const uint32_t n_reads = b.n_reads;
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) { *seq_count = 0u; *cursor = 0ull; }
+    // first read that can intersect the staged region of every tile (the region starts at most 160 samples early)
+    for (uint32_t t = g; t < n_tiles; t += gridDim.x * blockDim.x) {
+        const long long p = (long long)t * T - 160;
+        tile_read0[t] = find_read(b.read_off, n_reads, (uint64_t)(p < 0 ? 0 : p));
+    }
     for (uint32_t r = g; r < n_reads; r += gridDim.x * blockDim.x) {
         wit_min[r] = 0xffffffffu;
         wit_max[r] = 0u;
@@ -821,8 +902,9 @@ int fast_configure() {
 
 int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
                       cudaStream_t st) {
-    init_reads_kernel<<<grid_cap(b.n_reads, 256, sm_count * 8), 256, 0, st>>>(b.n_reads, sc.wit_min, sc.wit_max,
-                                                                             seq_flag, fixups, sc.seq_count, sc.cursor);
+    const uint32_t n_tiles = fast_tiles_for(b.span);
+    init_reads_kernel<<<grid_cap(max(b.n_reads, n_tiles), 256, sm_count * 8), 256, 0, st>>>(
+        b, n_tiles, sc.wit_min, sc.wit_max, seq_flag, fixups, sc.seq_count, sc.cursor, sc.tile_read0);
     return 1;
 }
 
@@ -833,13 +915,19 @@ int launch_fast_detect(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* 
     const int grid = grid_cap(n_tiles, 1, sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 1));
     if (b.rna)
         detect_tiles_kernel<1><<<grid, NT, sizeof(DetectSmem), st>>>(b, n_tiles, pa_out, sc.bitmap, sc.st_begin,
-                                                                      sc.st_end, sc.wit_min, sc.wit_max, seq_flag);
+                                                                      sc.st_end, sc.wit_min, sc.wit_max, seq_flag, sc.tile_read0);
     else
         detect_tiles_kernel<0><<<grid, NT, sizeof(DetectSmem), st>>>(b, n_tiles, pa_out, sc.bitmap, sc.st_begin,
-                                                                      sc.st_end, sc.wit_min, sc.wit_max, seq_flag);
+                                                                      sc.st_end, sc.wit_min, sc.wit_max, seq_flag, sc.tile_read0);
+    return 1;
+}
+
+int launch_verify_tiles(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
+                        cudaStream_t st) {
+    const uint32_t n_tiles = fast_tiles_for(b.span);
     verify_tiles_kernel<<<grid_cap(n_tiles, 256, sm_count * 8), 256, 0, st>>>(b, n_tiles, sc.st_begin, sc.st_end,
                                                                              seq_flag, fixups);
-    return 2;
+    return 1;
 }
 
 int launch_build_seq_list(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int force_all, int sm_count,
@@ -865,7 +953,7 @@ int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* 
     const uint32_t n_tiles = fast_tiles_for(b.span);
     const int ctas_per_sm = (int)((227u * 1024u) / (sizeof(EmitSmem) + 1024u));
     emit_tiles_kernel<<<grid_cap(n_tiles, 1, sm_count * ctas_per_sm), ENT, sizeof(EmitSmem), st>>>(
-        b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status);
+        b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0);
     sum_fixups_kernel<<<grid_cap(b.n_reads, 256, sm_count * 4), 256, 0, st>>>(b.n_reads, fixups, sc.counters);
     return 2;
 }

@@ -29,6 +29,7 @@ struct Scratch {
     // per tile
     int* st_begin; int* st_end;      // detector state at the first / after the last sample of every tile
     uint32_t* tile_cnt; uint64_t* tile_base;
+    uint32_t* tile_read0;            // first read that can intersect the tile's staged region
     uint32_t max_tiles;
     // per read
     uint32_t* wit_min; uint32_t* wit_max;  // exact-sum witness: min nonzero |pA| / max |pA| bit patterns
@@ -56,6 +57,8 @@ int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32
                       cudaStream_t st);
 int launch_fast_detect(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups,
                        int sm_count, cudaStream_t st);
+int launch_verify_tiles(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
+                        cudaStream_t st);
 int launch_build_seq_list(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int force_all, int sm_count,
                           cudaStream_t st);
 int launch_rank_events(const DevBatch& b, Scratch& sc, uint64_t* ev_off, int sm_count, cudaStream_t st);
