@@ -292,6 +292,7 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     CUC(dev_alloc(&sc.st_end, (uint64_t)sc.max_tiles * 8));
     CUC(dev_alloc(&sc.tile_cnt, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_read0, sc.max_tiles));
+    CUC(dev_alloc(&sc.macro_read0, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_base, (uint64_t)sc.max_tiles + 1));
     CUC(dev_alloc(&sc.wit_min, max_reads));
     CUC(dev_alloc(&sc.wit_max, max_reads));
@@ -358,7 +359,7 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     cudaDeviceSynchronize();
     Scratch& sc = ctx->sc;
     cudaFree(sc.Sinc); cudaFree(sc.Qinc); cudaFree(sc.t1); cudaFree(sc.t2); cudaFree(sc.bitmap);
-    cudaFree(sc.st_begin); cudaFree(sc.st_end); cudaFree(sc.tile_cnt); cudaFree(sc.tile_base); cudaFree(sc.tile_read0);
+    cudaFree(sc.st_begin); cudaFree(sc.st_end); cudaFree(sc.tile_cnt); cudaFree(sc.tile_base); cudaFree(sc.tile_read0); cudaFree(sc.macro_read0);
     cudaFree(sc.wit_min); cudaFree(sc.wit_max); cudaFree(ctx->dev_seq); cudaFree(ctx->dev_fix);
     cudaFree(sc.seq_list); cudaFree(sc.seq_sbase); cudaFree(sc.seq_count); cudaFree(sc.cursor);
     cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status); cudaFree(sc.counters);

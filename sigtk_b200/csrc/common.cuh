@@ -78,14 +78,16 @@ __device__ __forceinline__ double div_w(double a) {
     const double e = __fma_rn(-(double)W, q0, a);
     return __fma_rn(e, r, q0);
 }
-template <int W>
+template <int W, bool GUARD = true>
 __device__ __forceinline__ float div_w(float a) {
     constexpr float r = 1.0f / (float)W;
     const float q0 = __fmul_rn(a, r);
     const float e = __fmaf_rn(-(float)W, q0, a);
     float q = __fmaf_rn(e, r, q0);
-    const uint32_t b = __float_as_uint(a);
-    if ((b & 0x7fffffffu) < 0x02000000u && b != 0u) q = __fdiv_rn(a, (float)W);
+    if (GUARD) {  // callers drop the guard only when they know |a| >= 2^-125 or a == +0
+        const uint32_t b = __float_as_uint(a);
+        if ((b & 0x7fffffffu) < 0x02000000u && b != 0u) q = __fdiv_rn(a, (float)W);
+    }
     return q;
 }
 
@@ -113,15 +115,17 @@ __device__ __forceinline__ float tstat_tail(float delta, float scaled) {
 }
 
 // The reference chain of events.c:338-361 with the shortcuts above (bit-identical to tstat_reference_chain).
-template <int W>
+// BIG: the caller guarantees that every nonzero sample of the windows has |x| >= 2^-60, so that the window sums
+// (nonzero multiples of 2^-83) and sums of squares (>= 2^-120) are outside the guarded range of div_w<float>.
+template <int W, bool BIG = false>
 __device__ __forceinline__ float tstat_fast(double sum1, double ssq1, double sum2d, double ssq2d) {
     const float sum2 = __double2float_rn(sum2d);
     const float ssq2 = __double2float_rn(ssq2d);
     const float mean1 = __double2float_rn(div_w<W>(sum1));
-    const float mean2 = div_w<W>(sum2);
+    const float mean2 = div_w<W, !BIG>(sum2);
     const float m1sq = __fmul_rn(mean1, mean1);
     const float m2sq = __fmul_rn(mean2, mean2);
-    const float v2 = div_w<W>(ssq2);
+    const float v2 = div_w<W, !BIG>(ssq2);
     double acc = div_w<W>(ssq1);
     acc = __dsub_rn(acc, (double)m1sq);
     acc = __dadd_rn(acc, (double)v2);

@@ -29,7 +29,8 @@ struct Scratch {
     // per tile
     int* st_begin; int* st_end;      // detector state at the first / after the last sample of every tile
     uint32_t* tile_cnt; uint64_t* tile_base;
-    uint32_t* tile_read0;            // first read that can intersect the tile's staged region
+    uint32_t* tile_read0;            // first read that can intersect a 2048-sample tile (emit_tiles_kernel)
+    uint32_t* macro_read0;           // same for the macro tiles of detect_tiles_kernel
     uint32_t max_tiles;
     // per read
     uint32_t* wit_min; uint32_t* wit_max;  // exact-sum witness: min nonzero |pA| / max |pA| bit patterns
@@ -52,6 +53,7 @@ uint32_t scan_tiles_for(uint32_t n);
 
 // fast.cu (tiled fast path)
 int fast_configure();
+int detect_configure();
 uint32_t fast_tiles_for(uint64_t span);
 int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
                       cudaStream_t st);

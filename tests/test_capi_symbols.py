@@ -51,4 +51,5 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("test infrastructure", ""), f"{f} mentions the oracle"
+                code = "\n".join(ln.split("//")[0] for ln in src.splitlines())  # comments may cite the proofs
+                assert "oracle" not in code and "libsigtk_ref" not in code and "_ref/" not in code, f"{f} uses the oracle"
