@@ -33,8 +33,11 @@ static inline int tail_fast(float delta, float scaled, float y0f, float *out) {
     const uint64_t b = d_bits(q);
     const uint32_t lo29 = (uint32_t)(b & 0x1fffffffull);
     const uint32_t ex = (uint32_t)(b >> 52) & 0x7ff;
-    const uint32_t dist = lo29 > 0x10000000u ? lo29 - 0x10000000u : 0x10000000u - lo29;
-    if (b != 0 && (ex <= 1023 - 127 || ex >= 1023 + 127 || dist < 512u)) return 0;
+    /* the guard of tstat_tail() in sigtk_b200/csrc/common.cuh: 2^-126 <= q < 2^126, the 29 bits below float
+     * precision not within 512 of the rounding midpoint, scaled not tiny (the GPU seed flushes denormals) */
+    const int in_range = ex >= 1023 - 126 && ex < 1023 + 126;
+    const int off_mid = (uint32_t)(lo29 - (0x10000000u - 512u)) >= 1024u;
+    if (!(in_range && off_mid && scaled >= 1.0e-30f)) return 0;
     *out = (float)q;
     return 1;
 }

@@ -97,21 +97,23 @@ __device__ __forceinline__ float div_w(float a) {
 // midpoint (or outside the normal float range); those values (about 2 in a million) take the IEEE sqrt + division.
 __device__ __forceinline__ float tstat_tail(float delta, float scaled) {
     const double c = (double)scaled;
-    const double y0 = (double)rsqrtf(scaled);
+    float y0f;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(scaled));  // 2 ulp; denormal inputs are caught below
+    const double y0 = (double)y0f;
     const double t = __dmul_rn(c, y0);
     const double e = __fma_rn(-t, y0, 1.0);
     const double p = __fma_rn(0.375, e, 0.5);
     const double ye = __dmul_rn(y0, e);
     const double y = __fma_rn(ye, p, y0);
     const double q = __dmul_rn(fabs((double)delta), y);
-    const uint32_t lo29 = (uint32_t)__double2loint(q) & 0x1fffffffu;
-    const uint32_t hi = (uint32_t)__double2hiint(q);
-    const uint32_t ex = (hi >> 20) & 0x7ffu;
-    const uint32_t dist = (uint32_t)abs((int)lo29 - 0x10000000);
-    const bool zero = ((hi & 0x7fffffffu) | (uint32_t)__double2loint(q)) == 0u;
-    if (!zero && (ex <= 1023u - 127u || ex >= 1023u + 127u || dist < 512u))
+    const uint32_t lo = (uint32_t)__double2loint(q), hi = (uint32_t)__double2hiint(q);
+    // accept when 2^-126 <= q < 2^126 and the 29 bits below float precision are not within 512 of the midpoint
+    const bool in_range = ((hi & 0x7ff00000u) - ((1023u - 126u) << 20)) < (252u << 20);
+    const bool off_mid = (((lo & 0x1fffffffu) - (0x10000000u - 512u))) >= 1024u;
+    // delta == 0 gives exactly +0 on both routes (scaled > 0); it is common in quantised data, so accept it here
+    if (!((in_range && off_mid && scaled >= 1.0e-30f) || delta == 0.0f))
         return __double2float_rn(__ddiv_rn(fabs((double)delta), __dsqrt_rn(c)));
-    return __double2float_rn(q);
+    return delta == 0.0f ? 0.0f : __double2float_rn(q);
 }
 
 // The reference chain of events.c:338-361 with the shortcuts above (bit-identical to tstat_reference_chain).
@@ -132,7 +134,9 @@ __device__ __forceinline__ float tstat_fast(double sum1, double ssq1, double sum
     acc = __dsub_rn(acc, (double)m2sq);
     const float cv = fmaxf(__double2float_rn(acc), FLT_MIN);
     const float delta = __fsub_rn(mean2, mean1);
-    return tstat_tail(delta, div_w<W>(cv));
+    float scaled = div_w<W, false>(cv);              // cv >= FLT_MIN > 0
+    if (cv < 1.0e-36f) scaled = __fdiv_rn(cv, (float)W);  // below 2^-119: outside the validated range of the shortcut
+    return tstat_tail(delta, scaled);
 }
 
 // Event statistics from the two prefix-sum differences (src/events.c:457-473).

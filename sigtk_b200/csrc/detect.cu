@@ -146,12 +146,29 @@ __global__ void __launch_bounds__(DNT, 1) detect_tiles_kernel(DevBatch b, uint32
             {
                 const int r0 = tid * 4;
                 const int vg = vb + r0;
-                const int sidx = sm.grp[(vg + PH) >> 3];
+                int sidx = sm.grp[(vg + PH) >> 3];
                 float x[4];
                 bool starts = false;
                 uint32_t mn = 0xffffffffu, mx = 0u, own_mn = 0xffffffffu;
+                Seg sg;
+                if (sidx != 255) sg = segs[sidx];
+                const bool ovf = sm.ovfbuf[sb] != 0;
+                if (ovf) {
+                    // more reads than the segment list holds: all of them go to the sequential-order kernels, but
+                    // their pA is still stored here, so every thread looks its read up in global memory
+                    sidx = 255;
+                    const long long fp = v0_flat + vg;
+                    if (fp >= 0 && fp < span) {
+                        const uint32_t r = find_read(b.read_off, b.n_reads, (uint64_t)fp);
+                        const long long rs = (long long)b.read_off[r];
+                        if (fp - rs < (long long)b.read_len[r]) {
+                            sg.u0 = (int)(rs - v0_flat); sg.len = b.read_len[r]; sg.read = r;
+                            sg.off = b.offset[r]; sg.unit = b.unit[r];
+                            sidx = 254;
+                        }
+                    }
+                }
                 if (sidx != 255) {
-                    const Seg sg = segs[sidx];
                     starts = (sg.u0 == vg);
                     const int2 rawv = *reinterpret_cast<const int2*>(&sm.raw[buf][r0]);
                     const int v[4] = {(int)(int16_t)(rawv.x & 0xffff), rawv.x >> 16, (int)(int16_t)(rawv.y & 0xffff),
@@ -170,15 +187,15 @@ __global__ void __launch_bounds__(DNT, 1) detect_tiles_kernel(DevBatch b, uint32
                     const bool own = r0 >= PH && r0 < PH + PC && vg >= G::W && vg < G::W + G::MS;
                     if (own && pa_out)
                         *reinterpret_cast<float4*>(pa_out + (v0_flat + vg)) = make_float4(x[0], x[1], x[2], x[3]);
-                    if (!own) { mx = 0u; }
-                    own_mn = own ? mn : 0xffffffffu;
+                    if (!own || ovf) { mx = 0u; }
+                    own_mn = (own && !ovf) ? mn : 0xffffffffu;
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; k++) x[k] = 0.0f;
                 }
                 {   // exact-sum witness of the owned samples and the pass minimum: one shared atomic per warp
                     const int s0 = __shfl_sync(0xffffffffu, sidx, 0);
-                    const bool uni = __all_sync(0xffffffffu, sidx == s0);
+                    const bool uni = __all_sync(0xffffffffu, sidx == s0) && !ovf;
                     const uint32_t pmn = __reduce_min_sync(0xffffffffu, mn);
                     if (uni) {
                         const uint32_t wmn = __reduce_min_sync(0xffffffffu, own_mn);
@@ -199,13 +216,13 @@ __global__ void __launch_bounds__(DNT, 1) detect_tiles_kernel(DevBatch b, uint32
             if (interior && sm.pass_min >= 0x21800000u) {  // all staged |pA| >= 2^-60: lean loop, no per-position checks
 #pragma unroll 2
                 for (int r = PH + tid; r < PH + PC; r += DNT) {
-                    const double s_i = sm.sS[pad4(r - 1)], q_i = sm.sQ[pad4(r - 1)];
+                    const double s_i = sm.sS[ix4(r - 1)], q_i = sm.sQ[ix4(r - 1)];
                     const float r1 = tstat_fast<G::w1, true>(
-                        __dsub_rn(s_i, sm.sS[pad4(r - G::w1 - 1)]), __dsub_rn(q_i, sm.sQ[pad4(r - G::w1 - 1)]),
-                        __dsub_rn(sm.sS[pad4(r + G::w1 - 1)], s_i), __dsub_rn(sm.sQ[pad4(r + G::w1 - 1)], q_i));
+                        __dsub_rn(s_i, sm.sS[ix4(r - G::w1 - 1)]), __dsub_rn(q_i, sm.sQ[ix4(r - G::w1 - 1)]),
+                        __dsub_rn(sm.sS[ix4(r + G::w1 - 1)], s_i), __dsub_rn(sm.sQ[ix4(r + G::w1 - 1)], q_i));
                     const float r2 = tstat_fast<G::w2, true>(
-                        __dsub_rn(s_i, sm.sS[pad4(r - G::w2 - 1)]), __dsub_rn(q_i, sm.sQ[pad4(r - G::w2 - 1)]),
-                        __dsub_rn(sm.sS[pad4(r + G::w2 - 1)], s_i), __dsub_rn(sm.sQ[pad4(r + G::w2 - 1)], q_i));
+                        __dsub_rn(s_i, sm.sS[ix4(r - G::w2 - 1)]), __dsub_rn(q_i, sm.sQ[ix4(r - G::w2 - 1)]),
+                        __dsub_rn(sm.sS[ix4(r + G::w2 - 1)], s_i), __dsub_rn(sm.sQ[ix4(r + G::w2 - 1)], q_i));
                     sm.t1[pad32(vb + r)] = r1;
                     sm.t2[pad32(vb + r)] = r2;
                 }
@@ -219,22 +236,22 @@ __global__ void __launch_bounds__(DNT, 1) detect_tiles_kernel(DevBatch b, uint32
                         const uint32_t n = segs[sidx].len;
                         const uint32_t i = (uint32_t)(v - su0);
                         if (i < n) {
-                            const double s_i = sm.sS[pad4(r - 1)], q_i = sm.sQ[pad4(r - 1)];  // i >= w >= 2 where used
+                            const double s_i = sm.sS[ix4(r - 1)], q_i = sm.sQ[ix4(r - 1)];  // i >= w >= 2 where used
                             if (n >= 2u * G::w1 && i >= (uint32_t)G::w1 && i + G::w1 <= n) {
                                 const bool first = (i == (uint32_t)G::w1);
-                                const double sl = first ? 0.0 : sm.sS[pad4(r - G::w1 - 1)];
-                                const double ql = first ? 0.0 : sm.sQ[pad4(r - G::w1 - 1)];
+                                const double sl = first ? 0.0 : sm.sS[ix4(r - G::w1 - 1)];
+                                const double ql = first ? 0.0 : sm.sQ[ix4(r - G::w1 - 1)];
                                 r1 = tstat_fast<G::w1>(__dsub_rn(s_i, sl), __dsub_rn(q_i, ql),
-                                                       __dsub_rn(sm.sS[pad4(r + G::w1 - 1)], s_i),
-                                                       __dsub_rn(sm.sQ[pad4(r + G::w1 - 1)], q_i));
+                                                       __dsub_rn(sm.sS[ix4(r + G::w1 - 1)], s_i),
+                                                       __dsub_rn(sm.sQ[ix4(r + G::w1 - 1)], q_i));
                             }
                             if (n >= 2u * G::w2 && i >= (uint32_t)G::w2 && i + G::w2 <= n) {
                                 const bool first = (i == (uint32_t)G::w2);
-                                const double sl = first ? 0.0 : sm.sS[pad4(r - G::w2 - 1)];
-                                const double ql = first ? 0.0 : sm.sQ[pad4(r - G::w2 - 1)];
+                                const double sl = first ? 0.0 : sm.sS[ix4(r - G::w2 - 1)];
+                                const double ql = first ? 0.0 : sm.sQ[ix4(r - G::w2 - 1)];
                                 r2 = tstat_fast<G::w2>(__dsub_rn(s_i, sl), __dsub_rn(q_i, ql),
-                                                       __dsub_rn(sm.sS[pad4(r + G::w2 - 1)], s_i),
-                                                       __dsub_rn(sm.sQ[pad4(r + G::w2 - 1)], q_i));
+                                                       __dsub_rn(sm.sS[ix4(r + G::w2 - 1)], s_i),
+                                                       __dsub_rn(sm.sQ[ix4(r + G::w2 - 1)], q_i));
                             }
                         }
                     }
@@ -271,6 +288,8 @@ __global__ void __launch_bounds__(DNT, 1) detect_tiles_kernel(DevBatch b, uint32
             // 16 positions per kind word; wa, cs and ce are multiples of 32
             auto walk16 = [&](int u0, bool record) {
                 const uint32_t kw = sm.kind[u0 >> 4];
+                const float* const a1 = sm.t1 + pad32(u0);  // u0 is a multiple of 16: the 16 positions are contiguous
+                const float* const a2 = sm.t2 + pad32(u0);
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const int u = u0 + q;
@@ -280,9 +299,9 @@ __global__ void __launch_bounds__(DNT, 1) detect_tiles_kernel(DevBatch b, uint32
                         det_set(p.s, u);
                         det_set(p.l, u);
                     }
-                    const bool e1 = step_one<true, RNA>(p.s, p.l, u, sm.t1[pad32(u)], &pos);
+                    const bool e1 = step_one<true, RNA>(p.s, p.l, u, a1[q], &pos);
                     if (record && e1 && pos >= cs) sm.flag[pos] = 1;
-                    const bool e2 = step_one<false, RNA>(p.l, p.l, u, sm.t2[pad32(u)], &pos);
+                    const bool e2 = step_one<false, RNA>(p.l, p.l, u, a2[q], &pos);
                     if (record && e2 && pos >= cs) sm.flag[pos] = 1;
                 }
             };

@@ -108,13 +108,13 @@ constexpr int ENT = 256;  // threads of emit_tiles_kernel (8 samples each = one 
 struct EmitSmem {
     double sS[T + T / 8 + 8];
     double sQ[T + T / 8 + 8];
-    Seg segs[SEG_MAX];
+    Seg segs[SEG_MAX];       // reads intersecting the EMT tiles of this round, positions relative to the first tile
+    Seg gseg[T / 8];         // the read owning every 8-sample group of the current tile (len 0 = none), tile coords
     double warp_v[2 * (ENT / 32)];
     double warp_c[2 * (ENT / 32)];
     int warp_f[ENT / 32];
     uint32_t bits[T / 32];
     uint32_t excl[T / 32];
-    short grp[T / 8];
     int nseg, overflow;
     int spill_u;            // tile index of the start of the event that runs past the tile end, or -1
     unsigned long long spill_k;
@@ -128,14 +128,20 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    constexpr int EMT = 8;  // consecutive tiles per segment collection
+    for (uint32_t tile0 = blockIdx.x * EMT; tile0 < n_tiles; tile0 += gridDim.x * EMT) {
+      __syncthreads();
+      if (tid == 0) {
+          int ovf = 0;
+          const long long f0 = (long long)tile0 * T;
+          sm.nseg = collect_segments(b, f0, f0 + (long long)EMT * T, f0, sm.segs, &ovf, nullptr, tile_read0[tile0]);
+          sm.overflow = ovf;  // more reads than the list holds: every thread looks its read up in global memory
+      }
+      __syncthreads();
+      for (uint32_t tile = tile0; tile < min(tile0 + EMT, n_tiles); tile++) {
         const long long ts = (long long)tile * T;
-        if (tid == 0) {
-            int ovf = 0;
-            sm.nseg = collect_segments(b, ts, ts + T, ts, sm.segs, &ovf, nullptr, tile_read0[tile]);
-            sm.overflow = ovf;  // such reads were routed to the sequential-order kernels by detect_tiles_kernel
-            sm.spill_u = -1;
-        }
+        const int toff = (int)(tile - tile0) * T;
+        if (tid == 0) sm.spill_u = -1;
         if (tid < T / 32) sm.bits[tid] = bitmap[(size_t)tile * (T / 32) + tid];
         __syncthreads();
         const int nseg = sm.nseg;
@@ -151,13 +157,25 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
             sm.excl[2 * lane + 1] = inc - c1;
         }
         const int u0 = tid * 8;
-        const int sidx = group_segment(sm.segs, nseg, u0);
-        sm.grp[tid] = (short)sidx;
+        Seg sg;  // the read owning this thread's 8 samples, in tile coordinates (len 0: none)
+        sg.len = 0u; sg.u0 = 0; sg.read = 0u; sg.off = 0.0f; sg.unit = 0.0f;
+        if (!sm.overflow) {
+            const int sidx = group_segment(sm.segs, nseg, toff + u0);
+            if (sidx >= 0) { sg = sm.segs[sidx]; sg.u0 -= toff; }
+        } else if (ts + u0 < (long long)b.span) {
+            const uint32_t r = find_read(b.read_off, b.n_reads, (uint64_t)(ts + u0));
+            const long long rs = (long long)b.read_off[r];
+            const uint32_t len = b.read_len[r];
+            if (ts + u0 - rs < (long long)len) {
+                sg.u0 = (int)(rs - ts); sg.len = len; sg.read = r; sg.off = b.offset[r]; sg.unit = b.unit[r];
+            }
+        }
+        sm.gseg[tid] = sg;
+        const int sidx = sg.len ? 0 : -1;
         {
             float x[8];
             bool starts = false;
             if (sidx >= 0 && ts + u0 < (long long)b.span) {
-                const Seg sg = sm.segs[sidx];
                 starts = (sg.u0 == u0);
                 const int4 rawv = __ldg(reinterpret_cast<const int4*>(b.samples + ts + u0));
                 int v[8];
@@ -175,7 +193,6 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
         __syncthreads();
         // every event start bit in this thread's 8 samples
         if (sidx >= 0) {
-            const Seg sg = sm.segs[sidx];
             uint32_t byte = (sm.bits[u0 >> 5] >> (u0 & 31)) & 0xffu;
             while (byte) {
                 const int m = __ffs(byte) - 1;
@@ -218,8 +235,7 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
         // the event that continues into the following tiles: warp 0 walks the flat array
         if (tid < 32 && sm.spill_u >= 0) {
             const int u = sm.spill_u;
-            const int sx = sm.grp[u >> 3];
-            const Seg sg = sm.segs[sx];
+            const Seg sg = sm.gseg[u >> 3];
             const long long read_end = ts + sg.u0 + (long long)sg.len;  // flat
             const bool at0 = (u == sg.u0) || (u == 0);
             double ds = __dsub_rn(sm.sS[pad8(T - 1)], at0 ? 0.0 : sm.sS[pad8(u - 1)]);
@@ -265,6 +281,7 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
             }
         }
         __syncthreads();
+      }
     }
 }
 
@@ -343,7 +360,7 @@ int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* 
                      float* ev_stdv, const uint32_t* fixups, int sm_count, cudaStream_t st) {
     const uint32_t n_tiles = fast_tiles_for(b.span);
     const int ctas_per_sm = (int)((227u * 1024u) / (sizeof(EmitSmem) + 1024u));
-    emit_tiles_kernel<<<grid_cap(n_tiles, 1, sm_count * ctas_per_sm), ENT, sizeof(EmitSmem), st>>>(
+    emit_tiles_kernel<<<grid_cap((n_tiles + 7) / 8, 1, sm_count * ctas_per_sm), ENT, sizeof(EmitSmem), st>>>(
         b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0);
     sum_fixups_kernel<<<grid_cap(b.n_reads, 256, sm_count * 4), 256, 0, st>>>(b.n_reads, fixups, sc.counters);
     return 2;

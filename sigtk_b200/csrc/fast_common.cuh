@@ -40,7 +40,7 @@ struct Seg {           // one read intersecting the staged region, in region (t-
 };
 
 __device__ __forceinline__ int pad8(int u) { return u + (u >> 3); }     // doubles: 8-sample groups, stride 9
-__device__ __forceinline__ int pad4(int u) { return u + (u >> 2); }     // doubles: 4-sample groups, stride 5
+__device__ __forceinline__ int ix4(int u) { return u + (u >> 2); }      // doubles of detect_tiles_kernel: 4-sample groups, stride 5
 __device__ __forceinline__ int pad32(int u) { return u + (u >> 5); }    // floats: chunk starts land in distinct banks
 
 // ---- mbarrier / bulk-copy (TMA) helpers ---------------------------------------------------------------------
@@ -167,7 +167,7 @@ __device__ __forceinline__ void region_prefix(const float (&x)[ITEMS], bool star
     if (starts_read) { bs = 0.0; bq = 0.0; }
     else if (ef) { bs = es; bq = eq; }
     else { bs = __dadd_rn(cs, es); bq = __dadd_rn(cq, eq); }
-    const int base = ITEMS == 8 ? pad8(threadIdx.x * 8) : pad4(threadIdx.x * 4);
+    const int base = ITEMS == 8 ? pad8(threadIdx.x * 8) : ix4(threadIdx.x * 4);
 #pragma unroll
     for (int m = 0; m < ITEMS; m++) {
         sS[base + m] = __dadd_rn(bs, s[m]);

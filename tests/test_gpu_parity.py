@@ -164,6 +164,22 @@ def test_ragged_and_tiny_reads(ctx, orc):
         check_against_oracle(orc, res, reads, rna_flag)
 
 
+def test_many_tiny_reads_overflow_the_segment_lists(ctx, orc):
+    """hundreds of reads of a few dozen samples inside one tile: more reads than the per-tile segment lists hold,
+    so the fast path hands them to the sequential-order kernels / the global look-up"""
+    rng = np.random.default_rng(12)
+    base = synth.make_read(3, 40000, seed=8)
+    reads, p = [], 0
+    for k in range(700):
+        n = int(rng.integers(1, 60))
+        reads.append((base[0][p:p + n].copy(), base[1], float(k % 53), base[3]))
+        p += n
+    reads.insert(350, synth.make_read(5, 30000, seed=8))  # a normal read in the middle
+    for rna_flag in (0, 1):
+        res = ctx.run(reads, rna=rna_flag, want=ALL)
+        check_against_oracle(orc, res, reads, rna_flag)
+
+
 def test_constant_and_extreme_signals(ctx, orc):
     n = 5000
     ramp = (np.arange(n) % 4000 - 2000).astype(np.int16)
