@@ -118,6 +118,12 @@ struct EmitSmem {
     int nseg, overflow;
     int spill_u;            // tile index of the start of the event that runs past the tile end, or -1
     unsigned long long spill_k;
+    // the open event carried from tile to tile inside one group of EMT tiles
+    int carry_on;
+    unsigned long long carry_k;
+    double carry_s, carry_q;
+    long long carry_start, carry_read_end;  // flat positions
+    float carry_off, carry_unit;
 };
 
 __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_tiles, const uint32_t* __restrict__ bitmap,
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmitSmem& sm = *reinterpret_cast<EmitSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    constexpr int EMT = 8;  // consecutive tiles per segment collection
+    constexpr int EMT = 16;  // consecutive tiles per segment collection
     for (uint32_t tile0 = blockIdx.x * EMT; tile0 < n_tiles; tile0 += gridDim.x * EMT) {
       __syncthreads();
       if (tid == 0) {
@@ -136,16 +142,33 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
           const long long f0 = (long long)tile0 * T;
           sm.nseg = collect_segments(b, f0, f0 + (long long)EMT * T, f0, sm.segs, &ovf, nullptr, tile_read0[tile0]);
           sm.overflow = ovf;  // more reads than the list holds: every thread looks its read up in global memory
+          sm.carry_on = 0;
       }
+      const uint32_t tile_end = min(tile0 + EMT, n_tiles);
+      // software prefetch: the global loads of tile t+1 are issued before tile t is processed
+      auto load_raw = [&](uint32_t t) {
+          const long long p = (long long)t * T + threadIdx.x * 8;
+          return (t < tile_end && p < (long long)b.span) ? __ldg(reinterpret_cast<const int4*>(b.samples + p))
+                                                         : make_int4(0, 0, 0, 0);
+      };
+      auto load_bits = [&](uint32_t t) { return (t < tile_end && tid < T / 32) ? bitmap[(size_t)t * (T / 32) + tid] : 0u; };
+      auto load_base = [&](uint32_t t) { return t < tile_end ? tile_base[t] : 0ull; };
+      int4 raw_nx = load_raw(tile0);
+      uint32_t bits_nx = load_bits(tile0);
+      uint64_t base_nx = load_base(tile0);
       __syncthreads();
-      for (uint32_t tile = tile0; tile < min(tile0 + EMT, n_tiles); tile++) {
+      for (uint32_t tile = tile0; tile < tile_end; tile++) {
         const long long ts = (long long)tile * T;
         const int toff = (int)(tile - tile0) * T;
+        const int4 rawv = raw_nx;
+        const uint64_t base = base_nx;
         if (tid == 0) sm.spill_u = -1;
-        if (tid < T / 32) sm.bits[tid] = bitmap[(size_t)tile * (T / 32) + tid];
+        if (tid < T / 32) sm.bits[tid] = bits_nx;
+        raw_nx = load_raw(tile + 1);
+        bits_nx = load_bits(tile + 1);
+        base_nx = load_base(tile + 1);
         __syncthreads();
         const int nseg = sm.nseg;
-        const uint64_t base = tile_base[tile];
         if (tid < 32) {  // exclusive popcount scan of the 64 words
             const uint32_t c0 = __popc(sm.bits[2 * lane]), c1 = __popc(sm.bits[2 * lane + 1]);
             uint32_t inc = c0 + c1;
@@ -177,7 +200,6 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
             bool starts = false;
             if (sidx >= 0 && ts + u0 < (long long)b.span) {
                 starts = (sg.u0 == u0);
-                const int4 rawv = __ldg(reinterpret_cast<const int4*>(b.samples + ts + u0));
                 int v[8];
                 unpack8(rawv, v);
                 const uint32_t left = sg.len - (uint32_t)(u0 - sg.u0);
@@ -232,52 +254,97 @@ __global__ void __launch_bounds__(ENT) emit_tiles_kernel(DevBatch b, uint32_t n_
             }
         }
         __syncthreads();
-        // the event that continues into the following tiles: warp 0 walks the flat array
-        if (tid < 32 && sm.spill_u >= 0) {
-            const int u = sm.spill_u;
-            const Seg sg = sm.gseg[u >> 3];
-            const long long read_end = ts + sg.u0 + (long long)sg.len;  // flat
-            const bool at0 = (u == sg.u0) || (u == 0);
-            double ds = __dsub_rn(sm.sS[pad8(T - 1)], at0 ? 0.0 : sm.sS[pad8(u - 1)]);
-            double dq = __dsub_rn(sm.sQ[pad8(T - 1)], at0 ? 0.0 : sm.sQ[pad8(u - 1)]);
-            // find the next event start at or after the tile end (bounded by the end of the read)
-            long long end = read_end;
-            for (long long wbase = (ts + T) >> 5; (wbase << 5) < read_end; wbase += 32) {
-                const long long wi = wbase + lane;
-                uint32_t w = ((wi << 5) < read_end) ? bitmap[wi] : 0u;
-                const uint32_t any = __ballot_sync(0xffffffffu, w != 0u);
-                if (any) {
-                    const int first = __ffs(any) - 1;
-                    const uint32_t fw = __shfl_sync(0xffffffffu, w, first);
-                    const long long cand = ((wbase + first) << 5) + __ffs(fw) - 1;
-                    if (cand < end) end = cand;
-                    break;
+        // events that cross tile ends: carried from tile to tile inside the group by warp 0; only at the end of
+        // the group the rest of the event is summed from global memory
+        if (tid < 32) {
+            if (sm.carry_on) {  // (a) the event carried in: it ends at the first start bit of this tile or at its read's end
+                const uint32_t w0 = sm.bits[lane], w1 = sm.bits[lane + 32];
+                const uint32_t any0 = __ballot_sync(0xffffffffu, w0 != 0u), any1 = __ballot_sync(0xffffffffu, w1 != 0u);
+                long long end = (long long)T + 1;
+                if (any0) {
+                    const int f = __ffs(any0) - 1;
+                    end = (f << 5) + __ffs(__shfl_sync(0xffffffffu, w0, f)) - 1;
+                } else if (any1) {
+                    const int f = __ffs(any1) - 1;
+                    end = ((f + 32) << 5) + __ffs(__shfl_sync(0xffffffffu, w1, f)) - 1;
                 }
-            }
-            // add the samples [tile end, end): 8 per lane per step
-            double as = 0.0, aq = 0.0;
-            for (long long p = ts + T + (long long)lane * 8; p < end; p += 256) {
-                const int4 rawv = __ldg(reinterpret_cast<const int4*>(b.samples + p));
-                int v[8];
-                unpack8(rawv, v);
-#pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    if (p + m < end) {
-                        const float xv = __fmul_rn(__fadd_rn((float)v[m], sg.off), sg.unit);
-                        as = __dadd_rn(as, (double)xv);
-                        aq = __dadd_rn(aq, (double)__fmul_rn(xv, xv));
+                const long long read_end = sm.carry_read_end - ts;
+                if (end > read_end) end = read_end;
+                if (lane == 0) {
+                    if (end <= T) {
+                        const double as = end > 0 ? sm.sS[pad8((int)end - 1)] : 0.0;
+                        const double aq = end > 0 ? sm.sQ[pad8((int)end - 1)] : 0.0;
+                        float mean, stdv;
+                        event_stats(__dadd_rn(sm.carry_s, as), __dadd_rn(sm.carry_q, aq),
+                                    (uint32_t)(ts + end - sm.carry_start), &mean, &stdv);
+                        ev_mean[sm.carry_k] = mean;
+                        ev_stdv[sm.carry_k] = stdv;
+                        sm.carry_on = 0;
+                    } else {  // the read covers the whole tile and no event starts in it
+                        sm.carry_s = __dadd_rn(sm.carry_s, sm.sS[pad8(T - 1)]);
+                        sm.carry_q = __dadd_rn(sm.carry_q, sm.sQ[pad8(T - 1)]);
                     }
                 }
+                __syncwarp();
             }
-            for (int o = 16; o; o >>= 1) {
-                as = __dadd_rn(as, __shfl_xor_sync(0xffffffffu, as, o));
-                aq = __dadd_rn(aq, __shfl_xor_sync(0xffffffffu, aq, o));
+            if (sm.spill_u >= 0 && lane == 0) {  // (b) the last event of this tile runs past the tile end
+                const int u = sm.spill_u;
+                const Seg sg = sm.gseg[u >> 3];
+                const bool at0 = (u == sg.u0) || (u == 0);
+                sm.carry_s = __dsub_rn(sm.sS[pad8(T - 1)], at0 ? 0.0 : sm.sS[pad8(u - 1)]);
+                sm.carry_q = __dsub_rn(sm.sQ[pad8(T - 1)], at0 ? 0.0 : sm.sQ[pad8(u - 1)]);
+                sm.carry_k = sm.spill_k;
+                sm.carry_start = ts + u;
+                sm.carry_read_end = ts + sg.u0 + (long long)sg.len;
+                sm.carry_off = sg.off;
+                sm.carry_unit = sg.unit;
+                sm.carry_on = 1;
             }
-            if (lane == 0) {
-                float mean, stdv;
-                event_stats(__dadd_rn(ds, as), __dadd_rn(dq, aq), (uint32_t)(end - (ts + u)), &mean, &stdv);
-                ev_mean[sm.spill_k] = mean;
-                ev_stdv[sm.spill_k] = stdv;
+            __syncwarp();
+            if (sm.carry_on && tile + 1 == tile_end) {  // (c) end of the group: finish the event from global memory
+                const long long read_end = sm.carry_read_end;
+                const float off = sm.carry_off, unit = sm.carry_unit;
+                // the next event start at or after the end of this tile (bounded by the end of the read)
+                long long end = read_end;
+                for (long long wbase = (ts + T) >> 5; (wbase << 5) < read_end; wbase += 32) {
+                    const long long wi = wbase + lane;
+                    uint32_t w = ((wi << 5) < read_end) ? bitmap[wi] : 0u;
+                    const uint32_t any = __ballot_sync(0xffffffffu, w != 0u);
+                    if (any) {
+                        const int first = __ffs(any) - 1;
+                        const uint32_t fw = __shfl_sync(0xffffffffu, w, first);
+                        const long long cand = ((wbase + first) << 5) + __ffs(fw) - 1;
+                        if (cand < end) end = cand;
+                        break;
+                    }
+                }
+                // add the samples [tile end, end): 8 per lane per step
+                double as = 0.0, aq = 0.0;
+                for (long long p = ts + T + (long long)lane * 8; p < end; p += 256) {
+                    const int4 rv = __ldg(reinterpret_cast<const int4*>(b.samples + p));
+                    int v[8];
+                    unpack8(rv, v);
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {
+                        if (p + m < end) {
+                            const float xv = __fmul_rn(__fadd_rn((float)v[m], off), unit);
+                            as = __dadd_rn(as, (double)xv);
+                            aq = __dadd_rn(aq, (double)__fmul_rn(xv, xv));
+                        }
+                    }
+                }
+                for (int o = 16; o; o >>= 1) {
+                    as = __dadd_rn(as, __shfl_xor_sync(0xffffffffu, as, o));
+                    aq = __dadd_rn(aq, __shfl_xor_sync(0xffffffffu, aq, o));
+                }
+                if (lane == 0) {
+                    float mean, stdv;
+                    event_stats(__dadd_rn(sm.carry_s, as), __dadd_rn(sm.carry_q, aq), (uint32_t)(end - sm.carry_start),
+                                &mean, &stdv);
+                    ev_mean[sm.carry_k] = mean;
+                    ev_stdv[sm.carry_k] = stdv;
+                    sm.carry_on = 0;
+                }
             }
         }
         __syncthreads();
@@ -360,7 +427,7 @@ int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* 
                      float* ev_stdv, const uint32_t* fixups, int sm_count, cudaStream_t st) {
     const uint32_t n_tiles = fast_tiles_for(b.span);
     const int ctas_per_sm = (int)((227u * 1024u) / (sizeof(EmitSmem) + 1024u));
-    emit_tiles_kernel<<<grid_cap((n_tiles + 7) / 8, 1, sm_count * ctas_per_sm), ENT, sizeof(EmitSmem), st>>>(
+    emit_tiles_kernel<<<grid_cap((n_tiles + 15) / 16, 1, sm_count * ctas_per_sm), ENT, sizeof(EmitSmem), st>>>(
         b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0);
     sum_fixups_kernel<<<grid_cap(b.n_reads, 256, sm_count * 4), 256, 0, st>>>(b.n_reads, fixups, sc.counters);
     return 2;
