@@ -1,0 +1,480 @@
+/* sigtk_main.c -- drop-in `sigtk event | pa | stat` on top of the B200 hot path (C99 host, links slow5lib).
+ *
+ * Same command line, stdout bytes, stderr information lines and exit codes as the reference tool for the three
+ * sub-commands of the raw-signal path:
+ *     reference src/main.c:76-123   (command switch, footer)
+ *     reference src/cmain.c:40-156  (options -h -n -c -V --version --help --print-stat -o, record iteration,
+ *                                    read-id random access)
+ *     reference src/cfunc.c:16-159  (output formats of event / pa / stat)
+ *     reference src/misc.c:34-101   (DNA/RNA and pore detection from the BLOW5 header)
+ * What changes is the execution model: instead of one record -> compute -> printf, decoded records are batched
+ * into pinned slots of the CUDA library (include/sigtk_b200.h), several batches are in flight on one or more
+ * GPUs, and the per-read results are printed in input order.  There is no CPU implementation of the path in
+ * here: without a usable GPU the tool exits with an error.
+ * Additive options (default off / 1): --gpus N, --batch-samples S.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <getopt.h>
+#include <inttypes.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/resource.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+
+#include <slow5/slow5.h>
+
+#include "sigtk_b200.h"
+
+#define SIGTK_VERSION "0.2.0" /* reference src/sigtk.h:11 */
+
+#define INFO(msg, ...) fprintf(stderr, "[%s::INFO]\033[1;34m " msg "\033[0m\n", __func__, __VA_ARGS__)
+#define WARNING(msg, ...) \
+    fprintf(stderr, "[%s::WARNING]\033[1;33m " msg "\033[0m At %s:%d\n", __func__, __VA_ARGS__, __FILE__, __LINE__ - 1)
+#define ERROR(msg, ...) \
+    fprintf(stderr, "[%s::ERROR]\033[1;31m " msg "\033[0m At %s:%d\n", __func__, __VA_ARGS__, __FILE__, __LINE__ - 1)
+
+enum { MODE_EVENT, MODE_PA, MODE_STAT };
+
+typedef struct {
+    int mode;
+    int compact;
+    int rna;
+} opt_t;
+
+/* ---- timing footer (reference src/misc.h:19-43) ------------------------------------------------------------- */
+static double realtime(void) {
+    struct timeval tp;
+    gettimeofday(&tp, NULL);
+    return (double)tp.tv_sec + (double)tp.tv_usec * 1e-6;
+}
+static double cputime(void) {
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return (double)r.ru_utime.tv_sec + (double)r.ru_stime.tv_sec + 1e-6 * (double)(r.ru_utime.tv_usec + r.ru_stime.tv_usec);
+}
+static long peakrss(void) {
+    struct rusage r;
+    getrusage(RUSAGE_SELF, &r);
+    return r.ru_maxrss * 1024;
+}
+
+/* ---- header inspection (reference src/misc.c:34-101) ---------------------------------------------------------- */
+static int drna_detect(slow5_file_t *sp) {
+    const slow5_hdr_t *hdr = sp->header;
+    int rna = 0;
+    char *exp = slow5_hdr_get("experiment_type", 0, hdr);
+    if (exp == NULL) {
+        WARNING("%s", "experiment_type not found in SLOW5 header. Assuming genomic_dna");
+        return 0;
+    }
+    if (strcmp(exp, "genomic_dna") == 0) {
+        INFO("%s", "DNA data detected.");
+    } else if (strcmp(exp, "rna") == 0) {
+        rna = 1;
+        INFO("%s", "RNA data detected.");
+    } else {
+        WARNING("Unknown experiment type: %s. Assuming genomic_dna", exp);
+    }
+    for (uint32_t i = 1; i < hdr->num_read_groups; i++) {
+        char *curr = slow5_hdr_get("experiment_type", i, hdr);
+        if (curr && strcmp(curr, exp))
+            WARNING("Experiment type mismatch: %s != %s in read group %d. Defaulted to %s", curr, exp, (int)i, exp);
+    }
+    return rna;
+}
+
+static void pore_detect(slow5_file_t *sp) { /* only `prefix` uses the pore; the messages are kept */
+    const slow5_hdr_t *hdr = sp->header;
+    char *kit = slow5_hdr_get("sequencing_kit", 0, hdr);
+    if (kit == NULL) {
+        WARNING("%s", "sequencing_kit not found in SLOW5 header. Assuming R9.4.1");
+        return;
+    }
+    if (strstr(kit, "114") != NULL) {
+        INFO("%s", "R10 data detected.");
+    } else if (strstr(kit, "rna004") != NULL) {
+        INFO("%s", "RNA004 data detected.");
+    } else {
+        INFO("%s", "R9 data detected.");
+    }
+    for (uint32_t i = 1; i < hdr->num_read_groups; i++) {
+        char *curr = slow5_hdr_get("sequencing_kit", i, hdr);
+        if (curr && strcmp(curr, kit))
+            WARNING("sequencing_kit type mismatch: %s != %s in read group %d. Defaulted to %s", curr, kit, (int)i, kit);
+    }
+}
+
+/* ---- batches in flight ------------------------------------------------------------------------------------------ */
+typedef struct {
+    sgpu_ctx_t *ctx;
+    uint32_t slot;
+    int busy;          /* submitted, not yet printed */
+    uint32_t n_reads;
+    char *ids;         /* read ids, NUL separated */
+    size_t ids_len, ids_cap;
+    size_t *id_off;    /* [n_reads] */
+    size_t id_off_cap;
+} lane_t;
+
+typedef struct {
+    lane_t *lanes;
+    int n_lanes;
+    int cur;       /* lane being filled */
+    int oldest;    /* oldest busy lane (print order) */
+    int n_busy;
+    int n_gpus;
+    uint64_t cap_samples;
+    uint32_t cap_reads;
+    opt_t opt;
+    uint32_t want;
+    uint64_t n_seq_order, n_fixups, n_reads_total;
+} engine_t;
+
+static void die_sgpu(sgpu_ctx_t *ctx, int rc, const char *what) {
+    ERROR("%s failed: %s (%s)", what, sgpu_strerror(rc), ctx ? sgpu_last_error(ctx) : "-");
+    exit(EXIT_FAILURE);
+}
+
+static void engine_open(engine_t *e, int n_gpus, uint64_t cap_samples) {
+    const int avail = sgpu_device_count();
+    if (avail <= 0) {
+        ERROR("%s", "no CUDA device found: the B200 hot path has no CPU fallback");
+        exit(EXIT_FAILURE);
+    }
+    if (n_gpus > avail) n_gpus = avail;
+    e->n_gpus = n_gpus;
+    e->cap_samples = cap_samples;
+    e->cap_reads = (uint32_t)(cap_samples / 256 + 1024);
+    e->n_lanes = 2 * n_gpus;
+    e->lanes = (lane_t *)calloc((size_t)e->n_lanes, sizeof(lane_t));
+    for (int g = 0; g < n_gpus; g++) {
+        sgpu_ctx_t *ctx = NULL;
+        int rc = sgpu_create(&ctx, g, cap_samples, e->cap_reads, 2, SGPU_F_DEFAULT);
+        if (rc) die_sgpu(NULL, rc, "sgpu_create");
+        for (uint32_t s = 0; s < 2; s++) {
+            lane_t *l = &e->lanes[s * n_gpus + g]; /* consecutive lanes alternate between the GPUs */
+            l->ctx = ctx;
+            l->slot = s;
+        }
+    }
+    e->cur = 0;
+    e->oldest = 0;
+    e->n_busy = 0;
+    int rc = sgpu_slot_reset(e->lanes[0].ctx, e->lanes[0].slot, (uint32_t)e->opt.rna);
+    if (rc) die_sgpu(e->lanes[0].ctx, rc, "sgpu_slot_reset");
+}
+
+static void engine_close(engine_t *e) {
+    for (int g = 0; g < e->n_gpus; g++) sgpu_destroy(e->lanes[g].ctx);
+    for (int k = 0; k < e->n_lanes; k++) {
+        free(e->lanes[k].ids);
+        free(e->lanes[k].id_off);
+    }
+    free(e->lanes);
+    e->lanes = NULL;
+}
+
+/* ---- output (reference src/cfunc.c) -------------------------------------------------------------------------------- */
+static void print_header(const opt_t *opt) {
+    if (opt->mode == MODE_EVENT) {
+        if (opt->compact) printf("read_id\tlen_raw_signal\traw_start\traw_end\tnum_event\tevents\n");
+        else printf("read_id\tevent_idx\traw_start\traw_end\tevent_mean\tevent_std\n");
+    } else if (opt->mode == MODE_STAT) {
+        printf("read_id\tlen_raw_signal\traw_mean\tpa_mean\traw_std\tpa_std\traw_median\tpa_median\n");
+    } else {
+        printf("read_id\tlen_raw_signal\tpa\n");
+    }
+}
+
+static void print_lane(engine_t *e, lane_t *l) {
+    sgpu_result_t res;
+    int rc = sgpu_wait(l->ctx, l->slot, &res);
+    if (rc) die_sgpu(l->ctx, rc, "sgpu_wait");
+    sgpu_batch_t *b = NULL;
+    rc = sgpu_slot_batch(l->ctx, l->slot, &b);
+    if (rc) die_sgpu(l->ctx, rc, "sgpu_slot_batch");
+    const opt_t *opt = &e->opt;
+    for (uint32_t r = 0; r < l->n_reads; r++) {
+        const char *rid = l->ids + l->id_off[r];
+        const long n = (long)b->read_len[r];
+        if (opt->mode == MODE_EVENT) {
+            const uint64_t k0 = res.ev_off[r], k1 = res.ev_off[r + 1];
+            e->n_seq_order += res.seq_order[r];
+            e->n_fixups += res.fixups[r];
+            if (opt->compact) { /* cfunc.c:19-49 */
+                printf("%s\t%ld\t", rid, n);
+                if (k1 > k0) {
+                    printf("%ld\t%ld\t", (long)res.ev_start[k0], n);
+                    printf("%ld\t", (long)(k1 - k0));
+                    for (uint64_t k = k0; k < k1; k++) {
+                        const long end = (k + 1 < k1) ? (long)res.ev_start[k + 1] : n;
+                        const int len = (int)(float)(end - (long)res.ev_start[k]);
+                        if (len) {
+                            if (k + 1 < k1) printf("%d,", len); else printf("%d", len);
+                        }
+                    }
+                } else {
+                    printf(".\t.\t.\t.");
+                }
+                printf("\n");
+            } else { /* cfunc.c:51-58 */
+                for (uint64_t k = k0; k < k1; k++) {
+                    const long start = (long)res.ev_start[k];
+                    const long end = (k + 1 < k1) ? (long)res.ev_start[k + 1] : n;
+                    const float length = (float)(end - start);
+                    printf("%s\t%d\t%ld\t%ld\t%f\t%f\n", rid, (int)(k - k0), start, start + (int)length,
+                           res.ev_mean[k], res.ev_stdv[k]);
+                }
+                printf("\n");
+            }
+        } else if (opt->mode == MODE_PA) { /* cfunc.c:85-102 */
+            const float *pa = res.pa + b->read_off[r];
+            printf("%s\t%ld\t", rid, n);
+            for (long i = 0; i < n; i++) {
+                if (i == n - 1) printf("%f", pa[i]); else printf("%f,", pa[i]);
+            }
+            printf("\n");
+        } else { /* cfunc.c:126-159: note the tab before the newline */
+            const float *s = res.stat + (size_t)r * 6;
+            printf("%s\t%ld\t", rid, n);
+            printf("%f\t%f\t%f\t%f\t%d\t%f\t", s[0], s[1], s[2], s[3], (int)(int16_t)s[4], s[5]);
+            printf("\n");
+        }
+    }
+    e->n_reads_total += l->n_reads;
+    l->busy = 0;
+    l->n_reads = 0;
+    l->ids_len = 0;
+}
+
+static void engine_submit_current(engine_t *e) {
+    lane_t *l = &e->lanes[e->cur];
+    if (l->n_reads == 0) return;
+    int rc = sgpu_submit(l->ctx, l->slot, e->want);
+    if (rc) die_sgpu(l->ctx, rc, "sgpu_submit");
+    l->busy = 1;
+    e->n_busy++;
+    /* next lane; if it still holds an unprinted batch, that one is the oldest: print it first */
+    e->cur = (e->cur + 1) % e->n_lanes;
+    lane_t *nx = &e->lanes[e->cur];
+    if (nx->busy) {
+        print_lane(e, nx);
+        e->n_busy--;
+        e->oldest = (e->cur + 1) % e->n_lanes;
+    }
+    rc = sgpu_slot_reset(nx->ctx, nx->slot, (uint32_t)e->opt.rna);
+    if (rc) die_sgpu(nx->ctx, rc, "sgpu_slot_reset");
+}
+
+static void engine_drain(engine_t *e) {
+    engine_submit_current(e);
+    /* print what is still in flight, oldest first: lanes are used round-robin */
+    for (int k = 0; k < e->n_lanes; k++) {
+        lane_t *l = &e->lanes[(e->cur + k) % e->n_lanes];
+        if (l->busy) {
+            print_lane(e, l);
+            e->n_busy--;
+        }
+    }
+}
+
+static void engine_add(engine_t *e, const slow5_rec_t *rec) {
+    for (int attempt = 0; attempt < 3; attempt++) {
+        lane_t *l = &e->lanes[e->cur];
+        int64_t rc = sgpu_slot_add_read(l->ctx, l->slot, rec->raw_signal, rec->len_raw_signal, rec->digitisation,
+                                        rec->offset, rec->range);
+        if (rc >= 0) {
+            const size_t idl = strlen(rec->read_id) + 1;
+            if (l->ids_len + idl > l->ids_cap) {
+                l->ids_cap = (l->ids_len + idl) * 2 + 4096;
+                l->ids = (char *)realloc(l->ids, l->ids_cap);
+            }
+            if (l->n_reads + 1 > l->id_off_cap) {
+                l->id_off_cap = l->id_off_cap * 2 + 1024;
+                l->id_off = (size_t *)realloc(l->id_off, l->id_off_cap * sizeof(size_t));
+            }
+            if (!l->ids || !l->id_off) {
+                ERROR("%s", "out of memory");
+                exit(EXIT_FAILURE);
+            }
+            memcpy(l->ids + l->ids_len, rec->read_id, idl);
+            l->id_off[l->n_reads++] = l->ids_len;
+            l->ids_len += idl;
+            return;
+        }
+        if (rc == SGPU_E_FULL) {
+            engine_submit_current(e);
+            continue;
+        }
+        if (rc == SGPU_E_TOOBIG && rec->len_raw_signal < (1ull << 31)) {
+            /* one read larger than a whole slot: finish what is in flight and reopen with bigger slots */
+            engine_drain(e);
+            const int n_gpus = e->n_gpus;
+            uint64_t cap = e->cap_samples;
+            while (cap < rec->len_raw_signal + 64) cap *= 2;
+            engine_close(e);
+            engine_open(e, n_gpus, cap);
+            continue;
+        }
+        die_sgpu(l->ctx, (int)rc, "sgpu_slot_add_read");
+    }
+    ERROR("%s", "could not place a read into a batch");
+    exit(EXIT_FAILURE);
+}
+
+/* ---- sub-command driver (reference src/cmain.c) ----------------------------------------------------------------------- */
+static struct option long_options[] = {{"verbose", required_argument, 0, 'v'},
+                                       {"help", no_argument, 0, 'h'},
+                                       {"version", no_argument, 0, 'V'},
+                                       {"output", required_argument, 0, 'o'},
+                                       {"print-stat", no_argument, 0, 0},
+                                       {"no-header", no_argument, 0, 'n'},
+                                       {"compact", no_argument, 0, 'c'},
+                                       {"gpus", required_argument, 0, 0},          /* 7 (additive) */
+                                       {"batch-samples", required_argument, 0, 0}, /* 8 (additive) */
+                                       {0, 0, 0, 0}};
+
+static int cmain(int argc, char *argv[], const char *mode) {
+    const char *optstring = "o:hVnc";
+    int longindex = 0, c = -1;
+    FILE *fp_help = stderr;
+    int hdr = 1, n_gpus = 1;
+    uint64_t batch_samples = 0;
+    engine_t eng;
+    memset(&eng, 0, sizeof eng);
+
+    while ((c = getopt_long(argc, argv, optstring, long_options, &longindex)) >= 0) {
+        if (c == 'V') {
+            fprintf(stdout, "sigtk %s\n", SIGTK_VERSION);
+            exit(EXIT_SUCCESS);
+        } else if (c == 'h') {
+            fp_help = stdout;
+        } else if (c == 'n') {
+            hdr = 0;
+        } else if (c == 'c') {
+            eng.opt.compact = 1;
+        } else if (c == 0 && longindex == 7) {
+            n_gpus = atoi(optarg);
+            if (n_gpus < 1) n_gpus = 1;
+        } else if (c == 0 && longindex == 8) {
+            batch_samples = strtoull(optarg, NULL, 10);
+        }
+    }
+    if (argc - optind < 1 || fp_help == stdout) {
+        fprintf(fp_help, "Usage: sigtk %s reads.blow5 read_id1 read_id2 .. \n", mode);
+        fprintf(fp_help, "       sigtk %s reads.blow5\n", mode);
+        fprintf(fp_help, "\nbasic options:\n");
+        fprintf(fp_help, "   -h                         help\n");
+        fprintf(fp_help, "   -n                         suppress header\n");
+        fprintf(fp_help, "   -c                         compact output\n");
+        fprintf(fp_help, "   --version                  print version\n");
+        if (fp_help == stdout) exit(EXIT_SUCCESS);
+        exit(EXIT_FAILURE);
+    }
+    slow5_file_t *sp = slow5_open(argv[optind], "r");
+    if (!sp) {
+        ERROR("cannot open %s. \n", argv[optind]);
+        exit(EXIT_FAILURE);
+    }
+    eng.opt.rna = drna_detect(sp);
+    pore_detect(sp);
+    if (strcmp(mode, "event") == 0) {
+        eng.opt.mode = MODE_EVENT;
+        eng.want = SGPU_WANT_EVENTS;
+    } else if (strcmp(mode, "stat") == 0) {
+        eng.opt.mode = MODE_STAT;
+        eng.want = SGPU_WANT_STAT;
+    } else {
+        eng.opt.mode = MODE_PA;
+        eng.want = SGPU_WANT_PA;
+    }
+    if (hdr) print_header(&eng.opt);
+
+    if (batch_samples == 0) { /* slots sized from the file: small files must not pay for large pinned buffers */
+        struct stat st;
+        uint64_t bytes = (stat(argv[optind], &st) == 0) ? (uint64_t)st.st_size : (64ull << 20);
+        batch_samples = bytes * 8;
+        if (batch_samples < (1ull << 20)) batch_samples = 1ull << 20;
+        if (batch_samples > (1ull << 26)) batch_samples = 1ull << 26;
+    }
+    engine_open(&eng, n_gpus, batch_samples);
+
+    slow5_rec_t *rec = NULL;
+    int ret = 0;
+    if (argc - optind == 1) {
+        while ((ret = slow5_get_next(&rec, sp)) >= 0) engine_add(&eng, rec);
+        if (ret != SLOW5_ERR_EOF) {
+            fprintf(stderr, "Error in slow5_get_next. Error code %d\n", ret);
+            exit(EXIT_FAILURE);
+        }
+    } else {
+        if (slow5_idx_load(sp) < 0) {
+            ERROR("Error loading index file for %s\n", argv[optind]);
+            exit(EXIT_FAILURE);
+        }
+        for (int i = optind + 1; i < argc; i++) {
+            fprintf(stderr, "Read ID %s\n", argv[i]);
+            if (slow5_get(argv[i], &rec, sp) < 0) {
+                ERROR("%s", "Error when fetching the read\n");
+                exit(EXIT_FAILURE);
+            }
+            engine_add(&eng, rec);
+        }
+        slow5_idx_unload(sp);
+    }
+    engine_drain(&eng);
+    fflush(stdout);
+    if (eng.opt.mode == MODE_EVENT && (eng.n_seq_order || eng.n_fixups))
+        fprintf(stderr, "[%s] %" PRIu64 " of %" PRIu64 " reads took the sequential-order kernels (%" PRIu64
+                        " detector boundary mismatches); results are bit-identical either way\n",
+                __func__, eng.n_seq_order, eng.n_reads_total, eng.n_fixups);
+    engine_close(&eng);
+    slow5_rec_free(rec);
+    slow5_close(sp);
+    return 0;
+}
+
+static int print_usage(FILE *fp_help) {
+    fprintf(fp_help, "Usage: sigtk <command> [options]\n\n");
+    fprintf(fp_help, "command:\n");
+    fprintf(fp_help, "         pa        print raw signal in pico-amperes\n");
+    fprintf(fp_help, "         event     segment raw signal into events\n");
+    fprintf(fp_help, "         stat      print statistics of the raw signal\n");
+    fprintf(fp_help, "(B200 build: the raw-signal hot path only; sref, prefix, jnn, ss, ent and qts are served by the\n");
+    fprintf(fp_help, " reference sigtk)\n");
+    exit(fp_help == stderr ? EXIT_FAILURE : EXIT_SUCCESS);
+}
+
+int main(int argc, char *argv[]) {
+    const double realtime0 = realtime();
+    int ret = 1;
+    static char outbuf[1 << 22];
+    setvbuf(stdout, outbuf, _IOFBF, sizeof outbuf);
+    if (argc < 2) {
+        return print_usage(stderr);
+    } else if (strcmp(argv[1], "event") == 0 || strcmp(argv[1], "stat") == 0 || strcmp(argv[1], "pa") == 0) {
+        ret = cmain(argc - 1, argv + 1, argv[1]);
+    } else if (strcmp(argv[1], "--version") == 0 || strcmp(argv[1], "-V") == 0) {
+        fprintf(stdout, "sigtk %s\n", SIGTK_VERSION);
+        exit(EXIT_SUCCESS);
+    } else if (strcmp(argv[1], "--help") == 0 || strcmp(argv[1], "-h") == 0) {
+        print_usage(stdout);
+    } else if (strcmp(argv[1], "sref") == 0 || strcmp(argv[1], "prefix") == 0 || strcmp(argv[1], "jnn") == 0 ||
+               strcmp(argv[1], "ss") == 0 || strcmp(argv[1], "ent") == 0 || strcmp(argv[1], "qts") == 0) {
+        fprintf(stderr, "[sigtk] command %s is outside the B200 raw-signal hot path; use the reference sigtk for it\n",
+                argv[1]);
+        exit(EXIT_FAILURE);
+    } else {
+        fprintf(stderr, "[sigtk] Unrecognised command %s\n", argv[1]);
+        print_usage(stderr);
+    }
+    fprintf(stderr, "[%s] Version: %s\n", __func__, SIGTK_VERSION);
+    fprintf(stderr, "[%s] CMD:", __func__);
+    for (int i = 0; i < argc; ++i) fprintf(stderr, " %s", argv[i]);
+    fprintf(stderr, "\n[%s] Real time: %.3f sec; CPU time: %.3f sec; Peak RAM: %.3f GB\n\n", __func__,
+            realtime() - realtime0, cputime(), (double)peakrss() / 1024.0 / 1024.0 / 1024.0);
+    return ret;
+}

@@ -1,0 +1,98 @@
+"""The drop-in command line (cli/sigtk: C99 host + slow5lib + libsigtk_b200.so) against the stdout of the compiled,
+unmodified reference (fixtures in tests/golden/, made by make_golden.py). Byte for byte."""
+import gzip
+import hashlib
+import json
+import os
+import shutil
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+CLI = os.path.join(ROOT, "cli", "sigtk")
+SHA = json.load(open(os.path.join(G, "sha256.json")))
+
+
+def run(args, **kw):
+    assert os.path.exists(CLI), "cli/sigtk is built by __graft_entry__.build() in the build container"
+    return subprocess.run([CLI] + args, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+
+
+@pytest.fixture(scope="module")
+def sp1(tmp_path_factory):
+    d = tmp_path_factory.mktemp("blow5")
+    shutil.copy(os.path.join(G, "sp1_dna.blow5"), d / "sp1_dna.blow5")  # read-id access writes an index beside it
+    return str(d / "sp1_dna.blow5")
+
+
+RNA = os.path.join(G, "synth_rna.blow5")
+
+
+def test_event_compact_dna(sp1):
+    p = run(["event", "-c", sp1])
+    assert p.stdout == open(os.path.join(G, "ref_sp1_event_c.txt"), "rb").read()
+    assert b"DNA data detected." in p.stderr and b"Real time:" in p.stderr
+
+
+def test_event_long_pa_stat_dna_full_output_hashes(sp1):
+    assert hashlib.sha256(run(["event", sp1]).stdout).hexdigest() == SHA["sp1_event"]
+    assert hashlib.sha256(run(["pa", sp1]).stdout).hexdigest() == SHA["sp1_pa"]
+    out = run(["stat", sp1]).stdout
+    assert out == open(os.path.join(G, "ref_sp1_stat.txt"), "rb").read()
+    assert hashlib.sha256(out).hexdigest() == SHA["sp1_stat"]
+
+
+def test_event_by_read_id_equals_the_reference_golden_file(sp1):
+    """scripts/test.sh:70-72 of the reference: one read by id, long form, vs test/event_dna.exp (stale header line)"""
+    p = run(["event", sp1, "05d90f17-f4a6-4349-924c-3ffd3457a99d"])
+    exp = open(os.path.join(G, "event_dna.exp"), "rb").read().split(b"\n", 1)[1]
+    assert p.stdout.split(b"\n", 1)[1] == exp
+    assert b"Read ID 05d90f17-f4a6-4349-924c-3ffd3457a99d" in p.stderr
+
+
+def test_read_ids_in_argv_order_and_options_after_positionals(sp1):
+    ids = [l.split(b"\t")[0].decode() for l in open(os.path.join(G, "ref_sp1_event_c.txt"), "rb").read().splitlines()[1:]]
+    pick = [ids[7], ids[2], ids[40]]
+    p = run(["event", sp1] + pick + ["-n", "-c"])
+    got = [l.split(b"\t")[0].decode() for l in p.stdout.splitlines()]
+    assert got == pick
+
+
+def test_rna_long_compact_stat_pa():
+    assert run(["event", RNA]).stdout == gzip.open(os.path.join(G, "ref_rna_event.txt.gz"), "rb").read()
+    p = run(["event", "-c", RNA])
+    assert p.stdout == open(os.path.join(G, "ref_rna_event_c.txt"), "rb").read()
+    assert b"RNA data detected." in p.stderr
+    assert run(["stat", RNA]).stdout == open(os.path.join(G, "ref_rna_stat.txt"), "rb").read()
+    assert hashlib.sha256(run(["pa", RNA]).stdout).hexdigest() == SHA["rna_pa"]
+
+
+def test_small_batches_give_the_same_bytes(sp1):
+    """many batches in flight (slots of 1M samples... forced down to a few reads per batch)"""
+    p = run(["event", "-c", "--batch-samples", "20000", sp1])
+    assert p.stdout == open(os.path.join(G, "ref_sp1_event_c.txt"), "rb").read()
+
+
+def test_no_header_version_help_and_errors(sp1):
+    p = run(["stat", "-n", sp1])
+    assert p.stdout == open(os.path.join(G, "ref_sp1_stat.txt"), "rb").read().split(b"\n", 1)[1]
+    assert run(["--version"]).stdout == b"sigtk 0.2.0\n"
+    assert run(["event", "-h"]).stdout.startswith(b"Usage: sigtk event reads.blow5")
+    r = subprocess.run([CLI, "event"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and r.stderr.startswith(b"Usage: sigtk event")
+    r = subprocess.run([CLI, "event", "/nonexistent.blow5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"cannot open /nonexistent.blow5" in r.stderr
+    r = subprocess.run([CLI, "prefix", sp1], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1
+
+
+def test_two_gpus_same_bytes(sp1):
+    import ctypes as C
+    from sigtk_b200 import _lib
+    if _lib.load().sgpu_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    p = run(["event", "-c", "--gpus", "2", "--batch-samples", "50000", sp1])
+    assert p.stdout == open(os.path.join(G, "ref_sp1_event_c.txt"), "rb").read()
