@@ -12,7 +12,7 @@ data path; torch.distributed is used for the barrier and the max-over-ranks only
   value      whole-job Gsamples/s, inputs resident in HBM, CUDA-event time of the K steps, max over ranks
   e2e        the same metric through the host C-ABI (pinned slot -> sgpu_submit -> sgpu_wait): H2D of the samples
              and D2H of the event table (+ pA in event+pa mode) inside the timed region
-  roofline   dominant kernel (detect_tiles_kernel): algorithmic bytes of the path per launch / its CUDA-event time
+  roofline   dominant kernel (walk_chunks_kernel): algorithmic bytes of the path per launch / its CUDA-event time
   cpu_baseline  the UNMODIFIED reference functions (oracle/_ref/libsigtk_ref.so: signal_in_picoamps + getevents)
              on 1 host thread over a bounded sample of the same reads (N=1, rank 0 only)
 
@@ -320,18 +320,18 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
-    dom = "detect_tiles"
+    dom = "walk_chunks"
     dom_ms = stage_ms.get(dom, 0.0) / max(args.steps, 1)
     bytes_step = alg_bytes(n_samples, n_reads, n_events, pa_mode) / max(args.steps, 1)
     achieved = bytes_step / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "detect_tiles_bytes_per_sample_pa" if pa_mode else "detect_tiles_bytes_per_sample"
+        key = "walk_chunks_bytes_per_sample_pa" if pa_mode else "walk_chunks_bytes_per_sample"
         traffic = float(tj[key]) * n_samples / max(args.steps, 1)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "detect_tiles_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "walk_chunks_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms_per_launch": dom_ms, "algorithmic_bytes_per_launch": bytes_step,
                 "path_frac": bytes_step / (ms_max / max(args.steps, 1) * 1e-3) / 1e9 / peak,

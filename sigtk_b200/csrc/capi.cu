@@ -166,7 +166,7 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
     const bool events = (want & SGPU_WANT_EVENTS) != 0;
     if (want & SGPU_WANT_PA) {
         if (!o.pa) CU(dev_alloc(&o.pa, align_up(ctx->max_samples, SGPU_ALIGN)));
-        // with events on the fast path the pA store is fused into detect_tiles_kernel
+        // with events on the fast path the pA store is fused into walk_chunks_kernel
         if (!events || force_generic) marks.done("pa", launch_pa(b, o.pa, ctx->sm_count, st));
     }
     if (want & SGPU_WANT_STAT) marks.done("stat", launch_stat(b, o.stat, ctx->sm_count, st));
@@ -179,11 +179,10 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
             marks.done("init", n);
         } else {
             marks.done("init", n);
-            marks.done("detect_tiles", launch_fast_detect(b, sc, (want & SGPU_WANT_PA) ? o.pa : nullptr, d_seq, d_fix,
-                                                          ctx->sm_count, st));
+            marks.done("walk_chunks", launch_walk(b, sc, (want & SGPU_WANT_PA) ? o.pa : nullptr, d_seq, d_fix,
+                                                   ctx->sm_count, st));
         }
-        n = force_generic ? 0 : launch_verify_tiles(b, sc, d_seq, d_fix, ctx->sm_count, st);
-        n += launch_build_seq_list(b, sc, d_seq, force_generic ? 1 : 0, ctx->sm_count, st);
+        n = launch_build_seq_list(b, sc, d_seq, force_generic ? 1 : 0, ctx->sm_count, st);
         WorkList wl{sc.seq_list, sc.seq_sbase, sc.seq_count};
         n += launch_generic_detect(b, wl, sc, ctx->sm_count, st);
         marks.done("sequential_order_detect", n);
@@ -288,11 +287,13 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     sc.max_tiles = fast_tiles_for(max_samples) + 1;
     sc.bitmap_words = (uint64_t)sc.max_tiles * (FAST_TILE / 32);
     CUC(dev_alloc(&sc.bitmap, sc.bitmap_words));
-    CUC(dev_alloc(&sc.st_begin, (uint64_t)sc.max_tiles * 8));
-    CUC(dev_alloc(&sc.st_end, (uint64_t)sc.max_tiles * 8));
+    sc.wk_slots = walk_state_slots(max_samples, max_reads);
+    CUC(dev_alloc(&sc.wk_begin, sc.wk_slots * 8));
+    CUC(dev_alloc(&sc.wk_end, sc.wk_slots * 8));
+    CUC(dev_alloc(&sc.wk_cnt, max_reads));
+    CUC(dev_alloc(&sc.wk_ibase, (uint64_t)max_reads + 1));
     CUC(dev_alloc(&sc.tile_cnt, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_read0, sc.max_tiles));
-    CUC(dev_alloc(&sc.macro_read0, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_base, (uint64_t)sc.max_tiles + 1));
     CUC(dev_alloc(&sc.wit_min, max_reads));
     CUC(dev_alloc(&sc.wit_max, max_reads));
@@ -302,7 +303,7 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     CUC(dev_alloc(&sc.seq_sbase, (uint64_t)max_reads + 1));
     CUC(dev_alloc(&sc.seq_count, 1));
     CUC(dev_alloc(&sc.cursor, 1));
-    CUC(dev_alloc(&sc.scan_status, scan_tiles_for(sc.max_tiles) + 1));
+    CUC(dev_alloc(&sc.scan_status, scan_tiles_for(sc.max_tiles > max_reads ? sc.max_tiles : max_reads) + 1));
     if (flags & SGPU_F_STAGE_TIMERS)
         for (int k = 0; k <= sgpu_ctx::MAX_STAGES; k++) CUC(cudaEventCreate(&ctx->stage_ev[k]));
     CUC(dev_alloc(&sc.scan_ticket, 1));
@@ -359,7 +360,8 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     cudaDeviceSynchronize();
     Scratch& sc = ctx->sc;
     cudaFree(sc.Sinc); cudaFree(sc.Qinc); cudaFree(sc.t1); cudaFree(sc.t2); cudaFree(sc.bitmap);
-    cudaFree(sc.st_begin); cudaFree(sc.st_end); cudaFree(sc.tile_cnt); cudaFree(sc.tile_base); cudaFree(sc.tile_read0); cudaFree(sc.macro_read0);
+    cudaFree(sc.wk_begin); cudaFree(sc.wk_end); cudaFree(sc.wk_cnt); cudaFree(sc.wk_ibase);
+    cudaFree(sc.tile_cnt); cudaFree(sc.tile_base); cudaFree(sc.tile_read0);
     cudaFree(sc.wit_min); cudaFree(sc.wit_max); cudaFree(ctx->dev_seq); cudaFree(ctx->dev_fix);
     cudaFree(sc.seq_list); cudaFree(sc.seq_sbase); cudaFree(sc.seq_count); cudaFree(sc.cursor);
     cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status); cudaFree(sc.counters);

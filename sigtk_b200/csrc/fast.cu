@@ -44,13 +44,17 @@ __global__ void __launch_bounds__(256) build_seq_list_kernel(DevBatch b, const u
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += gridDim.x * blockDim.x) {
         const uint32_t n = b.read_len[r];
         bool flag = force_all || seq_flag[r] != 0u;
+        // the walker's unguarded shortcuts need unit > 0 (no -0 sums) and 32-bit positions with headroom
+        const float unit = b.unit[r];
+        if (!(unit > 0.0f && unit <= FLT_MAX) || n >= (1u << 30)) flag = true;
         if (!flag && n > 0) {
             const uint32_t mn = wit_min[r], mx = wit_max[r];
             if (mx != 0u) {  // not all zero
+                if (mn < 0x21800000u) flag = true;  // a nonzero |pA| below 2^-60: outside the range of the float shortcuts
                 const uint32_t log2n = n > 1 ? 32u - __clz(n - 1) : 0u;
                 const float fmn = __uint_as_float(mn), fmx = __uint_as_float(mx);
                 const uint32_t qmn = __float_as_uint(__fmul_rn(fmn, fmn)), qmx = __float_as_uint(__fmul_rn(fmx, fmx));
-                flag = !(sums_exact(mn >> 23, mx >> 23, log2n) && sums_exact(qmn >> 23, qmx >> 23, log2n));
+                if (!(sums_exact(mn >> 23, mx >> 23, log2n) && sums_exact(qmn >> 23, qmx >> 23, log2n))) flag = true;
             }
         }
         if (n == 0) flag = false;
@@ -391,7 +395,6 @@ static inline int grid_cap(uint64_t work, int block, int max_blocks) {
 uint32_t fast_tiles_for(uint64_t span) { return (uint32_t)((span + T - 1) / T); }
 
 int fast_configure() {
-    if (detect_configure() != 0) return -1;
     cudaError_t e =
         cudaFuncSetAttribute(emit_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem));
     return e == cudaSuccess ? 0 : -1;

@@ -27,10 +27,13 @@ struct Scratch {
     // event-start bitmap over the flat sample span: bit p set <=> an event starts at flat sample p
     uint32_t* bitmap; uint64_t bitmap_words;
     // per tile
-    int* st_begin; int* st_end;      // detector state at the first / after the last sample of every tile
     uint32_t* tile_cnt; uint64_t* tile_base;
     uint32_t* tile_read0;            // first read that can intersect a 2048-sample tile (emit_tiles_kernel)
-    uint32_t* macro_read0;           // same for the macro tiles of detect_tiles_kernel
+    // chunk walker (walk.cu)
+    uint32_t* wk_cnt;                // [max_reads] interior chunks per read
+    uint64_t* wk_ibase;              // [max_reads+1] exclusive scan of wk_cnt
+    int* wk_begin; int* wk_end;      // [wk_slots*8] detector state after the warm-up / after the last step of a chunk
+    uint64_t wk_slots;
     uint32_t max_tiles;
     // per read
     uint32_t* wit_min; uint32_t* wit_max;  // exact-sum witness: min nonzero |pA| / max |pA| bit patterns
@@ -53,14 +56,15 @@ uint32_t scan_tiles_for(uint32_t n);
 
 // fast.cu (tiled fast path)
 int fast_configure();
-int detect_configure();
 uint32_t fast_tiles_for(uint64_t span);
 int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
                       cudaStream_t st);
-int launch_fast_detect(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups,
-                       int sm_count, cudaStream_t st);
-int launch_verify_tiles(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
-                        cudaStream_t st);
+// walk.cu (chunk walker: pA, t-statistics, peak detector -> event-start bitmap)
+int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
+                cudaStream_t st);
+uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads);
+uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count);
+uint32_t walk_warmup(int rna);
 int launch_build_seq_list(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int force_all, int sm_count,
                           cudaStream_t st);
 int launch_rank_events(const DevBatch& b, Scratch& sc, uint64_t* ev_off, int sm_count, cudaStream_t st);

@@ -1,0 +1,237 @@
+// walk.cu -- walk_chunks_kernel: the first (and dominant) kernel of the fast path.
+//
+// Every read is cut into CHUNKS of L samples (the last chunk takes the remainder, L..2L-1 samples); ONE THREAD
+// walks one chunk with the register-resident walker of walk_core.cuh. A chunk starts W samples early from a cold
+// detector state (plus two ring-fill blocks), so chunks are independent: no shared memory, no barriers, no
+// inter-thread communication. The detector state a chunk reaches at its first owned position (after the warm-up)
+// and the state it ends in are written out (32 B each); verify_chunks_kernel compares every chunk's warm-up state
+// with its predecessor's end state. By induction from the read's first chunk (which starts from the reference's
+// initial state) all chunks of a read are proven to follow the reference's trajectory; a mismatch routes the read
+// to the sequential-order kernels and is counted in fixups[read].
+//
+// Peaks are owned by the STEP that emits them (not by position): every detector step belongs to exactly one
+// chunk, so every peak of the true trajectory is recorded exactly once, with a RED.OR into the event-start bitmap.
+//
+// Thread blocks [0, edge_blocks) walk the first / last chunks of the reads (bounds-checked variant, they take
+// longest and start first); the remaining blocks walk the interior chunks with the unchecked variant.
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "walk_core.cuh"
+
+namespace sgpu {
+
+namespace {
+
+using namespace walk;
+
+constexpr int WNT = 128;  // threads per block of walk_chunks_kernel
+
+struct WalkParams {
+    DevBatch b;
+    int L, W;                       // chunk length, detector warm-up (multiples of U; L >= W + 2U)
+    const uint64_t* ibase;          // [n_reads+1] exclusive scan of the interior chunk counts
+    float* pa;                      // optional pA output (same layout as samples)
+    uint32_t* bitmap;
+    int* st_begin;                  // [(2*n_reads + n_interior) * 8] state after the warm-up
+    int* st_end;                    // same indexing: state after the chunk's last step
+    uint32_t* wit_min;
+    uint32_t* wit_max;
+    uint32_t edge_blocks;
+};
+
+// the memory side of one chunk walk (see walk_core.cuh)
+struct DevIo {
+    const int16_t* __restrict__ sp;   // the read's first sample
+    float* __restrict__ pa;           // the read's first pA (or null)
+    uint32_t* __restrict__ bm;        // the bitmap word that holds the read's first sample
+    int* __restrict__ st_begin;       // this chunk's state slots
+    int* __restrict__ st_end;
+    uint32_t* __restrict__ wit_min;   // this read's witness
+    uint32_t* __restrict__ wit_max;
+    float off, unit;
+
+    __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
+        const int4 w = __ldg(reinterpret_cast<const int4*>(sp + t));
+        v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+    }
+    __device__ __forceinline__ bool want_pa() const { return pa != nullptr; }
+    __device__ __forceinline__ void store_pa8(int t, const float* x) const {
+        float4* dst = reinterpret_cast<float4*>(pa + t);
+        dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+        dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+    }
+    __device__ __forceinline__ void store_pa1(int t, float x) const { pa[t] = x; }
+    __device__ __forceinline__ void peak(int pos) const { atomicOr(bm + (pos >> 5), 1u << (pos & 31)); }
+    static __device__ __forceinline__ void store_canon(int* __restrict__ dst, const Canon& c) {
+        int4* p = reinterpret_cast<int4*>(dst);
+        p[0] = make_int4(c.v[0], c.v[1], c.v[2], c.v[3]);
+        p[1] = make_int4(c.v[4], c.v[5], c.v[6], c.v[7]);
+    }
+    __device__ __forceinline__ void put_begin(const Canon& c) const { store_canon(st_begin, c); }
+    __device__ __forceinline__ void put_end(const Canon& c) const { store_canon(st_end, c); }
+    // Exact-sum witness of a chunk from the extreme raw values: pA is monotone in raw, so the extreme |pA| sit
+    // at the ends of [rmin, rmax]. If the range contains a zero or a sign change, the smallest nonzero |pA| is
+    // bounded below by |unit| when the offset is integral (|raw + off| >= 1), else nothing is known (the read fails).
+    __device__ __forceinline__ void witness(int rmin, int rmax) const {
+        const float xl = __fmul_rn(__fadd_rn((float)rmin, off), unit), xh = __fmul_rn(__fadd_rn((float)rmax, off), unit);
+        const uint32_t bl = __float_as_uint(xl), bh = __float_as_uint(xh);
+        const uint32_t al = bl & 0x7fffffffu, ah = bh & 0x7fffffffu;
+        const uint32_t mx = max(al, ah);
+        if (mx == 0u) return;  // every sample of the chunk is exactly 0
+        uint32_t mn;
+        if (al != 0u && ah != 0u && ((bl ^ bh) >> 31) == 0u) {
+            mn = min(al, ah);
+        } else {
+            const bool integral = off == truncf(off) && fabsf(off) < 8388608.0f;
+            mn = integral ? (__float_as_uint(unit) & 0x7fffffffu) : 1u;
+            if (mn == 0u) mn = 1u;
+        }
+        atomicMin(wit_min, mn);
+        atomicMax(wit_max, mx);
+    }
+};
+
+__device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64_t sid, int* sh) {
+    const uint64_t base = p.b.read_off[r];
+    *sh = (int)(base & 31u);
+    DevIo io;
+    io.sp = p.b.samples + base;
+    io.pa = p.pa ? p.pa + base : nullptr;
+    io.bm = p.bitmap + (base >> 5);
+    io.st_begin = p.st_begin + sid * 8;
+    io.st_end = p.st_end + sid * 8;
+    io.wit_min = p.wit_min + r;
+    io.wit_max = p.wit_max + r;
+    io.off = p.b.offset[r];
+    io.unit = p.b.unit[r];
+    return io;
+}
+
+template <int RNA>
+__device__ __noinline__ void walk_edge_dev(const WalkParams& p, uint32_t r, int last) {
+    int sh;
+    DevIo io = make_io(p, r, 2ull * r + (uint64_t)last, &sh);
+    walk_edge<RNA>(io, (int)p.b.read_len[r], io.off, io.unit, sh, p.L, p.W, last);
+}
+
+// largest r with ibase[r] <= i (ibase is non-decreasing, ibase[n_reads] > i)
+__device__ __forceinline__ uint32_t find_chunk_read(const uint64_t* __restrict__ ibase, uint32_t n_reads, uint64_t i) {
+    uint32_t lo = 0, hi = n_reads;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (ibase[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int RNA>
+__global__ void __launch_bounds__(WNT, RNA ? 1 : 4) walk_chunks_kernel(const WalkParams p) {
+    if (blockIdx.x < p.edge_blocks) {
+        const uint64_t e = (uint64_t)blockIdx.x * WNT + threadIdx.x;
+        if (e < 2ull * p.b.n_reads) walk_edge_dev<RNA>(p, (uint32_t)(e >> 1), (int)(e & 1));
+        return;
+    }
+    const uint64_t i = (uint64_t)(blockIdx.x - p.edge_blocks) * WNT + threadIdx.x;
+    if (i >= p.ibase[p.b.n_reads]) return;
+    const uint32_t r = find_chunk_read(p.ibase, p.b.n_reads, i);
+    int sh;
+    DevIo io = make_io(p, r, 2ull * p.b.n_reads + i, &sh);
+    walk_interior<RNA>(io, (int)p.b.read_len[r], io.off, io.unit, sh, p.L, p.W, (int)(i - p.ibase[r]) + 1);
+}
+
+// ---- chunk counts and verification ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chunk_count_kernel(DevBatch b, uint32_t L, uint32_t* __restrict__ cnt) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += gridDim.x * blockDim.x) {
+        const uint32_t nch = n_chunks(b.read_len[r], L);
+        cnt[r] = nch > 2u ? nch - 2u : 0u;
+    }
+}
+
+// every chunk that started from a speculative (warm-up) state must have reached its predecessor's end state
+__global__ void __launch_bounds__(256) verify_chunks_kernel(DevBatch b, uint32_t L, const uint64_t* __restrict__ ibase,
+                                                            const int* __restrict__ st_begin,
+                                                            const int* __restrict__ st_end,
+                                                            uint32_t* __restrict__ seq_flag,
+                                                            uint32_t* __restrict__ fixups) {
+    const uint64_t n_int = ibase[b.n_reads];
+    const uint64_t total = n_int + b.n_reads;  // interior chunks, then the last chunk of every read
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t r;
+        uint64_t cur, prev;
+        if (t < n_int) {
+            r = find_chunk_read(ibase, b.n_reads, t);
+            cur = 2ull * b.n_reads + t;
+            prev = (t == ibase[r]) ? 2ull * r : cur - 1;
+        } else {
+            r = (uint32_t)(t - n_int);
+            const uint32_t nch = n_chunks(b.read_len[r], L);
+            if (nch < 2u) continue;
+            cur = 2ull * r + 1;
+            prev = (nch == 2u) ? 2ull * r : 2ull * b.n_reads + ibase[r + 1] - 1;
+        }
+        const int4* a = reinterpret_cast<const int4*>(st_begin + cur * 8);
+        const int4* e = reinterpret_cast<const int4*>(st_end + prev * 8);
+        const int4 a0 = a[0], a1 = a[1], e0 = e[0], e1 = e[1];
+        const bool same = a0.x == e0.x && a0.y == e0.y && a0.z == e0.z && a0.w == e0.w && a1.x == e1.x && a1.y == e1.y;
+        if (!same) {
+            seq_flag[r] = 1u;
+            atomicAdd(&fixups[r], 1u);
+        }
+    }
+}
+
+static inline int grid_cap(uint64_t work, int block, int max_blocks) {
+    uint64_t g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (uint64_t)max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+}  // namespace
+
+// chunk length for a batch: as long as possible (the warm-up is amortised over it) while the batch still yields
+// a few waves of chunks
+uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count) {
+    const uint32_t lmin = rna ? 512u : 128u;
+    const uint64_t want_chunks = (uint64_t)sm_count * 512ull * 4ull;
+    uint32_t L = rna ? 4096u : 1024u;
+    while (L > lmin && span / L < want_chunks) L >>= 1;
+    if (const char* e = getenv("SGPU_CHUNK_LEN")) {
+        const uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
+        if (v >= lmin && (v & (v - 1)) == 0u) L = v;
+    }
+    return L;
+}
+uint32_t walk_warmup(int rna) {
+    uint32_t W = rna ? 384u : 64u;
+    if (const char* e = getenv("SGPU_WARMUP")) {  // tests force short warm-ups to exercise the mismatch path
+        const uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
+        const uint32_t u = rna ? 16u : 8u;
+        if (v % u == 0u && v <= W) W = v;
+    }
+    return W;
+}
+uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads) { return 2ull * max_reads + max_samples / 128u + 1u; }
+
+int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
+                cudaStream_t st) {
+    const uint32_t L = walk_chunk_len(b.span, b.rna, sm_count), W = walk_warmup(b.rna);
+    const uint64_t words = (uint64_t)fast_tiles_for(b.span) * (FAST_TILE / 32);
+    cudaMemsetAsync(sc.bitmap, 0, (size_t)words * sizeof(uint32_t), st);
+    chunk_count_kernel<<<grid_cap(b.n_reads, 256, sm_count * 8), 256, 0, st>>>(b, L, sc.wk_cnt);
+    int n = 1 + launch_scan_u32(sc.wk_cnt, b.n_reads, sc.wk_ibase, nullptr, sc, st);
+    WalkParams p;
+    p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
+    p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max;
+    p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
+    const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
+    const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;
+    if (b.rna) walk_chunks_kernel<1><<<(unsigned)grid, WNT, 0, st>>>(p);
+    else walk_chunks_kernel<0><<<(unsigned)grid, WNT, 0, st>>>(p);
+    verify_chunks_kernel<<<grid_cap(max_interior + b.n_reads, 256, sm_count * 8), 256, 0, st>>>(
+        b, L, sc.wk_ibase, sc.wk_begin, sc.wk_end, seq_flag, fixups);
+    return n + 2;
+}
+
+}  // namespace sgpu

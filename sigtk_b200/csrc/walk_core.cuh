@@ -1,0 +1,465 @@
+// walk_core.cuh -- the per-thread CHUNK WALKER of the fast path (walk.cu).
+//
+// One thread walks one chunk of one read sample by sample, entirely in registers:
+//
+//   int16 -> pA (misc.c:26-29) -> running FP64 prefix of x and x*x (a small register ring) -> the window sums of
+//   both window lengths (w2 = 2*w1: the long window is the sum of two short ones) -> both t-statistics
+//   (events.c:338-361, every rounding step written out) -> both peak detectors (events.c:387-437).
+//
+// Nothing per-sample is staged in shared or global memory: the only per-sample traffic is the 2-byte load (and
+// the optional 4-byte pA store); emitted peaks set bits of the event-start bitmap with fire-and-forget RED.OR.
+//
+// Timeline of one walker step (newest sample index j, all indices relative to the read):
+//     P(j+1)            = P(j) + x[j]                      running prefix sums (exact, see below)
+//     D1(j1), j1=j-w1+1 = P(j+1) - P(j1)                   short-window sums, ring of w1
+//     D2(j2), j2=j1-w1  = D1(j2) + D1(j1)                  long-window sums
+//     t1(j1)  from the window terms of D1(j1-w1), D1(j1)   -> ring of w1
+//     t2(j2)  from the window terms of D2(j2-w2), D2(j2)
+//     detector step at position p = j2 = j - (w2-1) with t1(p) (from the ring) and t2(p)
+//
+// Why any summation order gives the reference's bits: the reference's S[i], Q[i] are sequential double sums of
+// floats. If every value of a read is a multiple of 2^k and the sum of magnitudes stays below 2^(k+53), no
+// addition ever rounds, every partial sum of any subset is exact, and S[b]-S[a] is the exact sum of the samples
+// in [a,b) however it is formed. The per-read witness (min/max |pA| collected by the walker, evaluated by
+// build_seq_list_kernel) checks that sufficient condition; reads that fail are redone by the sequential-order
+// kernels (generic.cu).
+//
+// The file is `__host__ __device__` clean so that tests/tools/host_walk.cu can run the very same chunk logic on
+// the CPU against the oracle (a checker for the chunking / ring / boundary logic; never part of the product).
+#pragma once
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define SGW_HD __host__ __device__ __forceinline__
+#else
+#define SGW_HD inline
+#endif
+
+namespace sgpu {
+namespace walk {
+
+// ---- arithmetic with explicit rounding (device: intrinsics, never contracted; host: plain IEEE ops) -------------
+#if defined(__CUDA_ARCH__)
+SGW_HD double dadd(double a, double b) { return __dadd_rn(a, b); }
+SGW_HD double dsub(double a, double b) { return __dsub_rn(a, b); }
+SGW_HD double dmul(double a, double b) { return __dmul_rn(a, b); }
+SGW_HD double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+SGW_HD double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+SGW_HD double dsqrt(double a) { return __dsqrt_rn(a); }
+SGW_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+SGW_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
+SGW_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+SGW_HD float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SGW_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+SGW_HD float d2f(double a) { return __double2float_rn(a); }
+SGW_HD uint32_t d_hi(double a) { return (uint32_t)__double2hiint(a); }
+SGW_HD uint32_t d_lo(double a) { return (uint32_t)__double2loint(a); }
+SGW_HD uint32_t f_bits(float a) { return __float_as_uint(a); }
+SGW_HD float rsqrt_seed(float a) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    return y;
+}
+#else
+SGW_HD double dadd(double a, double b) { return a + b; }
+SGW_HD double dsub(double a, double b) { return a - b; }
+SGW_HD double dmul(double a, double b) { return a * b; }
+SGW_HD double dfma(double a, double b, double c) { return fma(a, b, c); }
+SGW_HD double ddiv(double a, double b) { return a / b; }
+SGW_HD double dsqrt(double a) { return sqrt(a); }
+SGW_HD float fadd(float a, float b) { return a + b; }
+SGW_HD float fsub(float a, float b) { return a - b; }
+SGW_HD float fmul(float a, float b) { return a * b; }
+SGW_HD float ffma(float a, float b, float c) { return fmaf(a, b, c); }
+SGW_HD float fdiv(float a, float b) { return a / b; }
+SGW_HD float d2f(double a) { return (float)a; }
+SGW_HD uint32_t d_hi(double a) { uint64_t b; memcpy(&b, &a, 8); return (uint32_t)(b >> 32); }
+SGW_HD uint32_t d_lo(double a) { uint64_t b; memcpy(&b, &a, 8); return (uint32_t)b; }
+SGW_HD uint32_t f_bits(float a) { uint32_t b; memcpy(&b, &a, 4); return b; }
+SGW_HD float rsqrt_seed(float a) { return (float)(1.0 / sqrt((double)a)); }  // the guard below absorbs +-4 ulp
+#endif
+
+// ---- parameters (events.c:35-54) ----------------------------------------------------------------------------------
+template <int RNA>
+struct Cfg {
+    static constexpr int w1 = RNA ? 7 : 3;
+    static constexpr int w2 = 2 * w1;
+    static constexpr int LAG = w2 - 1;        // detector position = newest sample index - LAG
+    static constexpr int R1 = RNA ? 8 : 4;    // ring size of the depth-w1 rings (> w1, power of two)
+    static constexpr int R2 = RNA ? 16 : 8;   // ring size of the depth-w2 rings (> w2, power of two)
+    static constexpr int U = RNA ? 16 : 8;    // samples per block (multiple of R2: every ring index is static)
+    static constexpr int FILL = 2;            // blocks that only fill the rings before the first detector step
+    static_assert(FILL * U >= 2 * w2 - 1, "fill covers the look-back of the first step");
+};
+template <int RNA> SGW_HD float thr_short() { return RNA ? 2.5f : 1.4f; }
+template <int RNA> SGW_HD float thr_long() { return 9.0f; }
+template <int RNA> SGW_HD float peak_h() { return RNA ? 1.0f : 0.2f; }
+
+// ---- exact shortcuts (validated on the CPU by oracle/proofs/*.c) --------------------------------------------------
+// a / W, W in {3,6,7,14}: reciprocal multiply + one FMA residual correction (Markstein). Equal to the IEEE
+// quotient for every double the path can produce, and for every float with |a| >= 2^-125 or a == +0
+// (exhaustive check over all floats). The walker only uses the float form on values that the per-read witness
+// certifies to be in that range (nonzero |pA| >= 2^-60, unit > 0), or on cv >= 2e-29.
+template <int W>
+SGW_HD double ddivw(double a) {
+    constexpr double r = 1.0 / (double)W;
+    const double q0 = dmul(a, r);
+    const double e = dfma(-(double)W, q0, a);
+    return dfma(e, r, q0);
+}
+template <int W>
+SGW_HD float fdivw(float a) {
+    constexpr float r = 1.0f / (float)W;
+    const float q0 = fmul(a, r);
+    const float e = ffma(-(float)W, q0, a);
+    return ffma(e, r, q0);
+}
+
+// the reference's own operations for the last step (events.c:355-360); taken by about 2 values in a million
+template <int W>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+float tail_ieee(float delta, float cv) {
+    if (delta == 0.0f) return 0.0f;  // (float)(0.0 / sqrt(c)) = +0 for c > 0
+    const float scaled = fdiv(cv, (float)W);
+    return d2f(ddiv(fabs((double)delta), dsqrt((double)scaled)));
+}
+
+// t = (float)(fabs((double)delta) / sqrt((double)(cv / W)))  (events.c:360) through a 22-bit reciprocal square
+// root and one third-order correction in double. The product is within a few ulp(double) of the true quotient,
+// so it rounds to the same float as the reference's doubly rounded value unless it lies next to a float rounding
+// midpoint or outside the normal float range; those values take tail_ieee (oracle/proofs/tstat_tail_check.c).
+template <int W>
+SGW_HD float tail(float delta, float cv) {
+    const float scaled = fdivw<W>(cv);  // cv >= FLT_MIN > 0; shortcut valid for cv >= 1e-36
+    const double c = (double)scaled;
+    const double y0 = (double)rsqrt_seed(scaled);
+    const double t = dmul(c, y0);
+    const double e = dfma(-t, y0, 1.0);
+    const double p = dfma(0.375, e, 0.5);
+    const double ye = dmul(y0, e);
+    const double y = dfma(ye, p, y0);
+    const double q = dmul(fabs((double)delta), y);
+    const uint32_t lo = d_lo(q), hi = d_hi(q);
+    // accept when 2^-126 <= q < 2^126, the 29 bits below float precision are not within 512 of the midpoint,
+    // and scaled >= 1e-30 (cv >= 2e-29 implies it for W <= 14). delta == 0 gives q = 0: rejected, tail_ieee -> +0.
+    const bool in_range = (hi - ((1023u - 126u) << 20)) < (252u << 20);
+    const bool off_mid = ((lo & 0x1fffffffu) - (0x10000000u - 512u)) >= 1024u;
+    if (!(in_range && off_mid && cv >= 2.0e-29f)) return tail_ieee<W>(delta, cv);
+    return d2f(q);
+}
+
+// The terms of events.c:339-350 that depend on ONE window [j, j+W) only. The window is the right window of
+// position j (sum2/sumsq2, narrowed to float at once) and the left window of position j+W (kept in double).
+template <int W>
+SGW_HD void window_terms(double D, double E, float& A, double& Lq, float& B, double& Vd, double& B2d) {
+    A = d2f(ddivw<W>(D));                                 // mean1 = (float)(sum1 / w)
+    Lq = dsub(ddivw<W>(E), (double)fmul(A, A));           // sumsq1/w - (double)(mean1*mean1)
+    B = fdivw<W>(d2f(D));                                 // mean2 = (float)sum2 / w
+    Vd = (double)fdivw<W>(d2f(E));                        // (double)((float)sumsq2 / w)
+    B2d = (double)fmul(B, B);                             // (double)(mean2*mean2)
+}
+template <int W>
+SGW_HD float tstat_from(float A_left, double L_left, float B, double Vd, double B2d) {
+    const double acc = dsub(dadd(L_left, Vd), B2d);       // ((.. - m1sq) + v2) - m2sq, left to right in double
+    const float cv = fmaxf(d2f(acc), FLT_MIN);            // events.c:353
+    return tail<W>(fsub(B, A_left), cv);                  // delta = mean2 - mean1
+}
+
+// ---- the dual peak detector (events.c:371-443) --------------------------------------------------------------------
+// Positions are "shifted" read indices: index in the read + (read_off & 31), so that position >> 5 is a word of the
+// read's part of the event-start bitmap. NONE = -1 (a shifted position is never negative once a peak exists).
+struct WalkDet {
+    float s_pv; int s_pp; int s_valid;               // short detector (never masked after the read's first sample)
+    float l_pv; int l_pp; int l_valid; int l_mt;     // long detector; l_mt = masked_to
+};
+SGW_HD void det_cold(WalkDet& d, int first_step) {  // both detectors start at `first_step` from the reset state
+    d.s_pv = FLT_MAX; d.s_pp = -1; d.s_valid = 0;
+    d.l_pv = FLT_MAX; d.l_pp = -1; d.l_valid = 0; d.l_mt = first_step - 1;
+}
+
+// canonical form at boundary b (state before step b): 8 words, bit-comparable between the chunk that ends at b
+// and the chunk that starts there
+struct Canon { int v[8]; };
+SGW_HD Canon canon_of(const WalkDet& d, int b) {
+    Canon c;
+    c.v[0] = (int)f_bits(d.s_pv); c.v[1] = d.s_pp; c.v[2] = (int)f_bits(d.l_pv); c.v[3] = d.l_pp;
+    c.v[4] = d.l_mt >= b ? d.l_mt : -1;
+    c.v[5] = (d.s_valid ? 1 : 0) | (d.l_valid ? 2 : 0);
+    c.v[6] = 0; c.v[7] = 0;
+    return c;
+}
+
+// One position of both detectors, short first (events.c:385-440). `Sink::peak(pos)` records an emitted peak.
+template <int RNA, class Sink>
+SGW_HD void det_step(WalkDet& d, int u, float c1, float c2, bool rec, Sink& sink) {
+    constexpr int w1 = Cfg<RNA>::w1, w2 = Cfg<RNA>::w2;
+    const float h = peak_h<RNA>();
+    {   // short detector, always active
+        const bool none = d.s_pp < 0;
+        const float df = fsub(c1, d.s_pv);                // > 0: above the running value, < 0: below
+        const bool gt = df > 0.0f, lt = df < 0.0f;
+        const bool rise = df > h, drop = df < -h;         // pv - c > h  <=>  c - pv < -h (negation is exact)
+        const float pv2 = gt ? c1 : d.s_pv;               // CASE 2: new maximum
+        const int pp2 = gt ? u : d.s_pp;
+        const bool big = pv2 > thr_short<RNA>();
+        const bool valid2 = (d.s_valid != 0) | (drop & big);
+        const bool emit = !none & valid2 & ((u - pp2) > w1 / 2);
+        const bool maskl = !none & big;                   // the short detector dominates the long one (414-422)
+        d.l_mt = maskl ? pp2 + w1 : d.l_mt;
+        d.l_pp = maskl ? -1 : d.l_pp;
+        d.l_pv = maskl ? FLT_MAX : d.l_pv;
+        d.l_valid = maskl ? 0 : d.l_valid;
+        if (emit & rec) sink.peak(pp2);
+        const bool setc = none ? (lt | rise) : (gt | emit);
+        d.s_pv = setc ? c1 : d.s_pv;
+        d.s_pp = none ? (rise ? u : -1) : (emit ? -1 : pp2);
+        d.s_valid = (!none & valid2 & !emit) ? 1 : 0;
+    }
+    {   // long detector, skipped while masked
+        const bool act = d.l_mt < u;
+        const bool none = d.l_pp < 0;
+        const float df = fsub(c2, d.l_pv);
+        const bool gt = df > 0.0f, lt = df < 0.0f;
+        const bool rise = df > h, drop = df < -h;
+        const float pv2 = gt ? c2 : d.l_pv;
+        const int pp2 = gt ? u : d.l_pp;
+        const bool big = pv2 > thr_long<RNA>();
+        const bool valid2 = (d.l_valid != 0) | (drop & big);
+        const bool emit = act & !none & valid2 & ((u - pp2) > w2 / 2);
+        if (emit & rec) sink.peak(pp2);
+        const bool setc = act & (none ? (lt | rise) : (gt | emit));
+        d.l_pv = setc ? c2 : d.l_pv;
+        const int ppn = none ? (rise ? u : -1) : (emit ? -1 : pp2);
+        d.l_pp = act ? ppn : d.l_pp;
+        d.l_valid = act ? ((!none & valid2 & !emit) ? 1 : 0) : d.l_valid;
+    }
+}
+
+// ---- the register rings --------------------------------------------------------------------------------------------
+template <int RNA>
+struct Rings {
+    using C = Cfg<RNA>;
+    double P[C::R1], PQ[C::R1];    // P[j & (R1-1)] = sum of x over the walked samples before j
+    double D1[C::R1], E1[C::R1];   // short-window sums by window start
+    float A1[C::R1];               // left-window terms of the short window by window start
+    double L1[C::R1];
+    float T1[C::R1];               // t1 by position
+    float A2[C::R2];               // left-window terms of the long window by window start
+    double L2[C::R2];
+    SGW_HD void clear() {
+#pragma unroll
+        for (int k = 0; k < C::R1; k++) { P[k] = 0.0; PQ[k] = 0.0; D1[k] = 0.0; E1[k] = 0.0; A1[k] = 0.0f; L1[k] = 0.0; T1[k] = 0.0f; }
+#pragma unroll
+        for (int k = 0; k < C::R2; k++) { A2[k] = 0.0f; L2[k] = 0.0; }
+    }
+};
+
+// What one block does: KIND 0 = sums and window terms only, 1 = additionally t1 for the positions the first
+// detector step will need, 2 = everything (both t-statistics and the detector).
+// EDGE: the block may touch positions outside the read [0, n): samples there count as 0, t is 0 outside
+// w <= i <= n-w (events.c:328-338), the detector only steps positions 1 <= p < n (position 0 is masked: 387).
+//   x[m]   : pA of sample tau0 + m (0 outside the read when EDGE)
+//   tau0   : read index of the block's first sample, a multiple of U (may be negative only when EDGE... never: see walk.cu)
+//   sh     : read_off & 31
+template <int RNA, int KIND, bool EDGE, class Sink>
+SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U], int tau0, int n, int sh, bool rec,
+                       Sink& sink) {
+    using C = Cfg<RNA>;
+    constexpr int w1 = C::w1, w2 = C::w2, M1 = C::R1 - 1, M2 = C::R2 - 1;
+#pragma unroll
+    for (int m = 0; m < C::U; m++) {
+        // static ring slots: every index below is (m + const) & mask because tau0 is a multiple of U
+        const int j = tau0 + m;
+        const double xd = (double)x[m];
+        const double qd = (double)fmul(x[m], x[m]);                 // float square, widened afterwards (events.c:301)
+        const double pn = dadd(g.P[m & M1], xd), pqn = dadd(g.PQ[m & M1], qd);
+        g.P[(m + 1) & M1] = pn;
+        g.PQ[(m + 1) & M1] = pqn;
+        // short window [j1, j1+w1), j1 = j - w1 + 1
+        const int j1 = j - w1 + 1;
+        const int s1 = (m - w1 + 1) & M1;                           // slot of j1
+        const int s1l = (m - 2 * w1 + 1) & M1;                      // slot of j1 - w1
+        const double d1 = dsub(pn, g.P[s1]), e1 = dsub(pqn, g.PQ[s1]);
+        float a1, b1; double l1, v1, b1sq;
+        window_terms<w1>(d1, e1, a1, l1, b1, v1, b1sq);
+        // long window [j2, j2+w2) = short(j2) + short(j1), j2 = j1 - w1
+        const int j2 = j1 - w1;
+        const int s2 = (m - 2 * w1 + 1) & M2;                       // slot of j2
+        const int s2l = (m - 2 * w1 + 1 - w2) & M2;                 // slot of j2 - w2
+        const double d2 = dadd(g.D1[s1l], d1), e2 = dadd(g.E1[s1l], e1);
+        float a2, b2; double l2, v2, b2sq;
+        window_terms<w2>(d2, e2, a2, l2, b2, v2, b2sq);
+        if (KIND == 2 || (KIND == 1 && m >= C::U - w1)) {
+            float t1 = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq);
+            if (EDGE) t1 = (j1 >= w1 && j1 + w1 <= n) ? t1 : 0.0f;
+            if (KIND == 2) {
+                float t2 = tstat_from<w2>(g.A2[s2l], g.L2[s2l], b2, v2, b2sq);
+                if (EDGE) t2 = (j2 >= w2 && j2 + w2 <= n) ? t2 : 0.0f;
+                const float c1 = g.T1[s1l];                         // t1(j2), computed w1 samples ago
+                if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, j2 + sh, c1, t2, rec, sink);
+            }
+            g.T1[s1] = t1;
+        }
+        g.D1[s1] = d1; g.E1[s1] = e1;
+        g.A1[s1] = a1; g.L1[s1] = l1;
+        g.A2[s2] = a2; g.L2[s2] = l2;
+    }
+}
+
+
+// ---- chunk drivers -------------------------------------------------------------------------------------------------
+// Every read is cut into chunks of L samples; the last chunk takes the remainder (L..2L-1 samples), a read
+// shorter than 2L is a single chunk. `Io` supplies the memory side (device: walk.cu, host checker:
+// tests/tools/host_walk.cpp):
+//   load8(t, v)        the four 32-bit words holding samples [t, t+8) of the read (t multiple of 8)
+//   want_pa() / store_pa8(t, x) / store_pa1(t, x)
+//   peak(pos)          record an emitted peak (shifted position)
+//   put_begin(c) / put_end(c)   the chunk's canonical detector state after the warm-up / after its last step
+//   witness(rmin, rmax)         extreme raw values of the samples the chunk owns
+SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return n < 2u * L ? (n ? 1u : 0u) : n / L; }
+
+SGW_HD void cvt8(const int (&v)[4], float off, float unit, float* x) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int lo = (int)(int16_t)(v[k] & 0xffff), hi = v[k] >> 16;
+        x[2 * k] = fmul(fadd((float)lo, off), unit);      // misc.c:28: float add, then float multiply
+        x[2 * k + 1] = fmul(fadd((float)hi, off), unit);
+    }
+}
+#if defined(__CUDA_ARCH__)
+SGW_HD uint32_t min_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+SGW_HD uint32_t max_s16x2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+#else
+SGW_HD uint32_t min_s16x2(uint32_t a, uint32_t b) {
+    const int16_t al = (int16_t)(a & 0xffff), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xffff), bh = (int16_t)(b >> 16);
+    return (uint32_t)(uint16_t)(al < bl ? al : bl) | ((uint32_t)(uint16_t)(ah < bh ? ah : bh) << 16);
+}
+SGW_HD uint32_t max_s16x2(uint32_t a, uint32_t b) {
+    const int16_t al = (int16_t)(a & 0xffff), ah = (int16_t)(a >> 16), bl = (int16_t)(b & 0xffff), bh = (int16_t)(b >> 16);
+    return (uint32_t)(uint16_t)(al > bl ? al : bl) | ((uint32_t)(uint16_t)(ah > bh ? ah : bh) << 16);
+}
+#endif
+
+// interior chunk k (1 <= k <= nch-2) of a read: every access is inside the read, no bounds checks
+template <int RNA, class Io>
+SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, int W, int k) {
+    using C = Cfg<RNA>;
+    constexpr int U = C::U;
+    const int s0 = k * L;                            // first sample this chunk owns
+    int tau = s0 - W - C::FILL * U;
+    Rings<RNA> g;
+    g.clear();
+    WalkDet d;
+    det_cold(d, tau + C::FILL * U - C::LAG + sh);    // first detector step
+    float x[U];
+    int v[4];
+#pragma unroll
+    for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
+    walk_block<RNA, 0, false>(g, d, x, tau, n, sh, false, io);
+    tau += U;
+#pragma unroll
+    for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
+    walk_block<RNA, 1, false>(g, d, x, tau, n, sh, false, io);
+    tau += U;
+    for (; tau < s0; tau += U) {                     // detector warm-up
+#pragma unroll
+        for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
+        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, false, io);
+    }
+    io.put_begin(canon_of(d, s0 - C::LAG + sh));
+    uint32_t vmin = 0x7fff7fffu, vmax = 0x80008000u;  // packed int16 min / max of the owned samples
+    const int s1 = s0 + L;
+    const bool pa = io.want_pa();
+    for (; tau < s1; tau += U) {
+#pragma unroll
+        for (int h = 0; h < U / 8; h++) {
+            io.load8(tau + 8 * h, v);
+            vmin = min_s16x2(min_s16x2(vmin, (uint32_t)v[0]), min_s16x2((uint32_t)v[1], min_s16x2((uint32_t)v[2], (uint32_t)v[3])));
+            vmax = max_s16x2(max_s16x2(vmax, (uint32_t)v[0]), max_s16x2((uint32_t)v[1], max_s16x2((uint32_t)v[2], (uint32_t)v[3])));
+            cvt8(v, off, unit, x + 8 * h);
+            if (pa) io.store_pa8(tau + 8 * h, x + 8 * h);
+        }
+        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, true, io);
+    }
+    io.put_end(canon_of(d, s1 - C::LAG + sh));
+    const int rmin0 = (int)(int16_t)(vmin & 0xffffu), rmin1 = (int)vmin >> 16;
+    const int rmax0 = (int)(int16_t)(vmax & 0xffffu), rmax1 = (int)vmax >> 16;
+    io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1);
+}
+
+// first chunk (last == 0) or last chunk (last == 1; only when the read has >= 2 chunks) of a read: bounds-checked
+template <int RNA, class Io>
+SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W, int last) {
+    using C = Cfg<RNA>;
+    constexpr int U = C::U;
+    const uint32_t nch = n_chunks((uint32_t)n, (uint32_t)L);
+    if (nch == 0u || (last && nch < 2u)) return;
+    // owned samples [s0, s1); owned detector steps [s0 - LAG, s1 - LAG), all remaining steps for the read's last chunk
+    const int s0 = last ? (int)(nch - 1u) * L : 0;
+    const bool to_end = last || nch == 1u;
+    const int s1 = to_end ? n : L;
+    Rings<RNA> g;
+    g.clear();
+    WalkDet d;
+    float x[U];
+    int rmin = 32767, rmax = -32768;
+    const bool pa = io.want_pa();
+    auto load = [&](int t, bool own) {
+#pragma unroll
+        for (int h = 0; h < U / 8; h++) {
+            const int t8 = t + 8 * h;
+            int v[4] = {0, 0, 0, 0};
+            if (t8 < n) io.load8(t8, v);  // t8 < n: inside the read's padded span
+            float y[8];
+            cvt8(v, off, unit, y);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const bool in = t8 + q < n;
+                x[8 * h + q] = in ? y[q] : 0.0f;
+                if (own && in && t8 + q < s1) {
+                    const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
+                    rmin = raw < rmin ? raw : rmin;
+                    rmax = raw > rmax ? raw : rmax;
+                    if (pa) io.store_pa1(t8 + q, y[q]);
+                }
+            }
+        }
+    };
+    int tau;
+    if (!last) {
+        tau = 0;
+        det_cold(d, sh + 1);  // the reference's initial state: masked_to = 0, position 0 is skipped (events.c:516-536, 387)
+    } else {
+        tau = s0 - W - C::FILL * U;  // >= 0 because L >= W + 2U
+        det_cold(d, tau + C::FILL * U - C::LAG + sh);
+        load(tau, false);
+        walk_block<RNA, 0, true>(g, d, x, tau, n, sh, false, io);
+        tau += U;
+        load(tau, false);
+        walk_block<RNA, 1, true>(g, d, x, tau, n, sh, false, io);
+        tau += U;
+        for (; tau < s0; tau += U) {
+            load(tau, false);
+            walk_block<RNA, 2, true>(g, d, x, tau, n, sh, false, io);
+        }
+        io.put_begin(canon_of(d, s0 - C::LAG + sh));
+    }
+    const int step_end = to_end ? n : s1 - C::LAG;  // owned blocks: until every owned step has been taken
+    for (; tau - C::LAG < step_end; tau += U) {
+        load(tau, true);
+        walk_block<RNA, 2, true>(g, d, x, tau, n, sh, true, io);
+    }
+    if (!to_end) io.put_end(canon_of(d, s1 - C::LAG + sh));
+    if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)
+    if (rmin <= rmax) io.witness(rmin, rmax);
+}
+
+}  // namespace walk
+}  // namespace sgpu
