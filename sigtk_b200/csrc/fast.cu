@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(256) build_seq_list_kernel(DevBatch b, const u
         if (!(unit > 0.0f && unit <= FLT_MAX) || n >= (1u << 30)) flag = true;
         if (!flag && n > 0) {
             const uint32_t mn = wit_min[r], mx = wit_max[r];
-            if (mx != 0u) {  // not all zero
-                if (mn < 0x21800000u) flag = true;  // a nonzero |pA| below 2^-60: outside the range of the float shortcuts
+            // every sample must be a positive float >= 2^-60 (the range of the walker's shortcuts) ...
+            if (mn < 0x21800000u || mn > mx) flag = true;
+            else {  // ... and the sums of x and x*x must be exact whatever the order
                 const uint32_t log2n = n > 1 ? 32u - __clz(n - 1) : 0u;
                 const float fmn = __uint_as_float(mn), fmx = __uint_as_float(mx);
                 const uint32_t qmn = __float_as_uint(__fmul_rn(fmn, fmn)), qmx = __float_as_uint(__fmul_rn(fmx, fmx));

@@ -62,7 +62,11 @@ struct DevIo {
         dst[1] = make_float4(x[4], x[5], x[6], x[7]);
     }
     __device__ __forceinline__ void store_pa1(int t, float x) const { pa[t] = x; }
-    __device__ __forceinline__ void peak(int pos) const { atomicOr(bm + (pos >> 5), 1u << (pos & 31)); }
+    __device__ __forceinline__ void peak(int pos) const { atomicOr(bm + ((uint32_t)pos >> 5), 1u << (pos & 31)); }
+    __device__ __forceinline__ void peak_if(int pos, bool on) const {  // predicated RED: no branch in the walker's inner loop
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p red.global.or.b32 [%0], %1;\n\t}"
+                     :: "l"(bm + ((uint32_t)pos >> 5)), "r"(1u << (pos & 31)), "r"((int)on) : "memory");
+    }
     static __device__ __forceinline__ void store_canon(int* __restrict__ dst, const Canon& c) {
         int4* p = reinterpret_cast<int4*>(dst);
         p[0] = make_int4(c.v[0], c.v[1], c.v[2], c.v[3]);
@@ -70,25 +74,15 @@ struct DevIo {
     }
     __device__ __forceinline__ void put_begin(const Canon& c) const { store_canon(st_begin, c); }
     __device__ __forceinline__ void put_end(const Canon& c) const { store_canon(st_end, c); }
-    // Exact-sum witness of a chunk from the extreme raw values: pA is monotone in raw, so the extreme |pA| sit
-    // at the ends of [rmin, rmax]. If the range contains a zero or a sign change, the smallest nonzero |pA| is
-    // bounded below by |unit| when the offset is integral (|raw + off| >= 1), else nothing is known (the read fails).
+    // Exact-sum witness of a chunk from the extreme raw values: pA is monotone in raw (unit > 0 is checked by
+    // build_seq_list_kernel), so the extreme pA sit at the ends of [rmin, rmax]. The walker's arithmetic
+    // (widen_pos, the unguarded float shortcuts) needs every sample strictly positive: anything else publishes
+    // the smallest possible minimum, which fails the read (it is then redone by the sequential-order kernels).
     __device__ __forceinline__ void witness(int rmin, int rmax) const {
         const float xl = __fmul_rn(__fadd_rn((float)rmin, off), unit), xh = __fmul_rn(__fadd_rn((float)rmax, off), unit);
-        const uint32_t bl = __float_as_uint(xl), bh = __float_as_uint(xh);
-        const uint32_t al = bl & 0x7fffffffu, ah = bh & 0x7fffffffu;
-        const uint32_t mx = max(al, ah);
-        if (mx == 0u) return;  // every sample of the chunk is exactly 0
-        uint32_t mn;
-        if (al != 0u && ah != 0u && ((bl ^ bh) >> 31) == 0u) {
-            mn = min(al, ah);
-        } else {
-            const bool integral = off == truncf(off) && fabsf(off) < 8388608.0f;
-            mn = integral ? (__float_as_uint(unit) & 0x7fffffffu) : 1u;
-            if (mn == 0u) mn = 1u;
-        }
-        atomicMin(wit_min, mn);
-        atomicMax(wit_max, mx);
+        const uint32_t al = __float_as_uint(xl) & 0x7fffffffu, ah = __float_as_uint(xh) & 0x7fffffffu;
+        atomicMin(wit_min, xl > 0.0f ? al : 1u);
+        atomicMax(wit_max, max(al, ah));
     }
 };
 

@@ -63,6 +63,15 @@ SGW_HD float rsqrt_seed(float a) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
     return y;
 }
+// (double)a for a POSITIVE NORMAL float, exactly, with one integer multiply-add on the FMA pipe instead of a
+// conversion on the (16 lanes/clk/SM) XU pipe: double bits = float bits * 2^29 + (1023-127) * 2^52.
+// Any other input gives garbage; callers only use the result where the input is known to be positive and normal.
+SGW_HD double widen_pos(float a) {
+    return __longlong_as_double((long long)((unsigned long long)__float_as_uint(a) * 0x20000000ull + 0x3800000000000000ull));
+}
+SGW_HD double widen_abs(float a) {  // (double)fabsf(a), a normal and nonzero
+    return __longlong_as_double((long long)((unsigned long long)(__float_as_uint(a) & 0x7fffffffu) * 0x20000000ull + 0x3800000000000000ull));
+}
 #else
 SGW_HD double dadd(double a, double b) { return a + b; }
 SGW_HD double dsub(double a, double b) { return a - b; }
@@ -80,6 +89,16 @@ SGW_HD uint32_t d_hi(double a) { uint64_t b; memcpy(&b, &a, 8); return (uint32_t
 SGW_HD uint32_t d_lo(double a) { uint64_t b; memcpy(&b, &a, 8); return (uint32_t)b; }
 SGW_HD uint32_t f_bits(float a) { uint32_t b; memcpy(&b, &a, 4); return b; }
 SGW_HD float rsqrt_seed(float a) { return (float)(1.0 / sqrt((double)a)); }  // the guard below absorbs +-4 ulp
+SGW_HD double widen_pos(float a) {  // same bit arithmetic as the device version (garbage for non-positive / denormal a)
+    uint32_t b; memcpy(&b, &a, 4);
+    const uint64_t v = (uint64_t)b * 0x20000000ull + 0x3800000000000000ull;
+    double r; memcpy(&r, &v, 8); return r;
+}
+SGW_HD double widen_abs(float a) {
+    uint32_t b; memcpy(&b, &a, 4);
+    const uint64_t v = (uint64_t)(b & 0x7fffffffu) * 0x20000000ull + 0x3800000000000000ull;
+    double r; memcpy(&r, &v, 8); return r;
+}
 #endif
 
 // ---- parameters (events.c:35-54) ----------------------------------------------------------------------------------
@@ -118,58 +137,103 @@ SGW_HD float fdivw(float a) {
     return ffma(e, r, q0);
 }
 
-// the reference's own operations for the last step (events.c:355-360); taken by about 2 values in a million
-template <int W>
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#else
-inline
-#endif
-float tail_ieee(float delta, float cv) {
-    if (delta == 0.0f) return 0.0f;  // (float)(0.0 / sqrt(c)) = +0 for c > 0
-    const float scaled = fdiv(cv, (float)W);
-    return d2f(ddiv(fabs((double)delta), dsqrt((double)scaled)));
-}
-
 // t = (float)(fabs((double)delta) / sqrt((double)(cv / W)))  (events.c:360) through a 22-bit reciprocal square
 // root and one third-order correction in double. The product is within a few ulp(double) of the true quotient,
 // so it rounds to the same float as the reference's doubly rounded value unless it lies next to a float rounding
-// midpoint or outside the normal float range; those values take tail_ieee (oracle/proofs/tstat_tail_check.c).
+// midpoint or outside the normal float range (oracle/proofs/tstat_tail_check.c); such values (about 2 in a
+// million) raise `bad`, and the caller recomputes the block's t-statistics with the reference's own operations
+// (exact_block). delta == 0 gives +0 on both routes whatever cv is (flat stretches of the signal).
 template <int W>
-SGW_HD float tail(float delta, float cv) {
+SGW_HD float tail(float delta, float cv, bool& bad) {
     const float scaled = fdivw<W>(cv);  // cv >= FLT_MIN > 0; shortcut valid for cv >= 1e-36
-    const double c = (double)scaled;
-    const double y0 = (double)rsqrt_seed(scaled);
+    const double c = widen_pos(scaled);
+    const double y0 = widen_pos(rsqrt_seed(scaled));
     const double t = dmul(c, y0);
     const double e = dfma(-t, y0, 1.0);
     const double p = dfma(0.375, e, 0.5);
     const double ye = dmul(y0, e);
     const double y = dfma(ye, p, y0);
-    const double q = dmul(fabs((double)delta), y);
+    const double q = dmul(widen_abs(delta), y);
     const uint32_t lo = d_lo(q), hi = d_hi(q);
     // accept when 2^-126 <= q < 2^126, the 29 bits below float precision are not within 512 of the midpoint,
-    // and scaled >= 1e-30 (cv >= 2e-29 implies it for W <= 14). delta == 0 gives q = 0: rejected, tail_ieee -> +0.
+    // and scaled >= 1e-30 (cv >= 2e-29 implies it for W <= 14)
     const bool in_range = (hi - ((1023u - 126u) << 20)) < (252u << 20);
     const bool off_mid = ((lo & 0x1fffffffu) - (0x10000000u - 512u)) >= 1024u;
-    if (!(in_range && off_mid && cv >= 2.0e-29f)) return tail_ieee<W>(delta, cv);
-    return d2f(q);
+    const bool zero = delta == 0.0f;
+    bad = bad | !(zero | (in_range & off_mid & (cv >= 2.0e-29f)));
+    return zero ? 0.0f : d2f(q);
 }
 
 // The terms of events.c:339-350 that depend on ONE window [j, j+W) only. The window is the right window of
 // position j (sum2/sumsq2, narrowed to float at once) and the left window of position j+W (kept in double).
+// The float products and quotients widened here are positive and normal for every window that lies inside a
+// read that passed the witness (all pA > 0, >= 2^-60).
 template <int W>
 SGW_HD void window_terms(double D, double E, float& A, double& Lq, float& B, double& Vd, double& B2d) {
     A = d2f(ddivw<W>(D));                                 // mean1 = (float)(sum1 / w)
-    Lq = dsub(ddivw<W>(E), (double)fmul(A, A));           // sumsq1/w - (double)(mean1*mean1)
+    Lq = dsub(ddivw<W>(E), widen_pos(fmul(A, A)));        // sumsq1/w - (double)(mean1*mean1)
     B = fdivw<W>(d2f(D));                                 // mean2 = (float)sum2 / w
-    Vd = (double)fdivw<W>(d2f(E));                        // (double)((float)sumsq2 / w)
-    B2d = (double)fmul(B, B);                             // (double)(mean2*mean2)
+    Vd = widen_pos(fdivw<W>(d2f(E)));                     // (double)((float)sumsq2 / w)
+    B2d = widen_pos(fmul(B, B));                          // (double)(mean2*mean2)
 }
 template <int W>
-SGW_HD float tstat_from(float A_left, double L_left, float B, double Vd, double B2d) {
+SGW_HD float tstat_from(float A_left, double L_left, float B, double Vd, double B2d, bool& bad) {
     const double acc = dsub(dadd(L_left, Vd), B2d);       // ((.. - m1sq) + v2) - m2sq, left to right in double
     const float cv = fmaxf(d2f(acc), FLT_MIN);            // events.c:353
-    return tail<W>(fsub(B, A_left), cv);                  // delta = mean2 - mean1
+    return tail<W>(fsub(B, A_left), cv, bad);             // delta = mean2 - mean1
+}
+
+// ---- the reference's own operation sequence, from the raw samples (rare path) ---------------------------------------
+template <class Io>
+SGW_HD float sample_pa(const Io& io, int i, int n, float off, float unit) {
+    if (i < 0 || i >= n) return 0.0f;
+    int v[4];
+    io.load8(i & ~7, v);
+    const int q = i & 7;
+    const int word = q < 2 ? v[0] : q < 4 ? v[1] : q < 6 ? v[2] : v[3];
+    const int raw = (q & 1) ? (word >> 16) : (int)(int16_t)(word & 0xffff);
+    return fmul(fadd((float)raw, off), unit);
+}
+template <class Io>
+SGW_HD void window_sums(const Io& io, int a, int w, int n, float off, float unit, double& S, double& Q) {
+    S = 0.0; Q = 0.0;
+    for (int i = a; i < a + w; i++) {
+        const float x = sample_pa(io, i, n, off, unit);
+        S = dadd(S, (double)x);
+        Q = dadd(Q, (double)fmul(x, x));
+    }
+}
+// events.c:338-361 for position i with window length w (the sums are exact, so forming them per window is the
+// same as the reference's prefix differences)
+template <class Io>
+SGW_HD float tstat_exact(const Io& io, int i, int w, int n, float off, float unit) {
+    double sum1, ssq1, sum2d, ssq2d;
+    window_sums(io, i - w, w, n, off, unit, sum1, ssq1);
+    window_sums(io, i, w, n, off, unit, sum2d, ssq2d);
+    const float wf = (float)w;
+    const float sum2 = d2f(sum2d), ssq2 = d2f(ssq2d);
+    const float mean1 = d2f(ddiv(sum1, (double)wf));
+    const float mean2 = fdiv(sum2, wf);
+    double acc = ddiv(ssq1, (double)wf);
+    acc = dsub(acc, (double)fmul(mean1, mean1));
+    acc = dadd(acc, (double)fdiv(ssq2, wf));
+    acc = dsub(acc, (double)fmul(mean2, mean2));
+    const float cv = fmaxf(d2f(acc), FLT_MIN);
+    const float delta = fsub(mean2, mean1);
+    return d2f(ddiv(fabs((double)delta), dsqrt((double)fdiv(cv, wf))));
+}
+// recompute the t-statistics of one block: t1v[m] (m >= m1) belongs to position tau0+m-w1+1, t2v[m] to tau0+m-w2+1
+template <int RNA, class Io>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void exact_block(const Io& io, int tau0, int n, float off, float unit, int m1, int want_t2, float* t1v, float* t2v) {
+    using C = Cfg<RNA>;
+    for (int m = m1; m < C::U; m++) t1v[m] = tstat_exact(io, tau0 + m - C::w1 + 1, C::w1, n, off, unit);
+    if (want_t2)
+        for (int m = 0; m < C::U; m++) t2v[m] = tstat_exact(io, tau0 + m - C::w2 + 1, C::w2, n, off, unit);
 }
 
 // ---- the dual peak detector (events.c:371-443) --------------------------------------------------------------------
@@ -216,7 +280,7 @@ SGW_HD void det_step(WalkDet& d, int u, float c1, float c2, bool rec, Sink& sink
         d.l_pp = maskl ? -1 : d.l_pp;
         d.l_pv = maskl ? FLT_MAX : d.l_pv;
         d.l_valid = maskl ? 0 : d.l_valid;
-        if (emit & rec) sink.peak(pp2);
+        sink.peak_if(pp2, emit & rec);
         const bool setc = none ? (lt | rise) : (gt | emit);
         d.s_pv = setc ? c1 : d.s_pv;
         d.s_pp = none ? (rise ? u : -1) : (emit ? -1 : pp2);
@@ -233,7 +297,7 @@ SGW_HD void det_step(WalkDet& d, int u, float c1, float c2, bool rec, Sink& sink
         const bool big = pv2 > thr_long<RNA>();
         const bool valid2 = (d.l_valid != 0) | (drop & big);
         const bool emit = act & !none & valid2 & ((u - pp2) > w2 / 2);
-        if (emit & rec) sink.peak(pp2);
+        sink.peak_if(pp2, emit & rec);
         const bool setc = act & (none ? (lt | rise) : (gt | emit));
         d.l_pv = setc ? c2 : d.l_pv;
         const int ppn = none ? (rise ? u : -1) : (emit ? -1 : pp2);
@@ -250,12 +314,14 @@ struct Rings {
     double D1[C::R1], E1[C::R1];   // short-window sums by window start
     float A1[C::R1];               // left-window terms of the short window by window start
     double L1[C::R1];
-    float T1[C::R1];               // t1 by position
+    float T1c[C::w1];              // t1 of the last w1 positions of the previous block
     float A2[C::R2];               // left-window terms of the long window by window start
     double L2[C::R2];
     SGW_HD void clear() {
 #pragma unroll
-        for (int k = 0; k < C::R1; k++) { P[k] = 0.0; PQ[k] = 0.0; D1[k] = 0.0; E1[k] = 0.0; A1[k] = 0.0f; L1[k] = 0.0; T1[k] = 0.0f; }
+        for (int k = 0; k < C::R1; k++) { P[k] = 0.0; PQ[k] = 0.0; D1[k] = 0.0; E1[k] = 0.0; A1[k] = 0.0f; L1[k] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < C::w1; k++) T1c[k] = 0.0f;
 #pragma unroll
         for (int k = 0; k < C::R2; k++) { A2[k] = 0.0f; L2[k] = 0.0; }
     }
@@ -263,56 +329,88 @@ struct Rings {
 
 // What one block does: KIND 0 = sums and window terms only, 1 = additionally t1 for the positions the first
 // detector step will need, 2 = everything (both t-statistics and the detector).
+// Phase 1 computes the block's t-statistics without a single branch; phase 2 steps the detector through them.
 // EDGE: the block may touch positions outside the read [0, n): samples there count as 0, t is 0 outside
 // w <= i <= n-w (events.c:328-338), the detector only steps positions 1 <= p < n (position 0 is masked: 387).
 //   x[m]   : pA of sample tau0 + m (0 outside the read when EDGE)
-//   tau0   : read index of the block's first sample, a multiple of U (may be negative only when EDGE... never: see walk.cu)
+//   tau0   : read index of the block's first sample, a multiple of U
 //   sh     : read_off & 31
-template <int RNA, int KIND, bool EDGE, class Sink>
+template <int RNA, int KIND, bool EDGE, class Io>
 SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U], int tau0, int n, int sh, bool rec,
-                       Sink& sink) {
+                       float off, float unit, Io& io) {
     using C = Cfg<RNA>;
-    constexpr int w1 = C::w1, w2 = C::w2, M1 = C::R1 - 1, M2 = C::R2 - 1;
+    constexpr int w1 = C::w1, w2 = C::w2, M1 = C::R1 - 1, M2 = C::R2 - 1, U = C::U;
+    float t1v[U], t2v[U];
+    bool bad = false;
 #pragma unroll
-    for (int m = 0; m < C::U; m++) {
+    for (int m = 0; m < U; m++) {
         // static ring slots: every index below is (m + const) & mask because tau0 is a multiple of U
-        const int j = tau0 + m;
-        const double xd = (double)x[m];
-        const double qd = (double)fmul(x[m], x[m]);                 // float square, widened afterwards (events.c:301)
-        const double pn = dadd(g.P[m & M1], xd), pqn = dadd(g.PQ[m & M1], qd);
+        const double xd = widen_pos(x[m]);
+        const double qd = widen_pos(fmul(x[m], x[m]));              // float square, widened afterwards (events.c:301)
+        const double pn = dadd(g.P[m & M1], EDGE ? (x[m] > 0.0f ? xd : 0.0) : xd);
+        const double pqn = dadd(g.PQ[m & M1], EDGE ? (x[m] > 0.0f ? qd : 0.0) : qd);
         g.P[(m + 1) & M1] = pn;
         g.PQ[(m + 1) & M1] = pqn;
-        // short window [j1, j1+w1), j1 = j - w1 + 1
-        const int j1 = j - w1 + 1;
+        // short window [j1, j1+w1), j1 = tau0 + m - w1 + 1
         const int s1 = (m - w1 + 1) & M1;                           // slot of j1
         const int s1l = (m - 2 * w1 + 1) & M1;                      // slot of j1 - w1
         const double d1 = dsub(pn, g.P[s1]), e1 = dsub(pqn, g.PQ[s1]);
         float a1, b1; double l1, v1, b1sq;
         window_terms<w1>(d1, e1, a1, l1, b1, v1, b1sq);
         // long window [j2, j2+w2) = short(j2) + short(j1), j2 = j1 - w1
-        const int j2 = j1 - w1;
         const int s2 = (m - 2 * w1 + 1) & M2;                       // slot of j2
         const int s2l = (m - 2 * w1 + 1 - w2) & M2;                 // slot of j2 - w2
         const double d2 = dadd(g.D1[s1l], d1), e2 = dadd(g.E1[s1l], e1);
         float a2, b2; double l2, v2, b2sq;
         window_terms<w2>(d2, e2, a2, l2, b2, v2, b2sq);
-        if (KIND == 2 || (KIND == 1 && m >= C::U - w1)) {
-            float t1 = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq);
-            if (EDGE) t1 = (j1 >= w1 && j1 + w1 <= n) ? t1 : 0.0f;
-            if (KIND == 2) {
-                float t2 = tstat_from<w2>(g.A2[s2l], g.L2[s2l], b2, v2, b2sq);
-                if (EDGE) t2 = (j2 >= w2 && j2 + w2 <= n) ? t2 : 0.0f;
-                const float c1 = g.T1[s1l];                         // t1(j2), computed w1 samples ago
-                if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, j2 + sh, c1, t2, rec, sink);
-            }
-            g.T1[s1] = t1;
+        if (KIND == 2 || (KIND == 1 && m >= U - w1)) {
+            bool bd = false;
+            t1v[m] = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, bd);
+            if (EDGE) { const int j1 = tau0 + m - w1 + 1; bd = bd & (j1 >= w1) & (j1 + w1 <= n); }
+            bad = bad | bd;
+        }
+        if (KIND == 2) {
+            bool bd = false;
+            t2v[m] = tstat_from<w2>(g.A2[s2l], g.L2[s2l], b2, v2, b2sq, bd);
+            if (EDGE) { const int j2 = tau0 + m - w2 + 1; bd = bd & (j2 >= w2) & (j2 + w2 <= n); }
+            bad = bad | bd;
         }
         g.D1[s1] = d1; g.E1[s1] = e1;
         g.A1[s1] = a1; g.L1[s1] = l1;
         g.A2[s2] = a2; g.L2[s2] = l2;
     }
+    if (KIND >= 1) {
+        if (bad) {  // rare: the copies keep t1v / t2v in registers (only e1 / e2 live in local memory)
+            float e1[U], e2[U];
+            exact_block<RNA>(io, tau0, n, off, unit, KIND == 2 ? 0 : U - w1, KIND == 2 ? 1 : 0, e1, e2);
+#pragma unroll
+            for (int m = 0; m < U; m++) {
+                if (KIND == 2 || m >= U - w1) t1v[m] = e1[m];
+                if (KIND == 2) t2v[m] = e2[m];
+            }
+        }
+        if (EDGE) {
+#pragma unroll
+            for (int m = 0; m < U; m++) {
+                const int j1 = tau0 + m - w1 + 1, j2 = tau0 + m - w2 + 1;
+                if (KIND == 2 || m >= U - w1) t1v[m] = (j1 >= w1 && j1 + w1 <= n) ? t1v[m] : 0.0f;
+                if (KIND == 2) t2v[m] = (j2 >= w2 && j2 + w2 <= n) ? t2v[m] : 0.0f;
+            }
+        }
+    }
+    if (KIND == 2) {
+#pragma unroll
+        for (int m = 0; m < U; m++) {
+            const int j2 = tau0 + m - w2 + 1;
+            const float c1 = m >= w1 ? t1v[m - w1] : g.T1c[m];     // t1(j2), computed w1 samples ago
+            if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, j2 + sh, c1, t2v[m], rec, io);
+        }
+    }
+    if (KIND >= 1) {
+#pragma unroll
+        for (int k = 0; k < w1; k++) g.T1c[k] = t1v[U - w1 + k];
+    }
 }
-
 
 // ---- chunk drivers -------------------------------------------------------------------------------------------------
 // Every read is cut into chunks of L samples; the last chunk takes the remainder (L..2L-1 samples), a read
@@ -362,16 +460,16 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
     int v[4];
 #pragma unroll
     for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
-    walk_block<RNA, 0, false>(g, d, x, tau, n, sh, false, io);
+    walk_block<RNA, 0, false>(g, d, x, tau, n, sh, false, off, unit, io);
     tau += U;
 #pragma unroll
     for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
-    walk_block<RNA, 1, false>(g, d, x, tau, n, sh, false, io);
+    walk_block<RNA, 1, false>(g, d, x, tau, n, sh, false, off, unit, io);
     tau += U;
     for (; tau < s0; tau += U) {                     // detector warm-up
 #pragma unroll
         for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
-        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, false, io);
+        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, false, off, unit, io);
     }
     io.put_begin(canon_of(d, s0 - C::LAG + sh));
     uint32_t vmin = 0x7fff7fffu, vmax = 0x80008000u;  // packed int16 min / max of the owned samples
@@ -386,7 +484,7 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
             cvt8(v, off, unit, x + 8 * h);
             if (pa) io.store_pa8(tau + 8 * h, x + 8 * h);
         }
-        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, true, io);
+        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, true, off, unit, io);
     }
     io.put_end(canon_of(d, s1 - C::LAG + sh));
     const int rmin0 = (int)(int16_t)(vmin & 0xffffu), rmin1 = (int)vmin >> 16;
@@ -440,21 +538,21 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
         tau = s0 - W - C::FILL * U;  // >= 0 because L >= W + 2U
         det_cold(d, tau + C::FILL * U - C::LAG + sh);
         load(tau, false);
-        walk_block<RNA, 0, true>(g, d, x, tau, n, sh, false, io);
+        walk_block<RNA, 0, true>(g, d, x, tau, n, sh, false, off, unit, io);
         tau += U;
         load(tau, false);
-        walk_block<RNA, 1, true>(g, d, x, tau, n, sh, false, io);
+        walk_block<RNA, 1, true>(g, d, x, tau, n, sh, false, off, unit, io);
         tau += U;
         for (; tau < s0; tau += U) {
             load(tau, false);
-            walk_block<RNA, 2, true>(g, d, x, tau, n, sh, false, io);
+            walk_block<RNA, 2, true>(g, d, x, tau, n, sh, false, off, unit, io);
         }
         io.put_begin(canon_of(d, s0 - C::LAG + sh));
     }
     const int step_end = to_end ? n : s1 - C::LAG;  // owned blocks: until every owned step has been taken
     for (; tau - C::LAG < step_end; tau += U) {
         load(tau, true);
-        walk_block<RNA, 2, true>(g, d, x, tau, n, sh, true, io);
+        walk_block<RNA, 2, true>(g, d, x, tau, n, sh, true, off, unit, io);
     }
     if (!to_end) io.put_end(canon_of(d, s1 - C::LAG + sh));
     if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)

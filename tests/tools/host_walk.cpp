@@ -26,6 +26,7 @@ struct HostIo {
     void store_pa8(int t, const float* x) const { memcpy(pa + t, x, 32); }
     void store_pa1(int t, float x) const { pa[t] = x; }
     void peak(int pos) const { bm[pos >> 5] |= 1u << (pos & 31); }
+    void peak_if(int pos, bool on) const { if (on) peak(pos); }
     void put_begin(const Canon& c) const { *begin = c; }
     void put_end(const Canon& c) const { *end = c; }
     void witness(int lo, int hi) const { if (lo < *rmin) *rmin = lo; if (hi > *rmax) *rmax = hi; }
