@@ -275,11 +275,6 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     // one eighth of the batch otherwise (reads that fail the fast path's checks are rare)
     sc.gen_cap = (max_samples <= (64ull << 20) || (flags & SGPU_F_FORCE_GENERIC)) ? max_samples : max_samples / 8;
     if (const char* e = getenv("SGPU_GEN_CAP")) { uint64_t v = strtoull(e, nullptr, 10); if (v) sc.gen_cap = v; }
-    if (fast_configure() != 0) {
-        snprintf(ctx->err, sizeof ctx->err, "cudaFuncSetAttribute(max dynamic shared memory) failed");
-        fprintf(stderr, "[sigtk_b200] %s\n", ctx->err);
-        return fail(SGPU_E_CUDA);
-    }
     CUC(dev_alloc(&sc.Sinc, sc.gen_cap));
     CUC(dev_alloc(&sc.Qinc, sc.gen_cap));
     CUC(dev_alloc(&sc.t1, sc.gen_cap));

@@ -1,0 +1,170 @@
+// emit.cu -- emit_events_kernel: the event table (create_events / create_event, events.c:457-504) from the
+// event-start bitmap. One WARP per 1024 consecutive samples of the flat array (32 bitmap words), no block-level
+// barriers, no scan over the samples:
+//
+//   1. every lane takes one bitmap word; a warp scan of the popcounts gives every event start its index in the
+//      warp tile, and the lanes scatter the start positions into a warp-private list in shared memory;
+//   2. the events are dealt to the lanes in order (event j0+lane): start = list[j], end = list[j+1] (or the next
+//      set bit after the tile, or the end of the read), and the lane sums its few samples (mean event length ~5)
+//      directly from global memory. Consecutive lanes read consecutive samples and write consecutive event slots.
+//
+// The sums are exact (see walk_core.cuh), so summing every event on its own gives the reference's bits.
+#include "kernels.cuh"
+#include "walk_core.cuh"
+
+namespace sgpu {
+
+namespace {
+
+constexpr int EWT = 1024;                // samples per warp tile
+constexpr int EWARPS = 8;                // warps per CTA
+constexpr int ELIST = EWT / 2 + 8;       // event starts are >= 3 samples apart inside a read; tiny reads add their starts
+constexpr int ELONG = 48;                // an event longer than this is finished by the whole warp
+
+// read that contains flat position p of a 2048-sample tile whose first candidate read is r0 (tile_read0)
+__device__ __forceinline__ uint32_t locate_read(const DevBatch& b, uint32_t r0, uint64_t p) {
+    uint32_t r = r0;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+        if (r + 1 >= b.n_reads || b.read_off[r + 1] > p) return r;
+        r++;
+    }
+    return find_read(b.read_off, b.n_reads, p);
+}
+
+__device__ __forceinline__ void add_sample(const int16_t* __restrict__ samples, long long i, float off, float unit,
+                                           double& as, double& aq) {
+    const float x = __fmul_rn(__fadd_rn((float)(int)__ldg(samples + i), off), unit);
+    // widen_pos: exact for the positive pA of every read that keeps the fast path's results (walk_core.cuh)
+    as = __dadd_rn(as, walk::widen_pos(x));
+    aq = __dadd_rn(aq, walk::widen_pos(__fmul_rn(x, x)));
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, uint32_t n_tiles,
+                                                                  const uint32_t* __restrict__ bitmap,
+                                                                  const uint64_t* __restrict__ tile_base, uint64_t ev_cap,
+                                                                  uint32_t* __restrict__ ev_start,
+                                                                  float* __restrict__ ev_mean, float* __restrict__ ev_stdv,
+                                                                  int* __restrict__ status,
+                                                                  const uint32_t* __restrict__ tile_read0) {
+    __shared__ uint16_t s_list[EWARPS][ELIST];
+    const int lane = threadIdx.x & 31;
+    uint16_t* __restrict__ list = s_list[threadIdx.x >> 5];
+    const uint64_t n_wt = (uint64_t)n_tiles * (FAST_TILE / EWT);
+    const uint64_t n_words = (uint64_t)n_tiles * (FAST_TILE / 32);
+    const uint64_t warp0 = (uint64_t)blockIdx.x * EWARPS + (threadIdx.x >> 5), n_warps = (uint64_t)gridDim.x * EWARPS;
+    const long long span = (long long)b.span;
+    for (uint64_t wt = warp0; wt < n_wt; wt += n_warps) {
+        const long long flat0 = (long long)wt * EWT;
+        if (flat0 >= span) break;
+        const uint32_t tile = (uint32_t)(wt / (FAST_TILE / EWT)), half = (uint32_t)(wt % (FAST_TILE / EWT));
+        const uint32_t word = bitmap[wt * 32 + lane];
+        uint32_t before = half ? (uint32_t)__popc(bitmap[(uint64_t)tile * (FAST_TILE / 32) + lane]) : 0u;
+        before = __reduce_add_sync(0xffffffffu, before);  // FAST_TILE / EWT == 2: at most one warp tile before this one
+        uint32_t incl = __popc(word);
+        const uint32_t own = incl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0u) continue;
+        if (total > (uint32_t)ELIST) { total = ELIST; if (lane == 0) atomicExch(status, SGPU_DEV_E_EVCAP); }  // malformed bitmap
+        __syncwarp();  // the previous tile's readers are done with the list
+        {
+            uint32_t rem = word, idx = incl - own;
+            while (rem) {
+                if (idx < (uint32_t)ELIST) list[idx] = (uint16_t)(lane * 32 + __ffs(rem) - 1);
+                idx++;
+                rem &= rem - 1u;
+            }
+        }
+        __syncwarp();
+        const uint64_t kbase = tile_base[tile] + before;
+        const uint32_t r0 = tile_read0[tile];
+        for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool have = j < total;
+            long long i = 0, e = 0, rs = 0;
+            float off = 0.0f, unit = 0.0f;
+            double as = 0.0, aq = 0.0;
+            uint32_t len = 0;
+            if (have) {
+                const long long s = flat0 + list[j];
+                const uint32_t r = locate_read(b, r0, (uint64_t)s);
+                rs = (long long)b.read_off[r];
+                const long long rend = rs + (long long)b.read_len[r];
+                off = b.offset[r];
+                unit = b.unit[r];
+                if (j + 1 < total) {
+                    e = flat0 + list[j + 1];
+                } else {  // the next event start lies after this warp tile (or the read ends first)
+                    e = rend;
+                    for (uint64_t w = (wt + 1) * 32; w < n_words && (long long)(w << 5) < rend; w++) {
+                        const uint32_t nx = bitmap[w];
+                        if (nx) { e = (long long)(w << 5) + __ffs(nx) - 1; break; }
+                    }
+                }
+                if (e > rend) e = rend;
+                len = (uint32_t)(e - s);
+                i = s;
+                const long long stop = e - s > ELONG ? s + ELONG : e;
+                for (; i < stop; i++) add_sample(b.samples, i, off, unit, as, aq);
+            }
+            // long events (rare): the whole warp sums the rest
+            uint32_t longs = __ballot_sync(0xffffffffu, have && i < e);
+            while (longs) {
+                const int src = __ffs(longs) - 1;
+                longs &= longs - 1u;
+                const long long li = __shfl_sync(0xffffffffu, i, src), le = __shfl_sync(0xffffffffu, e, src);
+                const float lo = __shfl_sync(0xffffffffu, off, src), lu = __shfl_sync(0xffffffffu, unit, src);
+                double ps = 0.0, pq = 0.0;
+                for (long long p = li + lane; p < le; p += 32) add_sample(b.samples, p, lo, lu, ps, pq);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, o));
+                    pq = __dadd_rn(pq, __shfl_xor_sync(0xffffffffu, pq, o));
+                }
+                if (lane == src) { as = __dadd_rn(as, ps); aq = __dadd_rn(aq, pq); }
+            }
+            if (have) {
+                const uint64_t k = kbase + j;
+                if (k >= ev_cap) { atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
+                float mean, stdv;
+                event_stats(as, aq, len, &mean, &stdv);
+                ev_start[k] = (uint32_t)(e - (long long)len - rs);
+                ev_mean[k] = mean;
+                ev_stdv[k] = stdv;
+            }
+        }
+    }
+}
+
+static inline int grid_cap(uint64_t work, int block, int max_blocks) {
+    uint64_t g = (work + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (uint64_t)max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+__global__ void __launch_bounds__(256) sum_fixups_kernel(uint32_t n_reads, const uint32_t* __restrict__ fixups,
+                                                         unsigned long long* __restrict__ counters) {
+    unsigned long long acc = 0;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += gridDim.x * blockDim.x) acc += fixups[r];
+    if (acc) atomicAdd(&counters[2], acc);
+}
+
+int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* ev_start, float* ev_mean,
+                     float* ev_stdv, const uint32_t* fixups, int sm_count, cudaStream_t st) {
+    const uint32_t n_tiles = fast_tiles_for(b.span);
+    const uint64_t n_wt = (uint64_t)n_tiles * (FAST_TILE / EWT);
+    emit_events_kernel<<<grid_cap(n_wt, EWARPS, sm_count * 8), EWARPS * 32, 0, st>>>(
+        b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0);
+    sum_fixups_kernel<<<grid_cap(b.n_reads, 256, sm_count * 4), 256, 0, st>>>(b.n_reads, fixups, sc.counters);
+    return 2;
+}
+
+}  // namespace sgpu

@@ -54,8 +54,7 @@ int launch_generic_emit(const DevBatch& b, const WorkList& wl, Scratch& sc, cons
 int launch_scan_u32(const uint32_t* cnt, uint32_t n, uint64_t* off, uint64_t* total_out, Scratch& sc, cudaStream_t st);
 uint32_t scan_tiles_for(uint32_t n);
 
-// fast.cu (tiled fast path)
-int fast_configure();
+// fast.cu (witness evaluation, event ranks) and emit.cu (event table)
 uint32_t fast_tiles_for(uint64_t span);
 int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
                       cudaStream_t st);
