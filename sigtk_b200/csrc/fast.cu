@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) build_seq_list_kernel(DevBatch b, const u
         bool flag = force_all || seq_flag[r] != 0u;
         // the walker's unguarded shortcuts need unit > 0 (no -0 sums) and 32-bit positions with headroom
         const float unit = b.unit[r];
-        if (!(unit > 0.0f && unit <= FLT_MAX) || n >= (1u << 30)) flag = true;
+        if (!(unit > 0.0f && unit <= FLT_MAX) || n >= (1u << 30) - 64u) flag = true;
         if (!flag && n > 0) {
             const uint32_t mn = wit_min[r], mx = wit_max[r];
             // every sample must be a positive float >= 2^-60 (the range of the walker's shortcuts) ...

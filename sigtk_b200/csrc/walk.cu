@@ -25,7 +25,13 @@ namespace {
 
 using namespace walk;
 
-constexpr int WNT = 128;  // threads per block of walk_chunks_kernel
+#ifndef WALK_NT
+#define WALK_NT 128
+#endif
+#ifndef WALK_MINB
+#define WALK_MINB 4
+#endif
+constexpr int WNT = WALK_NT;  // threads per block of walk_chunks_kernel
 
 struct WalkParams {
     DevBatch b;
@@ -63,9 +69,13 @@ struct DevIo {
     }
     __device__ __forceinline__ void store_pa1(int t, float x) const { pa[t] = x; }
     __device__ __forceinline__ void peak(int pos) const { atomicOr(bm + ((uint32_t)pos >> 5), 1u << (pos & 31)); }
-    __device__ __forceinline__ void peak_if(int pos, bool on) const {  // predicated RED: no branch in the walker's inner loop
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p red.global.or.b32 [%0], %1;\n\t}"
-                     :: "l"(bm + ((uint32_t)pos >> 5)), "r"(1u << (pos & 31)), "r"((int)on) : "memory");
+    __device__ __forceinline__ void peak_if(int pos, bool on) const {  // predicated RED; address = one wide multiply-add
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t.reg .u32 i;\n\t"
+                     "setp.ne.s32 p, %3, 0;\n\t"
+                     "shr.u32 i, %1, 5;\n\t"
+                     "mad.wide.u32 a, i, 4, %0;\n\t"
+                     "@p red.global.or.b32 [a], %2;\n\t}"
+                     :: "l"(bm), "r"(pos), "r"(1u << (pos & 31)), "r"((int)on) : "memory");
     }
     static __device__ __forceinline__ void store_canon(int* __restrict__ dst, const Canon& c) {
         int4* p = reinterpret_cast<int4*>(dst);
@@ -120,10 +130,12 @@ __device__ __forceinline__ uint32_t find_chunk_read(const uint64_t* __restrict__
 }
 
 template <int RNA>
-__global__ void __launch_bounds__(WNT, RNA ? 1 : 4) walk_chunks_kernel(const WalkParams p) {
+__global__ void __launch_bounds__(WNT, RNA ? 1 : WALK_MINB) walk_chunks_kernel(const WalkParams p) {
     if (blockIdx.x < p.edge_blocks) {
+        // first chunks of all reads, then last chunks: the lanes of a warp walk chunks of the same kind
         const uint64_t e = (uint64_t)blockIdx.x * WNT + threadIdx.x;
-        if (e < 2ull * p.b.n_reads) walk_edge_dev<RNA>(p, (uint32_t)(e >> 1), (int)(e & 1));
+        if (e < p.b.n_reads) walk_edge_dev<RNA>(p, (uint32_t)e, 0);
+        else if (e < 2ull * p.b.n_reads) walk_edge_dev<RNA>(p, (uint32_t)(e - p.b.n_reads), 1);
         return;
     }
     const uint64_t i = (uint64_t)(blockIdx.x - p.edge_blocks) * WNT + threadIdx.x;

@@ -158,7 +158,7 @@ SGW_HD float tail(float delta, float cv, bool& bad) {
     // accept when 2^-126 <= q < 2^126, the 29 bits below float precision are not within 512 of the midpoint,
     // and scaled >= 1e-30 (cv >= 2e-29 implies it for W <= 14)
     const bool in_range = (hi - ((1023u - 126u) << 20)) < (252u << 20);
-    const bool off_mid = ((lo & 0x1fffffffu) - (0x10000000u - 512u)) >= 1024u;
+    const bool off_mid = (lo * 8u - ((0x10000000u - 512u) << 3)) >= (1024u << 3);  // the low 29 bits, shifted up
     const bool zero = delta == 0.0f;
     bad = bad | !(zero | (in_range & off_mid & (cv >= 2.0e-29f)));
     return zero ? 0.0f : d2f(q);
@@ -238,14 +238,21 @@ void exact_block(const Io& io, int tau0, int n, float off, float unit, int m1, i
 
 // ---- the dual peak detector (events.c:371-443) --------------------------------------------------------------------
 // Positions are "shifted" read indices: index in the read + (read_off & 31), so that position >> 5 is a word of the
-// read's part of the event-start bitmap. NONE = -1 (a shifted position is never negative once a peak exists).
+// read's part of the event-start bitmap; they stay below 2^30 (reads of 2^30 samples or more take the
+// sequential-order kernels). One word `ps` per detector packs peak_pos and valid_peak of the reference's Detector
+// (events.c:269-281):   ps = PS_NONE              peak_pos == -1 (CASE 1 of events.c:393)
+//                       ps = peak_pos | PS_OPEN   CASE 2, valid_peak == false
+//                       ps = peak_pos             CASE 2, valid_peak == true
+// so that "valid_peak && i - peak_pos > w/2" (events.c:429) is the single comparison  i - ps > w/2.
+constexpr int PS_NONE = 0x7fffffff;
+constexpr int PS_OPEN = 0x40000000;
 struct WalkDet {
-    float s_pv; int s_pp; int s_valid;               // short detector (never masked after the read's first sample)
-    float l_pv; int l_pp; int l_valid; int l_mt;     // long detector; l_mt = masked_to
+    float s_pv; int s_ps;               // short detector (never masked after the read's first sample)
+    float l_pv; int l_ps; int l_mt;     // long detector; l_mt = masked_to
 };
 SGW_HD void det_cold(WalkDet& d, int first_step) {  // both detectors start at `first_step` from the reset state
-    d.s_pv = FLT_MAX; d.s_pp = -1; d.s_valid = 0;
-    d.l_pv = FLT_MAX; d.l_pp = -1; d.l_valid = 0; d.l_mt = first_step - 1;
+    d.s_pv = FLT_MAX; d.s_ps = PS_NONE;
+    d.l_pv = FLT_MAX; d.l_ps = PS_NONE; d.l_mt = first_step - 1;
 }
 
 // canonical form at boundary b (state before step b): 8 words, bit-comparable between the chunk that ends at b
@@ -253,57 +260,53 @@ SGW_HD void det_cold(WalkDet& d, int first_step) {  // both detectors start at `
 struct Canon { int v[8]; };
 SGW_HD Canon canon_of(const WalkDet& d, int b) {
     Canon c;
-    c.v[0] = (int)f_bits(d.s_pv); c.v[1] = d.s_pp; c.v[2] = (int)f_bits(d.l_pv); c.v[3] = d.l_pp;
+    c.v[0] = (int)f_bits(d.s_pv); c.v[1] = d.s_ps; c.v[2] = (int)f_bits(d.l_pv); c.v[3] = d.l_ps;
     c.v[4] = d.l_mt >= b ? d.l_mt : -1;
-    c.v[5] = (d.s_valid ? 1 : 0) | (d.l_valid ? 2 : 0);
-    c.v[6] = 0; c.v[7] = 0;
+    c.v[5] = 0; c.v[6] = 0; c.v[7] = 0;
     return c;
 }
 
-// One position of both detectors, short first (events.c:385-440). `Sink::peak(pos)` records an emitted peak.
+// One detector, one position (events.c:393-437). Returns true when a peak is emitted (*pos = its position).
+// `act` = the detector is not masked at u (events.c:387); the state is left untouched when !act.
+template <bool SHORT, int RNA>
+SGW_HD bool det_one(float& pv, int& ps, int u, float c, bool act, bool& big_case2, int& peak_if_big, int* pos) {
+    constexpr int w = SHORT ? Cfg<RNA>::w1 : Cfg<RNA>::w2;
+    const float h = peak_h<RNA>();
+    const float thr = SHORT ? thr_short<RNA>() : thr_long<RNA>();
+    const bool none = ps == PS_NONE;
+    const float df = fsub(c, pv);                          // > 0: above the running value, < 0: below
+    const bool gt = df > 0.0f, rise = df > h;
+    const bool lt_or_rise = (df < 0.0f) | rise;
+    const float pv2 = fmaxf(pv, c);                        // CASE 2: the running maximum
+    const int ps2 = gt ? ((ps & PS_OPEN) | u) : ps;        // a new maximum moves the peak, valid_peak is kept
+    const bool big = pv2 > thr;
+    const bool drop_big = (df < -h) & big;                 // pv - c > h (negation is exact) && pv > threshold
+    const int ps3 = drop_big ? (ps2 & ~PS_OPEN) : ps2;     // valid_peak = true
+    const bool emit = act & ((u - ps3) > w / 2);           // false in CASE 1 (ps3 >= 2^30 - 1) and while not valid
+    big_case2 = !none & big;
+    peak_if_big = ps2 & ~PS_OPEN;
+    *pos = ps3;
+    const bool setc = act & ((none & lt_or_rise) | (!none & (gt | emit)));
+    pv = setc ? c : pv;
+    const int ps_case1 = rise ? (u | PS_OPEN) : PS_NONE;
+    const int ps_case2 = emit ? PS_NONE : ps3;
+    ps = act ? (none ? ps_case1 : ps_case2) : ps;
+    return emit;
+}
+
+// One position of both detectors, short first (events.c:385-440). `Sink::peak_if(pos, on)` records an emitted peak.
 template <int RNA, class Sink>
 SGW_HD void det_step(WalkDet& d, int u, float c1, float c2, bool rec, Sink& sink) {
-    constexpr int w1 = Cfg<RNA>::w1, w2 = Cfg<RNA>::w2;
-    const float h = peak_h<RNA>();
-    {   // short detector, always active
-        const bool none = d.s_pp < 0;
-        const float df = fsub(c1, d.s_pv);                // > 0: above the running value, < 0: below
-        const bool gt = df > 0.0f, lt = df < 0.0f;
-        const bool rise = df > h, drop = df < -h;         // pv - c > h  <=>  c - pv < -h (negation is exact)
-        const float pv2 = gt ? c1 : d.s_pv;               // CASE 2: new maximum
-        const int pp2 = gt ? u : d.s_pp;
-        const bool big = pv2 > thr_short<RNA>();
-        const bool valid2 = (d.s_valid != 0) | (drop & big);
-        const bool emit = !none & valid2 & ((u - pp2) > w1 / 2);
-        const bool maskl = !none & big;                   // the short detector dominates the long one (414-422)
-        d.l_mt = maskl ? pp2 + w1 : d.l_mt;
-        d.l_pp = maskl ? -1 : d.l_pp;
-        d.l_pv = maskl ? FLT_MAX : d.l_pv;
-        d.l_valid = maskl ? 0 : d.l_valid;
-        sink.peak_if(pp2, emit & rec);
-        const bool setc = none ? (lt | rise) : (gt | emit);
-        d.s_pv = setc ? c1 : d.s_pv;
-        d.s_pp = none ? (rise ? u : -1) : (emit ? -1 : pp2);
-        d.s_valid = (!none & valid2 & !emit) ? 1 : 0;
-    }
-    {   // long detector, skipped while masked
-        const bool act = d.l_mt < u;
-        const bool none = d.l_pp < 0;
-        const float df = fsub(c2, d.l_pv);
-        const bool gt = df > 0.0f, lt = df < 0.0f;
-        const bool rise = df > h, drop = df < -h;
-        const float pv2 = gt ? c2 : d.l_pv;
-        const int pp2 = gt ? u : d.l_pp;
-        const bool big = pv2 > thr_long<RNA>();
-        const bool valid2 = (d.l_valid != 0) | (drop & big);
-        const bool emit = act & !none & valid2 & ((u - pp2) > w2 / 2);
-        sink.peak_if(pp2, emit & rec);
-        const bool setc = act & (none ? (lt | rise) : (gt | emit));
-        d.l_pv = setc ? c2 : d.l_pv;
-        const int ppn = none ? (rise ? u : -1) : (emit ? -1 : pp2);
-        d.l_pp = act ? ppn : d.l_pp;
-        d.l_valid = act ? ((!none & valid2 & !emit) ? 1 : 0) : d.l_valid;
-    }
+    bool maskl; int pk, pos;
+    const bool e1 = det_one<true, RNA>(d.s_pv, d.s_ps, u, c1, true, maskl, pk, &pos);
+    sink.peak_if(pos, e1 & rec);
+    // the short detector dominates the long one while it holds a peak above its threshold (events.c:414-422)
+    d.l_mt = maskl ? pk + Cfg<RNA>::w1 : d.l_mt;
+    d.l_ps = maskl ? PS_NONE : d.l_ps;
+    d.l_pv = maskl ? FLT_MAX : d.l_pv;
+    bool unused_b; int unused_p;
+    const bool e2 = det_one<false, RNA>(d.l_pv, d.l_ps, u, c2, d.l_mt < u, unused_b, unused_p, &pos);
+    sink.peak_if(pos, e2 & rec);
 }
 
 // ---- the register rings --------------------------------------------------------------------------------------------
@@ -327,21 +330,23 @@ struct Rings {
     }
 };
 
-// What one block does: KIND 0 = sums and window terms only, 1 = additionally t1 for the positions the first
-// detector step will need, 2 = everything (both t-statistics and the detector).
-// Phase 1 computes the block's t-statistics without a single branch; phase 2 steps the detector through them.
+// One block of U samples. Phase 1 computes the block's t-statistics without a single branch; phase 2 steps the
+// detector through them. The same code also fills the rings at the start of a chunk: the two blocks before the
+// first detector step run it with live == false (their t-statistics come from partly filled rings and are never
+// used, the detector state is reset afterwards), except that the last w1 values of t1 of the second of them ARE
+// the ones the first real steps read (live_t1).
 // EDGE: the block may touch positions outside the read [0, n): samples there count as 0, t is 0 outside
 // w <= i <= n-w (events.c:328-338), the detector only steps positions 1 <= p < n (position 0 is masked: 387).
 //   x[m]   : pA of sample tau0 + m (0 outside the read when EDGE)
 //   tau0   : read index of the block's first sample, a multiple of U
 //   sh     : read_off & 31
-template <int RNA, int KIND, bool EDGE, class Io>
+template <int RNA, bool EDGE, class Io>
 SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U], int tau0, int n, int sh, bool rec,
-                       float off, float unit, Io& io) {
+                       bool live, bool live_t1, float off, float unit, Io& io) {
     using C = Cfg<RNA>;
     constexpr int w1 = C::w1, w2 = C::w2, M1 = C::R1 - 1, M2 = C::R2 - 1, U = C::U;
     float t1v[U], t2v[U];
-    bool bad = false;
+    bool bad = false, bad_t1 = false;  // bad_t1: among the last w1 values of t1
 #pragma unroll
     for (int m = 0; m < U; m++) {
         // static ring slots: every index below is (m + const) & mask because tau0 is a multiple of U
@@ -363,13 +368,13 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
         const double d2 = dadd(g.D1[s1l], d1), e2 = dadd(g.E1[s1l], e1);
         float a2, b2; double l2, v2, b2sq;
         window_terms<w2>(d2, e2, a2, l2, b2, v2, b2sq);
-        if (KIND == 2 || (KIND == 1 && m >= U - w1)) {
+        {
             bool bd = false;
             t1v[m] = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, bd);
             if (EDGE) { const int j1 = tau0 + m - w1 + 1; bd = bd & (j1 >= w1) & (j1 + w1 <= n); }
-            bad = bad | bd;
+            if (m >= U - w1) bad_t1 = bad_t1 | bd; else bad = bad | bd;
         }
-        if (KIND == 2) {
+        {
             bool bd = false;
             t2v[m] = tstat_from<w2>(g.A2[s2l], g.L2[s2l], b2, v2, b2sq, bd);
             if (EDGE) { const int j2 = tau0 + m - w2 + 1; bd = bd & (j2 >= w2) & (j2 + w2 <= n); }
@@ -379,49 +384,40 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
         g.A1[s1] = a1; g.L1[s1] = l1;
         g.A2[s2] = a2; g.L2[s2] = l2;
     }
-    if (KIND >= 1) {
-        if (bad) {  // rare: the copies keep t1v / t2v in registers (only e1 / e2 live in local memory)
-            float e1[U], e2[U];
-            exact_block<RNA>(io, tau0, n, off, unit, KIND == 2 ? 0 : U - w1, KIND == 2 ? 1 : 0, e1, e2);
+    if ((bad & live) | (bad_t1 & live_t1)) {  // rare: the copies keep t1v / t2v in registers (only e1 / e2 live in local memory)
+        float e1[U], e2[U];
+        exact_block<RNA>(io, tau0, n, off, unit, 0, 1, e1, e2);
 #pragma unroll
-            for (int m = 0; m < U; m++) {
-                if (KIND == 2 || m >= U - w1) t1v[m] = e1[m];
-                if (KIND == 2) t2v[m] = e2[m];
-            }
-        }
-        if (EDGE) {
-#pragma unroll
-            for (int m = 0; m < U; m++) {
-                const int j1 = tau0 + m - w1 + 1, j2 = tau0 + m - w2 + 1;
-                if (KIND == 2 || m >= U - w1) t1v[m] = (j1 >= w1 && j1 + w1 <= n) ? t1v[m] : 0.0f;
-                if (KIND == 2) t2v[m] = (j2 >= w2 && j2 + w2 <= n) ? t2v[m] : 0.0f;
-            }
-        }
+        for (int m = 0; m < U; m++) { t1v[m] = e1[m]; t2v[m] = e2[m]; }
     }
-    if (KIND == 2) {
+    if (EDGE) {
 #pragma unroll
         for (int m = 0; m < U; m++) {
-            const int j2 = tau0 + m - w2 + 1;
-            const float c1 = m >= w1 ? t1v[m - w1] : g.T1c[m];     // t1(j2), computed w1 samples ago
-            if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, j2 + sh, c1, t2v[m], rec, io);
+            const int j1 = tau0 + m - w1 + 1, j2 = tau0 + m - w2 + 1;
+            t1v[m] = (j1 >= w1 && j1 + w1 <= n) ? t1v[m] : 0.0f;
+            t2v[m] = (j2 >= w2 && j2 + w2 <= n) ? t2v[m] : 0.0f;
         }
     }
-    if (KIND >= 1) {
 #pragma unroll
-        for (int k = 0; k < w1; k++) g.T1c[k] = t1v[U - w1 + k];
+    for (int m = 0; m < U; m++) {
+        const int j2 = tau0 + m - w2 + 1;
+        const float c1 = m >= w1 ? t1v[m - w1] : g.T1c[m];         // t1(j2), computed w1 samples ago
+        if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, j2 + sh, c1, t2v[m], rec, io);
     }
+#pragma unroll
+    for (int k = 0; k < w1; k++) g.T1c[k] = t1v[U - w1 + k];
 }
 
 // ---- chunk drivers -------------------------------------------------------------------------------------------------
-// Every read is cut into chunks of L samples; the last chunk takes the remainder (L..2L-1 samples), a read
-// shorter than 2L is a single chunk. `Io` supplies the memory side (device: walk.cu, host checker:
+// Every read is cut into chunks of L samples; the last chunk takes the remainder (1..L samples), a read of at
+// most L samples is a single chunk. `Io` supplies the memory side (device: walk.cu, host checker:
 // tests/tools/host_walk.cpp):
 //   load8(t, v)        the four 32-bit words holding samples [t, t+8) of the read (t multiple of 8)
 //   want_pa() / store_pa8(t, x) / store_pa1(t, x)
-//   peak(pos)          record an emitted peak (shifted position)
+//   peak_if(pos, on)   record an emitted peak (shifted position) when `on`
 //   put_begin(c) / put_end(c)   the chunk's canonical detector state after the warm-up / after its last step
-//   witness(rmin, rmax)         extreme raw values of the samples the chunk owns
-SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return n < 2u * L ? (n ? 1u : 0u) : n / L; }
+//   witness(rmin, rmax)         extreme raw values of samples of the read (any superset of the owned samples)
+SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return (n + L - 1u) / L; }
 
 SGW_HD void cvt8(const int (&v)[4], float off, float unit, float* x) {
 #pragma unroll
@@ -445,46 +441,43 @@ SGW_HD uint32_t max_s16x2(uint32_t a, uint32_t b) {
 }
 #endif
 
-// interior chunk k (1 <= k <= nch-2) of a read: every access is inside the read, no bounds checks
+// interior chunk k (1 <= k <= nch-2) of a read: every access is inside the read, no bounds checks.
+// ONE loop (one copy of the block code in the instruction cache) runs the two ring-fill blocks, the detector
+// warm-up and the owned samples.
 template <int RNA, class Io>
 SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, int W, int k) {
     using C = Cfg<RNA>;
     constexpr int U = C::U;
-    const int s0 = k * L;                            // first sample this chunk owns
-    int tau = s0 - W - C::FILL * U;
+    const int s0 = k * L, s1 = s0 + L;               // the samples this chunk owns
+    const int t_live = s0 - W;                       // block whose first step is the first real detector step
     Rings<RNA> g;
     g.clear();
     WalkDet d;
-    det_cold(d, tau + C::FILL * U - C::LAG + sh);    // first detector step
+    det_cold(d, 0);
     float x[U];
     int v[4];
-#pragma unroll
-    for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
-    walk_block<RNA, 0, false>(g, d, x, tau, n, sh, false, off, unit, io);
-    tau += U;
-#pragma unroll
-    for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
-    walk_block<RNA, 1, false>(g, d, x, tau, n, sh, false, off, unit, io);
-    tau += U;
-    for (; tau < s0; tau += U) {                     // detector warm-up
-#pragma unroll
-        for (int h = 0; h < U / 8; h++) { io.load8(tau + 8 * h, v); cvt8(v, off, unit, x + 8 * h); }
-        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, false, off, unit, io);
-    }
-    io.put_begin(canon_of(d, s0 - C::LAG + sh));
-    uint32_t vmin = 0x7fff7fffu, vmax = 0x80008000u;  // packed int16 min / max of the owned samples
-    const int s1 = s0 + L;
+    uint32_t vmin = 0x7fff7fffu, vmax = 0x80008000u;  // packed int16 min / max (over warm-up and owned samples)
     const bool pa = io.want_pa();
-    for (; tau < s1; tau += U) {
+    int vn[U / 8][4];                                 // the next block's samples, loaded one block ahead
+#pragma unroll
+    for (int h = 0; h < U / 8; h++) io.load8(t_live - C::FILL * U + 8 * h, vn[h]);
+#pragma unroll 1
+    for (int tau = t_live - C::FILL * U; tau < s1; tau += U) {
+        const bool own = tau >= s0;
+        if (tau == t_live) det_cold(d, t_live - C::LAG + sh);   // forget the steps taken on partly filled rings
+        if (tau == s0) io.put_begin(canon_of(d, s0 - C::LAG + sh));
+        const int tn = tau + U < s1 ? tau + U : tau;  // (the last block is simply loaded again)
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {
-            io.load8(tau + 8 * h, v);
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = vn[h][q];
+            io.load8(tn + 8 * h, vn[h]);
             vmin = min_s16x2(min_s16x2(vmin, (uint32_t)v[0]), min_s16x2((uint32_t)v[1], min_s16x2((uint32_t)v[2], (uint32_t)v[3])));
             vmax = max_s16x2(max_s16x2(vmax, (uint32_t)v[0]), max_s16x2((uint32_t)v[1], max_s16x2((uint32_t)v[2], (uint32_t)v[3])));
             cvt8(v, off, unit, x + 8 * h);
-            if (pa) io.store_pa8(tau + 8 * h, x + 8 * h);
+            if (pa && own) io.store_pa8(tau + 8 * h, x + 8 * h);
         }
-        walk_block<RNA, 2, false>(g, d, x, tau, n, sh, true, off, unit, io);
+        walk_block<RNA, false>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, off, unit, io);
     }
     io.put_end(canon_of(d, s1 - C::LAG + sh));
     const int rmin0 = (int)(int16_t)(vmin & 0xffffu), rmin1 = (int)vmin >> 16;
@@ -503,16 +496,23 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
     const int s0 = last ? (int)(nch - 1u) * L : 0;
     const bool to_end = last || nch == 1u;
     const int s1 = to_end ? n : L;
+    const int t_live = last ? s0 - W : 0;            // >= 2U for a last chunk because L >= W + 2U
+    const int step_end = to_end ? n : s1 - C::LAG;   // owned blocks: until every owned step has been taken
     Rings<RNA> g;
     g.clear();
     WalkDet d;
+    det_cold(d, sh + 1);  // first chunk: the reference's initial state, masked_to = 0: position 0 is skipped (events.c:516-536, 387)
     float x[U];
     int rmin = 32767, rmax = -32768;
     const bool pa = io.want_pa();
-    auto load = [&](int t, bool own) {
+#pragma unroll 1
+    for (int tau = last ? t_live - C::FILL * U : 0; tau - C::LAG < step_end; tau += U) {
+        const bool own = tau >= s0;
+        if (last && tau == t_live) det_cold(d, t_live - C::LAG + sh);
+        if (last && tau == s0) io.put_begin(canon_of(d, s0 - C::LAG + sh));
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {
-            const int t8 = t + 8 * h;
+            const int t8 = tau + 8 * h;
             int v[4] = {0, 0, 0, 0};
             if (t8 < n) io.load8(t8, v);  // t8 < n: inside the read's padded span
             float y[8];
@@ -529,33 +529,10 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
                 }
             }
         }
-    };
-    int tau;
-    if (!last) {
-        tau = 0;
-        det_cold(d, sh + 1);  // the reference's initial state: masked_to = 0, position 0 is skipped (events.c:516-536, 387)
-    } else {
-        tau = s0 - W - C::FILL * U;  // >= 0 because L >= W + 2U
-        det_cold(d, tau + C::FILL * U - C::LAG + sh);
-        load(tau, false);
-        walk_block<RNA, 0, true>(g, d, x, tau, n, sh, false, off, unit, io);
-        tau += U;
-        load(tau, false);
-        walk_block<RNA, 1, true>(g, d, x, tau, n, sh, false, off, unit, io);
-        tau += U;
-        for (; tau < s0; tau += U) {
-            load(tau, false);
-            walk_block<RNA, 2, true>(g, d, x, tau, n, sh, false, off, unit, io);
-        }
-        io.put_begin(canon_of(d, s0 - C::LAG + sh));
-    }
-    const int step_end = to_end ? n : s1 - C::LAG;  // owned blocks: until every owned step has been taken
-    for (; tau - C::LAG < step_end; tau += U) {
-        load(tau, true);
-        walk_block<RNA, 2, true>(g, d, x, tau, n, sh, true, off, unit, io);
+        walk_block<RNA, true>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, off, unit, io);
     }
     if (!to_end) io.put_end(canon_of(d, s1 - C::LAG + sh));
-    if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)
+    if (!last) io.peak_if(sh, true);  // event 0 starts at the read's first sample (events.c:490-497)
     if (rmin <= rmax) io.witness(rmin, rmax);
 }
 
