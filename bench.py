@@ -327,7 +327,7 @@ def run_ours(args):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "walk_chunks_bytes_per_sample_pa" if pa_mode else "walk_chunks_bytes_per_sample"
+        key = "walk_chunks_bytes_per_sample_pa" if pa_mode else "walk_chunks_bytes_per_sample"  # ncu, profiles/traffic.json
         traffic = float(tj[key]) * n_samples / max(args.steps, 1)
     except Exception:
         pass

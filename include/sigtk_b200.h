@@ -91,7 +91,8 @@ typedef struct {
     float    *stat;        /* [n_reads][6]: raw_mean, pa_mean, raw_std, pa_std, raw_median, pa_median */
     uint32_t *seq_order;   /* [n_reads] 1 if the read went through the sequential-order kernels
                               (exact-sum witness failed, or forced); such reads are still bit-exact */
-    uint32_t *fixups;      /* [n_reads] number of detector chunks re-run after a boundary-state mismatch */
+    uint32_t *fixups;      /* [n_reads] number of detector chunks whose warm-up state did not match (the read is then redone
+                              by the sequential-order kernels) */
     uint64_t  n_events;    /* total events in the batch (host result only; 0 from sgpu_run_device) */
 } sgpu_result_t;
 
@@ -144,7 +145,7 @@ int  sgpu_run_device(sgpu_ctx_t *ctx, const sgpu_dev_batch_t *batch, uint32_t wa
 typedef struct {
     uint64_t n_events;
     uint64_t n_seq_order_reads;   /* reads routed to the sequential-order kernels */
-    uint64_t n_fixups;            /* detector chunks re-run after boundary-state mismatch */
+    uint64_t n_fixups;            /* detector chunks with a boundary-state mismatch */
     uint64_t n_kernel_launches;   /* kernels launched by the last run */
     int32_t  status;              /* 0 or SGPU_E_EVCAP / SGPU_E_SCRATCH reported by the device */
 } sgpu_counters_t;
@@ -153,7 +154,7 @@ int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
 /* Device time of every kernel group of the last run, measured with CUDA events on the stream the kernels were
  * launched on (needs SGPU_F_STAGE_TIMERS). Returns the number of entries written, or a negative code. */
 typedef struct {
-    const char *name;     /* e.g. "detect_tiles", "emit_tiles" */
+    const char *name;     /* e.g. "walk_chunks", "emit_events" */
     float       ms;
     uint32_t    launches; /* kernels in the group */
 } sgpu_stage_time_t;

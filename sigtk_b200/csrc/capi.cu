@@ -187,7 +187,7 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
         n += launch_generic_detect(b, wl, sc, ctx->sm_count, st);
         marks.done("sequential_order_detect", n);
         marks.done("rank_events", launch_rank_events(b, sc, o.ev_off, ctx->sm_count, st));
-        marks.done("emit_tiles", launch_fast_emit(b, sc, ctx->ev_cap, o.ev_start, o.ev_mean, o.ev_stdv, d_fix,
+        marks.done("emit_events", launch_fast_emit(b, sc, ctx->ev_cap, o.ev_start, o.ev_mean, o.ev_stdv, d_fix,
                                                   ctx->sm_count, st));
         marks.done("sequential_order_emit", launch_generic_emit(b, wl, sc, o.ev_off, ctx->ev_cap, o.ev_start, o.ev_mean,
                                                                 o.ev_stdv, ctx->sm_count, st));

@@ -28,7 +28,7 @@ struct Scratch {
     uint32_t* bitmap; uint64_t bitmap_words;
     // per tile
     uint32_t* tile_cnt; uint64_t* tile_base;
-    uint32_t* tile_read0;            // first read that can intersect a 2048-sample tile (emit_tiles_kernel)
+    uint32_t* tile_read0;            // first read that can intersect a 2048-sample tile (emit_events_kernel)
     // chunk walker (walk.cu)
     uint32_t* wk_cnt;                // [max_reads] interior chunks per read
     uint64_t* wk_ibase;              // [max_reads+1] exclusive scan of wk_cnt

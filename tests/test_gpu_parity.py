@@ -139,8 +139,8 @@ def test_fast_equals_sequential_order_path(ctx, ctx_generic, rna_flag):
 
 
 @pytest.mark.parametrize("rna_flag", [0, 1])
-def test_long_reads_cross_tile(ctx, orc, rna_flag):
-    """reads much longer than one tile / one CTA: cross-tile scan carry and detector chunk hand-over"""
+def test_long_reads_many_chunks(ctx, orc, rna_flag):
+    """reads of hundreds of chunks: detector hand-over between chunks, events that span warp tiles of the emitter"""
     reads = [synth.make_read(900 + k, n, seed=4, p_change=0.025 if rna_flag else 0.1)
              for k, n in enumerate((1_000_003, 250_000, 2048, 777_777))]
     res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS | sg.WANT_STAT)
@@ -164,9 +164,9 @@ def test_ragged_and_tiny_reads(ctx, orc):
         check_against_oracle(orc, res, reads, rna_flag)
 
 
-def test_many_tiny_reads_overflow_the_segment_lists(ctx, orc):
-    """hundreds of reads of a few dozen samples inside one tile: more reads than the per-tile segment lists hold,
-    so the fast path hands them to the sequential-order kernels / the global look-up"""
+def test_many_tiny_reads(ctx, orc):
+    """hundreds of reads of a few dozen samples: every read is a single (bounds-checked) chunk, dozens of reads per
+    bitmap tile of the emitter"""
     rng = np.random.default_rng(12)
     base = synth.make_read(3, 40000, seed=8)
     reads, p = [], 0
@@ -206,6 +206,43 @@ def test_flat_stretch_inside_a_read(ctx, orc):
     for rna_flag in (0, 1):
         res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
         check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS)
+
+
+@pytest.mark.parametrize("chunk_len", [128, 256, 512, 1024])
+def test_chunk_lengths(ctx, orc, chunk_len, monkeypatch):
+    """the chunk length is chosen from the batch size; force every value the DNA path can take"""
+    monkeypatch.setenv("SGPU_CHUNK_LEN", str(chunk_len))
+    reads = synth.make_reads(24, mean=9000.0, seed=61)
+    reads.append(synth.make_read(99, 3 * chunk_len, seed=61))       # exact multiple of the chunk length
+    reads.append(synth.make_read(98, 2 * chunk_len + 1, seed=61))   # one-sample last chunk
+    res = ctx.run(reads, rna=0, want=ALL)
+    check_against_oracle(orc, res, reads, 0)
+    assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0
+
+
+def test_short_warmup_falls_back(ctx, orc, monkeypatch):
+    """an 8-sample detector warm-up leaves many chunks in a wrong state: the boundary-state check must catch every
+    one of them (fixups > 0), route those reads to the sequential-order kernels, and the results stay bit-exact"""
+    monkeypatch.setenv("SGPU_WARMUP", "8")
+    monkeypatch.setenv("SGPU_CHUNK_LEN", "128")
+    reads = synth.make_reads(40, mean=12000.0, seed=62)
+    res = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)
+    check_against_oracle(orc, res, reads, 0, want=sg.WANT_EVENTS)
+    assert int(res.fixups.sum()) > 0
+    assert np.all(res.seq_order[res.fixups > 0] == 1)
+
+
+def test_non_positive_pa_takes_the_sequential_order_path(ctx, orc):
+    """the walker's arithmetic assumes pA > 0 (witness): reads with zero or negative pA are flagged and redone"""
+    rd = synth.make_read(7, 9000, seed=63)
+    neg = rd[0].copy()
+    neg[4000:4003] = -300                       # (raw + offset) < 0
+    zero = rd[0].copy()
+    zero[100] = -int(rd[2])                     # raw + offset == 0
+    reads = [rd, (neg, rd[1], rd[2], rd[3]), (zero, rd[1], rd[2], rd[3]), synth.make_read(8, 9000, seed=63)]
+    res = ctx.run(reads, rna=0, want=ALL)
+    check_against_oracle(orc, res, reads, 0)
+    assert list(res.seq_order) == [0, 1, 1, 0]
 
 
 def test_empty_batch_and_reuse(ctx):

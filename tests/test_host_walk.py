@@ -1,0 +1,65 @@
+"""CPU tests of the chunk walker logic (sigtk_b200/csrc/walk_core.cuh compiled for the host by tests/_hostwalk.py)
+against the oracle: event boundaries and pA bit-exact for every chunk length / warm-up / bitmap shift, and the
+soundness of the boundary-state check (a read without a mismatch is exact even with a far too short warm-up)."""
+import numpy as np
+import pytest
+
+import _hostwalk
+from _oracle import Oracle
+from sigtk_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _hostwalk.load()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+def check(lib, orc, rd, rna, L, W, sh, must_verify=True):
+    raw, dig, off, rng = rd
+    st = orc.events(raw, dig, off, rng, rna=rna)[0].astype(np.int64)
+    mism, starts, pa, mm = _hostwalk.walk(lib, raw, dig, off, rng, rna, L, W, sh)
+    if must_verify:
+        assert mism == 0
+    if mism == 0:
+        assert np.array_equal(starts, st), f"n={len(raw)} L={L} W={W} sh={sh}"
+    assert np.array_equal(pa.view(np.uint32), orc.pa(raw, dig, off, rng).view(np.uint32))
+    assert mm == (int(raw.min()), int(raw.max()))
+    return mism
+
+
+@pytest.mark.parametrize("rna,L,W", [(0, 128, 64), (0, 256, 64), (0, 1024, 64), (1, 512, 384), (1, 1024, 384)])
+def test_walker_equals_oracle(lib, orc, rna, L, W):
+    reads = synth.make_reads(6, mean=9000.0, seed=41 + rna, rna=bool(rna))
+    for k, rd in enumerate(reads):
+        check(lib, orc, rd, rna, L, W, (0, 8, 16, 24)[k % 4])
+
+
+@pytest.mark.parametrize("rna,L,W", [(0, 128, 64), (1, 512, 384)])
+def test_ragged_lengths(lib, orc, rna, L, W):
+    """lengths around the window sizes, the block size and the chunk length (single chunk, 2 chunks, short last chunk)"""
+    base = synth.make_read(3, 3 * L + 40, seed=9)
+    for n in [1, 2, 5, 6, 7, 8, 9, 12, 13, 14, 15, 16, 17, 27, 28, 29, 31, 33, 63, 65, 199, 200, L - 1, L, L + 1, L + 7,
+              L + 8, L + 9, 2 * L - 1, 2 * L, 2 * L + 1, 3 * L, 3 * L + 5]:
+        check(lib, orc, (base[0][:n].copy(), base[1], base[2], base[3]), rna, L, W, 8)
+
+
+def test_short_warmup_is_detected_not_trusted(lib, orc):
+    """with an 8-sample warm-up many chunks start from a wrong state: the boundary check must say so, and every
+    read it passes must still be exact"""
+    reads = synth.make_reads(12, mean=15000.0, seed=5)
+    flagged = sum(check(lib, orc, rd, 0, 128, 8, 0, must_verify=False) > 0 for rd in reads)
+    assert flagged > 0
+
+
+def test_flat_stretch(lib, orc):
+    """a long constant stretch: t-statistics exactly 0 (delta == 0 with the variance floor); SURVEY 7.3(2)"""
+    rd = synth.make_read(11, 20000, seed=3)
+    raw = rd[0].copy()
+    raw[6000:14000] = raw[5999]
+    for rna, L, W in ((0, 256, 64), (1, 512, 384)):
+        check(lib, orc, (raw, rd[1], rd[2], rd[3]), rna, L, W, 0, must_verify=False)
