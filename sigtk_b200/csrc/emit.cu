@@ -1,14 +1,19 @@
 // emit.cu -- emit_events_kernel: the event table (create_events / create_event, events.c:457-504) from the
 // event-start bitmap. One WARP per 1024 consecutive samples of the flat array (32 bitmap words), no block-level
-// barriers, no scan over the samples:
+// barriers, no scan over the samples. The sums are exact (see walk_core.cuh), so every grouping of the additions
+// gives the reference's bits.
 //
 //   1. every lane takes one bitmap word; a warp scan of the popcounts gives every event start its index in the
 //      warp tile, and the lanes scatter the start positions into a warp-private list in shared memory;
-//   2. the events are dealt to the lanes in order (event j0+lane): start = list[j], end = list[j+1] (or the next
-//      set bit after the tile, or the end of the read), and the lane sums its few samples (mean event length ~5)
-//      directly from global memory. Consecutive lanes read consecutive samples and write consecutive event slots.
-//
-// The sums are exact (see walk_core.cuh), so summing every event on its own gives the reference's bits.
+//   2. FAST PATH (the warp tile lies inside one read; reads are much longer than 1024 samples): every lane walks the
+//      32 samples of its word once and cuts the running sums of x and x*x at its event-start bits: the piece
+//      before its first bit (`head`), and one piece per bit (up to the next bit or the end of the word), all
+//      stored in shared memory. Every lane does the same 32 steps: no divergence in the sample loop.
+//   3. the events are dealt to the lanes in order (event j0+lane); an event is its own piece, plus -- when it is
+//      the last one of its word -- the heads of the following words up to the next event start. Only the last
+//      event of the tile can run past it; its lane adds those few samples straight from global memory.
+//      Consecutive lanes write consecutive event slots.
+//   GENERAL PATH (a read starts or ends inside the warp tile): every lane sums the samples of its event directly.
 #include "kernels.cuh"
 #include "walk_core.cuh"
 
@@ -17,9 +22,16 @@ namespace sgpu {
 namespace {
 
 constexpr int EWT = 1024;                // samples per warp tile
-constexpr int EWARPS = 8;                // warps per CTA
+constexpr int EWARPS = 4;                // warps per CTA
 constexpr int ELIST = EWT / 2 + 8;       // event starts are >= 3 samples apart inside a read; tiny reads add their starts
-constexpr int ELONG = 48;                // an event longer than this is finished by the whole warp
+constexpr int EFAST = EWT / 3 + 8;       // bound inside ONE read
+constexpr int ELONG = 48;                // general path: an event longer than this is finished by the whole warp
+
+struct EmitWarp {
+    double S[EFAST + 32];                // pieces by event index, then the 32 heads
+    double Q[EFAST + 32];
+    uint16_t list[ELIST];
+};
 
 // read that contains flat position p of a 2048-sample tile whose first candidate read is r0 (tile_read0)
 __device__ __forceinline__ uint32_t locate_read(const DevBatch& b, uint32_t r0, uint64_t p) {
@@ -32,12 +44,24 @@ __device__ __forceinline__ uint32_t locate_read(const DevBatch& b, uint32_t r0, 
     return find_read(b.read_off, b.n_reads, p);
 }
 
-__device__ __forceinline__ void add_sample(const int16_t* __restrict__ samples, long long i, float off, float unit,
-                                           double& as, double& aq) {
-    const float x = __fmul_rn(__fadd_rn((float)(int)__ldg(samples + i), off), unit);
+__device__ __forceinline__ void add_raw(int raw, float off, float unit, double& as, double& aq) {
+    const float x = __fmul_rn(__fadd_rn((float)raw, off), unit);
     // widen_pos: exact for the positive pA of every read that keeps the fast path's results (walk_core.cuh)
     as = __dadd_rn(as, walk::widen_pos(x));
     aq = __dadd_rn(aq, walk::widen_pos(__fmul_rn(x, x)));
+}
+
+// next event start at or after bitmap word w0, bounded by the end of the read
+__device__ __forceinline__ long long next_start(const uint32_t* __restrict__ bitmap, uint64_t w0, uint64_t n_words,
+                                                long long rend) {
+    for (uint64_t w = w0; w < n_words && (long long)(w << 5) < rend; w++) {
+        const uint32_t nx = bitmap[w];
+        if (nx) {
+            const long long e = (long long)(w << 5) + __ffs(nx) - 1;
+            return e < rend ? e : rend;
+        }
+    }
+    return rend;
 }
 
 }  // namespace
@@ -49,9 +73,9 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
                                                                   float* __restrict__ ev_mean, float* __restrict__ ev_stdv,
                                                                   int* __restrict__ status,
                                                                   const uint32_t* __restrict__ tile_read0) {
-    __shared__ uint16_t s_list[EWARPS][ELIST];
+    __shared__ EmitWarp smem[EWARPS];
     const int lane = threadIdx.x & 31;
-    uint16_t* __restrict__ list = s_list[threadIdx.x >> 5];
+    EmitWarp& sm = smem[threadIdx.x >> 5];
     const uint64_t n_wt = (uint64_t)n_tiles * (FAST_TILE / EWT);
     const uint64_t n_words = (uint64_t)n_tiles * (FAST_TILE / 32);
     const uint64_t warp0 = (uint64_t)blockIdx.x * EWARPS + (threadIdx.x >> 5), n_warps = (uint64_t)gridDim.x * EWARPS;
@@ -73,18 +97,83 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
         uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         if (total == 0u) continue;
         if (total > (uint32_t)ELIST) { total = ELIST; if (lane == 0) atomicExch(status, SGPU_DEV_E_EVCAP); }  // malformed bitmap
-        __syncwarp();  // the previous tile's readers are done with the list
+        __syncwarp();  // the previous tile's readers are done with the shared arrays
         {
             uint32_t rem = word, idx = incl - own;
             while (rem) {
-                if (idx < (uint32_t)ELIST) list[idx] = (uint16_t)(lane * 32 + __ffs(rem) - 1);
+                if (idx < (uint32_t)ELIST) sm.list[idx] = (uint16_t)(lane * 32 + __ffs(rem) - 1);
                 idx++;
                 rem &= rem - 1u;
             }
         }
-        __syncwarp();
         const uint64_t kbase = tile_base[tile] + before;
-        const uint32_t r0 = tile_read0[tile];
+        // the read of the tile's first sample; when it covers the whole warp tile every event of the tile shares
+        // its parameters
+        const uint32_t r_first = locate_read(b, tile_read0[tile], (uint64_t)flat0);
+        const long long rs_first = (long long)b.read_off[r_first];
+        const long long rend_first = rs_first + (long long)b.read_len[r_first];
+        const float off_first = b.offset[r_first], unit_first = b.unit[r_first];
+        const bool one_read = rs_first <= flat0 && flat0 + EWT <= rend_first && total <= (uint32_t)EFAST;
+        if (one_read) {
+            // ---- fast path, step 2: the pieces of this lane's 32 samples ----------------------------------------------
+            const int4* __restrict__ src = reinterpret_cast<const int4*>(b.samples + flat0 + lane * 32);
+            int slot = EFAST + lane;             // where the running piece goes: first the head of this word
+            int next = (int)(incl - own);        // index of this word's first event
+            double as = 0.0, aq = 0.0;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int4 rv = __ldg(src + g);
+                const int v[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    if ((word >> (8 * g + m)) & 1u) {  // an event starts here: the running piece is complete
+                        sm.S[slot] = as;
+                        sm.Q[slot] = aq;
+                        slot = next++;
+                        as = 0.0;
+                        aq = 0.0;
+                    }
+                    add_raw((m & 1) ? (v[m >> 1] >> 16) : (int)(int16_t)(v[m >> 1] & 0xffff), off_first, unit_first, as, aq);
+                }
+            }
+            sm.S[slot] = as;
+            sm.Q[slot] = aq;
+            __syncwarp();
+            // ---- step 3: events in order ---------------------------------------------------------------------------------
+            for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                if (j >= total) continue;
+                const int pos = sm.list[j];
+                double es = sm.S[j], eq = sm.Q[j];
+                long long e;
+                if (j + 1 < total) {
+                    const int pe = sm.list[j + 1];
+                    e = flat0 + pe;
+                    for (int l2 = (pos >> 5) + 1; l2 <= (pe >> 5); l2++) {  // heads of the words up to the next start
+                        es = __dadd_rn(es, sm.S[EFAST + l2]);
+                        eq = __dadd_rn(eq, sm.Q[EFAST + l2]);
+                    }
+                } else {  // the last event of the tile: heads of the remaining words, then past the tile
+                    for (int l2 = (pos >> 5) + 1; l2 < 32; l2++) {
+                        es = __dadd_rn(es, sm.S[EFAST + l2]);
+                        eq = __dadd_rn(eq, sm.Q[EFAST + l2]);
+                    }
+                    e = next_start(bitmap, (wt + 1) * 32, n_words, rend_first);
+                    for (long long i = flat0 + EWT; i < e; i++) add_raw((int)__ldg(b.samples + i), off_first, unit_first, es, eq);
+                }
+                const uint64_t k = kbase + j;
+                if (k >= ev_cap) { atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
+                const long long s = flat0 + pos;
+                float mean, stdv;
+                event_stats(es, eq, (uint32_t)(e - s), &mean, &stdv);
+                ev_start[k] = (uint32_t)(s - rs_first);
+                ev_mean[k] = mean;
+                ev_stdv[k] = stdv;
+            }
+            continue;
+        }
+        // ---- general path: a read boundary inside the warp tile ---------------------------------------------------------
+        __syncwarp();
         for (uint32_t j0 = 0; j0 < total; j0 += 32) {
             const uint32_t j = j0 + lane;
             const bool have = j < total;
@@ -93,26 +182,18 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
             double as = 0.0, aq = 0.0;
             uint32_t len = 0;
             if (have) {
-                const long long s = flat0 + list[j];
-                const uint32_t r = locate_read(b, r0, (uint64_t)s);
+                const long long s = flat0 + sm.list[j];
+                const uint32_t r = locate_read(b, r_first, (uint64_t)s);
                 rs = (long long)b.read_off[r];
                 const long long rend = rs + (long long)b.read_len[r];
                 off = b.offset[r];
                 unit = b.unit[r];
-                if (j + 1 < total) {
-                    e = flat0 + list[j + 1];
-                } else {  // the next event start lies after this warp tile (or the read ends first)
-                    e = rend;
-                    for (uint64_t w = (wt + 1) * 32; w < n_words && (long long)(w << 5) < rend; w++) {
-                        const uint32_t nx = bitmap[w];
-                        if (nx) { e = (long long)(w << 5) + __ffs(nx) - 1; break; }
-                    }
-                }
+                e = j + 1 < total ? flat0 + sm.list[j + 1] : next_start(bitmap, (wt + 1) * 32, n_words, rend);
                 if (e > rend) e = rend;
                 len = (uint32_t)(e - s);
                 i = s;
                 const long long stop = e - s > ELONG ? s + ELONG : e;
-                for (; i < stop; i++) add_sample(b.samples, i, off, unit, as, aq);
+                for (; i < stop; i++) add_raw((int)__ldg(b.samples + i), off, unit, as, aq);
             }
             // long events (rare): the whole warp sums the rest
             uint32_t longs = __ballot_sync(0xffffffffu, have && i < e);
@@ -122,7 +203,7 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
                 const long long li = __shfl_sync(0xffffffffu, i, src), le = __shfl_sync(0xffffffffu, e, src);
                 const float lo = __shfl_sync(0xffffffffu, off, src), lu = __shfl_sync(0xffffffffu, unit, src);
                 double ps = 0.0, pq = 0.0;
-                for (long long p = li + lane; p < le; p += 32) add_sample(b.samples, p, lo, lu, ps, pq);
+                for (long long p = li + lane; p < le; p += 32) add_raw((int)__ldg(b.samples + p), lo, lu, ps, pq);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) {
                     ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, o));
