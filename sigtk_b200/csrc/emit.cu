@@ -85,6 +85,16 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
         if (flat0 >= span) break;
         const uint32_t tile = (uint32_t)(wt / (FAST_TILE / EWT)), half = (uint32_t)(wt % (FAST_TILE / EWT));
         const uint32_t word = bitmap[wt * 32 + lane];
+        // issue this lane's 32 samples right away (used by the fast path; their latency hides behind the index work)
+        int4 rv[4];
+        {
+            const long long p0 = flat0 + lane * 32;
+            const int4* __restrict__ src = reinterpret_cast<const int4*>(b.samples + p0);
+#pragma unroll
+            for (int g = 0; g < 4; g++) rv[g] = p0 + 8 * g + 8 <= span ? __ldg(src + g) : make_int4(0, 0, 0, 0);
+        }
+        const uint64_t tbase = tile_base[tile];
+        const uint32_t tr0 = tile_read0[tile];
         uint32_t before = half ? (uint32_t)__popc(bitmap[(uint64_t)tile * (FAST_TILE / 32) + lane]) : 0u;
         before = __reduce_add_sync(0xffffffffu, before);  // FAST_TILE / EWT == 2: at most one warp tile before this one
         uint32_t incl = __popc(word);
@@ -106,24 +116,22 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
                 rem &= rem - 1u;
             }
         }
-        const uint64_t kbase = tile_base[tile] + before;
+        const uint64_t kbase = tbase + before;
         // the read of the tile's first sample; when it covers the whole warp tile every event of the tile shares
         // its parameters
-        const uint32_t r_first = locate_read(b, tile_read0[tile], (uint64_t)flat0);
+        const uint32_t r_first = locate_read(b, tr0, (uint64_t)flat0);
         const long long rs_first = (long long)b.read_off[r_first];
         const long long rend_first = rs_first + (long long)b.read_len[r_first];
         const float off_first = b.offset[r_first], unit_first = b.unit[r_first];
         const bool one_read = rs_first <= flat0 && flat0 + EWT <= rend_first && total <= (uint32_t)EFAST;
         if (one_read) {
             // ---- fast path, step 2: the pieces of this lane's 32 samples ----------------------------------------------
-            const int4* __restrict__ src = reinterpret_cast<const int4*>(b.samples + flat0 + lane * 32);
             int slot = EFAST + lane;             // where the running piece goes: first the head of this word
             int next = (int)(incl - own);        // index of this word's first event
             double as = 0.0, aq = 0.0;
 #pragma unroll
             for (int g = 0; g < 4; g++) {
-                const int4 rv = __ldg(src + g);
-                const int v[4] = {rv.x, rv.y, rv.z, rv.w};
+                const int v[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
 #pragma unroll
                 for (int m = 0; m < 8; m++) {
                     if ((word >> (8 * g + m)) & 1u) {  // an event starts here: the running piece is complete
@@ -139,6 +147,22 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
             sm.S[slot] = as;
             sm.Q[slot] = aq;
             __syncwarp();
+            // the head of a word with event starts (and the empty words before it) belongs to the last event of the
+            // previous word with starts: exactly one lane adds to any event
+            const uint32_t nz = __ballot_sync(0xffffffffu, own != 0u);
+            if (own != 0u && incl != own) {
+                double hs = sm.S[EFAST + lane], hq = sm.Q[EFAST + lane];
+                const uint32_t lower = nz & ((1u << lane) - 1u);   // non-empty because incl != own
+                for (int l2 = lane - 1; l2 > 31 - __clz(lower); l2--) {
+                    hs = __dadd_rn(hs, sm.S[EFAST + l2]);
+                    hq = __dadd_rn(hq, sm.Q[EFAST + l2]);
+                }
+                const int prev = (int)(incl - own) - 1;
+                sm.S[prev] = __dadd_rn(sm.S[prev], hs);
+                sm.Q[prev] = __dadd_rn(sm.Q[prev], hq);
+            }
+            __syncwarp();
+            const int last_word = 31 - __clz(nz);
             // ---- step 3: events in order ---------------------------------------------------------------------------------
             for (uint32_t j0 = 0; j0 < total; j0 += 32) {
                 const uint32_t j = j0 + lane;
@@ -147,14 +171,9 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
                 double es = sm.S[j], eq = sm.Q[j];
                 long long e;
                 if (j + 1 < total) {
-                    const int pe = sm.list[j + 1];
-                    e = flat0 + pe;
-                    for (int l2 = (pos >> 5) + 1; l2 <= (pe >> 5); l2++) {  // heads of the words up to the next start
-                        es = __dadd_rn(es, sm.S[EFAST + l2]);
-                        eq = __dadd_rn(eq, sm.Q[EFAST + l2]);
-                    }
-                } else {  // the last event of the tile: heads of the remaining words, then past the tile
-                    for (int l2 = (pos >> 5) + 1; l2 < 32; l2++) {
+                    e = flat0 + sm.list[j + 1];
+                } else {  // the last event of the tile: the empty words after it, then past the tile
+                    for (int l2 = last_word + 1; l2 < 32; l2++) {
                         es = __dadd_rn(es, sm.S[EFAST + l2]);
                         eq = __dadd_rn(eq, sm.Q[EFAST + l2]);
                     }
