@@ -80,19 +80,32 @@ __global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, ui
     const uint64_t n_words = (uint64_t)n_tiles * (FAST_TILE / 32);
     const uint64_t warp0 = (uint64_t)blockIdx.x * EWARPS + (threadIdx.x >> 5), n_warps = (uint64_t)gridDim.x * EWARPS;
     const long long span = (long long)b.span;
+    // the bitmap word and the 32 samples of a lane are loaded one warp tile ahead (their latency hides behind the
+    // previous tile's work)
+    auto load_tile = [&](uint64_t wt, uint32_t& word, int4 (&rv)[4]) {
+        const long long p0 = (long long)wt * EWT + lane * 32;
+        word = 0u;
+#pragma unroll
+        for (int g = 0; g < 4; g++) rv[g] = make_int4(0, 0, 0, 0);
+        if (wt < n_wt && (long long)wt * EWT < span) {
+            word = bitmap[wt * 32 + lane];
+            const int4* __restrict__ src = reinterpret_cast<const int4*>(b.samples + p0);
+#pragma unroll
+            for (int g = 0; g < 4; g++) if (p0 + 8 * g + 8 <= span) rv[g] = __ldg(src + g);
+        }
+    };
+    uint32_t word_n;
+    int4 rv_n[4];
+    load_tile(warp0, word_n, rv_n);
     for (uint64_t wt = warp0; wt < n_wt; wt += n_warps) {
         const long long flat0 = (long long)wt * EWT;
         if (flat0 >= span) break;
         const uint32_t tile = (uint32_t)(wt / (FAST_TILE / EWT)), half = (uint32_t)(wt % (FAST_TILE / EWT));
-        const uint32_t word = bitmap[wt * 32 + lane];
-        // issue this lane's 32 samples right away (used by the fast path; their latency hides behind the index work)
+        const uint32_t word = word_n;
         int4 rv[4];
-        {
-            const long long p0 = flat0 + lane * 32;
-            const int4* __restrict__ src = reinterpret_cast<const int4*>(b.samples + p0);
 #pragma unroll
-            for (int g = 0; g < 4; g++) rv[g] = p0 + 8 * g + 8 <= span ? __ldg(src + g) : make_int4(0, 0, 0, 0);
-        }
+        for (int g = 0; g < 4; g++) rv[g] = rv_n[g];
+        load_tile(wt + n_warps, word_n, rv_n);
         const uint64_t tbase = tile_base[tile];
         const uint32_t tr0 = tile_read0[tile];
         uint32_t before = half ? (uint32_t)__popc(bitmap[(uint64_t)tile * (FAST_TILE / 32) + lane]) : 0u;
