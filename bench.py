@@ -239,7 +239,8 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     pa_mode = args.mode == "event+pa"
