@@ -11,11 +11,15 @@
  * into pinned slots of the CUDA library (include/sigtk_b200.h), several batches are in flight on one or more
  * GPUs, and the per-read results are printed in input order.  There is no CPU implementation of the path in
  * here: without a usable GPU the tool exits with an error.
- * Additive options (default off / 1): --gpus N, --batch-samples S.
+ * The batch loader and the output path are parallel: records are read serially (slow5_get_next_bytes) and decoded
+ * by a pool of threads (slow5_decode: zlib + svb-zd), and every finished batch is formatted by the same pool with
+ * exact re-implementations of the reference's printf conversions (fastfmt.h) and written in input order.
+ * Additive options (default off / 1): --gpus N, --batch-samples S, --threads T.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <getopt.h>
 #include <inttypes.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,9 +27,11 @@
 #include <sys/resource.h>
 #include <sys/stat.h>
 #include <sys/time.h>
+#include <unistd.h>
 
 #include <slow5/slow5.h>
 
+#include "fastfmt.h"
 #include "sigtk_b200.h"
 
 #define SIGTK_VERSION "0.2.0" /* reference src/sigtk.h:11 */
@@ -107,6 +113,96 @@ static void pore_detect(slow5_file_t *sp) { /* only `prefix` uses the pore; the 
     }
 }
 
+/* optional wall-clock breakdown of the host side (SIGTK_PROFILE=1): read, decode, add, wait, format, write */
+static double g_prof[8];
+
+/* ---- fork-join thread pool ---------------------------------------------------------------------------------------- */
+typedef void (*task_fn)(void *arg, int item);
+typedef struct {
+    pthread_t *th;
+    int n_threads; /* workers besides the caller */
+    pthread_mutex_t mu;
+    pthread_cond_t go, done;
+    task_fn fn;
+    void *arg;
+    int n_items;
+    volatile int next;
+    unsigned gen;
+    int busy, stop;
+} pool_t;
+
+static void pool_work(pool_t *p) {
+    for (;;) {
+        const int i = __sync_fetch_and_add(&p->next, 1);
+        if (i >= p->n_items) break;
+        p->fn(p->arg, i);
+    }
+}
+static void *pool_main(void *vp) {
+    pool_t *p = (pool_t *)vp;
+    unsigned seen = 0;
+    pthread_mutex_lock(&p->mu);
+    for (;;) {
+        while (!p->stop && p->gen == seen) pthread_cond_wait(&p->go, &p->mu);
+        if (p->stop) break;
+        seen = p->gen;
+        pthread_mutex_unlock(&p->mu);
+        pool_work(p);
+        pthread_mutex_lock(&p->mu);
+        if (--p->busy == 0) pthread_cond_signal(&p->done);
+    }
+    pthread_mutex_unlock(&p->mu);
+    return NULL;
+}
+static void pool_open(pool_t *p, int n_threads) {
+    memset(p, 0, sizeof *p);
+    pthread_mutex_init(&p->mu, NULL);
+    pthread_cond_init(&p->go, NULL);
+    pthread_cond_init(&p->done, NULL);
+    p->n_threads = n_threads > 1 ? n_threads - 1 : 0;
+    p->th = (pthread_t *)calloc((size_t)p->n_threads + 1, sizeof(pthread_t));
+    for (int k = 0; k < p->n_threads; k++)
+        if (pthread_create(&p->th[k], NULL, pool_main, p) != 0) { p->n_threads = k; break; }
+}
+/* runs fn(arg, 0..n_items-1) on the pool and the calling thread; returns when all items are done */
+static void pool_run(pool_t *p, task_fn fn, void *arg, int n_items) {
+    if (n_items <= 0) return;
+    p->fn = fn; p->arg = arg; p->n_items = n_items; p->next = 0;
+    if (p->n_threads > 0 && n_items > 1) {
+        pthread_mutex_lock(&p->mu);
+        p->busy = p->n_threads;
+        p->gen++;
+        pthread_cond_broadcast(&p->go);
+        pthread_mutex_unlock(&p->mu);
+        pool_work(p);
+        pthread_mutex_lock(&p->mu);
+        while (p->busy) pthread_cond_wait(&p->done, &p->mu);
+        pthread_mutex_unlock(&p->mu);
+    } else {
+        pool_work(p);
+    }
+}
+static void pool_close(pool_t *p) {
+    pthread_mutex_lock(&p->mu);
+    p->stop = 1;
+    pthread_cond_broadcast(&p->go);
+    pthread_mutex_unlock(&p->mu);
+    for (int k = 0; k < p->n_threads; k++) pthread_join(p->th[k], NULL);
+    free(p->th);
+}
+
+/* ---- growable output buffer ------------------------------------------------------------------------------------------- */
+typedef struct { char *p; size_t len, cap; } obuf_t;
+static inline char *obuf_reserve(obuf_t *o, size_t need) {
+    if (o->cap - o->len < need) {
+        size_t cap = o->cap * 2 + need + (1u << 16);
+        char *np = (char *)realloc(o->p, cap);
+        if (!np) { fprintf(stderr, "[sigtk] out of memory\n"); exit(EXIT_FAILURE); }
+        o->p = np; o->cap = cap;
+    }
+    return o->p + o->len;
+}
+
 /* ---- batches in flight ------------------------------------------------------------------------------------------ */
 typedef struct {
     sgpu_ctx_t *ctx;
@@ -131,6 +227,9 @@ typedef struct {
     opt_t opt;
     uint32_t want;
     uint64_t n_seq_order, n_fixups, n_reads_total;
+    pool_t pool;
+    obuf_t *obufs;   /* one per formatting chunk */
+    int n_obufs;
 } engine_t;
 
 static void die_sgpu(sgpu_ctx_t *ctx, int rc, const char *what) {
@@ -189,61 +288,147 @@ static void print_header(const opt_t *opt) {
     }
 }
 
+/* one read, formatted exactly as the reference's printf calls do (fastfmt.h), appended to `o` */
+static void format_read(const opt_t *opt, const sgpu_result_t *res, const sgpu_batch_t *b, uint32_t r, const char *rid,
+                        obuf_t *o) {
+    const long n = (long)b->read_len[r];
+    const size_t idl = strlen(rid);
+    char *p;
+    if (opt->mode == MODE_EVENT) {
+        const uint64_t k0 = res->ev_off[r], k1 = res->ev_off[r + 1];
+        if (opt->compact) { /* cfunc.c:19-49 */
+            p = obuf_reserve(o, idl + 128 + (size_t)(k1 - k0) * 12);
+            memcpy(p, rid, idl); p += idl; *p++ = '\t';
+            p = fmt_i64(p, n); *p++ = '\t';
+            if (k1 > k0) {
+                p = fmt_i64(p, (long)res->ev_start[k0]); *p++ = '\t';
+                p = fmt_i64(p, n); *p++ = '\t';
+                p = fmt_i64(p, (long)(k1 - k0)); *p++ = '\t';
+                for (uint64_t k = k0; k < k1; k++) {
+                    const long end = (k + 1 < k1) ? (long)res->ev_start[k + 1] : n;
+                    const int len = (int)(float)(end - (long)res->ev_start[k]);
+                    if (len) {
+                        p = fmt_i64(p, len);
+                        if (k + 1 < k1) *p++ = ',';
+                    }
+                }
+            } else {
+                memcpy(p, ".\t.\t.\t.", 7); p += 7;
+            }
+            *p++ = '\n';
+            o->len = (size_t)(p - o->p);
+        } else { /* cfunc.c:51-58 */
+            for (uint64_t k = k0; k < k1; k++) {
+                p = obuf_reserve(o, idl + 192);
+                const long start = (long)res->ev_start[k];
+                const long end = (k + 1 < k1) ? (long)res->ev_start[k + 1] : n;
+                const float length = (float)(end - start);
+                memcpy(p, rid, idl); p += idl; *p++ = '\t';
+                p = fmt_i64(p, (int)(k - k0)); *p++ = '\t';
+                p = fmt_i64(p, start); *p++ = '\t';
+                p = fmt_i64(p, start + (int)length); *p++ = '\t';
+                p = fmt_f6(p, res->ev_mean[k]); *p++ = '\t';
+                p = fmt_f6(p, res->ev_stdv[k]); *p++ = '\n';
+                o->len = (size_t)(p - o->p);
+            }
+            p = obuf_reserve(o, 1);
+            *p++ = '\n';
+            o->len = (size_t)(p - o->p);
+        }
+    } else if (opt->mode == MODE_PA) { /* cfunc.c:85-102 */
+        const float *pa = res->pa + b->read_off[r];
+        p = obuf_reserve(o, idl + 64);
+        memcpy(p, rid, idl); p += idl; *p++ = '\t';
+        p = fmt_i64(p, n); *p++ = '\t';
+        o->len = (size_t)(p - o->p);
+        for (long i = 0; i < n; i += 64) {
+            const long m = n - i < 64 ? n - i : 64;
+            p = obuf_reserve(o, 64 * 49 + 2);
+            for (long q = 0; q < m; q++) {
+                p = fmt_f6(p, pa[i + q]);
+                if (i + q != n - 1) *p++ = ',';
+            }
+            o->len = (size_t)(p - o->p);
+        }
+        p = obuf_reserve(o, 1);
+        *p++ = '\n';
+        o->len = (size_t)(p - o->p);
+    } else { /* cfunc.c:126-159: note the tab before the newline */
+        const float *s = res->stat + (size_t)r * 6;
+        p = obuf_reserve(o, idl + 400);
+        memcpy(p, rid, idl); p += idl; *p++ = '\t';
+        p = fmt_i64(p, n); *p++ = '\t';
+        p = fmt_f6(p, s[0]); *p++ = '\t';
+        p = fmt_f6(p, s[1]); *p++ = '\t';
+        p = fmt_f6(p, s[2]); *p++ = '\t';
+        p = fmt_f6(p, s[3]); *p++ = '\t';
+        p = fmt_i64(p, (int)(int16_t)s[4]); *p++ = '\t';
+        p = fmt_f6(p, s[5]); *p++ = '\t';
+        *p++ = '\n';
+        o->len = (size_t)(p - o->p);
+    }
+}
+
+typedef struct {
+    engine_t *e;
+    lane_t *l;
+    const sgpu_result_t *res;
+    const sgpu_batch_t *b;
+    const uint32_t *first; /* [n_chunks + 1] read ranges of the formatting chunks */
+} fmt_job_t;
+
+static void format_chunk(void *arg, int c) {
+    fmt_job_t *j = (fmt_job_t *)arg;
+    obuf_t *o = &j->e->obufs[c];
+    o->len = 0;
+    for (uint32_t r = j->first[c]; r < j->first[c + 1]; r++)
+        format_read(&j->e->opt, j->res, j->b, r, j->l->ids + j->l->id_off[r], o);
+}
+
 static void print_lane(engine_t *e, lane_t *l) {
     sgpu_result_t res;
+    double t0 = realtime();
     int rc = sgpu_wait(l->ctx, l->slot, &res);
     if (rc) die_sgpu(l->ctx, rc, "sgpu_wait");
+    g_prof[3] += realtime() - t0;
     sgpu_batch_t *b = NULL;
     rc = sgpu_slot_batch(l->ctx, l->slot, &b);
     if (rc) die_sgpu(l->ctx, rc, "sgpu_slot_batch");
-    const opt_t *opt = &e->opt;
-    for (uint32_t r = 0; r < l->n_reads; r++) {
-        const char *rid = l->ids + l->id_off[r];
-        const long n = (long)b->read_len[r];
-        if (opt->mode == MODE_EVENT) {
-            const uint64_t k0 = res.ev_off[r], k1 = res.ev_off[r + 1];
+    if (e->opt.mode == MODE_EVENT)
+        for (uint32_t r = 0; r < l->n_reads; r++) {
             e->n_seq_order += res.seq_order[r];
             e->n_fixups += res.fixups[r];
-            if (opt->compact) { /* cfunc.c:19-49 */
-                printf("%s\t%ld\t", rid, n);
-                if (k1 > k0) {
-                    printf("%ld\t%ld\t", (long)res.ev_start[k0], n);
-                    printf("%ld\t", (long)(k1 - k0));
-                    for (uint64_t k = k0; k < k1; k++) {
-                        const long end = (k + 1 < k1) ? (long)res.ev_start[k + 1] : n;
-                        const int len = (int)(float)(end - (long)res.ev_start[k]);
-                        if (len) {
-                            if (k + 1 < k1) printf("%d,", len); else printf("%d", len);
-                        }
-                    }
-                } else {
-                    printf(".\t.\t.\t.");
-                }
-                printf("\n");
-            } else { /* cfunc.c:51-58 */
-                for (uint64_t k = k0; k < k1; k++) {
-                    const long start = (long)res.ev_start[k];
-                    const long end = (k + 1 < k1) ? (long)res.ev_start[k + 1] : n;
-                    const float length = (float)(end - start);
-                    printf("%s\t%d\t%ld\t%ld\t%f\t%f\n", rid, (int)(k - k0), start, start + (int)length,
-                           res.ev_mean[k], res.ev_stdv[k]);
-                }
-                printf("\n");
-            }
-        } else if (opt->mode == MODE_PA) { /* cfunc.c:85-102 */
-            const float *pa = res.pa + b->read_off[r];
-            printf("%s\t%ld\t", rid, n);
-            for (long i = 0; i < n; i++) {
-                if (i == n - 1) printf("%f", pa[i]); else printf("%f,", pa[i]);
-            }
-            printf("\n");
-        } else { /* cfunc.c:126-159: note the tab before the newline */
-            const float *s = res.stat + (size_t)r * 6;
-            printf("%s\t%ld\t", rid, n);
-            printf("%f\t%f\t%f\t%f\t%d\t%f\t", s[0], s[1], s[2], s[3], (int)(int16_t)s[4], s[5]);
-            printf("\n");
         }
+    /* formatting chunks: contiguous read ranges of about equal sample counts, a few per thread */
+    int n_chunks = 4 * (e->pool.n_threads + 1);
+    if ((uint32_t)n_chunks > l->n_reads) n_chunks = (int)l->n_reads;
+    if (n_chunks > e->n_obufs) {
+        e->obufs = (obuf_t *)realloc(e->obufs, (size_t)n_chunks * sizeof(obuf_t));
+        memset(e->obufs + e->n_obufs, 0, (size_t)(n_chunks - e->n_obufs) * sizeof(obuf_t));
+        e->n_obufs = n_chunks;
     }
+    uint32_t *first = (uint32_t *)malloc(((size_t)n_chunks + 1) * sizeof(uint32_t));
+    if (!first || (n_chunks && !e->obufs)) { ERROR("%s", "out of memory"); exit(EXIT_FAILURE); }
+    const uint64_t total = l->n_reads ? b->read_off[l->n_reads] : 0;
+    uint32_t r = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        first[c] = r;
+        const uint64_t upto = total / (uint64_t)n_chunks * (uint64_t)(c + 1);
+        while (r < l->n_reads && (c == n_chunks - 1 || b->read_off[r + 1] <= upto || r == first[c])) r++;
+    }
+    first[n_chunks] = l->n_reads;
+    fmt_job_t job = {e, l, &res, b, first};
+    t0 = realtime();
+    pool_run(&e->pool, format_chunk, &job, n_chunks);
+    g_prof[4] += realtime() - t0;
+    t0 = realtime();
+    for (int c = 0; c < n_chunks; c++)
+        if (e->obufs[c].len && fwrite(e->obufs[c].p, 1, e->obufs[c].len, stdout) != e->obufs[c].len) {
+            ERROR("%s", "write to stdout failed");
+            exit(EXIT_FAILURE);
+        }
+    g_prof[5] += realtime() - t0;
+    free(first);
     e->n_reads_total += l->n_reads;
     l->busy = 0;
     l->n_reads = 0;
@@ -325,6 +510,22 @@ static void engine_add(engine_t *e, const slow5_rec_t *rec) {
     exit(EXIT_FAILURE);
 }
 
+/* ---- batch loader: parallel decode of one group of records ------------------------------------------------------------ */
+typedef struct {
+    slow5_file_t *sp;
+    char **mem;         /* the records' bytes as read from the file (slow5_get_next_bytes) */
+    size_t *bytes;
+    slow5_rec_t **rec;  /* decoded records, reused from group to group */
+    int *err;
+} load_job_t;
+
+static void decode_item(void *arg, int i) { /* slow5_decode: zlib inflate + svb-zd; thread safe (slow5.h:660) */
+    load_job_t *j = (load_job_t *)arg;
+    j->err[i] = slow5_decode(&j->mem[i], &j->bytes[i], &j->rec[i], j->sp);
+    free(j->mem[i]);
+    j->mem[i] = NULL;
+}
+
 /* ---- sub-command driver (reference src/cmain.c) ----------------------------------------------------------------------- */
 static struct option long_options[] = {{"verbose", required_argument, 0, 'v'},
                                        {"help", no_argument, 0, 'h'},
@@ -335,13 +536,14 @@ static struct option long_options[] = {{"verbose", required_argument, 0, 'v'},
                                        {"compact", no_argument, 0, 'c'},
                                        {"gpus", required_argument, 0, 0},          /* 7 (additive) */
                                        {"batch-samples", required_argument, 0, 0}, /* 8 (additive) */
+                                       {"threads", required_argument, 0, 0},       /* 9 (additive) */
                                        {0, 0, 0, 0}};
 
 static int cmain(int argc, char *argv[], const char *mode) {
     const char *optstring = "o:hVnc";
     int longindex = 0, c = -1;
     FILE *fp_help = stderr;
-    int hdr = 1, n_gpus = 1;
+    int hdr = 1, n_gpus = 1, n_threads = 0;
     uint64_t batch_samples = 0;
     engine_t eng;
     memset(&eng, 0, sizeof eng);
@@ -361,6 +563,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
             if (n_gpus < 1) n_gpus = 1;
         } else if (c == 0 && longindex == 8) {
             batch_samples = strtoull(optarg, NULL, 10);
+        } else if (c == 0 && longindex == 9) {
+            n_threads = atoi(optarg);
         }
     }
     if (argc - optind < 1 || fp_help == stdout) {
@@ -398,18 +602,67 @@ static int cmain(int argc, char *argv[], const char *mode) {
         uint64_t bytes = (stat(argv[optind], &st) == 0) ? (uint64_t)st.st_size : (64ull << 20);
         batch_samples = bytes * 8;
         if (batch_samples < (1ull << 20)) batch_samples = 1ull << 20;
-        if (batch_samples > (1ull << 26)) batch_samples = 1ull << 26;
+        if (batch_samples > (1ull << 24)) batch_samples = 1ull << 24; /* pinned memory is slow to allocate; the GPU
+                                                                          is far from the limit of this pipeline */
     }
-    engine_open(&eng, n_gpus, batch_samples);
+    if (n_threads <= 0) { /* decode and formatting threads: the host's cores, at most 32 */
+        const long nc = sysconf(_SC_NPROCESSORS_ONLN);
+        n_threads = nc < 1 ? 1 : nc > 32 ? 32 : (int)nc;
+    }
+    pool_open(&eng.pool, n_threads);
+    if (eng.opt.mode == MODE_PA && batch_samples > (1ull << 23)) batch_samples = 1ull << 23; /* 13 text bytes per sample */
+    {
+        const double t0 = realtime();
+        engine_open(&eng, n_gpus, batch_samples);
+        g_prof[6] = realtime() - t0;
+    }
 
     slow5_rec_t *rec = NULL;
     int ret = 0;
     if (argc - optind == 1) {
-        while ((ret = slow5_get_next(&rec, sp)) >= 0) engine_add(&eng, rec);
+        /* batch loader: the records' bytes are read serially, a group at a time, and decoded by the pool */
+        enum { GROUP = 512 };
+        load_job_t job;
+        memset(&job, 0, sizeof job);
+        job.sp = sp;
+        job.mem = (char **)calloc(GROUP, sizeof(char *));
+        job.bytes = (size_t *)calloc(GROUP, sizeof(size_t));
+        job.rec = (slow5_rec_t **)calloc(GROUP, sizeof(slow5_rec_t *));
+        job.err = (int *)calloc(GROUP, sizeof(int));
+        if (!job.mem || !job.bytes || !job.rec || !job.err) { ERROR("%s", "out of memory"); exit(EXIT_FAILURE); }
+        int eof = 0;
+        while (!eof) {
+            int n = 0;
+            size_t group_bytes = 0;
+            double t0 = realtime();
+            while (n < GROUP && group_bytes < (64u << 20)) {
+                if (slow5_get_next_bytes(&job.mem[n], &job.bytes[n], sp) < 0) {
+                    ret = slow5_errno;
+                    eof = 1;
+                    break;
+                }
+                group_bytes += job.bytes[n++];
+            }
+            g_prof[0] += realtime() - t0;
+            t0 = realtime();
+            pool_run(&eng.pool, decode_item, &job, n);
+            g_prof[1] += realtime() - t0;
+            t0 = realtime();
+            for (int i = 0; i < n; i++) {
+                if (job.err[i] < 0) {
+                    fprintf(stderr, "Error in slow5_get_next. Error code %d\n", job.err[i]);
+                    exit(EXIT_FAILURE);
+                }
+                engine_add(&eng, job.rec[i]);
+            }
+            g_prof[2] += realtime() - t0; /* includes the submits and prints that engine_add triggers */
+        }
         if (ret != SLOW5_ERR_EOF) {
             fprintf(stderr, "Error in slow5_get_next. Error code %d\n", ret);
             exit(EXIT_FAILURE);
         }
+        for (int i = 0; i < GROUP; i++) slow5_rec_free(job.rec[i]);
+        free(job.mem); free(job.bytes); free(job.rec); free(job.err);
     } else {
         if (slow5_idx_load(sp) < 0) {
             ERROR("Error loading index file for %s\n", argv[optind]);
@@ -431,7 +684,18 @@ static int cmain(int argc, char *argv[], const char *mode) {
         fprintf(stderr, "[%s] %" PRIu64 " of %" PRIu64 " reads took the sequential-order kernels (%" PRIu64
                         " detector boundary mismatches); results are bit-identical either way\n",
                 __func__, eng.n_seq_order, eng.n_reads_total, eng.n_fixups);
-    engine_close(&eng);
+    {
+        const double t0 = realtime();
+        engine_close(&eng);
+        g_prof[7] = realtime() - t0;
+    }
+    if (getenv("SIGTK_PROFILE"))
+        fprintf(stderr, "[%s] host wall clock: open (CUDA context, pinned slots) %.3f s, read %.3f s, decode %.3f s (%d threads), "
+                        "add+submit+print %.3f s of which wait %.3f s, format %.3f s, write %.3f s, close %.3f s\n", __func__,
+                g_prof[6], g_prof[0], g_prof[1], eng.pool.n_threads + 1, g_prof[2], g_prof[3], g_prof[4], g_prof[5], g_prof[7]);
+    pool_close(&eng.pool);
+    for (int c = 0; c < eng.n_obufs; c++) free(eng.obufs[c].p);
+    free(eng.obufs);
     slow5_rec_free(rec);
     slow5_close(sp);
     return 0;
