@@ -42,6 +42,10 @@ N_SET = 1_000_000          # reads of the named synthetic set
 METRIC = "event_detection_throughput"
 UNIT = "Gsamples/s"
 WORKLOAD = "synthetic 1M DNA reads, int16, lognormal length mean 40k samples (sigma 0.6), {mode}"
+WORKLOADS = {"dna40k": WORKLOAD,
+             "dna178k": "synthetic DNA reads, int16, fixed 178,000 samples (20 kb-equivalent), {mode}",
+             "ultralong": "synthetic ultra-long DNA reads, int16, 2,000,000 samples each, {mode}",
+             "rna40k": "synthetic RNA-parameter reads, int16, lognormal length mean 40k samples, {mode}"}
 
 
 def alg_bytes(n_samples: int, n_reads: int, n_events: int, pa: bool) -> int:
@@ -105,7 +109,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def device_batch(torch, dev, lens: np.ndarray, first_index: int, seed: int):
+def device_batch(torch, dev, lens: np.ndarray, first_index: int, seed: int, p_change: float = 0.1):
     """One batch of synthetic reads generated on the device (signal model of sigtk_b200/synth.py).
     -> dict(samples i16[span], read_off i64[n+1], read_len i32[n], offset f32[n], unit f32[n], span, n_samples)"""
     n = len(lens)
@@ -125,7 +129,7 @@ def device_batch(torch, dev, lens: np.ndarray, first_index: int, seed: int):
         r1 = min(max(r1 - 1, r0 + 1), n)
         a, b = int(off[r0]), int(off[r1])
         m = b - a
-        change = torch.rand(m, device=dev, generator=gen) < 0.1
+        change = torch.rand(m, device=dev, generator=gen) < p_change
         change[0] = True
         seg = torch.cumsum(change.to(torch.int32), 0, dtype=torch.int32) - 1
         nlev = int(seg[-1].item()) + 1
@@ -246,7 +250,16 @@ def run_ours(args):
     pa_mode = args.mode == "event+pa"
     want = sg.WANT_EVENTS | (sg.WANT_PA if pa_mode else 0)
     B = args.reads_per_step
-    lens_all = synth.read_lengths(N_SET)
+    rna = 1 if args.workload == "rna40k" else 0
+    p_change = 0.025 if rna else 0.1
+    if args.workload == "dna178k":      # SURVEY 8(d) C3': "20 kb-equivalent" reads, fixed 178,000 samples
+        lens_all = np.full(N_SET, 178_000, dtype=np.int64)
+        B = min(B, 3670)
+    elif args.workload == "ultralong":  # BASELINE config 5: 2,000,000-sample reads
+        lens_all = np.full(N_SET, 2_000_000, dtype=np.int64)
+        B = min(B, 320)
+    else:
+        lens_all = synth.read_lengths(N_SET)
     pool_n = max(1, min(args.pool, args.steps + args.warmup))
     from sigtk_b200.shard import shard_ranges
     pool = []
@@ -254,7 +267,8 @@ def run_ours(args):
         # step j works on the next world*B reads of the set, split into contiguous read ranges balanced by samples
         g0 = (j * world * B) % (N_SET - world * B)
         lo, hi = shard_ranges(lens_all[g0:g0 + world * B], world)[rank]
-        pool.append(device_batch(torch, dev, lens_all[g0 + lo:g0 + hi], g0 + lo, synth.SEED + 7919 * (j * world + rank)))
+        pool.append(device_batch(torch, dev, lens_all[g0 + lo:g0 + hi], g0 + lo, synth.SEED + 7919 * (j * world + rank),
+                                 p_change))
     torch.cuda.synchronize()
     max_span = max(p["span"] for p in pool)
     max_reads = max(p["n_reads"] for p in pool)
@@ -264,7 +278,7 @@ def run_ours(args):
 
     def step(p):
         return ctx.run_device(p["samples"].data_ptr(), p["read_off"].data_ptr(), p["read_len"].data_ptr(),
-                              p["offset"].data_ptr(), p["unit"].data_ptr(), p["n_reads"], p["span"], 0, want, stream)
+                              p["offset"].data_ptr(), p["unit"].data_ptr(), p["n_reads"], p["span"], rna, want, stream)
 
     for w in range(args.warmup):
         step(pool[w % pool_n])
@@ -318,7 +332,7 @@ def run_ours(args):
     value = all_samples / (ms_max * 1e-3) / 1e9
 
     # ---- end to end through the host C-ABI: pinned slots, H2D + kernels + D2H per step ----------------------------
-    e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist)
+    e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna)
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
@@ -342,8 +356,9 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         chk, kind = load_checker()
-        reads = host_reads_of(pool[0], args.cpu_reads)
-        dt, ns, ne = chk.time_events(reads, 0)
+        n_cpu = min(args.cpu_reads, max(1, int(np.searchsorted(np.cumsum(pool[0]["host_len"]), 80_000_000))))
+        reads = host_reads_of(pool[0], n_cpu)
+        dt, ns, ne = chk.time_events(reads, rna)
         cpu = {"value": ns / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
                "sample": f"first {len(reads)} reads of batch 0 ({ns} samples, {ne} events, {dt:.1f} s)"}
     if rank == 0:
@@ -351,7 +366,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(mode=args.mode), "reads_per_step_per_gpu": B_step, "sharding": "contiguous read ranges balanced by samples, no collective",
+            "config": {"workload": WORKLOADS[args.workload].format(mode=args.mode), "reads_per_step_per_gpu": B_step, "sharding": "contiguous read ranges balanced by samples, no collective",
                        "samples_per_step_per_gpu": n_samples // max(args.steps, 1),
                        "events_per_sample": all_events / max(all_samples, 1.0),
                        "l2": f"inputs {2 * max_span / 1e6:.0f} MB per step > 126 MB L2; pool of {pool_n} distinct batches",
@@ -365,7 +380,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist):
+def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0):
     """K steps of (pinned slot -> H2D -> kernels -> D2H -> host-visible event table), two slots in flight."""
     B = min(args.e2e_reads, batch["n_reads"])
     off, lens = batch["host_off"], batch["host_len"]
@@ -373,7 +388,7 @@ def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist):
     span = int(off[B])
     hctx = sg.Context(device=local, max_samples=span + 64, max_reads=B, n_slots=2)
     for s in (0, 1):
-        hctx.fill(s, reads, 0)  # the batch loader's job (decode into the pinned slot): outside the timed region
+        hctx.fill(s, reads, rna)  # the batch loader's job (decode into the pinned slot): outside the timed region
     n_samp = int(lens[:B].sum())
 
     def wait(slot):
@@ -414,6 +429,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="event+pa", choices=["event+pa", "event"])
+    ap.add_argument("--workload", default="dna40k", choices=["dna40k", "dna178k", "ultralong", "rna40k"],
+                    help="dna40k = BASELINE.json configs[2] (the headline); the others are reported in DESIGN.md")
     ap.add_argument("--reads-per-step", type=int, default=16384)
     ap.add_argument("--pool", type=int, default=4, help="distinct device-resident batches cycled through")
     ap.add_argument("--e2e-reads", type=int, default=4096)

@@ -332,3 +332,47 @@ def test_device_resident_path(ctx):
     assert np.array_equal(dctx.d2h(res.ev_off, np.uint64, len(reads) + 1), host.ev_off)
     assert np.array_equal(bits(dctx.d2h(res.ev_mean, np.float32, ne)), bits(host.ev_mean))
     dctx.close()
+
+
+def test_full_size_batch(orc):
+    """One batch of the size bench.py runs (16,384 synthetic DNA reads, ~650 M samples, generated on the device):
+    size-independent properties over ALL events, and bit-exact parity with the oracle for a spread of reads."""
+    torch = pytest.importorskip("torch")
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    dev = torch.device("cuda:0")
+    lens = synth.read_lengths(16384)
+    p = bench.device_batch(torch, dev, lens, 0, 4242)
+    dctx = sg.Context(device=0, max_samples=p["span"], max_reads=p["n_reads"], flags=sg.F_NO_HOST_SLOTS)
+    st = torch.cuda.current_stream().cuda_stream
+    res = dctx.run_device(p["samples"].data_ptr(), p["read_off"].data_ptr(), p["read_len"].data_ptr(),
+                          p["offset"].data_ptr(), p["unit"].data_ptr(), p["n_reads"], p["span"], 0, sg.WANT_EVENTS, st)
+    torch.cuda.synchronize()
+    c = dctx.counters()
+    assert c["status"] == 0 and c["n_seq_order_reads"] == 0 and c["n_fixups"] == 0
+    ne, nr = c["n_events"], p["n_reads"]
+    ev_off = dctx.d2h(res.ev_off, np.uint64, nr + 1).astype(np.int64)
+    ev_start = dctx.d2h(res.ev_start, np.uint32, ne).astype(np.int64)
+    ev_mean = dctx.d2h(res.ev_mean, np.float32, ne)
+    ev_stdv = dctx.d2h(res.ev_stdv, np.float32, ne)
+    assert ev_off[0] == 0 and ev_off[-1] == ne and np.all(np.diff(ev_off) >= 1)
+    first = np.zeros(ne, dtype=bool)
+    first[ev_off[:-1]] = True
+    assert np.all(ev_start[first] == 0)                       # event 0 of every read starts at sample 0
+    gaps = np.diff(ev_start)[~first[1:]]
+    assert gaps.min() >= 3                                    # peaks are at least floor(w1/2)+2 = 3 samples apart
+    last = ev_start[ev_off[1:] - 1]
+    assert np.all(last < p["host_len"])
+    assert 0.15 < ne / p["n_samples"] < 0.25                  # the signal model gives ~0.19 events per sample
+    assert np.all(np.isfinite(ev_mean)) and np.all(ev_stdv >= 0)
+    assert 50.0 < float(ev_mean.mean()) < 130.0
+    # bit-exact against the oracle for reads spread over the batch (first, last, and in between)
+    off, hl = p["host_off"], p["host_len"]
+    for r in [0, 1, nr // 3, nr // 2, nr - 2, nr - 1, int(np.argmax(hl)), int(np.argmin(hl))]:
+        raw = p["samples"][int(off[r]): int(off[r]) + int(hl[r])].cpu().numpy()
+        s0, ln, mn, sd = orc.events(raw, synth.DIGITISATION, float(p["host_offset"][r]), synth.RANGE, rna=0)
+        a, b = ev_off[r], ev_off[r + 1]
+        assert np.array_equal(ev_start[a:b], s0.astype(np.int64)), f"read {r}: boundaries differ"
+        assert np.array_equal(bits(ev_mean[a:b]), bits(mn)) and np.array_equal(bits(ev_stdv[a:b]), bits(sd))
+    dctx.close()
