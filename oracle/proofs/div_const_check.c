@@ -1,5 +1,5 @@
 /* div_const_check.c -- TEST INFRASTRUCTURE. Validates the arithmetic shortcuts used by the CUDA fast path
- * (sigtk_b200/csrc/common.cuh) against IEEE division on the CPU:
+ * (sigtk_b200/csrc/walk_core.cuh) against IEEE division on the CPU:
  *   float : q = a / w  vs  q0 = a*r; e = fmaf(-w, q0, a); q = fmaf(e, r, q0)   EXHAUSTIVELY over all 2^32 floats
  *   double: same sequence on 4e9 random doubles per divisor in the magnitude range the path produces
  * for the window lengths w in {3, 6, 7, 14} (events.c:43-54).

@@ -33,7 +33,7 @@ static inline int tail_fast(float delta, float scaled, float y0f, float *out) {
     const uint64_t b = d_bits(q);
     const uint32_t lo29 = (uint32_t)(b & 0x1fffffffull);
     const uint32_t ex = (uint32_t)(b >> 52) & 0x7ff;
-    /* the guard of tstat_tail() in sigtk_b200/csrc/common.cuh: 2^-126 <= q < 2^126, the 29 bits below float
+    /* the guard of tail() in sigtk_b200/csrc/walk_core.cuh: 2^-126 <= q < 2^126, the 29 bits below float
      * precision not within 512 of the rounding midpoint, scaled not tiny (the GPU seed flushes denormals) */
     const int in_range = ex >= 1023 - 126 && ex < 1023 + 126;
     const int off_mid = (uint32_t)(lo29 - (0x10000000u - 512u)) >= 1024u;
