@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) build_seq_list_kernel(DevBatch b, const u
         if (!(unit > 0.0f && unit <= FLT_MAX) || n >= (1u << 30) - 64u) flag = true;
         if (!flag && n > 0) {
             const uint32_t mn = wit_min[r], mx = wit_max[r];
-            // every sample must be a positive float >= 2^-60 (the range of the walker's shortcuts) ...
-            if (mn < 0x21800000u || mn > mx) flag = true;
+            // every sample must be a positive float in [2^-60, 2^20) (the range of the walker's shortcuts) ...
+            if (mn < 0x21800000u || mn > mx || mx >= 0x49800000u) flag = true;
             else {  // ... and the sums of x and x*x must be exact whatever the order
                 const uint32_t log2n = n > 1 ? 32u - __clz(n - 1) : 0u;
                 const float fmn = __uint_as_float(mn), fmx = __uint_as_float(mx);

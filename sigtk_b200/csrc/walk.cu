@@ -43,6 +43,8 @@ struct WalkParams {
     int* st_end;                    // same indexing: state after the chunk's last step
     uint32_t* wit_min;
     uint32_t* wit_max;
+    uint32_t* seq_flag;
+    uint32_t* fixups;
     uint32_t edge_blocks;
 };
 
@@ -55,6 +57,8 @@ struct DevIo {
     int* __restrict__ st_end;
     uint32_t* __restrict__ wit_min;   // this read's witness
     uint32_t* __restrict__ wit_max;
+    uint32_t* __restrict__ far_flag;  // this read's sequential-order flag / fix-up counter (far_peak)
+    uint32_t* __restrict__ far_fix;
     float off, unit;
 
     __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
@@ -69,14 +73,16 @@ struct DevIo {
     }
     __device__ __forceinline__ void store_pa1(int t, float x) const { pa[t] = x; }
     __device__ __forceinline__ void peak(int pos) const { atomicOr(bm + ((uint32_t)pos >> 5), 1u << (pos & 31)); }
-    __device__ __forceinline__ void peak_if(int pos, bool on) const {  // predicated RED; address = one wide multiply-add
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t.reg .u32 i;\n\t"
-                     "setp.ne.s32 p, %3, 0;\n\t"
-                     "shr.u32 i, %1, 5;\n\t"
-                     "mad.wide.u32 a, i, 4, %0;\n\t"
-                     "@p red.global.or.b32 [a], %2;\n\t}"
-                     :: "l"(bm), "r"(pos), "r"(1u << (pos & 31)), "r"((int)on) : "memory");
+    // the peaks of one block: bit k of mk <=> a peak at shifted position ub + k (ub may be negative at the start
+    // of a read: those bits are zero, and a zero part is never written)
+    __device__ __forceinline__ void peaks32(int ub, uint32_t mk) const {
+        const uint32_t s = (uint32_t)ub & 31u;
+        const uint32_t lo = mk << s, hi = __funnelshift_l(mk, 0u, s);
+        uint32_t* w = bm + (ub >> 5);
+        if (lo) atomicOr(w, lo);
+        if (hi) atomicOr(w + 1, hi);
     }
+    __device__ __forceinline__ void far_peak() const { *far_flag = 1u; atomicAdd(far_fix, 1u); }
     static __device__ __forceinline__ void store_canon(int* __restrict__ dst, const Canon& c) {
         int4* p = reinterpret_cast<int4*>(dst);
         p[0] = make_int4(c.v[0], c.v[1], c.v[2], c.v[3]);
@@ -107,6 +113,8 @@ __device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64
     io.st_end = p.st_end + sid * 8;
     io.wit_min = p.wit_min + r;
     io.wit_max = p.wit_max + r;
+    io.far_flag = p.seq_flag + r;
+    io.far_fix = p.fixups + r;
     io.off = p.b.offset[r];
     io.unit = p.b.unit[r];
     return io;
@@ -230,6 +238,7 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
     p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max;
+    p.seq_flag = seq_flag; p.fixups = fixups;
     p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
     const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
     const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;

@@ -69,8 +69,11 @@ SGW_HD float rsqrt_seed(float a) {
 SGW_HD double widen_pos(float a) {
     return __longlong_as_double((long long)((unsigned long long)__float_as_uint(a) * 0x20000000ull + 0x3800000000000000ull));
 }
-SGW_HD double widen_abs(float a) {  // (double)fabsf(a), a normal and nonzero
-    return __longlong_as_double((long long)((unsigned long long)(__float_as_uint(a) & 0x7fffffffu) * 0x20000000ull + 0x3800000000000000ull));
+SGW_HD double widen_abs(float a) { return (double)fabsf(a); }  // any a (one conversion; 0 stays 0)
+SGW_HD uint32_t shr_clamp(uint32_t x, int s) {  // x >> s; 0 when s is outside [0, 31] (PTX shr clamps the amount)
+    uint32_t r;
+    asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+    return r;
 }
 #else
 SGW_HD double dadd(double a, double b) { return a + b; }
@@ -94,11 +97,8 @@ SGW_HD double widen_pos(float a) {  // same bit arithmetic as the device version
     const uint64_t v = (uint64_t)b * 0x20000000ull + 0x3800000000000000ull;
     double r; memcpy(&r, &v, 8); return r;
 }
-SGW_HD double widen_abs(float a) {
-    uint32_t b; memcpy(&b, &a, 4);
-    const uint64_t v = (uint64_t)(b & 0x7fffffffu) * 0x20000000ull + 0x3800000000000000ull;
-    double r; memcpy(&r, &v, 8); return r;
-}
+SGW_HD double widen_abs(float a) { return (double)fabsf(a); }
+SGW_HD uint32_t shr_clamp(uint32_t x, int s) { return (unsigned)s < 32u ? x >> s : 0u; }
 #endif
 
 // ---- parameters (events.c:35-54) ----------------------------------------------------------------------------------
@@ -140,11 +140,13 @@ SGW_HD float fdivw(float a) {
 // t = (float)(fabs((double)delta) / sqrt((double)(cv / W)))  (events.c:360) through a 22-bit reciprocal square
 // root and one third-order correction in double. The product is within a few ulp(double) of the true quotient,
 // so it rounds to the same float as the reference's doubly rounded value unless it lies next to a float rounding
-// midpoint or outside the normal float range (oracle/proofs/tstat_tail_check.c); such values (about 2 in a
-// million) raise `bad`, and the caller recomputes the block's t-statistics with the reference's own operations
-// (exact_block). delta == 0 gives +0 on both routes whatever cv is (flat stretches of the signal).
+// midpoint (oracle/proofs/tstat_tail_check.c); such values (about 2 in a million) and cv < 2e-29 clear `ok`, and
+// the caller recomputes the block's t-statistics with the reference's own operations (exact_block).
+// No range check is needed on the quotient q: the per-read witness bounds every pA to [2^-60, 2^20), so
+// |delta| is 0 or in [2^-84, 2^21], cv <= 2^42 and (checked here) cv >= 2e-29, hence q == 0 or 2^-105 < q < 2^72:
+// a normal float after rounding. delta == 0 gives q == +0 and t == +0 like the reference (flat stretches).
 template <int W>
-SGW_HD float tail(float delta, float cv, bool& bad) {
+SGW_HD float tail(float delta, float cv, bool& ok) {
     const float scaled = fdivw<W>(cv);  // cv >= FLT_MIN > 0; shortcut valid for cv >= 1e-36
     const double c = widen_pos(scaled);
     const double y0 = widen_pos(rsqrt_seed(scaled));
@@ -154,14 +156,9 @@ SGW_HD float tail(float delta, float cv, bool& bad) {
     const double ye = dmul(y0, e);
     const double y = dfma(ye, p, y0);
     const double q = dmul(widen_abs(delta), y);
-    const uint32_t lo = d_lo(q), hi = d_hi(q);
-    // accept when 2^-126 <= q < 2^126, the 29 bits below float precision are not within 512 of the midpoint,
-    // and scaled >= 1e-30 (cv >= 2e-29 implies it for W <= 14)
-    const bool in_range = (hi - ((1023u - 126u) << 20)) < (252u << 20);
-    const bool off_mid = (lo * 8u - ((0x10000000u - 512u) << 3)) >= (1024u << 3);  // the low 29 bits, shifted up
-    const bool zero = delta == 0.0f;
-    bad = bad | !(zero | (in_range & off_mid & (cv >= 2.0e-29f)));
-    return zero ? 0.0f : d2f(q);
+    // accept when the 29 bits below float precision are not within 512 of the midpoint (low word, shifted up)
+    ok = ok & ((d_lo(q) * 8u - ((0x10000000u - 512u) << 3)) >= (1024u << 3)) & (cv >= 2.0e-29f);
+    return d2f(q);
 }
 
 // The terms of events.c:339-350 that depend on ONE window [j, j+W) only. The window is the right window of
@@ -177,10 +174,10 @@ SGW_HD void window_terms(double D, double E, float& A, double& Lq, float& B, dou
     B2d = widen_pos(fmul(B, B));                          // (double)(mean2*mean2)
 }
 template <int W>
-SGW_HD float tstat_from(float A_left, double L_left, float B, double Vd, double B2d, bool& bad) {
+SGW_HD float tstat_from(float A_left, double L_left, float B, double Vd, double B2d, bool& ok) {
     const double acc = dsub(dadd(L_left, Vd), B2d);       // ((.. - m1sq) + v2) - m2sq, left to right in double
     const float cv = fmaxf(d2f(acc), FLT_MIN);            // events.c:353
-    return tail<W>(fsub(B, A_left), cv, bad);             // delta = mean2 - mean1
+    return tail<W>(fsub(B, A_left), cv, ok);              // delta = mean2 - mean1
 }
 
 // ---- the reference's own operation sequence, from the raw samples (rare path) ---------------------------------------
@@ -244,7 +241,7 @@ void exact_block(const Io& io, int tau0, int n, float off, float unit, int m1, i
 //                       ps = peak_pos | PS_OPEN   CASE 2, valid_peak == false
 //                       ps = peak_pos             CASE 2, valid_peak == true
 // so that "valid_peak && i - peak_pos > w/2" (events.c:429) is the single comparison  i - ps > w/2.
-constexpr int PS_NONE = 0x7fffffff;
+constexpr int PS_NONE = 0x7fff0000;  // (room below INT_MAX: position - PS_NONE must not wrap for positions >= -2^16)
 constexpr int PS_OPEN = 0x40000000;
 struct WalkDet {
     float s_pv; int s_ps;               // short detector (never masked after the read's first sample)
@@ -266,47 +263,57 @@ SGW_HD Canon canon_of(const WalkDet& d, int b) {
     return c;
 }
 
-// One detector, one position (events.c:393-437). Returns true when a peak is emitted (*pos = its position).
-// `act` = the detector is not masked at u (events.c:387); the state is left untouched when !act.
+// Emitted peaks of one block are collected in a register: bit k of `mk` <=> a peak at position ub + k. The
+// block's own steps sit at bits PK_LEAD .. PK_LEAD + U - 1, so a peak up to PK_LEAD positions older than the
+// step that emits it fits; an older one (a plateau within peak_height of a maximum above the threshold lasting
+// dozens of samples) sets `far`, and the read is redone by the sequential-order kernels.
+template <int RNA> struct PkCfg {
+    static constexpr int LEAD = 32 - Cfg<RNA>::U;
+    static constexpr int FAR = LEAD - (Cfg<RNA>::w2 / 2 + 1);  // largest (age - w/2 - 1) that always fits the mask
+};
+struct PeakAcc { uint32_t mk; int oldest; };
+
+// One detector, one position (events.c:393-437); the detector is not masked at u (events.c:387).
+//   m    : index of the step within its block (compile-time), u : its position
+//   c    : the t-statistic at u
+//   big2 : CASE 2 and the running maximum is above the threshold (the short detector then masks the long one)
+//   p2   : the (possibly moved) peak position with the PS_OPEN flag, valid when big2
 template <bool SHORT, int RNA>
-SGW_HD bool det_one(float& pv, int& ps, int u, float c, bool act, bool& big_case2, int& peak_if_big, int* pos) {
+SGW_HD void det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, bool& big2, int& p2) {
     constexpr int w = SHORT ? Cfg<RNA>::w1 : Cfg<RNA>::w2;
     const float h = peak_h<RNA>();
     const float thr = SHORT ? thr_short<RNA>() : thr_long<RNA>();
     const bool none = ps == PS_NONE;
     const float df = fsub(c, pv);                          // > 0: above the running value, < 0: below
-    const bool gt = df > 0.0f, rise = df > h;
-    const bool lt_or_rise = (df < 0.0f) | rise;
-    const float pv2 = fmaxf(pv, c);                        // CASE 2: the running maximum
-    const int ps2 = gt ? ((ps & PS_OPEN) | u) : ps;        // a new maximum moves the peak, valid_peak is kept
-    const bool big = pv2 > thr;
-    const bool drop_big = (df < -h) & big;                 // pv - c > h (negation is exact) && pv > threshold
-    const int ps3 = drop_big ? (ps2 & ~PS_OPEN) : ps2;     // valid_peak = true
-    const bool emit = act & ((u - ps3) > w / 2);           // false in CASE 1 (ps3 >= 2^30 - 1) and while not valid
-    big_case2 = !none & big;
-    peak_if_big = ps2 & ~PS_OPEN;
-    *pos = ps3;
-    const bool setc = act & ((none & lt_or_rise) | (!none & (gt | emit)));
-    pv = setc ? c : pv;
-    const int ps_case1 = rise ? (u | PS_OPEN) : PS_NONE;
-    const int ps_case2 = emit ? PS_NONE : ps3;
-    ps = act ? (none ? ps_case1 : ps_case2) : ps;
-    return emit;
+    const float pvm = none ? fminf(pv, c) : fmaxf(pv, c);  // CASE 1: running minimum (394); CASE 2: running maximum (408)
+    const bool rise1 = none & (df > h);                    // CASE 1 -> CASE 2 at u (399-403)
+    const bool gt2 = !none & (df > 0.0f);                  // CASE 2: a new maximum moves the peak, valid_peak is kept
+    big2 = !none & (pvm > thr);
+    const bool drop = big2 & (df < -h);                    // pv - c > h (the negation is exact) && pv > threshold (424)
+    p2 = gt2 ? ((ps & PS_OPEN) | u) : ps;
+    const int p3 = drop ? (p2 & ~PS_OPEN) : p2;            // valid_peak = true
+    const int over = (u - (w / 2 + 1)) - p3;               // age of the peak beyond w/2 + 1; negative in CASE 1 and
+    const bool emit = over >= 0;                           // while not valid (flag bits): events.c:429
+    acc.mk |= shr_clamp(1u << (PkCfg<RNA>::LEAD + m - (w / 2 + 1)), over);  // no bit unless 0 <= over <= 31
+    acc.oldest = acc.oldest > over ? acc.oldest : over;
+    pv = (rise1 | emit) ? c : pvm;                         // 395 / 400 / 409 / 433
+    ps = emit ? PS_NONE : p3;
+    ps = rise1 ? (u | PS_OPEN) : ps;
 }
 
-// One position of both detectors, short first (events.c:385-440). `Sink::peak_if(pos, on)` records an emitted peak.
-template <int RNA, class Sink>
-SGW_HD void det_step(WalkDet& d, int u, float c1, float c2, bool rec, Sink& sink) {
-    bool maskl; int pk, pos;
-    const bool e1 = det_one<true, RNA>(d.s_pv, d.s_ps, u, c1, true, maskl, pk, &pos);
-    sink.peak_if(pos, e1 & rec);
+// One position of both detectors, short first (events.c:385-440).
+template <int RNA>
+SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc) {
+    bool maskl, unused_b; int p2, unused_p;
+    det_one<true, RNA>(d.s_pv, d.s_ps, m, u, c1, acc, maskl, p2);
     // the short detector dominates the long one while it holds a peak above its threshold (events.c:414-422)
-    d.l_mt = maskl ? pk + Cfg<RNA>::w1 : d.l_mt;
+    d.l_mt = maskl ? (p2 & ~PS_OPEN) + Cfg<RNA>::w1 : d.l_mt;
     d.l_ps = maskl ? PS_NONE : d.l_ps;
     d.l_pv = maskl ? FLT_MAX : d.l_pv;
-    bool unused_b; int unused_p;
-    const bool e2 = det_one<false, RNA>(d.l_pv, d.l_ps, u, c2, d.l_mt < u, unused_b, unused_p, &pos);
-    sink.peak_if(pos, e2 & rec);
+    // a masked long detector is always in the reset state (masked_to is only ever set together with a reset, and
+    // a masked detector is not stepped), and the reset state does not react to FLT_MAX: no gating needed
+    const float c2m = d.l_mt < u ? c2 : FLT_MAX;
+    det_one<false, RNA>(d.l_pv, d.l_ps, m, u, c2m, acc, unused_b, unused_p);
 }
 
 // ---- the register rings --------------------------------------------------------------------------------------------
@@ -346,7 +353,7 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
     using C = Cfg<RNA>;
     constexpr int w1 = C::w1, w2 = C::w2, M1 = C::R1 - 1, M2 = C::R2 - 1, U = C::U;
     float t1v[U], t2v[U];
-    bool bad = false, bad_t1 = false;  // bad_t1: among the last w1 values of t1
+    bool ok = true, ok_t1 = true;  // ok_t1: among the last w1 values of t1
 #pragma unroll
     for (int m = 0; m < U; m++) {
         // static ring slots: every index below is (m + const) & mask because tau0 is a multiple of U
@@ -368,23 +375,25 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
         const double d2 = dadd(g.D1[s1l], d1), e2 = dadd(g.E1[s1l], e1);
         float a2, b2; double l2, v2, b2sq;
         window_terms<w2>(d2, e2, a2, l2, b2, v2, b2sq);
-        {
-            bool bd = false;
-            t1v[m] = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, bd);
-            if (EDGE) { const int j1 = tau0 + m - w1 + 1; bd = bd & (j1 >= w1) & (j1 + w1 <= n); }
-            if (m >= U - w1) bad_t1 = bad_t1 | bd; else bad = bad | bd;
-        }
-        {
-            bool bd = false;
-            t2v[m] = tstat_from<w2>(g.A2[s2l], g.L2[s2l], b2, v2, b2sq, bd);
-            if (EDGE) { const int j2 = tau0 + m - w2 + 1; bd = bd & (j2 >= w2) & (j2 + w2 <= n); }
-            bad = bad | bd;
+        if (EDGE) {  // positions whose windows leave the read do not count (their t is 0, set below)
+            bool k1 = true, k2 = true;
+            t1v[m] = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, k1);
+            t2v[m] = tstat_from<w2>(g.A2[s2l], g.L2[s2l], b2, v2, b2sq, k2);
+            const int j1 = tau0 + m - w1 + 1, j2 = tau0 + m - w2 + 1;
+            k1 = k1 | (j1 < w1) | (j1 + w1 > n);
+            k2 = k2 | (j2 < w2) | (j2 + w2 > n);
+            if (m >= U - w1) ok_t1 = ok_t1 & k1; else ok = ok & k1;
+            ok = ok & k2;
+        } else {
+            if (m >= U - w1) t1v[m] = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, ok_t1);
+            else t1v[m] = tstat_from<w1>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, ok);
+            t2v[m] = tstat_from<w2>(g.A2[s2l], g.L2[s2l], b2, v2, b2sq, ok);
         }
         g.D1[s1] = d1; g.E1[s1] = e1;
         g.A1[s1] = a1; g.L1[s1] = l1;
         g.A2[s2] = a2; g.L2[s2] = l2;
     }
-    if ((bad & live) | (bad_t1 & live_t1)) {  // rare: the copies keep t1v / t2v in registers (only e1 / e2 live in local memory)
+    if ((!ok & live) | (!ok_t1 & live_t1)) {  // rare: the copies keep t1v / t2v in registers (only e1 / e2 live in local memory)
         float e1[U], e2[U];
         exact_block<RNA>(io, tau0, n, off, unit, 0, 1, e1, e2);
 #pragma unroll
@@ -398,11 +407,18 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
             t2v[m] = (j2 >= w2 && j2 + w2 <= n) ? t2v[m] : 0.0f;
         }
     }
+    PeakAcc acc;
+    acc.mk = 0u; acc.oldest = 0;
+    const int u0 = tau0 - w2 + 1 + sh;                              // position of the block's first step
 #pragma unroll
     for (int m = 0; m < U; m++) {
         const int j2 = tau0 + m - w2 + 1;
         const float c1 = m >= w1 ? t1v[m - w1] : g.T1c[m];         // t1(j2), computed w1 samples ago
-        if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, j2 + sh, c1, t2v[m], rec, io);
+        if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, m, u0 + m, c1, t2v[m], acc);
+    }
+    if (rec) {  // peaks are owned by the step that emits them
+        if (acc.mk) io.peaks32(u0 - PkCfg<RNA>::LEAD, acc.mk);
+        if (acc.oldest > PkCfg<RNA>::FAR) io.far_peak();
     }
 #pragma unroll
     for (int k = 0; k < w1; k++) g.T1c[k] = t1v[U - w1 + k];
@@ -414,7 +430,9 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 // tests/tools/host_walk.cpp):
 //   load8(t, v)        the four 32-bit words holding samples [t, t+8) of the read (t multiple of 8)
 //   want_pa() / store_pa8(t, x) / store_pa1(t, x)
-//   peak_if(pos, on)   record an emitted peak (shifted position) when `on`
+//   peaks32(ub, mk)    record the emitted peaks of a block: bit k of mk (nonzero) <=> a peak at shifted position ub + k
+//   peak(pos)          record one peak
+//   far_peak()         a peak older than the block's mask was emitted: the read must be redone in sequential order
 //   put_begin(c) / put_end(c)   the chunk's canonical detector state after the warm-up / after its last step
 //   witness(rmin, rmax)         extreme raw values of samples of the read (any superset of the owned samples)
 SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return (n + L - 1u) / L; }
@@ -532,7 +550,7 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
         walk_block<RNA, true>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, off, unit, io);
     }
     if (!to_end) io.put_end(canon_of(d, s1 - C::LAG + sh));
-    if (!last) io.peak_if(sh, true);  // event 0 starts at the read's first sample (events.c:490-497)
+    if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)
     if (rmin <= rmax) io.witness(rmin, rmax);
 }
 
