@@ -242,8 +242,18 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
     p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
     const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
     const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;
-    if (b.rna) walk_chunks_kernel<1><<<(unsigned)grid, WNT, 0, st>>>(p);
-    else walk_chunks_kernel<0><<<(unsigned)grid, WNT, 0, st>>>(p);
+    // development knob: unused dynamic shared memory caps the resident blocks per SM (occupancy experiments)
+    static int dyn_smem = -1;
+    if (dyn_smem < 0) {
+        const char* e = getenv("SGPU_WALK_SMEM");
+        dyn_smem = e ? atoi(e) : 0;
+        if (dyn_smem > 0) {
+            cudaFuncSetAttribute(walk_chunks_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+            cudaFuncSetAttribute(walk_chunks_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
+        }
+    }
+    if (b.rna) walk_chunks_kernel<1><<<(unsigned)grid, WNT, dyn_smem, st>>>(p);
+    else walk_chunks_kernel<0><<<(unsigned)grid, WNT, dyn_smem, st>>>(p);
     verify_chunks_kernel<<<grid_cap(max_interior + b.n_reads, 256, sm_count * 8), 256, 0, st>>>(
         b, L, sc.wk_ibase, sc.wk_begin, sc.wk_end, seq_flag, fixups);
     return n + 2;

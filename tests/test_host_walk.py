@@ -63,3 +63,16 @@ def test_flat_stretch(lib, orc):
     raw[6000:14000] = raw[5999]
     for rna, L, W in ((0, 256, 64), (1, 512, 384)):
         check(lib, orc, (raw, rd[1], rd[2], rd[3]), rna, L, W, 0, must_verify=False)
+
+
+def test_exact_recompute_path(orc):
+    """the rare path (a t-statistic next to a float rounding midpoint: the block is recomputed with the reference's
+    own operations) forced on every third block, first / interior / last chunks, DNA and RNA"""
+    lib = _hostwalk.load(force_redo=True)
+    for rna, L, W in ((0, 128, 64), (0, 1024, 64), (1, 512, 384)):
+        reads = synth.make_reads(4, mean=7000.0, seed=77 + rna, rna=bool(rna))
+        for k, rd in enumerate(reads):
+            check(lib, orc, rd, rna, L, W, (0, 8, 16, 24)[k % 4])
+    base = synth.make_read(3, 600, seed=10)
+    for n in (5, 13, 29, 199, 200, 257, 600):
+        check(lib, orc, (base[0][:n].copy(), base[1], base[2], base[3]), 0, 128, 64, 8)
