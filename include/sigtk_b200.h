@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SGPU_ABI_VERSION 1
+#define SGPU_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define SGPU_OK            0
@@ -44,6 +44,7 @@ extern "C" {
 #define SGPU_E_STATE      -6  /* call out of order (e.g. wait on a slot that was not submitted) */
 #define SGPU_E_EVCAP      -7  /* event capacity exceeded (never for n/3+2 sizing; reported, not truncated) */
 #define SGPU_E_SCRATCH    -8  /* sequential-order scratch too small for the reads that need it */
+#define SGPU_E_STREAM     -9  /* malformed svb-zd stream (slow5lib: "Expected streamvbyte_decode to read ...", slow5_press.c:1103) */
 
 /* ---- what to compute (bitmask) ------------------------------------------ */
 #define SGPU_WANT_EVENTS   1u /* event table: getevents(), events.c:553-573 */
@@ -115,6 +116,15 @@ int  sgpu_slot_reset(sgpu_ctx_t *ctx, uint32_t slot, uint32_t rna);
  * it does not fit (submit and retry), SGPU_E_TOOBIG when it can never fit. */
 int64_t sgpu_slot_add_read(sgpu_ctx_t *ctx, uint32_t slot, const int16_t *raw, uint64_t len_raw_signal,
                            double digitisation, double offset, double range);
+/* Append one record whose raw signal is STILL svb-zd compressed: `stream` is the record's raw_signal field as
+ * slow5lib stores it with SLOW5_COMPRESS_SVB_ZD (uint32 count | ceil(count/4) key bytes | data bytes), i.e. what
+ * ptr_depress_svb_zd() (slow5lib/src/slow5_press.c:1116-1150; streamvbyte_decode.c:30-83,
+ * streamvbyte_zigzag.c:27-47) would expand on the CPU. Only these bytes cross PCIe; the int16 samples are
+ * produced in HBM (svbzd.cu). A batch holds either decoded records or svb-zd streams (SGPU_E_STATE when mixed).
+ * A stream whose length contradicts its header is refused here (SGPU_E_STREAM); one whose length contradicts its
+ * keys is reported by sgpu_wait (SGPU_E_STREAM), like slow5lib's error at slow5_press.c:1103. */
+int64_t sgpu_slot_add_read_svbzd(sgpu_ctx_t *ctx, uint32_t slot, const uint8_t *stream, uint64_t n_bytes,
+                                 double digitisation, double offset, double range);
 /* Asynchronous: copies the slot to the device, runs the kernels, copies the
  * results back, all on the slot's stream. */
 int  sgpu_submit(sgpu_ctx_t *ctx, uint32_t slot, uint32_t want);
@@ -139,6 +149,23 @@ typedef struct {
  * run on this context). */
 int  sgpu_run_device(sgpu_ctx_t *ctx, const sgpu_dev_batch_t *batch, uint32_t want,
                      void *stream, sgpu_result_t *out);
+
+/* Device-resident svb-zd decode (benchmarks / callers that hold the compressed records in HBM). All pointers are
+ * DEVICE pointers; `bytes` holds the streams back to back, each starting on a 16-byte boundary, and its
+ * allocation extends at least 8 bytes past n_bytes. n_blocks = sum over reads of ceil(read_len / 1024).
+ * Writes read r's samples to samples_out[read_off[r] ..]. No synchronisation; a malformed stream shows as
+ * status SGPU_E_STREAM in sgpu_counters(). */
+typedef struct {
+    const uint8_t  *bytes;
+    uint64_t        n_bytes;
+    const uint64_t *comp_off;   /* [n_reads] */
+    const uint32_t *comp_len;   /* [n_reads] */
+    const uint64_t *read_off;   /* [n_reads+1] multiples of SGPU_ALIGN */
+    const uint32_t *read_len;   /* [n_reads] = the count in each stream's header */
+    uint32_t n_reads;
+    uint64_t n_blocks;
+} sgpu_svb_dev_batch_t;
+int  sgpu_decode_svbzd_device(sgpu_ctx_t *ctx, const sgpu_svb_dev_batch_t *batch, int16_t *samples_out, void *stream);
 
 /* Counters of the last completed run (host path: after sgpu_wait; device path:
  * after the caller synchronised the stream). Synchronises the device. */

@@ -132,3 +132,25 @@ int ref_stat(const int16_t *raw, uint64_t n, double digitisation, double offset,
     out6[4] = (float)k1; out6[5] = k2;
     return 0;
 }
+
+/* svb-zd through the reference's own slow5lib (slow5_press.c:1055-1150). encode: returns the stream length or -1;
+ * decode: returns the number of samples or -1. */
+#include <slow5/slow5_press.h>
+int64_t ref_svbzd_encode(const int16_t *raw, uint64_t n, uint8_t *out, uint64_t cap) {
+    size_t bytes = 0;
+    void *p = slow5_ptr_compress_solo(SLOW5_COMPRESS_SVB_ZD, raw, (size_t)n * sizeof *raw, &bytes);
+    if (!p) return -1;
+    if (bytes > cap) { free(p); return -1; }
+    memcpy(out, p, bytes);
+    free(p);
+    return (int64_t)bytes;
+}
+int64_t ref_svbzd_decode(const uint8_t *in, uint64_t n_bytes, int16_t *out, uint64_t cap) {
+    size_t bytes = 0;
+    void *p = slow5_ptr_depress_solo(SLOW5_COMPRESS_SVB_ZD, in, (size_t)n_bytes, &bytes);
+    if (!p) return -1;
+    if (bytes / 2 > cap) { free(p); return -1; }
+    memcpy(out, p, bytes);
+    free(p);
+    return (int64_t)(bytes / 2);
+}

@@ -298,3 +298,52 @@ double orc_time_events(const int16_t *samples, const uint64_t *read_off,
     if (total_events) *total_events = nev;
     return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
 }
+
+/* ---- svb-zd signal compression ---------------------------------------------------------
+ * slow5lib stores the raw signal of a BLOW5 record as
+ *   uint32 count | ceil(count/4) key bytes (2 bits per value, low bits first) | data bytes
+ * where value i = zigzag(raw[i] - raw[i-1]) (raw[-1] = 0, 32-bit arithmetic) takes code+1 little-endian bytes
+ * (/root/reference/slow5lib/src/slow5_press.c:1055-1150; thirdparty/streamvbyte/src/streamvbyte_encode.c,
+ * streamvbyte_decode.c:30-83; streamvbyte_zigzag.c:5-47). */
+uint64_t orc_svbzd_bound(uint64_t n) { return 4u + (n + 3u) / 4u + 4u * n; }
+
+int64_t orc_svbzd_encode(const int16_t *raw, uint64_t n, uint8_t *out, uint64_t cap) {
+    if (n > 0xffffffffull || cap < orc_svbzd_bound(n)) return -1;
+    const uint32_t count = (uint32_t)n;
+    memcpy(out, &count, 4);
+    uint8_t *keys = out + 4, *data = keys + (n + 3u) / 4u;
+    memset(keys, 0, (size_t)((n + 3u) / 4u));
+    int32_t prev = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const int32_t cur = raw[i];
+        const int32_t d = (int32_t)((uint32_t)cur - (uint32_t)prev);           /* streamvbyte_zigzag.c:21-24 */
+        const uint32_t z = ((uint32_t)d + (uint32_t)d) ^ (uint32_t)(d >> 31);  /* streamvbyte_zigzag.c:6-8 */
+        prev = cur;
+        uint32_t code = z < (1u << 8) ? 0u : z < (1u << 16) ? 1u : z < (1u << 24) ? 2u : 3u;
+        for (uint32_t b = 0; b <= code; b++) *data++ = (uint8_t)(z >> (8u * b));
+        keys[i >> 2] |= (uint8_t)(code << (2u * (i & 3u)));
+    }
+    return (int64_t)(data - out);
+}
+
+/* returns the number of samples, or -1 when the stream is malformed (length mismatch: slow5_press.c:1103) */
+int64_t orc_svbzd_decode(const uint8_t *in, uint64_t n_bytes, int16_t *out, uint64_t cap) {
+    if (n_bytes < 4) return -1;
+    uint32_t count;
+    memcpy(&count, in, 4);
+    const uint64_t key_len = ((uint64_t)count + 3u) / 4u;
+    if (count > cap || 4u + key_len > n_bytes) return -1;
+    const uint8_t *keys = in + 4, *data = keys + key_len, *end = in + n_bytes;
+    int32_t prev = 0;
+    for (uint64_t i = 0; i < count; i++) {
+        const uint32_t code = (keys[i >> 2] >> (2u * (i & 3u))) & 3u;           /* streamvbyte_decode.c:62-75 */
+        if (data + code + 1u > end) return -1;
+        uint32_t z = 0;
+        for (uint32_t b = 0; b <= code; b++) z |= (uint32_t)data[b] << (8u * b);
+        data += code + 1u;
+        const int32_t d = (int32_t)((z >> 1) ^ (0u - (z & 1u)));                 /* streamvbyte_zigzag.c:27-29 */
+        out[i] = (int16_t)((uint32_t)d + (uint32_t)prev);                         /* streamvbyte_zigzag.c:41-46 */
+        prev = (int32_t)((uint32_t)prev + (uint32_t)d);
+    }
+    return data == end ? (int64_t)count : -1;
+}

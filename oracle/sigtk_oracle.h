@@ -73,6 +73,13 @@ int64_t orc_event_read(const int16_t *raw, uint64_t n, double digitisation,
 void orc_stat(const int16_t *raw, uint64_t n, double digitisation, double offset,
               double range, float *out6);
 
+/* svb-zd signal stream of a BLOW5 record (slow5_press.c:1055-1150, streamvbyte_decode.c:30-83,
+ * streamvbyte_zigzag.c): encode returns the stream length in bytes (cap >= orc_svbzd_bound(n)), decode the
+ * number of samples; -1 on a malformed stream. */
+uint64_t orc_svbzd_bound(uint64_t n);
+int64_t orc_svbzd_encode(const int16_t *raw, uint64_t n, uint8_t *out, uint64_t cap);
+int64_t orc_svbzd_decode(const uint8_t *in, uint64_t n_bytes, int16_t *out, uint64_t cap);
+
 /* single-thread timing of orc_event_read over a flat batch; returns seconds */
 double orc_time_events(const int16_t *samples, const uint64_t *read_off,
                        uint64_t n_reads, const double *digitisation,

@@ -24,6 +24,7 @@ EXPORTS = (
     "sgpu_abi_version", "sgpu_device_count", "sgpu_create", "sgpu_destroy", "sgpu_strerror",
     "sgpu_last_error", "sgpu_slot_batch", "sgpu_slot_reset", "sgpu_slot_add_read", "sgpu_submit",
     "sgpu_wait", "sgpu_run_device", "sgpu_counters", "sgpu_memcpy_d2h", "sgpu_stage_times",
+    "sgpu_slot_add_read_svbzd", "sgpu_decode_svbzd_device",
 )
 
 
@@ -53,6 +54,13 @@ class DevBatch(C.Structure):  # sgpu_dev_batch_t
     _fields_ = [
         ("samples", C.c_void_p), ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("offset_f", C.c_void_p),
         ("raw_unit_f", C.c_void_p), ("n_reads", C.c_uint32), ("rna", C.c_uint32), ("span", C.c_uint64),
+    ]
+
+
+class SvbDevBatch(C.Structure):  # sgpu_svb_dev_batch_t
+    _fields_ = [
+        ("bytes", C.c_void_p), ("n_bytes", C.c_uint64), ("comp_off", C.c_void_p), ("comp_len", C.c_void_p),
+        ("read_off", C.c_void_p), ("read_len", C.c_void_p), ("n_reads", C.c_uint32), ("n_blocks", C.c_uint64),
     ]
 
 
@@ -97,6 +105,10 @@ def load() -> C.CDLL:
     lib.sgpu_slot_reset.restype = i32
     lib.sgpu_slot_add_read.argtypes = [vp, u32, vp, u64, C.c_double, C.c_double, C.c_double]
     lib.sgpu_slot_add_read.restype = C.c_int64
+    lib.sgpu_slot_add_read_svbzd.argtypes = [vp, u32, vp, u64, C.c_double, C.c_double, C.c_double]
+    lib.sgpu_slot_add_read_svbzd.restype = C.c_int64
+    lib.sgpu_decode_svbzd_device.argtypes = [vp, C.POINTER(SvbDevBatch), vp, vp]
+    lib.sgpu_decode_svbzd_device.restype = i32
     lib.sgpu_submit.argtypes = [vp, u32, u32]
     lib.sgpu_submit.restype = i32
     lib.sgpu_wait.argtypes = [vp, u32, C.POINTER(Result)]

@@ -109,6 +109,28 @@ class Context:
                                               float(rng))
             self._check(int(rc))
 
+    def fill_svbzd(self, slot: int, reads: Sequence, rna: int) -> None:
+        """reads: (svb-zd stream uint8[], digitisation, offset, range) -- the record's raw_signal field as slow5lib
+        stores it with SLOW5_COMPRESS_SVB_ZD; the samples are decoded in HBM"""
+        self._check(self._lib.sgpu_slot_reset(self._h, slot, int(rna)))
+        for st, dig, off, rng in reads:
+            st = np.ascontiguousarray(st, dtype=np.uint8)
+            rc = self._lib.sgpu_slot_add_read_svbzd(self._h, slot, st.ctypes.data, st.shape[0], float(dig), float(off),
+                                                    float(rng))
+            self._check(int(rc))
+
+    def run_svbzd(self, reads: Sequence, rna: int = 0, want: int = WANT_EVENTS, slot: int = 0) -> BatchResult:
+        self.fill_svbzd(slot, reads, rna)
+        self.submit(slot, want)
+        return self.wait(slot, want)
+
+    def decode_svbzd_device(self, bytes_ptr: int, n_bytes: int, comp_off_ptr: int, comp_len_ptr: int, read_off_ptr: int,
+                            read_len_ptr: int, n_reads: int, n_blocks: int, samples_out_ptr: int, stream: int = 0) -> None:
+        sb = _lib.SvbDevBatch(bytes_ptr, n_bytes, comp_off_ptr, comp_len_ptr, read_off_ptr, read_len_ptr, n_reads,
+                              n_blocks)
+        self._check(self._lib.sgpu_decode_svbzd_device(self._h, C.byref(sb), C.c_void_p(samples_out_ptr),
+                                                       C.c_void_p(stream)))
+
     def submit(self, slot: int, want: int) -> None:
         self._check(self._lib.sgpu_submit(self._h, slot, want))
 

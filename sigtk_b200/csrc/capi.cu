@@ -54,6 +54,13 @@ struct Slot {
     cudaEvent_t in_ready = nullptr, kernels_done = nullptr, small_back = nullptr;
     bool submitted = false;
     uint32_t want = 0;
+    // svb-zd input (allocated on first use): the batch's compressed streams, decoded in HBM by svbzd.cu
+    int mode = 0;                    // 0: empty, 1: decoded int16 records, 2: svb-zd streams
+    uint8_t* h_comp = nullptr;       // pinned, comp_cap bytes
+    uint8_t* d_comp = nullptr;       // comp_cap + 16 bytes
+    uint64_t* h_comp_off = nullptr; uint64_t* d_comp_off = nullptr;
+    uint32_t* h_comp_len = nullptr; uint32_t* d_comp_len = nullptr;
+    uint64_t comp_used = 0, svb_blocks = 0;
 };
 
 }  // namespace
@@ -71,6 +78,8 @@ struct sgpu_ctx {
     uint32_t* dev_seq = nullptr; // seq_order / fixups of the device-resident path
     uint32_t* dev_fix = nullptr;
     Slot* slots = nullptr;
+    SvbScratch svb{};            // workspace of the svb-zd decoder (allocated on first use)
+    uint64_t comp_cap = 0;       // bytes of compressed input a slot can hold
     cudaStream_t compute = nullptr;
     uint64_t last_launches = 0;
     // optional per-stage CUDA-event timers (SGPU_F_STAGE_TIMERS)
@@ -150,8 +159,22 @@ struct StageMarks {  // records a CUDA event between kernel groups when the cont
 };
 
 // The kernel sequence of one batch. No host synchronisation, no host<->device copies.
+int alloc_svb_scratch(sgpu_ctx* ctx) {
+    SvbScratch& w = ctx->svb;
+    if (w.cnt) return SGPU_OK;
+    w.max_blocks = svbzd_max_blocks(ctx->max_samples, ctx->max_reads);
+    CU(dev_alloc(&w.cnt, ctx->max_reads));
+    CU(dev_alloc(&w.base, (uint64_t)ctx->max_reads + 1));
+    CU(dev_alloc(&w.blk_bytes, w.max_blocks));
+    CU(dev_alloc(&w.blk_gpos, w.max_blocks + 1));
+    CU(dev_alloc(&w.blk_sum, w.max_blocks));
+    CU(dev_alloc(&w.blk_vpos, w.max_blocks + 1));
+    CU(dev_alloc(&w.lane_sum, w.max_blocks * 32));
+    return SGPU_OK;
+}
+
 int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uint32_t* d_seq, uint32_t* d_fix,
-                 cudaStream_t st) {
+                 cudaStream_t st, const SvbBatch* svb = nullptr, int16_t* svb_out = nullptr) {
     Scratch& sc = ctx->sc;
     if (b.n_reads > ctx->max_reads || b.span > ctx->max_samples || (b.span & (SGPU_ALIGN - 1))) return SGPU_E_INVAL;
     CU(cudaMemsetAsync(sc.status, 0, sizeof(int), st));
@@ -162,6 +185,7 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
         ctx->last_launches = 0;
         return SGPU_OK;
     }
+    if (svb) marks.done("svbzd_decode", launch_svbzd_decode(*svb, ctx->svb, ctx->sc, svb_out, ctx->sm_count, st));
     const bool force_generic = (ctx->flags & SGPU_F_FORCE_GENERIC) != 0;
     const bool events = (want & SGPU_WANT_EVENTS) != 0;
     if (want & SGPU_WANT_PA) {
@@ -200,6 +224,7 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
 int map_dev_status(int s) {
     if (s == SGPU_DEV_E_EVCAP) return SGPU_E_EVCAP;
     if (s == SGPU_DEV_E_SCRATCH) return SGPU_E_SCRATCH;
+    if (s == SGPU_DEV_E_STREAM) return SGPU_E_STREAM;
     return SGPU_OK;
 }
 
@@ -226,6 +251,7 @@ const char* sgpu_strerror(int code) {
         case SGPU_E_STATE: return "call out of order";
         case SGPU_E_EVCAP: return "event capacity exceeded";
         case SGPU_E_SCRATCH: return "sequential-order scratch too small";
+        case SGPU_E_STREAM: return "malformed svb-zd stream (length does not match its keys)";
         default: return "unknown error";
     }
 }
@@ -298,7 +324,13 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     CUC(dev_alloc(&sc.seq_sbase, (uint64_t)max_reads + 1));
     CUC(dev_alloc(&sc.seq_count, 1));
     CUC(dev_alloc(&sc.cursor, 1));
-    CUC(dev_alloc(&sc.scan_status, scan_tiles_for(sc.max_tiles > max_reads ? sc.max_tiles : max_reads) + 1));
+    {
+        uint64_t most = sc.max_tiles > max_reads ? sc.max_tiles : max_reads;
+        const uint64_t svb_blocks = svbzd_max_blocks(max_samples, max_reads);
+        if (svb_blocks > most) most = svb_blocks;
+        CUC(dev_alloc(&sc.scan_status, scan_tiles_for((uint32_t)most) + 1));
+    }
+    ctx->comp_cap = 2 * max_samples;
     if (flags & SGPU_F_STAGE_TIMERS)
         for (int k = 0; k <= sgpu_ctx::MAX_STAGES; k++) CUC(cudaEventCreate(&ctx->stage_ev[k]));
     CUC(dev_alloc(&sc.scan_ticket, 1));
@@ -362,6 +394,11 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status); cudaFree(sc.counters);
     for (int k = 0; k <= sgpu_ctx::MAX_STAGES; k++) if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
     free_dev_out(ctx->dev_out);
+    {
+        SvbScratch& w = ctx->svb;
+        cudaFree(w.cnt); cudaFree(w.base); cudaFree(w.blk_bytes); cudaFree(w.blk_gpos); cudaFree(w.blk_sum);
+        cudaFree(w.blk_vpos); cudaFree(w.lane_sum);
+    }
     if (ctx->slots) {
         for (uint32_t s = 0; s < ctx->n_slots; s++) {
             Slot& sl = ctx->slots[s];
@@ -373,6 +410,8 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
             cudaFreeHost(sl.h_ev_off); cudaFreeHost(sl.h_ev_start); cudaFreeHost(sl.h_ev_mean);
             cudaFreeHost(sl.h_ev_stdv); cudaFreeHost(sl.h_pa); cudaFreeHost(sl.h_stat); cudaFreeHost(sl.h_seq);
             cudaFreeHost(sl.h_fix); cudaFreeHost(sl.h_counters); cudaFreeHost(sl.h_status);
+            cudaFreeHost(sl.h_comp); cudaFreeHost(sl.h_comp_off); cudaFreeHost(sl.h_comp_len);
+            cudaFree(sl.d_comp); cudaFree(sl.d_comp_off); cudaFree(sl.d_comp_len);
             if (sl.stream) cudaStreamDestroy(sl.stream);
             if (sl.in_ready) cudaEventDestroy(sl.in_ready);
             if (sl.kernels_done) cudaEventDestroy(sl.kernels_done);
@@ -398,6 +437,9 @@ int sgpu_slot_reset(sgpu_ctx_t* ctx, uint32_t slot, uint32_t rna) {
     sl.batch.rna = rna ? 1u : 0u;
     sl.batch.read_off[0] = 0;
     sl.used = 0;
+    sl.mode = 0;
+    sl.comp_used = 0;
+    sl.svb_blocks = 0;
     return SGPU_OK;
 }
 
@@ -406,17 +448,65 @@ int64_t sgpu_slot_add_read(sgpu_ctx_t* ctx, uint32_t slot, const int16_t* raw, u
     if (!ctx || slot >= ctx->n_slots || (!raw && n)) return SGPU_E_INVAL;
     Slot& sl = ctx->slots[slot];
     if (sl.submitted) return SGPU_E_STATE;
+    if (sl.mode == 2) return SGPU_E_STATE;  // a batch holds decoded records or svb-zd streams, not both
     if (n >= (1ull << 31)) return SGPU_E_TOOBIG;  // the reference itself narrows to int32_t (misc.c:20)
     const uint64_t need = align_up(n, SGPU_ALIGN);
     if (need > ctx->max_samples) return SGPU_E_TOOBIG;
     sgpu_batch_t& b = sl.batch;
     if (b.n_reads >= ctx->max_reads || sl.used + need > ctx->max_samples) return SGPU_E_FULL;
+    sl.mode = 1;
     const uint32_t r = b.n_reads;
     memcpy(b.samples + sl.used, raw, (size_t)n * sizeof(int16_t));
     b.read_off[r] = sl.used;
     b.read_len[r] = (uint32_t)n;
     // misc.c:17-19,26: narrow the three doubles to float first, then ONE float division
     const float range_f = (float)range, dig_f = (float)digitisation, off_f = (float)offset;
+    volatile float unit = range_f / dig_f;
+    b.offset_f[r] = off_f;
+    b.raw_unit_f[r] = unit;
+    sl.used += need;
+    b.n_reads = r + 1;
+    b.read_off[r + 1] = sl.used;
+    return (int64_t)r;
+}
+
+int64_t sgpu_slot_add_read_svbzd(sgpu_ctx_t* ctx, uint32_t slot, const uint8_t* stream, uint64_t n_bytes,
+                                 double digitisation, double offset, double range) {
+    if (!ctx || slot >= ctx->n_slots || !stream) return SGPU_E_INVAL;
+    Slot& sl = ctx->slots[slot];
+    if (sl.submitted || sl.mode == 1) return SGPU_E_STATE;
+    if (n_bytes < 4) return SGPU_E_STREAM;
+    uint32_t count;
+    memcpy(&count, stream, 4);  // slow5_press.c:1093: the original length leads the stream
+    const uint64_t n = count;
+    if (4u + (n + 3u) / 4u + n > n_bytes || n_bytes > 4u + (n + 3u) / 4u + 4u * n) return SGPU_E_STREAM;
+    if (n >= (1ull << 31)) return SGPU_E_TOOBIG;
+    const uint64_t need = align_up(n, SGPU_ALIGN), cneed = align_up(n_bytes, 16);
+    if (need > ctx->max_samples || cneed > ctx->comp_cap) return SGPU_E_TOOBIG;
+    sgpu_batch_t& b = sl.batch;
+    if (b.n_reads >= ctx->max_reads || sl.used + need > ctx->max_samples || sl.comp_used + cneed > ctx->comp_cap)
+        return SGPU_E_FULL;
+    if (!sl.h_comp) {
+        CU(cudaSetDevice(ctx->device));
+        const int rc = alloc_svb_scratch(ctx);
+        if (rc) return rc;
+        CU(pin_alloc(&sl.h_comp, ctx->comp_cap));
+        CU(dev_alloc(&sl.d_comp, ctx->comp_cap + 16));
+        CU(pin_alloc(&sl.h_comp_off, ctx->max_reads));
+        CU(dev_alloc(&sl.d_comp_off, ctx->max_reads));
+        CU(pin_alloc(&sl.h_comp_len, ctx->max_reads));
+        CU(dev_alloc(&sl.d_comp_len, ctx->max_reads));
+    }
+    sl.mode = 2;
+    const uint32_t r = b.n_reads;
+    memcpy(sl.h_comp + sl.comp_used, stream, (size_t)n_bytes);
+    sl.h_comp_off[r] = sl.comp_used;
+    sl.h_comp_len[r] = (uint32_t)n_bytes;
+    sl.comp_used += cneed;
+    sl.svb_blocks += svbzd_blocks_of(n);
+    b.read_off[r] = sl.used;
+    b.read_len[r] = (uint32_t)n;
+    const float range_f = (float)range, dig_f = (float)digitisation, off_f = (float)offset;  // misc.c:17-19,26
     volatile float unit = range_f / dig_f;
     b.offset_f[r] = off_f;
     b.raw_unit_f[r] = unit;
@@ -434,7 +524,17 @@ int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
     const sgpu_batch_t& hb = sl.batch;
     const uint32_t nr = hb.n_reads;
     cudaStream_t st = sl.stream;
-    CU(cudaMemcpyAsync(sl.d_samples, hb.samples, (size_t)sl.used * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    SvbBatch svb{};
+    const bool compressed = sl.mode == 2;
+    if (compressed) {
+        CU(cudaMemcpyAsync(sl.d_comp, sl.h_comp, (size_t)sl.comp_used, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sl.d_comp_off, sl.h_comp_off, (size_t)nr * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(sl.d_comp_len, sl.h_comp_len, (size_t)nr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        svb = SvbBatch{sl.d_comp, sl.comp_used, sl.d_comp_off, sl.d_comp_len, sl.d_read_off, sl.d_read_len, nr,
+                       sl.svb_blocks};
+    } else {
+        CU(cudaMemcpyAsync(sl.d_samples, hb.samples, (size_t)sl.used * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    }
     CU(cudaMemcpyAsync(sl.d_read_off, hb.read_off, ((size_t)nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(sl.d_read_len, hb.read_len, (size_t)nr * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(sl.d_offset, hb.offset_f, (size_t)nr * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -443,7 +543,8 @@ int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
     CU(cudaStreamWaitEvent(ctx->compute, sl.in_ready, 0));
     DevBatch b{sl.d_samples, sl.d_read_off, sl.d_read_len, sl.d_offset, sl.d_unit, nr, (int)hb.rna, sl.used};
     if ((want & SGPU_WANT_PA) && !sl.h_pa) CU(pin_alloc(&sl.h_pa, ctx->max_samples));
-    const int rc = run_pipeline(ctx, b, want, sl.dout, sl.d_seq, sl.d_fix, ctx->compute);
+    const int rc = run_pipeline(ctx, b, want, sl.dout, sl.d_seq, sl.d_fix, ctx->compute, compressed ? &svb : nullptr,
+                                sl.d_samples);
     if (rc) return rc;
     // small results come back right away; the big arrays are sized by n_events in sgpu_wait
     CU(cudaMemcpyAsync(sl.h_counters, ctx->sc.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -516,6 +617,22 @@ int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t wan
     out->stat = ctx->dev_out.stat;
     out->seq_order = ctx->dev_seq;
     out->fixups = ctx->dev_fix;
+    return SGPU_OK;
+}
+
+int sgpu_decode_svbzd_device(sgpu_ctx_t* ctx, const sgpu_svb_dev_batch_t* batch, int16_t* samples_out, void* stream) {
+    if (!ctx || !batch || !samples_out) return SGPU_E_INVAL;
+    if (batch->n_reads > ctx->max_reads || batch->n_blocks > svbzd_max_blocks(ctx->max_samples, ctx->max_reads))
+        return SGPU_E_INVAL;
+    CU(cudaSetDevice(ctx->device));
+    const int arc = alloc_svb_scratch(ctx);
+    if (arc) return arc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CU(cudaMemsetAsync(ctx->sc.status, 0, sizeof(int), st));
+    SvbBatch s{batch->bytes, batch->n_bytes, batch->comp_off, batch->comp_len, batch->read_off, batch->read_len,
+               batch->n_reads, batch->n_blocks};
+    ctx->last_launches = (uint64_t)launch_svbzd_decode(s, ctx->svb, ctx->sc, samples_out, ctx->sm_count, st);
+    CU(cudaGetLastError());
     return SGPU_OK;
 }
 

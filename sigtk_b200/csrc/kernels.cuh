@@ -5,7 +5,7 @@
 namespace sgpu {
 
 // device-side status codes (mapped to SGPU_E_* by capi.cu)
-enum { SGPU_DEV_OK = 0, SGPU_DEV_E_EVCAP = 1, SGPU_DEV_E_SCRATCH = 2 };
+enum { SGPU_DEV_OK = 0, SGPU_DEV_E_EVCAP = 1, SGPU_DEV_E_SCRATCH = 2, SGPU_DEV_E_STREAM = 3 };
 
 constexpr int FAST_TILE = 2048;  // samples per tile of the fast path; the event-start bitmap is tiled the same way
 
@@ -70,6 +70,28 @@ int launch_rank_events(const DevBatch& b, Scratch& sc, uint64_t* ev_off, int sm_
 int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* ev_start, float* ev_mean,
                      float* ev_stdv, const uint32_t* fixups, int sm_count, cudaStream_t st);
 int launch_pa(const DevBatch& b, float* pa, int sm_count, cudaStream_t st);
+
+// svbzd.cu (svb-zd signal streams -> int16 samples in HBM)
+struct SvbBatch {
+    const uint8_t*  bytes;     // the streams of the batch back to back, each starting on a 16-byte boundary;
+    uint64_t        n_bytes;   // the allocation extends at least 8 bytes past n_bytes
+    const uint64_t* comp_off;  // [n_reads] byte offset of every stream
+    const uint32_t* comp_len;  // [n_reads] stream length in bytes (header + keys + data)
+    const uint64_t* read_off;  // [n_reads+1] where the samples go (multiples of 8)
+    const uint32_t* read_len;  // [n_reads] = the count in every stream's header
+    uint32_t n_reads;
+    uint64_t n_blocks;         // sum of svbzd_blocks_of(read_len)
+};
+struct SvbScratch {
+    uint32_t* cnt; uint64_t* base;            // [max_reads], [max_reads+1]
+    uint32_t* blk_bytes; uint64_t* blk_gpos;  // [max_blocks], [max_blocks+1]
+    uint32_t* blk_sum; uint64_t* blk_vpos;
+    uint32_t* lane_sum;                       // [max_blocks*32]
+    uint64_t max_blocks;
+};
+uint64_t svbzd_max_blocks(uint64_t max_samples, uint32_t max_reads);
+uint32_t svbzd_blocks_of(uint64_t n);
+int launch_svbzd_decode(const SvbBatch& s, SvbScratch& w, Scratch& sc, int16_t* samples, int sm_count, cudaStream_t st);
 
 // stat.cu
 int launch_stat(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st);

@@ -53,6 +53,29 @@ class _EventLib:
         self._time = g("time_events")
         self._time.restype = C.c_double
         self._time.argtypes = [_i16p, _u64p, C.c_uint64, _f64p, _f64p, _f64p, C.c_int, _u64p]
+        self._svb_enc = g("svbzd_encode")
+        self._svb_enc.restype = C.c_int64
+        self._svb_enc.argtypes = [_i16p, C.c_uint64, C.c_void_p, C.c_uint64]
+        self._svb_dec = g("svbzd_decode")
+        self._svb_dec.restype = C.c_int64
+        self._svb_dec.argtypes = [C.c_void_p, C.c_uint64, _i16p, C.c_uint64]
+
+    def svbzd_encode(self, raw):
+        """int16 samples -> the svb-zd stream slow5lib stores in a BLOW5 record (uint8 array)"""
+        raw = np.ascontiguousarray(raw, dtype=np.int16)
+        out = np.empty(4 + (raw.shape[0] + 3) // 4 + 4 * raw.shape[0] + 16, dtype=np.uint8)
+        n = self._svb_enc(_p(raw, _i16p), raw.shape[0], out.ctypes.data, out.shape[0])
+        assert n >= 4, n
+        return out[:n].copy()
+
+    def svbzd_decode(self, stream, cap=None):
+        """-> int16 samples, or None when the stream is malformed"""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        if cap is None:
+            cap = int(stream[:4].view(np.uint32)[0]) if stream.shape[0] >= 4 else 0
+        out = np.empty(max(cap, 1), dtype=np.int16)
+        n = self._svb_dec(stream.ctypes.data, stream.shape[0], _p(out, _i16p), cap)
+        return None if n < 0 else out[:n].copy()
 
     def pa(self, raw, dig, off, rng):
         raw = np.ascontiguousarray(raw, dtype=np.int16)
