@@ -11,8 +11,9 @@
  * into pinned slots of the CUDA library (include/sigtk_b200.h), several batches are in flight on one or more
  * GPUs, and the per-read results are printed in input order.  There is no CPU implementation of the path in
  * here: without a usable GPU the tool exits with an error.
- * The batch loader and the output path are parallel: records are read serially (slow5_get_next_bytes) and decoded
- * by a pool of threads (slow5_decode: zlib + svb-zd), and every finished batch is formatted by the same pool with
+ * The batch loader and the output path are parallel: records are read serially (slow5_get_next_bytes); for BLOW5
+ * files with svb-zd signal compression the pool only inflates the records (zlib) and the svb-zd streams are decoded
+ * on the GPU (--cpu-decode: slow5_decode on the pool, as for every other format); every finished batch is formatted by the same pool with
  * exact re-implementations of the reference's printf conversions (fastfmt.h) and written in input order.
  * Additive options (default off / 1): --gpus N, --batch-samples S, --threads T.
  */
@@ -466,13 +467,25 @@ static void engine_drain(engine_t *e) {
     }
 }
 
-static void engine_add(engine_t *e, const slow5_rec_t *rec) {
+/* one record on its way into a batch: decoded samples (raw != NULL) or the still compressed svb-zd stream */
+typedef struct {
+    const char *read_id;
+    size_t read_id_len;       /* without the NUL */
+    double digitisation, offset, range;
+    const int16_t *raw;       /* decoded samples ... */
+    uint64_t len_raw_signal;
+    const uint8_t *svb;       /* ... or the record's raw_signal field as stored (SLOW5_COMPRESS_SVB_ZD) */
+    uint64_t svb_bytes;
+} rec_view_t;
+
+static void engine_add_view(engine_t *e, const rec_view_t *v) {
     for (int attempt = 0; attempt < 3; attempt++) {
         lane_t *l = &e->lanes[e->cur];
-        int64_t rc = sgpu_slot_add_read(l->ctx, l->slot, rec->raw_signal, rec->len_raw_signal, rec->digitisation,
-                                        rec->offset, rec->range);
+        int64_t rc = v->raw || !v->svb
+            ? sgpu_slot_add_read(l->ctx, l->slot, v->raw, v->len_raw_signal, v->digitisation, v->offset, v->range)
+            : sgpu_slot_add_read_svbzd(l->ctx, l->slot, v->svb, v->svb_bytes, v->digitisation, v->offset, v->range);
         if (rc >= 0) {
-            const size_t idl = strlen(rec->read_id) + 1;
+            const size_t idl = v->read_id_len + 1;
             if (l->ids_len + idl > l->ids_cap) {
                 l->ids_cap = (l->ids_len + idl) * 2 + 4096;
                 l->ids = (char *)realloc(l->ids, l->ids_cap);
@@ -485,7 +498,8 @@ static void engine_add(engine_t *e, const slow5_rec_t *rec) {
                 ERROR("%s", "out of memory");
                 exit(EXIT_FAILURE);
             }
-            memcpy(l->ids + l->ids_len, rec->read_id, idl);
+            memcpy(l->ids + l->ids_len, v->read_id, v->read_id_len);
+            l->ids[l->ids_len + v->read_id_len] = '\0';
             l->id_off[l->n_reads++] = l->ids_len;
             l->ids_len += idl;
             return;
@@ -494,12 +508,12 @@ static void engine_add(engine_t *e, const slow5_rec_t *rec) {
             engine_submit_current(e);
             continue;
         }
-        if (rc == SGPU_E_TOOBIG && rec->len_raw_signal < (1ull << 31)) {
+        if (rc == SGPU_E_TOOBIG && v->len_raw_signal < (1ull << 31)) {
             /* one read larger than a whole slot: finish what is in flight and reopen with bigger slots */
             engine_drain(e);
             const int n_gpus = e->n_gpus;
             uint64_t cap = e->cap_samples;
-            while (cap < rec->len_raw_signal + 64) cap *= 2;
+            while (cap < v->len_raw_signal + 64 || 2 * cap < v->svb_bytes + 64) cap *= 2;
             engine_close(e);
             engine_open(e, n_gpus, cap);
             continue;
@@ -508,6 +522,19 @@ static void engine_add(engine_t *e, const slow5_rec_t *rec) {
     }
     ERROR("%s", "could not place a read into a batch");
     exit(EXIT_FAILURE);
+}
+
+static void engine_add(engine_t *e, const slow5_rec_t *rec) {
+    rec_view_t v;
+    memset(&v, 0, sizeof v);
+    v.read_id = rec->read_id;
+    v.read_id_len = strlen(rec->read_id);
+    v.digitisation = rec->digitisation;
+    v.offset = rec->offset;
+    v.range = rec->range;
+    v.raw = rec->raw_signal;
+    v.len_raw_signal = rec->len_raw_signal;
+    engine_add_view(e, &v);
 }
 
 /* ---- batch loader: parallel decode of one group of records ------------------------------------------------------------ */
@@ -526,6 +553,54 @@ static void decode_item(void *arg, int i) { /* slow5_decode: zlib inflate + svb-
     j->mem[i] = NULL;
 }
 
+/* GPU signal decode: the pool only undoes the RECORD compression (zlib) and finds the main columns of the binary
+ * record (the layout slow5_rec_parse reads, slow5lib/src/slow5.c:2811-2926: uint16 read_id_len, read_id, uint32
+ * read_group, double digitisation / offset / range / sampling_rate, uint64 len_raw_signal = bytes of the stored
+ * signal, then the svb-zd stream); the stream itself goes to the GPU as it is. */
+typedef struct {
+    slow5_file_t *sp;
+    char **mem;
+    size_t *bytes;
+    rec_view_t *view;
+    int *err;
+} inflate_job_t;
+
+static void inflate_item(void *arg, int i) {
+    inflate_job_t *j = (inflate_job_t *)arg;
+    j->err[i] = 0;
+    const enum slow5_press_method rm = j->sp->compress->record_press->method;
+    if (rm != SLOW5_COMPRESS_NONE) {
+        size_t nb = 0;
+        char *nm = (char *)slow5_ptr_depress_solo(rm, j->mem[i], j->bytes[i], &nb);
+        if (!nm || nb == 0) { free(nm); j->err[i] = SLOW5_ERR_PRESS; return; }
+        free(j->mem[i]);
+        j->mem[i] = nm;
+        j->bytes[i] = nb;
+    }
+    const char *m = j->mem[i];
+    const size_t nb = j->bytes[i];
+    rec_view_t *v = &j->view[i];
+    memset(v, 0, sizeof *v);
+    uint16_t idl;
+    size_t at = 0;
+    if (nb < sizeof idl) { j->err[i] = SLOW5_ERR_RECPARSE; return; }
+    memcpy(&idl, m, sizeof idl);
+    at = sizeof idl;
+    if (nb < at + idl + 4u + 4u * 8u + 8u) { j->err[i] = SLOW5_ERR_RECPARSE; return; }
+    v->read_id = m + at;
+    v->read_id_len = idl;
+    at += idl + 4u; /* read_group is not used by this path */
+    double sampling_rate;
+    memcpy(&v->digitisation, m + at, 8); at += 8;
+    memcpy(&v->offset, m + at, 8); at += 8;
+    memcpy(&v->range, m + at, 8); at += 8;
+    memcpy(&sampling_rate, m + at, 8); at += 8;
+    memcpy(&v->svb_bytes, m + at, 8); at += 8;
+    if (v->svb_bytes > nb - at) { j->err[i] = SLOW5_ERR_RECPARSE; return; }
+    v->svb = (const uint8_t *)(m + at);
+    if (v->svb_bytes >= 4) { uint32_t cnt; memcpy(&cnt, v->svb, 4); v->len_raw_signal = cnt; }
+}
+
 /* ---- sub-command driver (reference src/cmain.c) ----------------------------------------------------------------------- */
 static struct option long_options[] = {{"verbose", required_argument, 0, 'v'},
                                        {"help", no_argument, 0, 'h'},
@@ -537,13 +612,14 @@ static struct option long_options[] = {{"verbose", required_argument, 0, 'v'},
                                        {"gpus", required_argument, 0, 0},          /* 7 (additive) */
                                        {"batch-samples", required_argument, 0, 0}, /* 8 (additive) */
                                        {"threads", required_argument, 0, 0},       /* 9 (additive) */
+                                       {"cpu-decode", no_argument, 0, 0},          /* 10 (additive) */
                                        {0, 0, 0, 0}};
 
 static int cmain(int argc, char *argv[], const char *mode) {
     const char *optstring = "o:hVnc";
     int longindex = 0, c = -1;
     FILE *fp_help = stderr;
-    int hdr = 1, n_gpus = 1, n_threads = 0;
+    int hdr = 1, n_gpus = 1, n_threads = 0, cpu_decode = 0;
     uint64_t batch_samples = 0;
     engine_t eng;
     memset(&eng, 0, sizeof eng);
@@ -565,6 +641,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
             batch_samples = strtoull(optarg, NULL, 10);
         } else if (c == 0 && longindex == 9) {
             n_threads = atoi(optarg);
+        } else if (c == 0 && longindex == 10) {
+            cpu_decode = 1;
         }
     }
     if (argc - optind < 1 || fp_help == stdout) {
@@ -619,7 +697,57 @@ static int cmain(int argc, char *argv[], const char *mode) {
 
     slow5_rec_t *rec = NULL;
     int ret = 0;
-    if (argc - optind == 1) {
+    /* BLOW5 with svb-zd signal compression (the default of slow5tools): the signal is decoded on the GPU */
+    const int gpu_decode = !cpu_decode && argc - optind == 1 && sp->format == SLOW5_FORMAT_BINARY && sp->compress &&
+                           sp->compress->record_press && sp->compress->signal_press &&
+                           sp->compress->signal_press->method == SLOW5_COMPRESS_SVB_ZD &&
+                           (sp->compress->record_press->method == SLOW5_COMPRESS_NONE ||
+                            sp->compress->record_press->method == SLOW5_COMPRESS_ZLIB);
+    if (gpu_decode) {
+        enum { GROUP = 512 };
+        inflate_job_t job;
+        memset(&job, 0, sizeof job);
+        job.sp = sp;
+        job.mem = (char **)calloc(GROUP, sizeof(char *));
+        job.bytes = (size_t *)calloc(GROUP, sizeof(size_t));
+        job.view = (rec_view_t *)calloc(GROUP, sizeof(rec_view_t));
+        job.err = (int *)calloc(GROUP, sizeof(int));
+        if (!job.mem || !job.bytes || !job.view || !job.err) { ERROR("%s", "out of memory"); exit(EXIT_FAILURE); }
+        int eof = 0;
+        while (!eof) {
+            int n = 0;
+            size_t group_bytes = 0;
+            double t0 = realtime();
+            while (n < GROUP && group_bytes < (64u << 20)) {
+                if (slow5_get_next_bytes(&job.mem[n], &job.bytes[n], sp) < 0) {
+                    ret = slow5_errno;
+                    eof = 1;
+                    break;
+                }
+                group_bytes += job.bytes[n++];
+            }
+            g_prof[0] += realtime() - t0;
+            t0 = realtime();
+            pool_run(&eng.pool, inflate_item, &job, n);
+            g_prof[1] += realtime() - t0;
+            t0 = realtime();
+            for (int i = 0; i < n; i++) {
+                if (job.err[i] < 0) {
+                    fprintf(stderr, "Error in slow5_get_next. Error code %d\n", job.err[i]);
+                    exit(EXIT_FAILURE);
+                }
+                engine_add_view(&eng, &job.view[i]);
+                free(job.mem[i]);
+                job.mem[i] = NULL;
+            }
+            g_prof[2] += realtime() - t0;
+        }
+        if (ret != SLOW5_ERR_EOF) {
+            fprintf(stderr, "Error in slow5_get_next. Error code %d\n", ret);
+            exit(EXIT_FAILURE);
+        }
+        free(job.mem); free(job.bytes); free(job.view); free(job.err);
+    } else if (argc - optind == 1) {
         /* batch loader: the records' bytes are read serially, a group at a time, and decoded by the pool */
         enum { GROUP = 512 };
         load_job_t job;
@@ -689,6 +817,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
         engine_close(&eng);
         g_prof[7] = realtime() - t0;
     }
+    if (getenv("SIGTK_PROFILE"))
+        fprintf(stderr, "[%s] signal decode: %s\n", __func__, gpu_decode ? "GPU (svb-zd)" : "host threads (slow5_decode)");
     if (getenv("SIGTK_PROFILE"))
         fprintf(stderr, "[%s] host wall clock: open (CUDA context, pinned slots) %.3f s, read %.3f s, decode %.3f s (%d threads), "
                         "add+submit+print %.3f s of which wait %.3f s, format %.3f s, write %.3f s, close %.3f s\n", __func__,

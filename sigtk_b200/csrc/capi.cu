@@ -475,11 +475,11 @@ int64_t sgpu_slot_add_read_svbzd(sgpu_ctx_t* ctx, uint32_t slot, const uint8_t* 
     if (!ctx || slot >= ctx->n_slots || !stream) return SGPU_E_INVAL;
     Slot& sl = ctx->slots[slot];
     if (sl.submitted || sl.mode == 1) return SGPU_E_STATE;
-    if (n_bytes < 4) return SGPU_E_STREAM;
-    uint32_t count;
-    memcpy(&count, stream, 4);  // slow5_press.c:1093: the original length leads the stream
-    const uint64_t n = count;
-    if (4u + (n + 3u) / 4u + n > n_bytes || n_bytes > 4u + (n + 3u) / 4u + 4u * n) return SGPU_E_STREAM;
+    if (n_bytes != 0 && n_bytes < 4) return SGPU_E_STREAM;
+    uint32_t count = 0;
+    if (n_bytes) memcpy(&count, stream, 4);  // slow5_press.c:1093: the original length leads the stream
+    const uint64_t n = count;                // (a record without signal stores no stream at all: n_bytes == 0)
+    if (n_bytes && (4u + (n + 3u) / 4u + n > n_bytes || n_bytes > 4u + (n + 3u) / 4u + 4u * n)) return SGPU_E_STREAM;
     if (n >= (1ull << 31)) return SGPU_E_TOOBIG;
     const uint64_t need = align_up(n, SGPU_ALIGN), cneed = align_up(n_bytes, 16);
     if (need > ctx->max_samples || cneed > ctx->comp_cap) return SGPU_E_TOOBIG;
@@ -499,7 +499,7 @@ int64_t sgpu_slot_add_read_svbzd(sgpu_ctx_t* ctx, uint32_t slot, const uint8_t* 
     }
     sl.mode = 2;
     const uint32_t r = b.n_reads;
-    memcpy(sl.h_comp + sl.comp_used, stream, (size_t)n_bytes);
+    if (n_bytes) memcpy(sl.h_comp + sl.comp_used, stream, (size_t)n_bytes);
     sl.h_comp_off[r] = sl.comp_used;
     sl.h_comp_len[r] = (uint32_t)n_bytes;
     sl.comp_used += cneed;

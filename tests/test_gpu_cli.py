@@ -96,3 +96,16 @@ def test_two_gpus_same_bytes(sp1):
         pytest.skip("needs two GPUs")
     p = run(["event", "-c", "--gpus", "2", "--batch-samples", "50000", sp1])
     assert p.stdout == open(os.path.join(G, "ref_sp1_event_c.txt"), "rb").read()
+
+
+def test_cpu_decode_flag_gives_the_same_bytes(sp1):
+    """sp1_dna.blow5 is zlib + svb-zd: by default the svb-zd streams are decoded on the GPU (svbzd.cu); --cpu-decode
+    keeps slow5_decode on the host threads. Both equal the reference."""
+    exp = open(os.path.join(G, "ref_sp1_event_c.txt"), "rb").read()
+    assert run(["event", "-c", "--cpu-decode", sp1]).stdout == exp
+    p = run(["event", "-c", sp1], env=dict(os.environ, SIGTK_PROFILE="1"))
+    assert p.stdout == exp and b"signal decode: GPU (svb-zd)" in p.stderr
+    assert hashlib.sha256(run(["pa", "--cpu-decode", sp1]).stdout).hexdigest() == SHA["sp1_pa"]
+    assert run(["stat", "--cpu-decode", "--batch-samples", "30000", sp1]).stdout == open(
+        os.path.join(G, "ref_sp1_stat.txt"), "rb").read()
+    assert run(["stat", "--batch-samples", "30000", sp1]).stdout == open(os.path.join(G, "ref_sp1_stat.txt"), "rb").read()
