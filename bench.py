@@ -333,6 +333,15 @@ def run_ours(args):
 
     # ---- end to end through the host C-ABI: pinned slots, H2D + kernels + D2H per step ----------------------------
     e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna)
+    # ---- the same with svb-zd compressed records as input (decoded in HBM), and the decoder alone ------------------
+    svb = run_svbzd(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna) if not args.no_svbzd else None
+    if svb and pa_mode:
+        # event-only through the host API: with pA not returned the input side dominates PCIe, which is where the
+        # compressed input pays (decoded int16 records vs svb-zd streams, same reads)
+        ev_raw = run_e2e(args, sg, torch, dev, local, pool[0], sg.WANT_EVENTS, False, dist, rna, n_reads=max(1, args.e2e_reads // 4))
+        ev_svb = run_svbzd(args, sg, torch, dev, local, pool[0], sg.WANT_EVENTS, False, dist, rna)
+        svb["event_only"] = {"e2e_int16_records": {k: ev_raw[k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                             "e2e_svbzd_streams": {k: ev_svb["e2e"][k] for k in ("value", "h2d_bytes_per_step", "d2h_bytes_per_step")}}
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------------
     peak, peak_src = measured_peak()
@@ -374,15 +383,17 @@ def run_ours(args):
                        "detector_fixups": sum(e[2] for e in ev_per_batch)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        if svb:
+            line["svbzd"] = svb
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:
         dist.destroy_process_group()
 
 
-def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0):
+def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0, n_reads=None):
     """K steps of (pinned slot -> H2D -> kernels -> D2H -> host-visible event table), two slots in flight."""
-    B = min(args.e2e_reads, batch["n_reads"])
+    B = min(n_reads or args.e2e_reads, batch["n_reads"])
     off, lens = batch["host_off"], batch["host_len"]
     reads = host_reads_of(batch, B)
     span = int(off[B])
@@ -422,6 +433,64 @@ def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0):
             "timing": "host wall clock around submit/wait of K steps, 2 pinned slots in flight, max over ranks"}
 
 
+def run_svbzd(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0):
+    """svb-zd compressed records (what a BLOW5 file holds) as the input: (a) end to end through the host C-ABI
+    (sgpu_slot_add_read_svbzd: only the compressed bytes cross PCIe), (b) the decoder alone, device resident."""
+    B = max(1, min(args.e2e_reads // 4, batch["n_reads"]))
+    reads = host_reads_of(batch, B)
+    streams = [(synth_mod().svbzd_encode(r[0]), r[1], r[2], r[3]) for r in reads]
+    lens = np.array([len(r[0]) for r in reads], dtype=np.int64)
+    n_samp = int(lens.sum())
+    span = int(((lens + 7) // 8 * 8).sum())
+    comp = np.array([len(st[0]) for st in streams], dtype=np.int64)
+    hctx = sg.Context(device=local, max_samples=span + 64, max_reads=B, n_slots=2, flags=sg.F_STAGE_TIMERS)
+    for s_ in (0, 1):
+        hctx.fill_svbzd(s_, streams, rna)
+
+    def wait(slot):
+        res = sg._lib.Result()
+        hctx._check(hctx._lib.sgpu_wait(hctx._h, slot, C.byref(res)))
+        return int(res.n_events)
+
+    hctx.submit(0, want); ne = wait(0)
+    hctx.submit(1, want); wait(1)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    steps = max(args.steps, 2)
+    t0 = time.perf_counter()
+    hctx.submit(0, want)
+    for k in range(1, steps):
+        hctx.submit(k & 1, want)
+        wait((k - 1) & 1)
+    wait((steps - 1) & 1)
+    dt = time.perf_counter() - t0
+    dec_ms = [ms for name, ms, _ in hctx.stage_times() if name == "svbzd_decode"]
+    hctx.close()
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_samp * steps)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    comp_bytes = int(((comp + 15) // 16 * 16).sum())
+    out = {"e2e": {"value": float(tot.item()) / float(t.item()) / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": comp_bytes + 32 * B,
+                   "d2h_bytes_per_step": 12 * ne + 8 * (B + 1) + 8 * B + (4 * span if pa_mode else 0),
+                   "reads_per_step_per_gpu": B, "samples_per_step_per_gpu": n_samp},
+           "compressed_bytes_per_sample": float(comp.sum()) / max(n_samp, 1)}
+    if dec_ms:  # CUDA events around the decoder's kernels of the last step (stream of the launch)
+        ms = dec_ms[0]
+        out["decode"] = {"ms": ms, "value": n_samp / (ms * 1e-3) / 1e9, "unit": UNIT,
+                         "algorithmic_gbs": (float(comp.sum()) + 2.0 * n_samp) / (ms * 1e-3) / 1e9,
+                         "note": "svb_bytes + svb_sums + svb_write + 3 scans; algorithmic bytes = stream in + int16 out"}
+    return out
+
+
+def synth_mod():
+    from sigtk_b200 import synth
+    return synth
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,6 +505,7 @@ def main():
     ap.add_argument("--e2e-reads", type=int, default=4096)
     ap.add_argument("--cpu-reads", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-svbzd", action="store_true", help="skip the compressed-input (svb-zd) measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -170,6 +170,7 @@ int alloc_svb_scratch(sgpu_ctx* ctx) {
     CU(dev_alloc(&w.blk_sum, w.max_blocks));
     CU(dev_alloc(&w.blk_vpos, w.max_blocks + 1));
     CU(dev_alloc(&w.lane_sum, w.max_blocks * 32));
+    CU(dev_alloc(&w.blk_read, w.max_blocks));
     return SGPU_OK;
 }
 
@@ -397,7 +398,7 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     {
         SvbScratch& w = ctx->svb;
         cudaFree(w.cnt); cudaFree(w.base); cudaFree(w.blk_bytes); cudaFree(w.blk_gpos); cudaFree(w.blk_sum);
-        cudaFree(w.blk_vpos); cudaFree(w.lane_sum);
+        cudaFree(w.blk_vpos); cudaFree(w.lane_sum); cudaFree(w.blk_read);
     }
     if (ctx->slots) {
         for (uint32_t s = 0; s < ctx->n_slots; s++) {

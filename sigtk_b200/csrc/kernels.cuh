@@ -87,6 +87,7 @@ struct SvbScratch {
     uint32_t* blk_bytes; uint64_t* blk_gpos;  // [max_blocks], [max_blocks+1]
     uint32_t* blk_sum; uint64_t* blk_vpos;
     uint32_t* lane_sum;                       // [max_blocks*32]
+    uint32_t* blk_read;                       // [max_blocks] read of every block
     uint64_t max_blocks;
 };
 uint64_t svbzd_max_blocks(uint64_t max_samples, uint32_t max_reads);

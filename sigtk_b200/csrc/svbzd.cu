@@ -43,9 +43,10 @@ __device__ __forceinline__ uint32_t find_block_read(const uint64_t* __restrict__
     return lo;
 }
 
-__device__ __forceinline__ SvbBlock load_block(const SvbBatch& s, const uint64_t* __restrict__ base, uint64_t b, int lane) {
+__device__ __forceinline__ SvbBlock load_block(const SvbBatch& s, const uint64_t* __restrict__ base, uint64_t b, int lane,
+                                               uint32_t r) {
     SvbBlock q;
-    q.r = find_block_read(base, s.n_reads, b);
+    q.r = r;
     q.k = (uint32_t)(b - base[q.r]);
     q.n = s.read_len[q.r];
     q.stream = s.comp_off[q.r];
@@ -81,20 +82,36 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     return inc - v;
 }
 
-// walks the valid values of one lane; f(j, delta) receives the zigzag-decoded delta of value j
-template <class F>
-__device__ __forceinline__ void walk_lane(const SvbBatch& s, const SvbBlock& q, uint64_t at, F f) {
+constexpr int SVB_STAGE_WORDS = SVB_BLOCK + 4;  // a block's data: at most 4 bytes per value, plus alignment slack
+
+// copies the data bytes [start, start + n_bytes) of one block into the warp's shared-memory stage (aligned words,
+// coalesced) and returns the byte offset of `start` inside the stage
+__device__ __forceinline__ uint32_t stage_block(const SvbBatch& s, uint64_t start, uint32_t n_bytes, uint32_t* stage, int lane) {
     const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(s.bytes);
-    const uint64_t last_word = (s.n_bytes >> 2);  // the buffer carries 8 bytes of slack: word last_word+1 exists
+    const uint64_t last_word = (s.n_bytes >> 2) + 1u;  // the buffer carries 8 bytes of slack
+    const uint64_t w0 = start >> 2;
+    const uint32_t lead = (uint32_t)start & 3u;
+    const uint32_t n_words = (lead + n_bytes + 3u) / 4u + 1u;  // one more: the last value's fetch reads a word pair
+    __syncwarp();  // the previous block's readers are done
+    for (uint32_t k = lane; k < n_words; k += 32) {
+        uint64_t wi = w0 + k;
+        if (wi > last_word) wi = last_word;  // malformed stream: stay inside the buffer (the length check reports it)
+        stage[k] = __ldg(words + wi);
+    }
+    __syncwarp();
+    return lead;
+}
+
+// walks the valid values of one lane from the staged bytes; f(j, delta) receives the zigzag-decoded delta of value j
+template <class F>
+__device__ __forceinline__ void walk_lane(const SvbBlock& q, const uint32_t* stage, uint32_t at, F f) {
     const uint32_t klo = (uint32_t)q.keys64, khi = (uint32_t)(q.keys64 >> 32);
 #pragma unroll
     for (uint32_t j = 0; j < 32u; j++) {  // unrolled: every index below is static
         if (j >= q.nv) break;
         const uint32_t code = ((j < 16u ? klo : khi) >> (2u * (j & 15u))) & 3u;
-        uint64_t wi = at >> 2;
-        if (wi > last_word) wi = last_word;  // malformed stream: stay inside the buffer (the length check reports it)
-        const uint32_t lo = __ldg(words + wi), hi = __ldg(words + wi + 1);
-        const uint32_t z = __funnelshift_r(lo, hi, ((uint32_t)at & 3u) * 8u) & (0xffffffffu >> (8u * (3u - code)));
+        const uint32_t i = at >> 2;
+        const uint32_t z = __funnelshift_r(stage[i], stage[i + 1], (at & 3u) * 8u) & (0xffffffffu >> (24u - 8u * code));
         f(j, (z >> 1) ^ (0u - (z & 1u)));  // streamvbyte_zigzag.c:27-29
         at += code + 1u;
     }
@@ -106,29 +123,34 @@ __global__ void __launch_bounds__(256) svb_count_kernel(SvbBatch s, uint32_t* __
 }
 
 __global__ void __launch_bounds__(SVB_WARPS * 32) svb_bytes_kernel(SvbBatch s, const uint64_t* __restrict__ base,
-                                                                   uint32_t* __restrict__ blk_bytes) {
+                                                                   uint32_t* __restrict__ blk_bytes,
+                                                                   uint32_t* __restrict__ blk_read) {
     const int lane = threadIdx.x & 31;
     const uint64_t n_blocks = base[s.n_reads];
     for (uint64_t b = (uint64_t)blockIdx.x * SVB_WARPS + (threadIdx.x >> 5); b < n_blocks; b += (uint64_t)gridDim.x * SVB_WARPS) {
-        const SvbBlock q = load_block(s, base, b, lane);
+        const SvbBlock q = load_block(s, base, b, lane, find_block_read(base, s.n_reads, b));
         const uint32_t tot = __reduce_add_sync(0xffffffffu, lane_bytes(q));
-        if (lane == 0) blk_bytes[b] = tot;
+        if (lane == 0) { blk_bytes[b] = tot; blk_read[b] = q.r; }  // the later passes reuse the block -> read map
     }
 }
 
 __global__ void __launch_bounds__(SVB_WARPS * 32) svb_sums_kernel(SvbBatch s, const uint64_t* __restrict__ base,
                                                                   const uint64_t* __restrict__ blk_gpos,
+                                                                  const uint32_t* __restrict__ blk_read,
                                                                   uint32_t* __restrict__ lane_sum,
                                                                   uint32_t* __restrict__ blk_sum, int* __restrict__ status) {
+    __shared__ uint32_t stage_all[SVB_WARPS][SVB_STAGE_WORDS];
+    uint32_t* stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint64_t n_blocks = base[s.n_reads];
     for (uint64_t b = (uint64_t)blockIdx.x * SVB_WARPS + (threadIdx.x >> 5); b < n_blocks; b += (uint64_t)gridDim.x * SVB_WARPS) {
-        const SvbBlock q = load_block(s, base, b, lane);
+        const SvbBlock q = load_block(s, base, b, lane, blk_read[b]);
         uint32_t blk_total;
         const uint32_t before = warp_excl_scan(lane_bytes(q), lane, &blk_total);
         const uint64_t boff = blk_gpos[b] - blk_gpos[base[q.r]];  // data bytes of the read before this block
+        const uint32_t lead = stage_block(s, q.stream + 4u + q.key_len + boff, blk_total, stage, lane);
         uint32_t sum = 0;
-        walk_lane(s, q, q.stream + 4u + q.key_len + boff + before, [&](uint32_t, uint32_t d) { sum += d; });
+        walk_lane(q, stage, lead + before, [&](uint32_t, uint32_t d) { sum += d; });
         lane_sum[b * 32 + lane] = sum;
         const uint32_t tot = __reduce_add_sync(0xffffffffu, sum);
         if (lane == 0) {
@@ -142,23 +164,27 @@ __global__ void __launch_bounds__(SVB_WARPS * 32) svb_sums_kernel(SvbBatch s, co
 
 __global__ void __launch_bounds__(SVB_WARPS * 32) svb_write_kernel(SvbBatch s, const uint64_t* __restrict__ base,
                                                                    const uint64_t* __restrict__ blk_gpos,
+                                                                   const uint32_t* __restrict__ blk_read,
                                                                    const uint32_t* __restrict__ lane_sum,
                                                                    const uint64_t* __restrict__ blk_vpos,
                                                                    int16_t* __restrict__ samples) {
+    __shared__ uint32_t stage_all[SVB_WARPS][SVB_STAGE_WORDS];
+    uint32_t* stage = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint64_t n_blocks = base[s.n_reads];
     for (uint64_t b = (uint64_t)blockIdx.x * SVB_WARPS + (threadIdx.x >> 5); b < n_blocks; b += (uint64_t)gridDim.x * SVB_WARPS) {
-        const SvbBlock q = load_block(s, base, b, lane);
+        const SvbBlock q = load_block(s, base, b, lane, blk_read[b]);
         uint32_t blk_total, unused;
         const uint32_t before = warp_excl_scan(lane_bytes(q), lane, &blk_total);
         const uint32_t vbefore = warp_excl_scan(lane_sum[b * 32 + lane], lane, &unused);
         const uint64_t boff = blk_gpos[b] - blk_gpos[base[q.r]];
         // value of the sample before this lane's first one: 32-bit wrap-around like the reference's int32 `prev`
         uint32_t prev = (uint32_t)(blk_vpos[b] - blk_vpos[base[q.r]]) + vbefore;
+        const uint32_t lead = stage_block(s, q.stream + 4u + q.key_len + boff, blk_total, stage, lane);
         uint32_t w[16];
 #pragma unroll
         for (int t = 0; t < 16; t++) w[t] = 0u;
-        walk_lane(s, q, q.stream + 4u + q.key_len + boff + before, [&](uint32_t j, uint32_t d) {
+        walk_lane(q, stage, lead + before, [&](uint32_t j, uint32_t d) {
             prev += d;                                   // streamvbyte_zigzag.c:44-45; the int16 store truncates
             w[j >> 1] |= (prev & 0xffffu) << (16u * (j & 1u));   // j is a compile-time constant after unrolling
         });
@@ -169,7 +195,9 @@ __global__ void __launch_bounds__(SVB_WARPS * 32) svb_write_kernel(SvbBatch s, c
 #pragma unroll
                 for (int t = 0; t < 4; t++) d4[t] = make_int4((int)w[4 * t], (int)w[4 * t + 1], (int)w[4 * t + 2], (int)w[4 * t + 3]);
             } else {
-                for (uint32_t j = 0; j < q.nv; j++) dst[j] = (int16_t)(w[j >> 1] >> (16u * (j & 1u)));
+#pragma unroll
+                for (uint32_t j = 0; j < 32u; j++)  // static indices keep w[] in registers
+                    if (j < q.nv) dst[j] = (int16_t)(w[j >> 1] >> (16u * (j & 1u)));
             }
         }
     }
@@ -194,11 +222,11 @@ int launch_svbzd_decode(const SvbBatch& s, SvbScratch& w, Scratch& sc, int16_t* 
     svb_count_kernel<<<grid_cap(s.n_reads, 256, sm_count * 8), 256, 0, st>>>(s, w.cnt);
     int n = 1 + launch_scan_u32(w.cnt, s.n_reads, w.base, nullptr, sc, st);
     const int grid = grid_cap(max_blocks, SVB_WARPS, sm_count * 16);
-    svb_bytes_kernel<<<grid, SVB_WARPS * 32, 0, st>>>(s, w.base, w.blk_bytes);
+    svb_bytes_kernel<<<grid, SVB_WARPS * 32, 0, st>>>(s, w.base, w.blk_bytes, w.blk_read);
     n += 1 + launch_scan_u32(w.blk_bytes, (uint32_t)max_blocks, w.blk_gpos, nullptr, sc, st);
-    svb_sums_kernel<<<grid, SVB_WARPS * 32, 0, st>>>(s, w.base, w.blk_gpos, w.lane_sum, w.blk_sum, sc.status);
+    svb_sums_kernel<<<grid, SVB_WARPS * 32, 0, st>>>(s, w.base, w.blk_gpos, w.blk_read, w.lane_sum, w.blk_sum, sc.status);
     n += 1 + launch_scan_u32(w.blk_sum, (uint32_t)max_blocks, w.blk_vpos, nullptr, sc, st);
-    svb_write_kernel<<<grid, SVB_WARPS * 32, 0, st>>>(s, w.base, w.blk_gpos, w.lane_sum, w.blk_vpos, samples);
+    svb_write_kernel<<<grid, SVB_WARPS * 32, 0, st>>>(s, w.base, w.blk_gpos, w.blk_read, w.lane_sum, w.blk_vpos, samples);
     return n + 1;
 }
 

@@ -46,3 +46,24 @@ def make_reads(n_reads: int, mean: float = 40000.0, sigma: float = 0.6, seed: in
     lens = read_lengths(n_reads, mean, sigma, seed, lo, hi)
     p = 0.025 if rna else 0.1
     return [make_read(i, int(lens[i]), seed, p_change=p) for i in range(n_reads)]
+
+
+def svbzd_encode(raw: np.ndarray) -> np.ndarray:
+    """The svb-zd stream slow5lib stores for `raw` in a BLOW5 record (SLOW5_COMPRESS_SVB_ZD; slow5_press.c:1055-1089,
+    streamvbyte_encode.c, streamvbyte_zigzag.c:5-25): uint32 count | 2-bit length codes, four per key byte | the
+    zigzag-coded deltas in 1..4 little-endian bytes. Vectorised numpy; used to make synthetic COMPRESSED input for the
+    benchmarks and the CLI tools (the decoder under test is the CUDA one; tests check this encoder against the
+    reference's own)."""
+    raw = np.ascontiguousarray(raw, dtype=np.int16)
+    n = raw.shape[0]
+    cur = raw.astype(np.int32)
+    prev = np.concatenate([np.zeros(1, np.int32), cur[:-1]]) if n else cur
+    d = (cur - prev).astype(np.int32)
+    z = ((d.astype(np.uint32) << np.uint32(1)) ^ (d >> 31).astype(np.uint32)).astype(np.uint32)
+    code = (z >= 1 << 8).astype(np.uint8) + (z >= 1 << 16).astype(np.uint8) + (z >= 1 << 24).astype(np.uint8)
+    pad = (-n) % 4
+    c4 = np.concatenate([code, np.zeros(pad, np.uint8)]).reshape(-1, 4)
+    keys = (c4[:, 0] | (c4[:, 1] << 2) | (c4[:, 2] << 4) | (c4[:, 3] << 6)).astype(np.uint8)
+    zb = z.astype("<u4").view(np.uint8).reshape(n, 4)
+    data = zb[np.arange(4, dtype=np.uint8)[None, :] <= code[:, None]]
+    return np.concatenate([np.array([n], dtype="<u4").view(np.uint8), keys, data])

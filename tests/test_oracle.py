@@ -176,3 +176,12 @@ def test_svbzd_equals_compiled_reference(orc):
             a, b = orc.svbzd_encode(raw), ref.svbzd_encode(raw)
             assert np.array_equal(a, b)
             assert np.array_equal(orc.svbzd_decode(a), raw) and np.array_equal(ref.svbzd_decode(a), raw)
+
+
+def test_synthetic_svbzd_encoder_equals_oracle(orc):
+    """sigtk_b200.synth.svbzd_encode (numpy; makes compressed input for bench.py) writes the reference's bytes"""
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 3, 4, 5, 1027, 20000):
+        for scale in (5, 300, 50000):
+            raw = np.clip(np.cumsum(rng.integers(-scale, scale + 1, n)), -32768, 32767).astype(np.int16)
+            assert np.array_equal(synth.svbzd_encode(raw), orc.svbzd_encode(raw)), (n, scale)
