@@ -66,7 +66,15 @@ __device__ __forceinline__ long long next_start(const uint32_t* __restrict__ bit
 
 }  // namespace
 
-__global__ void __launch_bounds__(EWARPS * 32) emit_events_kernel(DevBatch b, uint32_t n_tiles,
+// launch shape (measured, tools/run_variants.sh): 7 CTAs of 4 warps per SM (72 registers) and a grid of 64 CTAs per SM --
+// warp tiles differ in cost (read boundaries, event density), a finer static partition evens the tail out
+#ifndef EMIT_MINB
+#define EMIT_MINB 7
+#endif
+#ifndef EMIT_GRID
+#define EMIT_GRID 64
+#endif
+__global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(DevBatch b, uint32_t n_tiles,
                                                                   const uint32_t* __restrict__ bitmap,
                                                                   const uint64_t* __restrict__ tile_base, uint64_t ev_cap,
                                                                   uint32_t* __restrict__ ev_start,
@@ -274,7 +282,7 @@ int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* 
                      float* ev_stdv, const uint32_t* fixups, int sm_count, cudaStream_t st) {
     const uint32_t n_tiles = fast_tiles_for(b.span);
     const uint64_t n_wt = (uint64_t)n_tiles * (FAST_TILE / EWT);
-    emit_events_kernel<<<grid_cap(n_wt, EWARPS, sm_count * 8), EWARPS * 32, 0, st>>>(
+    emit_events_kernel<<<grid_cap(n_wt, EWARPS, sm_count * EMIT_GRID), EWARPS * 32, 0, st>>>(
         b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0);
     sum_fixups_kernel<<<grid_cap(b.n_reads, 256, sm_count * 4), 256, 0, st>>>(b.n_reads, fixups, sc.counters);
     return 2;
