@@ -43,8 +43,6 @@ struct WalkParams {
     int* st_end;                    // same indexing: state after the chunk's last step
     uint32_t* wit_min;
     uint32_t* wit_max;
-    uint32_t* seq_flag;
-    uint32_t* fixups;
     uint32_t edge_blocks;
 };
 
@@ -57,8 +55,6 @@ struct DevIo {
     int* __restrict__ st_end;
     uint32_t* __restrict__ wit_min;   // this read's witness
     uint32_t* __restrict__ wit_max;
-    uint32_t* __restrict__ far_flag;  // this read's sequential-order flag / fix-up counter (far_peak)
-    uint32_t* __restrict__ far_fix;
     float off, unit;
 
     __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
@@ -82,7 +78,6 @@ struct DevIo {
         if (lo) atomicOr(w, lo);
         if (hi) atomicOr(w + 1, hi);
     }
-    __device__ __forceinline__ void far_peak() const { *far_flag = 1u; atomicAdd(far_fix, 1u); }
     static __device__ __forceinline__ void store_canon(int* __restrict__ dst, const Canon& c) {
         int4* p = reinterpret_cast<int4*>(dst);
         p[0] = make_int4(c.v[0], c.v[1], c.v[2], c.v[3]);
@@ -113,8 +108,6 @@ __device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64
     io.st_end = p.st_end + sid * 8;
     io.wit_min = p.wit_min + r;
     io.wit_max = p.wit_max + r;
-    io.far_flag = p.seq_flag + r;
-    io.far_fix = p.fixups + r;
     io.off = p.b.offset[r];
     io.unit = p.b.unit[r];
     return io;
@@ -238,7 +231,6 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
     p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max;
-    p.seq_flag = seq_flag; p.fixups = fixups;
     p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
     const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
     const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;

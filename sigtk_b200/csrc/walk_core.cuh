@@ -326,20 +326,27 @@ SGW_HD Canon canon_of(const WalkDet& d, int b) {
 // Emitted peaks of one block are collected in a register: bit k of `mk` <=> a peak at position ub + k. The
 // block's own steps sit at bits PK_LEAD .. PK_LEAD + U - 1, so a peak up to PK_LEAD positions older than the
 // step that emits it fits; an older one (a plateau within peak_height of a maximum above the threshold lasting
-// dozens of samples) sets `far`, and the read is redone by the sequential-order kernels.
+// dozens of samples; seen in about 1 RNA read in 20,000) shows in `oldest`, and the block is redone by redo_block,
+// which records every peak on its own.
 template <int RNA> struct PkCfg {
     static constexpr int LEAD = 32 - Cfg<RNA>::U;
+#if defined(WALK_TEST_FAR)  // host tests: treat every peak older than w/2 + 2 as too old for the mask
+    static constexpr int FAR = 0;
+#else
     static constexpr int FAR = LEAD - (Cfg<RNA>::w2 / 2 + 1);  // largest (age - w/2 - 1) that always fits the mask
+#endif
 };
 struct PeakAcc { uint32_t mk; int oldest; };
+struct NoEmit { SGW_HD void operator()(int) const {} };
 
 // One detector, one position (events.c:393-437); the detector is not masked at u (events.c:387).
 //   m    : index of the step within its block (compile-time), u : its position
 //   c    : the t-statistic at u
 //   big2 : CASE 2 and the running maximum is above the threshold (the short detector then masks the long one)
 //   p2   : the (possibly moved) peak position with the PS_OPEN flag, valid when big2
-template <bool SHORT, int RNA>
-SGW_HD void det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, bool& big2, int& p2) {
+//   on_emit(pos) : called for an emitted peak (the fast path passes NoEmit and reads the mask instead)
+template <bool SHORT, int RNA, class E>
+SGW_HD void det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, bool& big2, int& p2, const E& on_emit) {
     constexpr int w = SHORT ? Cfg<RNA>::w1 : Cfg<RNA>::w2;
     const float h = peak_h<RNA>();
     const float thr = SHORT ? thr_short<RNA>() : thr_long<RNA>();
@@ -356,16 +363,17 @@ SGW_HD void det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, boo
     const bool emit = over >= 0;                           // while not valid (flag bits): events.c:429
     acc.mk |= shr_clamp(1u << (PkCfg<RNA>::LEAD + m - (w / 2 + 1)), over);  // no bit unless 0 <= over <= 31
     acc.oldest = acc.oldest > over ? acc.oldest : over;
+    if (emit) on_emit(p3);
     pv = (rise1 | emit) ? c : pvm;                         // 395 / 400 / 409 / 433
     ps = emit ? PS_NONE : p3;
     ps = rise1 ? (u | PS_OPEN) : ps;
 }
 
 // One position of both detectors, short first (events.c:385-440).
-template <int RNA>
-SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc) {
+template <int RNA, class E>
+SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc, const E& on_emit) {
     bool maskl, unused_b; int p2, unused_p;
-    det_one<true, RNA>(d.s_pv, d.s_ps, m, u, c1, acc, maskl, p2);
+    det_one<true, RNA>(d.s_pv, d.s_ps, m, u, c1, acc, maskl, p2, on_emit);
     // the short detector dominates the long one while it holds a peak above its threshold (events.c:414-422)
     d.l_mt = maskl ? (p2 & ~PS_OPEN) + Cfg<RNA>::w1 : d.l_mt;
     d.l_ps = maskl ? PS_NONE : d.l_ps;
@@ -373,7 +381,7 @@ SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc)
     // a masked long detector is always in the reset state (masked_to is only ever set together with a reset, and
     // a masked detector is not stepped), and the reset state does not react to FLT_MAX: no gating needed
     const float c2m = d.l_mt < u ? c2 : FLT_MAX;
-    det_one<false, RNA>(d.l_pv, d.l_ps, m, u, c2m, acc, unused_b, unused_p);
+    det_one<false, RNA>(d.l_pv, d.l_ps, m, u, c2m, acc, unused_b, unused_p, on_emit);
 }
 
 // ---- the register rings --------------------------------------------------------------------------------------------
@@ -408,7 +416,8 @@ struct Rings {
 //   tau0   : read index of the block's first sample, a multiple of U
 //   sh     : read_off & 31
 // The rare path of a block: the t-statistics of the whole block from the raw samples with the reference's own
-// operations, then the block's detector steps again from the state the block started in.
+// operations, then the block's detector steps again from the state the block started in; every emitted peak is
+// recorded on its own (io.peak), however old it is.
 template <int RNA> struct Redo { WalkDet d; PeakAcc acc; float t1c[Cfg<RNA>::w1]; };
 template <int RNA, bool EDGE, class Io>
 #if defined(__CUDACC__)
@@ -416,7 +425,7 @@ __host__ __device__ __noinline__
 #else
 inline
 #endif
-Redo<RNA> redo_block(const Io& io, Redo<RNA> in, int tau0, int n, int sh, float off, float unit) {
+Redo<RNA> redo_block(const Io& io, Redo<RNA> in, int tau0, int n, int sh, bool rec, float off, float unit) {
     using C = Cfg<RNA>;
     constexpr int w1 = C::w1, w2 = C::w2, U = C::U;
     float e1[U], e2[U];
@@ -432,11 +441,8 @@ Redo<RNA> redo_block(const Io& io, Redo<RNA> in, int tau0, int n, int sh, float 
         }
         const float c1 = m >= w1 ? e1[m - w1] : in.t1c[m];
         if (!EDGE || (j2 >= 1 && j2 < n)) {
-            // det_step wants a compile-time step index only for the mask constants: use the variable forms
-            PeakAcc one; one.mk = 0u; one.oldest = 0;
-            det_step<RNA>(r.d, 0, u0 + m, c1, e2[m], one);
-            r.acc.mk |= one.mk << m;  // a step-0 mask, moved to step m (bits shifted out are older than `oldest` allows)
-            r.acc.oldest = r.acc.oldest > one.oldest ? r.acc.oldest : one.oldest;  // (conservative: as if m == 0)
+            PeakAcc unused; unused.mk = 0u; unused.oldest = 0;   // the mask is not used here
+            det_step<RNA>(r.d, 0, u0 + m, c1, e2[m], unused, [&](int pos) { if (rec) io.peak(pos); });
         }
     }
     for (int k = 0; k < w1; k++) r.t1c[k] = e1[U - w1 + k];
@@ -516,25 +522,23 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
         g.A1[s1] = a1; g.L1[s1] = l1;
         g.A2[s2] = a2; g.L2[s2] = l2;
         const float c1 = m >= w1 ? t1v[m - w1] : g.T1c[m];         // t1(j2), computed w1 samples ago
-        if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, m, u0 + m, c1, t2m, acc);
+        if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, m, u0 + m, c1, t2m, acc, NoEmit());
     }
 #if defined(WALK_TEST_REDO)  // host tests: take the rare path on every third block
     ok = ok & ((tau0 / U) % 3 != 0);
 #endif
-    if ((!ok & live) | (!ok_t1 & live_t1)) {  // rare (about 3 blocks in 100,000)
+    // rare (about 3 blocks in 100,000): a t-statistic next to a rounding midpoint, or a peak too old for the mask
+    if ((!ok & live) | (!ok_t1 & live_t1) | (rec & (acc.oldest > PkCfg<RNA>::FAR))) {
         Redo<RNA> in;
         in.d = d0; in.acc = acc;
 #pragma unroll
         for (int k = 0; k < w1; k++) in.t1c[k] = g.T1c[k];
-        const Redo<RNA> r = redo_block<RNA, EDGE>(io, in, tau0, n, sh, off, unit);
+        const Redo<RNA> r = redo_block<RNA, EDGE>(io, in, tau0, n, sh, rec, off, unit);
         d = r.d; acc = r.acc;
 #pragma unroll
         for (int k = 0; k < w1; k++) t1v[U - w1 + k] = r.t1c[k];
     }
-    if (rec) {  // peaks are owned by the step that emits them
-        if (acc.mk) io.peaks32(u0 - PkCfg<RNA>::LEAD, acc.mk);
-        if (acc.oldest > PkCfg<RNA>::FAR) io.far_peak();
-    }
+    if (rec && acc.mk) io.peaks32(u0 - PkCfg<RNA>::LEAD, acc.mk);  // peaks are owned by the step that emits them
 #pragma unroll
     for (int k = 0; k < w1; k++) g.T1c[k] = t1v[U - w1 + k];
 }
@@ -547,7 +551,6 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 //   want_pa() / store_pa8(t, x) / store_pa1(t, x)
 //   peaks32(ub, mk)    record the emitted peaks of a block: bit k of mk (nonzero) <=> a peak at shifted position ub + k
 //   peak(pos)          record one peak
-//   far_peak()         a peak older than the block's mask was emitted: the read must be redone in sequential order
 //   put_begin(c) / put_end(c)   the chunk's canonical detector state after the warm-up / after its last step
 //   witness(rmin, rmax)         extreme raw values of samples of the read (any superset of the owned samples)
 SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return (n + L - 1u) / L; }

@@ -15,13 +15,16 @@ CORE = os.path.join(os.path.dirname(HERE), "sigtk_b200", "csrc", "walk_core.cuh"
 OUT = os.path.join(HERE, "tools", "libhostwalk.so")
 
 
-def load(force_redo=False):
-    """force_redo: the build takes the rare exact-recompute path on every third block (WALK_TEST_REDO)"""
-    out = OUT.replace(".so", "_redo.so") if force_redo else OUT
+def load(force_redo=False, force_far=False):
+    """force_redo: the build takes the rare exact-recompute path on every third block (WALK_TEST_REDO);
+    force_far: every peak emitted later than the earliest possible step counts as too old for the block's mask
+    (WALK_TEST_FAR), which sends its block through the same path"""
+    out = OUT.replace(".so", "_redo.so") if force_redo else OUT.replace(".so", "_far.so") if force_far else OUT
     newest = max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(__file__))
     if not os.path.exists(out) or os.path.getmtime(out) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC"]
-                              + (["-DWALK_TEST_REDO"] if force_redo else []) + ["-x", "c++", SRC, "-o", out])
+                              + (["-DWALK_TEST_REDO"] if force_redo else []) + (["-DWALK_TEST_FAR"] if force_far else [])
+                              + ["-x", "c++", SRC, "-o", out])
     lib = C.CDLL(out)
     lib.host_walk_read.restype = C.c_int
     lib.host_walk_read.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -376,3 +376,16 @@ def test_full_size_batch(orc):
         assert np.array_equal(ev_start[a:b], s0.astype(np.int64)), f"read {r}: boundaries differ"
         assert np.array_equal(bits(ev_mean[a:b]), bits(mn)) and np.array_equal(bits(ev_stdv[a:b]), bits(sd))
     dctx.close()
+
+
+@pytest.mark.parametrize("rna_flag", [0, 1])
+def test_plateaus_emit_old_peaks_on_the_fast_path(ctx, orc, rna_flag, monkeypatch):
+    """linear ramps keep the t-statistic within peak_height of its maximum: the peak is emitted dozens of samples
+    after its position, too old for the walker's per-block register mask; the block then records its peaks one by
+    one (redo_block) and the read stays on the fast path"""
+    from test_host_walk import ramp_read
+    monkeypatch.setenv("SGPU_CHUNK_LEN", "4096")
+    reads = [ramp_read(12000, seed=3), ramp_read(15000, seed=4)] + synth.make_reads(6, mean=9000.0, seed=63)
+    res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
+    check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS)
+    assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0

@@ -76,3 +76,31 @@ def test_exact_recompute_path(orc):
     base = synth.make_read(3, 600, seed=10)
     for n in (5, 13, 29, 199, 200, 257, 600):
         check(lib, orc, (base[0][:n].copy(), base[1], base[2], base[3]), 0, 128, 64, 8)
+
+
+def test_old_peaks_take_the_exact_path(orc):
+    """a peak older than the block's register mask (forced here: older than the earliest possible emission) makes
+    the block record its peaks one by one; events must not change"""
+    lib = _hostwalk.load(force_far=True)
+    for rna, L, W in ((0, 128, 64), (0, 1024, 64), (1, 512, 384)):
+        reads = synth.make_reads(4, mean=7000.0, seed=99 + rna, rna=bool(rna))
+        for k, rd in enumerate(reads):
+            check(lib, orc, rd, rna, L, W, (0, 8, 16, 24)[k % 4])
+
+
+def ramp_read(n=12000, seed=3):
+    """linear ramps give a t-statistic that stays within peak_height of its maximum for as long as the ramp lasts:
+    the peak is emitted dozens of samples after its position (older than the walker's per-block register mask)"""
+    rd = synth.make_read(5, n, seed=seed)
+    raw = rd[0].copy()
+    for start, step, ln in ((1300, 20, 150), (2400, -2, 180), (3500, 7, 90), (4500, 11, 40), (7000, 3, 60), (9000, 30, 100)):
+        raw[start:start + ln] = raw[start - 1] + step * np.arange(1, ln + 1)
+    assert raw.min() > 0
+    return raw, rd[1], rd[2], rd[3]
+
+
+def test_plateaus_emit_old_peaks(lib, orc):
+    rd = ramp_read()
+    for rna, L, W in ((0, 4096, 64), (0, 2048, 64), (1, 4096, 384)):
+        for sh in (0, 8, 24):
+            check(lib, orc, rd, rna, L, W, sh)

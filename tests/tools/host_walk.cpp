@@ -22,7 +22,6 @@ struct HostIo {
     Canon* end;
     int* rmin;
     int* rmax;
-    int* far;
     void load8(int t, int (&v)[4]) const { memcpy(v, sp + t, 16); }
     bool want_pa() const { return pa != nullptr; }
     void store_pa8(int t, const float* x) const { memcpy(pa + t, x, 32); }
@@ -32,7 +31,7 @@ struct HostIo {
         for (int k = 0; k < 32; k++)
             if (mk >> k & 1u) { if (ub + k < 0) abort(); peak(ub + k); }
     }
-    void far_peak() const { *far += 1; }
+
     void put_begin(const Canon& c) const { *begin = c; }
     void put_end(const Canon& c) const { *end = c; }
     void witness(int lo, int hi) const { if (lo < *rmin) *rmin = lo; if (hi > *rmax) *rmax = hi; }
@@ -44,14 +43,14 @@ int run(const int16_t* raw_padded, int n, float off, float unit, int L, int W, i
     const uint32_t nch = n_chunks((uint32_t)n, (uint32_t)L);
     if (nch == 0) return 0;
     std::vector<Canon> begin(nch), end(nch);
-    int rmin = 32767, rmax = -32768, far = 0;
+    int rmin = 32767, rmax = -32768;
     for (uint32_t k = 0; k < nch; k++) {
-        HostIo io{raw_padded, pa, bitmap, &begin[k], &end[k], &rmin, &rmax, &far};
+        HostIo io{raw_padded, pa, bitmap, &begin[k], &end[k], &rmin, &rmax};
         if (k == 0) walk_edge<RNA>(io, n, off, unit, sh, L, W, 0);
         else if (k == nch - 1) walk_edge<RNA>(io, n, off, unit, sh, L, W, 1);
         else walk_interior<RNA>(io, n, off, unit, sh, L, W, (int)k);
     }
-    int mism = far;  // a far peak routes the read to the sequential-order kernels like a boundary mismatch
+    int mism = 0;
     for (uint32_t k = 1; k < nch; k++) {
         bool same = true;
         for (int q = 0; q < 6; q++) same = same && begin[k].v[q] == end[k - 1].v[q];
