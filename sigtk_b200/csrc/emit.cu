@@ -50,6 +50,17 @@ __device__ __forceinline__ void add_raw(int raw, float off, float unit, double& 
     as = __dadd_rn(as, walk::widen_pos(x));
     aq = __dadd_rn(aq, walk::widen_pos(__fmul_rn(x, x)));
 }
+// the same for any sample (reads marked by the walker as holding samples with pA <= 0): real conversions
+__device__ __forceinline__ void add_raw_any(int raw, float off, float unit, double& as, double& aq) {
+    const float x = __fmul_rn(__fadd_rn((float)raw, off), unit);
+    if (x > 0.0f) {
+        as = __dadd_rn(as, walk::widen_pos(x));
+        aq = __dadd_rn(aq, walk::widen_pos(__fmul_rn(x, x)));
+    } else {
+        as = __dadd_rn(as, (double)x);
+        aq = __dadd_rn(aq, (double)__fmul_rn(x, x));
+    }
+}
 
 // next event start at or after bitmap word w0, bounded by the end of the read
 __device__ __forceinline__ long long next_start(const uint32_t* __restrict__ bitmap, uint64_t w0, uint64_t n_words,
@@ -80,7 +91,8 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                                                                   uint32_t* __restrict__ ev_start,
                                                                   float* __restrict__ ev_mean, float* __restrict__ ev_stdv,
                                                                   int* __restrict__ status,
-                                                                  const uint32_t* __restrict__ tile_read0) {
+                                                                  const uint32_t* __restrict__ tile_read0,
+                                                                  const uint32_t* __restrict__ nonpos) {
     __shared__ EmitWarp smem[EWARPS];
     const int lane = threadIdx.x & 31;
     EmitWarp& sm = smem[threadIdx.x >> 5];
@@ -144,7 +156,9 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
         const long long rs_first = (long long)b.read_off[r_first];
         const long long rend_first = rs_first + (long long)b.read_len[r_first];
         const float off_first = b.offset[r_first], unit_first = b.unit[r_first];
-        const bool one_read = rs_first <= flat0 && flat0 + EWT <= rend_first && total <= (uint32_t)EFAST;
+        // (a read with non-positive samples takes the general path: its sums need real conversions)
+        const bool one_read = rs_first <= flat0 && flat0 + EWT <= rend_first && total <= (uint32_t)EFAST &&
+                              nonpos[r_first] == 0u;
         if (one_read) {
             // ---- fast path, step 2: the pieces of this lane's 32 samples ----------------------------------------------
             int slot = EFAST + lane;             // where the running piece goes: first the head of this word
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                 len = (uint32_t)(e - s);
                 i = s;
                 const long long stop = e - s > ELONG ? s + ELONG : e;
-                for (; i < stop; i++) add_raw((int)__ldg(b.samples + i), off, unit, as, aq);
+                for (; i < stop; i++) add_raw_any((int)__ldg(b.samples + i), off, unit, as, aq);
             }
             // long events (rare): the whole warp sums the rest
             uint32_t longs = __ballot_sync(0xffffffffu, have && i < e);
@@ -243,7 +257,7 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                 const long long li = __shfl_sync(0xffffffffu, i, src), le = __shfl_sync(0xffffffffu, e, src);
                 const float lo = __shfl_sync(0xffffffffu, off, src), lu = __shfl_sync(0xffffffffu, unit, src);
                 double ps = 0.0, pq = 0.0;
-                for (long long p = li + lane; p < le; p += 32) add_raw((int)__ldg(b.samples + p), lo, lu, ps, pq);
+                for (long long p = li + lane; p < le; p += 32) add_raw_any((int)__ldg(b.samples + p), lo, lu, ps, pq);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) {
                     ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, o));
@@ -283,7 +297,7 @@ int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* 
     const uint32_t n_tiles = fast_tiles_for(b.span);
     const uint64_t n_wt = (uint64_t)n_tiles * (FAST_TILE / EWT);
     emit_events_kernel<<<grid_cap(n_wt, EWARPS, sm_count * EMIT_GRID), EWARPS * 32, 0, st>>>(
-        b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0);
+        b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0, sc.nonpos);
     sum_fixups_kernel<<<grid_cap(b.n_reads, 256, sm_count * 4), 256, 0, st>>>(b.n_reads, fixups, sc.counters);
     return 2;
 }

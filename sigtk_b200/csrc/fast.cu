@@ -9,7 +9,7 @@
 // reference's S[i], Q[i] (double) are exact (no rounding happened) whenever every value is a multiple of 2^k and
 // the sum of magnitudes stays below 2^(k+53); then ANY grouping of the same additions is exact too, and every
 // window / event difference S[b]-S[a] equals the exact sum of the samples in [a,b).  The witness checks that
-// sufficient condition per read from the smallest and largest pA (all pA must be positive); reads that fail it
+// sufficient condition per read from the smallest nonzero and the largest |pA|; reads that fail it
 // are recomputed in the reference's own order by generic.cu.
 #include "kernels.cuh"
 
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) build_seq_list_kernel(DevBatch b, const u
         if (!(unit > 0.0f && unit <= FLT_MAX) || n >= (1u << 30) - 64u) flag = true;
         if (!flag && n > 0) {
             const uint32_t mn = wit_min[r], mx = wit_max[r];
-            // every sample must be a positive float in [2^-60, 2^20) (the range of the walker's shortcuts) ...
+            // every nonzero |pA| must be in [2^-60, 2^20) (the range of the walker's shortcuts) ...
             if (mn < 0x21800000u || mn > mx || mx >= 0x49800000u) flag = true;
             else {  // ... and the sums of x and x*x must be exact whatever the order
                 const uint32_t log2n = n > 1 ? 32u - __clz(n - 1) : 0u;
@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(256) read_event_offsets_kernel(DevBatch b, con
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) init_reads_kernel(DevBatch b, uint32_t n_tiles, uint32_t* __restrict__ wit_min,
-                                                         uint32_t* __restrict__ wit_max, uint32_t* __restrict__ seq_flag,
+                                                         uint32_t* __restrict__ wit_max, uint32_t* __restrict__ nonpos,
+                                                         uint32_t* __restrict__ seq_flag,
                                                          uint32_t* __restrict__ fixups, uint32_t* __restrict__ seq_count,
                                                          unsigned long long* __restrict__ cursor,
                                                          uint32_t* __restrict__ tile_read0) {
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) init_reads_kernel(DevBatch b, uint32_t n_
     for (uint32_t r = g; r < n_reads; r += gridDim.x * blockDim.x) {
         wit_min[r] = 0xffffffffu;
         wit_max[r] = 0u;
+        nonpos[r] = 0u;
         seq_flag[r] = 0u;
         fixups[r] = 0u;
     }
@@ -135,7 +137,7 @@ int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32
                       cudaStream_t st) {
     const uint32_t n_tiles = fast_tiles_for(b.span);
     init_reads_kernel<<<grid_cap(max(b.n_reads, n_tiles), 256, sm_count * 8), 256, 0, st>>>(
-        b, n_tiles, sc.wit_min, sc.wit_max, seq_flag, fixups, sc.seq_count, sc.cursor, sc.tile_read0);
+        b, n_tiles, sc.wit_min, sc.wit_max, sc.nonpos, seq_flag, fixups, sc.seq_count, sc.cursor, sc.tile_read0);
     return 1;
 }
 

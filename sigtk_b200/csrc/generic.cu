@@ -28,17 +28,35 @@ __global__ void __launch_bounds__(128) gen_prefix_kernel(DevBatch b, WorkList wl
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
         const uint32_t r = wl.list[j];
         const uint64_t base = wl.sbase[j];
-        const int16_t* __restrict__ raw = b.samples + b.read_off[r];
-        const uint32_t n = b.read_len[r];
+        // reads start on 16-byte boundaries and the batch is padded to one: whole groups of 8 samples can be loaded
+        const int4* __restrict__ raw8 = reinterpret_cast<const int4*>(b.samples + b.read_off[r]);
+        const uint32_t n = b.read_len[r], n8 = (n + 7u) >> 3;
         const float off = b.offset[r], unit = b.unit[r];
         double s = 0.0, q = 0.0;
-        for (uint32_t i = 0; i < n; i++) {
-            const float x = pa_of(raw[i], off, unit);
-            const float xx = __fmul_rn(x, x);  // float product, widened afterwards (events.c:301)
-            s = __dadd_rn(s, (double)x);
-            q = __dadd_rn(q, (double)xx);
-            Sinc[base + i] = s;
-            Qinc[base + i] = q;
+        constexpr int AHEAD = 4;  // groups in flight: the additions are one dependent chain, the loads must not be
+        int4 buf[AHEAD];
+#pragma unroll
+        for (int k = 0; k < AHEAD; k++) buf[k] = (uint32_t)k < n8 ? __ldg(raw8 + k) : make_int4(0, 0, 0, 0);
+        for (uint32_t g0 = 0; g0 < n8; g0 += AHEAD) {
+#pragma unroll
+            for (int k = 0; k < AHEAD; k++) {
+                const uint32_t g = g0 + k;
+                const int4 cur = buf[k];
+                buf[k] = g + AHEAD < n8 ? __ldg(raw8 + g + AHEAD) : make_int4(0, 0, 0, 0);
+                if (g >= n8) continue;
+                const int v[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    const uint32_t i = g * 8u + m;
+                    if (i >= n) break;
+                    const float x = pa_of((int16_t)((m & 1) ? (v[m >> 1] >> 16) : (v[m >> 1] & 0xffff)), off, unit);
+                    const float xx = __fmul_rn(x, x);  // float product, widened afterwards (events.c:301)
+                    s = __dadd_rn(s, (double)x);
+                    q = __dadd_rn(q, (double)xx);
+                    Sinc[base + i] = s;
+                    Qinc[base + i] = q;
+                }
+            }
         }
     }
 }
@@ -129,7 +147,7 @@ __global__ void __launch_bounds__(128) gen_detect_kernel(DevBatch b, WorkList wl
     const DetParams p = det_params(b.rna);
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
         const uint32_t r = wl.list[j];
-        const uint64_t base = wl.sbase[j];
+        const uint64_t base = wl.sbase[j];  // a multiple of 8: 16-byte aligned float4 loads
         const uint64_t foff = b.read_off[r];
         const uint32_t n = b.read_len[r];
         if (n == 0) continue;
@@ -138,11 +156,36 @@ __global__ void __launch_bounds__(128) gen_detect_kernel(DevBatch b, WorkList wl
         DetState s, l;
         det_reset(s);
         det_reset(l);
-        for (uint32_t i = 0; i < n; i++) {
-            const int32_t ps = det_step(s, &l, true, i, t1[base + i], p.thr1, p.w1, p.height);
-            if (ps > 0) { const uint64_t f = foff + (uint32_t)ps; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
-            const int32_t pl = det_step(l, nullptr, false, i, t2[base + i], p.thr2, p.w2, p.height);
-            if (pl > 0) { const uint64_t f = foff + (uint32_t)pl; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
+        // the detector is one dependent chain per read; its inputs are loaded 16 positions at a time, one group ahead
+        // (the scratch holds whole groups: every read's share is padded to 8 samples and the arrays to 16)
+        const float4* __restrict__ a1 = reinterpret_cast<const float4*>(t1 + base);
+        const float4* __restrict__ a2 = reinterpret_cast<const float4*>(t2 + base);
+        const uint32_t n4 = (n + 3u) >> 2;
+        float4 c1[4], c2[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            c1[k] = (uint32_t)k < n4 ? __ldg(a1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            c2[k] = (uint32_t)k < n4 ? __ldg(a2 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (uint32_t g0 = 0; g0 < n4; g0 += 4) {
+            float u1[16], u2[16];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u1[4 * k] = c1[k].x; u1[4 * k + 1] = c1[k].y; u1[4 * k + 2] = c1[k].z; u1[4 * k + 3] = c1[k].w;
+                u2[4 * k] = c2[k].x; u2[4 * k + 1] = c2[k].y; u2[4 * k + 2] = c2[k].z; u2[4 * k + 3] = c2[k].w;
+                const uint32_t g = g0 + 4 + k;
+                c1[k] = g < n4 ? __ldg(a1 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+                c2[k] = g < n4 ? __ldg(a2 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int m = 0; m < 16; m++) {
+                const uint32_t i = g0 * 4u + m;
+                if (i >= n) break;
+                const int32_t ps = det_step(s, &l, true, i, u1[m], p.thr1, p.w1, p.height);
+                if (ps > 0) { const uint64_t f = foff + (uint32_t)ps; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
+                const int32_t pl = det_step(l, nullptr, false, i, u2[m], p.thr2, p.w2, p.height);
+                if (pl > 0) { const uint64_t f = foff + (uint32_t)pl; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
+            }
         }
     }
 }
@@ -226,39 +269,62 @@ __global__ void __launch_bounds__(128) gen_emit_kernel(DevBatch b, WorkList wl, 
                                                        const uint64_t* __restrict__ ev_off, uint64_t ev_cap,
                                                        uint32_t* __restrict__ ev_start, float* __restrict__ ev_mean,
                                                        float* __restrict__ ev_stdv, int* __restrict__ status) {
+    // one WARP per read: the lanes take consecutive bitmap words; a warp scan gives every event start its index
+    // and the start before it (the statistics only need the two prefix-sum entries at an event's ends)
     const uint32_t n_list = *wl.count;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = warp; j < n_list; j += n_warps) {
         const uint32_t r = wl.list[j];
         const uint64_t base = wl.sbase[j];
         const uint64_t p0 = b.read_off[r];
         const uint32_t n = b.read_len[r];
-        uint64_t k = ev_off[r];
-        if (ev_off[r + 1] > ev_cap) { atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
+        if (ev_off[r + 1] > ev_cap) { if (lane == 0) atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
         if (n == 0) continue;
-        uint32_t a = 0;  // start of the open event
-        if (n > 0) {
-            const uint64_t p1 = p0 + n;
-            for (uint64_t w = p0 >> 5; w <= ((p1 - 1) >> 5); w++) {
-                uint32_t v = bitmap[w];
-                while (v) {
-                    const int bit = __ffs(v) - 1;
-                    v &= v - 1;
-                    const uint64_t f = (w << 5) + bit;
-                    if (f <= p0 || f >= p1) continue;  // peaks[i] > 0 && peaks[i] < nsample (events.c:482)
-                    const uint32_t e = (uint32_t)(f - p0);
-                    float m, sd;
-                    event_stats(__dsub_rn(prefix_at(Sinc, base, e), prefix_at(Sinc, base, a)),
-                                __dsub_rn(prefix_at(Qinc, base, e), prefix_at(Qinc, base, a)), e - a, &m, &sd);
-                    ev_start[k] = a; ev_mean[k] = m; ev_stdv[k] = sd;
-                    k++;
-                    a = e;
-                }
+        const uint64_t p1 = p0 + n;
+        const uint64_t w_first = p0 >> 5, w_last = (p1 - 1) >> 5;
+        uint64_t k = ev_off[r];  // index of the read's open event (starts at `a`)
+        uint32_t a = 0;
+        for (uint64_t w0 = w_first; w0 <= w_last; w0 += 32) {
+            const uint64_t w = w0 + lane;
+            uint32_t v = w <= w_last ? bitmap[w] : 0u;
+            // peaks[i] > 0 && peaks[i] < nsample (events.c:482): drop the bits at or before p0 and at or after p1
+            if (w == w_first) v &= (p0 & 31) == 31 ? 0u : (0xffffffffu << ((p0 & 31) + 1));
+            if (w == w_last && ((p1 - 1) & 31) != 31) v &= 0xffffffffu >> (31 - ((p1 - 1) & 31));
+            const uint32_t cnt = __popc(v);
+            uint32_t inc = cnt;
+            // the last event start at or before the end of this lane's word (0xffffffff: none yet in this group)
+            uint32_t last = v ? (uint32_t)((w << 5) + (31 - __clz(v)) - p0) : 0xffffffffu;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                const uint32_t tl = __shfl_up_sync(0xffffffffu, last, o);
+                if (lane >= o) { inc += t; if (last == 0xffffffffu) last = tl; }
             }
+            uint32_t prev = __shfl_up_sync(0xffffffffu, last, 1);  // the start before this lane's first bit
+            if (lane == 0 || prev == 0xffffffffu) prev = a;
+            uint64_t kk = k + (inc - cnt);
+            while (v) {
+                const int bit = __ffs(v) - 1;
+                v &= v - 1;
+                const uint32_t e = (uint32_t)((w << 5) + bit - p0);
+                float m, sd;
+                event_stats(__dsub_rn(prefix_at(Sinc, base, e), prefix_at(Sinc, base, prev)),
+                            __dsub_rn(prefix_at(Qinc, base, e), prefix_at(Qinc, base, prev)), e - prev, &m, &sd);
+                ev_start[kk] = prev; ev_mean[kk] = m; ev_stdv[kk] = sd;
+                kk++;
+                prev = e;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31), tl = __shfl_sync(0xffffffffu, last, 31);
+            k += tot;
+            if (tl != 0xffffffffu) a = tl;
         }
-        float m, sd;  // last event ends at nsample (events.c:499-501)
-        event_stats(__dsub_rn(prefix_at(Sinc, base, n), prefix_at(Sinc, base, a)),
-                    __dsub_rn(prefix_at(Qinc, base, n), prefix_at(Qinc, base, a)), n - a, &m, &sd);
-        ev_start[k] = a; ev_mean[k] = m; ev_stdv[k] = sd;
+        if (lane == 0) {  // last event ends at nsample (events.c:499-501)
+            float m, sd;
+            event_stats(__dsub_rn(prefix_at(Sinc, base, n), prefix_at(Sinc, base, a)),
+                        __dsub_rn(prefix_at(Qinc, base, n), prefix_at(Qinc, base, a)), n - a, &m, &sd);
+            ev_start[k] = a; ev_mean[k] = m; ev_stdv[k] = sd;
+        }
     }
 }
 
@@ -314,7 +380,7 @@ int launch_scan_u32(const uint32_t* cnt, uint32_t n, uint64_t* off, uint64_t* to
 
 int launch_generic_emit(const DevBatch& b, const WorkList& wl, Scratch& sc, const uint64_t* ev_off, uint64_t ev_cap,
                         uint32_t* ev_start, float* ev_mean, float* ev_stdv, int sm_count, cudaStream_t st) {
-    gen_emit_kernel<<<sm_count * 4, 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.bitmap, ev_off, ev_cap, ev_start,
+    gen_emit_kernel<<<sm_count * 8, 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.bitmap, ev_off, ev_cap, ev_start,
                                                   ev_mean, ev_stdv, sc.status);
     return 1;
 }

@@ -37,6 +37,7 @@ struct Scratch {
     uint32_t max_tiles;
     // per read
     uint32_t* wit_min; uint32_t* wit_max;  // exact-sum witness: min nonzero |pA| / max |pA| bit patterns
+    uint32_t* nonpos;                      // 1: the read has a sample with pA <= 0 (set by the walker)
     uint32_t* seq_list;     // compacted list of reads routed to the sequential-order kernels
     uint64_t* seq_sbase;
     uint32_t* seq_count;    // device scalar

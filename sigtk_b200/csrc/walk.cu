@@ -43,6 +43,7 @@ struct WalkParams {
     int* st_end;                    // same indexing: state after the chunk's last step
     uint32_t* wit_min;
     uint32_t* wit_max;
+    uint32_t* nonpos;
     uint32_t edge_blocks;
 };
 
@@ -55,6 +56,7 @@ struct DevIo {
     int* __restrict__ st_end;
     uint32_t* __restrict__ wit_min;   // this read's witness
     uint32_t* __restrict__ wit_max;
+    uint32_t* __restrict__ nonpos;    // this read's "has a sample with pA <= 0" mark
     float off, unit;
 
     __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
@@ -86,14 +88,26 @@ struct DevIo {
     __device__ __forceinline__ void put_begin(const Canon& c) const { store_canon(st_begin, c); }
     __device__ __forceinline__ void put_end(const Canon& c) const { store_canon(st_end, c); }
     // Exact-sum witness of a chunk from the extreme raw values: pA is monotone in raw (unit > 0 is checked by
-    // build_seq_list_kernel), so the extreme pA sit at the ends of [rmin, rmax]. The walker's arithmetic
-    // (widen_pos, the unguarded float shortcuts) needs every sample strictly positive: anything else publishes
-    // the smallest possible minimum, which fails the read (it is then redone by the sequential-order kernels).
-    __device__ __forceinline__ void witness(int rmin, int rmax) const {
-        const float xl = __fmul_rn(__fadd_rn((float)rmin, off), unit), xh = __fmul_rn(__fadd_rn((float)rmax, off), unit);
-        const uint32_t al = __float_as_uint(xl) & 0x7fffffffu, ah = __float_as_uint(xh) & 0x7fffffffu;
-        atomicMin(wit_min, xl > 0.0f ? al : 1u);
-        atomicMax(wit_max, max(al, ah));
+    // build_seq_list_kernel), so the extreme pA sit at the ends of [rmin, rmax]. build_seq_list_kernel needs the
+    // smallest NONZERO |pA| and the largest |pA| of the read. Samples with raw <= low_t (LOW: pA <= 0 or barely above;
+    // walk_core.cuh) are not covered by the range's lower end: their blocks report their own magnitudes
+    // (witness_abs), so the minimum published here starts at pA(low_t + 1) > 0. A read with LOW samples is also
+    // marked for emit_events_kernel, whose widening shortcut needs positive samples.
+    __device__ __forceinline__ void witness(int rmin, int rmax, int low_t) const {
+        const float xh = __fmul_rn(__fadd_rn((float)rmax, off), unit);
+        const float xa = __fmul_rn(__fadd_rn((float)rmin, off), unit);
+        atomicMax(wit_max, max(__float_as_uint(xa) & 0x7fffffffu, __float_as_uint(xh) & 0x7fffffffu));
+        if (rmin <= low_t) *nonpos = 1u;
+        const int gmin = rmin > low_t ? rmin : low_t + 1;  // smallest raw value that is not LOW
+        if (gmin <= rmax) {
+            const float xl = __fmul_rn(__fadd_rn((float)gmin, off), unit);
+            atomicMin(wit_min, xl > 0.0f ? __float_as_uint(xl) : 1u);  // (xl > 0 by the definition of low_t)
+        }
+    }
+    __device__ __forceinline__ void witness_abs(uint32_t lo, uint32_t hi) const {
+        atomicMin(wit_min, lo);
+        atomicMax(wit_max, hi);
+        *nonpos = 1u;
     }
 };
 
@@ -108,6 +122,7 @@ __device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64
     io.st_end = p.st_end + sid * 8;
     io.wit_min = p.wit_min + r;
     io.wit_max = p.wit_max + r;
+    io.nonpos = p.nonpos + r;
     io.off = p.b.offset[r];
     io.unit = p.b.unit[r];
     return io;
@@ -230,7 +245,7 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
     int n = 1 + launch_scan_u32(sc.wk_cnt, b.n_reads, sc.wk_ibase, nullptr, sc, st);
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
-    p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max;
+    p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max; p.nonpos = sc.nonpos;
     p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
     const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
     const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;

@@ -384,6 +384,10 @@ SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc,
     det_one<false, RNA>(d.l_pv, d.l_ps, m, u, c2m, acc, unused_b, unused_p, on_emit);
 }
 
+// a sample enters windows whose t-statistics are computed at most two blocks later
+constexpr int DIRTY_BLOCKS = 3;  // the block with the sample and the next two hold every window that contains it
+static_assert(2 * Cfg<0>::w2 - 1 <= 2 * Cfg<0>::U + 0 && 2 * Cfg<1>::w2 - 1 <= 2 * Cfg<1>::U, "windows reach at most two blocks ahead");
+
 // ---- the register rings --------------------------------------------------------------------------------------------
 template <int RNA>
 struct Rings {
@@ -460,9 +464,15 @@ Redo<RNA> redo_block(const Io& io, Redo<RNA> in, int tau0, int n, int sh, bool r
 //   x[m]   : pA of sample tau0 + m (0 outside the read when EDGE)
 //   tau0   : read index of the block's first sample, a multiple of U
 //   sh     : read_off & 31
+// dirty > 0: a window of this block holds a LOW sample (pA <= 0 or barely above: a glitch; about 3 reads in 100 of
+// real R9.4 data have one). widen_pos does not apply to such a value, so the chunk drivers hand it to this code as
+// 0 (it then adds nothing to the running sums), and this block and the next two -- every window that contains the
+// sample -- take their t-statistics from redo_block, which works from the raw samples with the reference's own
+// operations. Every other window holds unmodified positive samples only, and its sums are differences of running
+// sums that miss the same samples on both sides: nothing else changes and the read stays on the fast path.
 template <int RNA, bool EDGE, class Io>
 SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U], int tau0, int n, int sh, bool rec,
-                       bool live, bool live_t1, float off, float unit, Io& io) {
+                       bool live, bool live_t1, int dirty, float off, float unit, Io& io) {
     using C = Cfg<RNA>;
     constexpr int w1 = C::w1, w2 = C::w2, M1 = C::R1 - 1, M2 = C::R2 - 1, U = C::U;
     float t1v[U];
@@ -481,8 +491,8 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 #pragma unroll
     for (int m = 0; m < U; m++) {
         // static ring slots: every index below is (m + const) & mask because tau0 is a multiple of U
-        const double xd = widen_pos(x[m]);
-        const double qd = widen_pos(xq[m]);                         // widened after the float multiply
+        const double xd = widen_pos(x[m]);                          // (a sample handed over as 0 widens to 2^-127: it is
+        const double qd = widen_pos(xq[m]);                         //  absorbed by the first addition to a real sum)
         const double pn = dadd(g.P[m & M1], EDGE ? (x[m] > 0.0f ? xd : 0.0) : xd);
         const double pqn = dadd(g.PQ[m & M1], EDGE ? (x[m] > 0.0f ? qd : 0.0) : qd);
         g.P[(m + 1) & M1] = pn;
@@ -527,6 +537,7 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 #if defined(WALK_TEST_REDO)  // host tests: take the rare path on every third block
     ok = ok & ((tau0 / U) % 3 != 0);
 #endif
+    if (dirty > 0) { ok = false; ok_t1 = false; }  // a window of this block holds a LOW sample
     // rare (about 3 blocks in 100,000): a t-statistic next to a rounding midpoint, or a peak too old for the mask
     if ((!ok & live) | (!ok_t1 & live_t1) | (rec & (acc.oldest > PkCfg<RNA>::FAR))) {
         Redo<RNA> in;
@@ -552,7 +563,9 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 //   peaks32(ub, mk)    record the emitted peaks of a block: bit k of mk (nonzero) <=> a peak at shifted position ub + k
 //   peak(pos)          record one peak
 //   put_begin(c) / put_end(c)   the chunk's canonical detector state after the warm-up / after its last step
-//   witness(rmin, rmax)         extreme raw values of samples of the read (any superset of the owned samples)
+//   witness(rmin, rmax, low_t)  extreme raw values of samples of the read (any superset of the owned samples);
+//                               samples with raw <= low_t are LOW (reported through witness_abs by their blocks)
+//   witness_abs(lo, hi)         smallest nonzero / largest |pA| bit patterns of a block with LOW samples
 SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return (n + L - 1u) / L; }
 
 // int16 -> float without a conversion instruction: with the sign bit flipped, the 16 bits are raw + 32768 in
@@ -586,6 +599,49 @@ SGW_HD uint32_t max_s16x2(uint32_t a, uint32_t b) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+SGW_HD bool any_le_s16x2(uint32_t a, uint32_t b) { return __vcmples2(a, b) != 0u; }  // a.lo <= b.lo || a.hi <= b.hi
+#else
+SGW_HD bool any_le_s16x2(uint32_t a, uint32_t b) {
+    return (int16_t)(a & 0xffff) <= (int16_t)(b & 0xffff) || (int16_t)(a >> 16) <= (int16_t)(b >> 16);
+}
+#endif
+// LOW samples: raw <= t, where t is LOW_MARGIN above the largest raw value whose pA is not positive
+// (fl((float)raw + off) <= 0; the unit is positive). They include every sample with pA <= 0 -- glitches -- and the
+// few levels just above zero, which no pore produces (t + 1 maps to about 11 pA for R9.4 scaling). The chunk drivers
+// zero them for the running sums (see walk_block), mark the blocks around them dirty and report their magnitudes
+// on their own, so that the exact-sum witness of all OTHER samples can start at pA(t + 1) instead of at the
+// smallest nonzero magnitude a range could hold.
+// Returns t clamped to int16; *can is false when no int16 value is low.
+constexpr int LOW_MARGIN = 64;
+SGW_HD int low_threshold(float off, bool* can) {
+    float tf = floorf(-off);
+    tf = tf < -40000.0f ? -40000.0f : tf > 40000.0f ? 40000.0f : tf;
+    int t = (int)tf;
+    for (int k = 0; k < 4 && fadd((float)(t + 1), off) <= 0.0f; k++) t++;
+    for (int k = 0; k < 4 && fadd((float)t, off) > 0.0f; k++) t--;
+    t += LOW_MARGIN;
+    *can = t >= -32768;
+    return t > 32767 ? 32767 : t < -32768 ? -32768 : t;
+}
+SGW_HD uint32_t pack_s16x2(int t) { return ((uint32_t)t & 0xffffu) * 0x10001u; }
+
+// the LOW samples of one group of 8: their magnitudes go to the witness, their values become 0 for the running sums
+template <class Io>
+SGW_HD void zero_low8(Io& io, const int (&v)[4], int low_t, float* x) {
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
+        if (raw <= low_t) {
+            const uint32_t a = f_bits(x[q]) & 0x7fffffffu;
+            if (a != 0u) { lo = a < lo ? a : lo; hi = a > hi ? a : hi; }
+            x[q] = 0.0f;
+        }
+    }
+    io.witness_abs(lo, hi);
+}
+
 // interior chunk k (1 <= k <= nch-2) of a read: every access is inside the read, no bounds checks.
 // ONE loop (one copy of the block code in the instruction cache) runs the two ring-fill blocks, the detector
 // warm-up and the owned samples.
@@ -602,6 +658,10 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
     float x[U];
     int v[4];
     uint32_t vmin = 0x7fff7fffu, vmax = 0x80008000u;  // packed int16 min / max (over warm-up and owned samples)
+    bool can_low;
+    const int low_t = low_threshold(off, &can_low);
+    const uint32_t low2 = pack_s16x2(low_t);
+    int dirty = 0;
     const bool pa = io.want_pa();
     int vn[U / 8][4];                                 // the next block's samples, loaded one block ahead
 #pragma unroll
@@ -612,22 +672,30 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
         if (tau == t_live) det_cold(d, t_live - C::LAG + sh);   // forget the steps taken on partly filled rings
         if (tau == s0) io.put_begin(canon_of(d, s0 - C::LAG + sh));
         const int tn = tau + U < s1 ? tau + U : tau;  // (the last block is simply loaded again)
+        uint32_t bmin = 0x7fff7fffu;                  // packed minimum of this block's samples
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {
 #pragma unroll
             for (int q = 0; q < 4; q++) v[q] = vn[h][q];
             io.load8(tn + 8 * h, vn[h]);
-            vmin = min_s16x2(min_s16x2(vmin, (uint32_t)v[0]), min_s16x2((uint32_t)v[1], min_s16x2((uint32_t)v[2], (uint32_t)v[3])));
+            const uint32_t m8 = min_s16x2(min_s16x2((uint32_t)v[0], (uint32_t)v[1]), min_s16x2((uint32_t)v[2], (uint32_t)v[3]));
+            bmin = min_s16x2(bmin, m8);
             vmax = max_s16x2(max_s16x2(vmax, (uint32_t)v[0]), max_s16x2((uint32_t)v[1], max_s16x2((uint32_t)v[2], (uint32_t)v[3])));
             cvt8(v, off, unit, x + 8 * h);
             if (pa && own) io.store_pa8(tau + 8 * h, x + 8 * h);
+            if (can_low & any_le_s16x2(m8, low2)) {   // LOW samples in this group (rare)
+                dirty = DIRTY_BLOCKS;
+                zero_low8(io, v, low_t, x + 8 * h);
+            }
         }
-        walk_block<RNA, false>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, off, unit, io);
+        vmin = min_s16x2(vmin, bmin);
+        walk_block<RNA, false>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, off, unit, io);
+        dirty = dirty > 0 ? dirty - 1 : 0;
     }
     io.put_end(canon_of(d, s1 - C::LAG + sh));
     const int rmin0 = (int)(int16_t)(vmin & 0xffffu), rmin1 = (int)vmin >> 16;
     const int rmax0 = (int)(int16_t)(vmax & 0xffffu), rmax1 = (int)vmax >> 16;
-    io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1);
+    io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1, can_low ? low_t : -32769);
 }
 
 // first chunk (last == 0) or last chunk (last == 1; only when the read has >= 2 chunks) of a read: bounds-checked
@@ -649,6 +717,10 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
     det_cold(d, sh + 1);  // first chunk: the reference's initial state, masked_to = 0: position 0 is skipped (events.c:516-536, 387)
     float x[U];
     int rmin = 32767, rmax = -32768;
+    bool can_low;
+    const int low_t0 = low_threshold(off, &can_low);
+    const int low_t = can_low ? low_t0 : -32769;
+    int dirty = 0;
     const bool pa = io.want_pa();
 #pragma unroll 1
     for (int tau = last ? t_live - C::FILL * U : 0; tau - C::LAG < step_end; tau += U) {
@@ -665,20 +737,27 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const bool in = t8 + q < n;
-                x[8 * h + q] = in ? y[q] : 0.0f;
+                const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
+                const bool low = in & (raw <= low_t);   // rare: handed to the block as 0, its windows are dirty
+                x[8 * h + q] = (in & !low) ? y[q] : 0.0f;
+                if (low) {
+                    dirty = DIRTY_BLOCKS;
+                    const uint32_t a = f_bits(y[q]) & 0x7fffffffu;
+                    if (a != 0u) io.witness_abs(a, a);
+                }
                 if (own && in && t8 + q < s1) {
-                    const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
                     rmin = raw < rmin ? raw : rmin;
                     rmax = raw > rmax ? raw : rmax;
                     if (pa) io.store_pa1(t8 + q, y[q]);
                 }
             }
         }
-        walk_block<RNA, true>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, off, unit, io);
+        walk_block<RNA, true>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, off, unit, io);
+        dirty = dirty > 0 ? dirty - 1 : 0;
     }
     if (!to_end) io.put_end(canon_of(d, s1 - C::LAG + sh));
     if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)
-    if (rmin <= rmax) io.witness(rmin, rmax);
+    if (rmin <= rmax) io.witness(rmin, rmax, low_t);
 }
 
 }  // namespace walk

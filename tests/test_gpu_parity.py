@@ -232,17 +232,40 @@ def test_short_warmup_falls_back(ctx, orc, monkeypatch):
     assert np.all(res.seq_order[res.fixups > 0] == 1)
 
 
-def test_non_positive_pa_takes_the_sequential_order_path(ctx, orc):
-    """the walker's arithmetic assumes pA > 0 (witness): reads with zero or negative pA are flagged and redone"""
+@pytest.mark.parametrize("rna_flag", [0, 1])
+def test_non_positive_pa_stays_on_the_fast_path(ctx, orc, rna_flag):
+    """samples with zero or negative pA (raw <= -offset; about 3 reads in 100 of real R9.4 data): the walker takes
+    the blocks around them through its exact path and the read stays on the fast path, bit-exact"""
+    from test_host_walk import glitch_read
     rd = synth.make_read(7, 9000, seed=63)
     neg = rd[0].copy()
     neg[4000:4003] = -300                       # (raw + offset) < 0
     zero = rd[0].copy()
     zero[100] = -int(rd[2])                     # raw + offset == 0
-    reads = [rd, (neg, rd[1], rd[2], rd[3]), (zero, rd[1], rd[2], rd[3]), synth.make_read(8, 9000, seed=63)]
+    real = synth.make_read(9, 30000, seed=63)   # glitches like those of sp1_dna.blow5: raw + offset = -44, -376
+    graw = real[0].copy()
+    for k, pos in enumerate([0, 1, 7, 8, 1023, 1024, 1025, 5000, 5001, 5002, 12345, 29998, 29999]):
+        graw[pos] = -int(real[2]) - (44, 376, 100, 0)[k % 4]
+    reads = [rd, (neg, rd[1], rd[2], rd[3]), (zero, rd[1], rd[2], rd[3]), synth.make_read(8, 9000, seed=63),
+             (graw, real[1], real[2], real[3]),
+             # magnitudes of one unit next to full-scale ones: the sums are not exact any more, these two reads go to
+             # the sequential-order kernels (and stay bit-exact)
+             glitch_read(9000, 12), glitch_read(30000, 13, where=tuple(range(5, 30000, 997)))]
+    res = ctx.run(reads, rna=rna_flag, want=ALL)
+    check_against_oracle(orc, res, reads, rna_flag)
+    assert list(res.seq_order[:5]) == [0] * 5 and int(res.fixups.sum()) == 0
+
+
+def test_fractional_offset_with_non_positive_pa(ctx, orc):
+    """a fractional offset makes the smallest nonzero |pA| a fraction of a unit; the blocks with low samples report
+    their exact magnitudes to the witness, whatever the offset"""
+    rd = synth.make_read(7, 9000, seed=64)
+    neg = rd[0].copy()
+    neg[4000] = -300
+    reads = [(neg, rd[1], 7.5, rd[3]), (rd[0], rd[1], 7.5, rd[3])]
     res = ctx.run(reads, rna=0, want=ALL)
     check_against_oracle(orc, res, reads, 0)
-    assert list(res.seq_order) == [0, 1, 1, 0]
+    assert list(res.seq_order) == [0, 0]
 
 
 def test_empty_batch_and_reuse(ctx):

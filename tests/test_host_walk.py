@@ -104,3 +104,29 @@ def test_plateaus_emit_old_peaks(lib, orc):
     for rna, L, W in ((0, 4096, 64), (0, 2048, 64), (1, 4096, 384)):
         for sh in (0, 8, 24):
             check(lib, orc, rd, rna, L, W, sh)
+
+
+def glitch_read(n=9000, seed=12, where=(0, 1, 7, 8, 100, 127, 128, 129, 1023, 1024, 1031, 2000, 2001, 2002, 2003, 4000)):
+    """samples whose pA is zero or negative (raw <= -offset): about 3 reads in 100 of real R9.4 data have some"""
+    rd = synth.make_read(7, n, seed=seed)
+    raw = rd[0].copy()
+    off = int(rd[2])
+    vals = [-off, -off - 1, -off - 300, -32768, -off, 0 - off - 7]
+    for k, p in enumerate(list(where) + [n - 1, n - 2, n - 9]):
+        if p < n:
+            raw[p] = vals[k % len(vals)]
+    return raw, rd[1], rd[2], rd[3]
+
+
+@pytest.mark.parametrize("rna,L,W", [(0, 128, 64), (0, 1024, 64), (1, 512, 384), (1, 4096, 384)])
+def test_non_positive_samples_stay_on_the_walker(lib, orc, rna, L, W):
+    for seed in (12, 13):
+        rd = glitch_read(9000, seed)
+        assert (orc.pa(*rd) <= 0).sum() >= 10
+        for sh in (0, 16):
+            check(lib, orc, rd, rna, L, W, sh)
+    # a read that is non-positive throughout, and one with a single zero
+    rd = synth.make_read(8, 3000, seed=5)
+    check(lib, orc, ((-rd[0] - 100).astype(np.int16), rd[1], rd[2], rd[3]), rna, L, W, 8, must_verify=False)
+    raw = rd[0].copy(); raw[1500] = -int(rd[2])
+    check(lib, orc, (raw, rd[1], rd[2], rd[3]), rna, L, W, 8)
