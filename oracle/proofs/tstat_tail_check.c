@@ -1,9 +1,13 @@
 /* tstat_tail_check.c -- TEST INFRASTRUCTURE. Validates the guarded shortcut for the last step of the
  * t-statistic (events.c:360)   t = (float)( fabs((double)delta) / sqrt((double)scaled) )
- * used by the CUDA fast path: y0 ~ 1/sqrt(scaled) to ~22 bits (MUFU.RSQ on the GPU; emulated here by a float
- * reciprocal square root perturbed by up to +-4 ulp), one third-order correction in double, q = |delta|*y,
- * accept (float)q unless q lies within 2^-44 (relative) of a float rounding midpoint or outside the normal float
- * range; otherwise the caller falls back to the IEEE sqrt + division. Reports mismatches among accepted values.
+ * used by the CUDA fast path: y0 ~ 1/sqrt(scaled) to ~22 bits (MUFU.RSQ on the GPU: PTX rsqrt.approx.f32, maximum
+ * relative error 2^-22.4; emulated here by any float within that bound of the true value), ONE second-order correction in double,
+ *     eh = 1/2 - (scaled/2) * y0^2,   q = |delta| * y0 * (1 + eh)        (4 double operations)
+ * whose method error is 1.5 eps^2 <= 2^-44.2 relative (<= 445 ulp of a double). (float)q is accepted unless the 29
+ * bits of q below float precision lie within 1024 of the rounding midpoint; otherwise the caller falls back to the
+ * IEEE sqrt + division. No range check: the caller guarantees delta == 0 or 2^-84 <= |delta| <= 2^21 and
+ * 1e-30 <= scaled <= 2^42 (walk_core.cuh, tail()), which is the domain sampled here. Reports mismatches among
+ * accepted values.
  * Build: gcc -O2 -mfma -ffp-contract=off -fopenmp tstat_tail_check.c -o tstat_tail_check -lm
  */
 #include <math.h>
@@ -23,21 +27,17 @@ static inline uint64_t splitmix(uint64_t *s) {
 
 /* returns 1 and *out when the shortcut accepts */
 static inline int tail_fast(float delta, float scaled, float y0f, float *out) {
-    const double c = (double)scaled, y0 = (double)y0f;
-    const double t = c * y0;
-    const double e = fma(-t, y0, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    const double ye = y0 * e;
-    const double y = fma(ye, p, y0);
-    const double q = fabs((double)delta) * y;
+    const double ch = (double)(scaled * 0.5f), y0 = (double)y0f;   /* scaled/2 is exact */
+    const double th = ch * y0;
+    const double eh = fma(-th, y0, 0.5);
+    const double q0 = fabs((double)delta) * y0;
+    const double q = fma(q0, eh, q0);
     const uint64_t b = d_bits(q);
-    const uint32_t lo29 = (uint32_t)(b & 0x1fffffffull);
-    const uint32_t ex = (uint32_t)(b >> 52) & 0x7ff;
-    /* the guard of tail() in sigtk_b200/csrc/walk_core.cuh: 2^-126 <= q < 2^126, the 29 bits below float
-     * precision not within 512 of the rounding midpoint, scaled not tiny (the GPU seed flushes denormals) */
-    const int in_range = ex >= 1023 - 126 && ex < 1023 + 126;
-    const int off_mid = (uint32_t)(lo29 - (0x10000000u - 512u)) >= 1024u;
-    if (!(in_range && off_mid && scaled >= 1.0e-30f)) return 0;
+    const uint32_t lo = (uint32_t)b;
+    /* the guard of tail() in sigtk_b200/csrc/walk_core.cuh: the 29 bits below float precision not within 1024 of
+     * the rounding midpoint (computed on the low word shifted up by 3, exactly as the kernel does) */
+    const int off_mid = (uint32_t)(lo * 8u - ((0x10000000u - 1024u) << 3)) >= (2048u << 3);
+    if (!off_mid) return 0;
     *out = (float)q;
     return 1;
 }
@@ -49,16 +49,17 @@ int main(void) {
         uint64_t s = 777ull * (t + 1);
         for (uint64_t i = 0; i < (1ull << 24); i++) {
             const uint64_t r1 = splitmix(&s), r2 = splitmix(&s), r3 = splitmix(&s);
-            /* scaled: positive float, exponent 2^-149 .. 2^60 ; delta: any sign, exponent 2^-60 .. 2^60 or zero */
-            uint32_t cb = (uint32_t)(r1 & 0x7fffff) | ((uint32_t)(1 + (r1 >> 23) % 187) << 23);
-            if ((r1 >> 40) % 1000 == 0) cb = (uint32_t)(r1 >> 41) & 0x7fffff;          /* denormal scaled */
-            if (cb == 0) cb = 1;
-            uint32_t db = (uint32_t)(r2 & 0x807fffff) | ((uint32_t)(67 + (r2 >> 32) % 121) << 23);
+            /* scaled: 2^-99 (< 1e-30) .. 2^43 ; delta: any sign, 2^-84 .. 2^21, or zero */
+            uint32_t cb = (uint32_t)(r1 & 0x7fffff) | ((uint32_t)(28 + (r1 >> 23) % 143) << 23);
+            if (f_from(cb) < 1.0e-30f) cb = f_bits(1.0e-30f);
+            uint32_t db = (uint32_t)(r2 & 0x807fffff) | ((uint32_t)(43 + (r2 >> 32) % 106) << 23);
             if ((r2 >> 50) % 1000 == 0) db = 0;
             const float scaled = f_from(cb), delta = f_from(db);
-            float y0 = (float)(1.0 / sqrt((double)scaled));
-            int pert = (int)(r3 % 9) - 4;
-            y0 = f_from(f_bits(y0) + pert);
+            /* the seed: any float within 2^-22.4 (relative) of 1/sqrt(scaled) -- the bound PTX states for
+             * rsqrt.approx.f32, and tools/microbench/rsqrt_err.cu measures on the GPU over all floats */
+            const double u = ((double)(r3 >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0) * 1.80e-7; /* 2^-22.4 = 1.81e-7 */
+            float y0 = (float)((1.0 / sqrt((double)scaled)) * (1.0 + u));
+            if (fabs((double)y0 * sqrt((double)scaled) - 1.0) > 1.81e-7) y0 = (float)(1.0 / sqrt((double)scaled));
             const float ref = (float)(fabs((double)delta) / sqrt((double)scaled));
             float got;
             total++;

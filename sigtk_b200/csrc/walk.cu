@@ -25,11 +25,13 @@ namespace {
 
 using namespace walk;
 
+// launch shape (measured, tools/run_variants.sh): 64-thread blocks, 6 per SM (168 registers, almost no spills, 3 warps
+// per scheduler) runs 2 % faster than 128 x 4 (128 registers, 4 warps per scheduler); 96 / 80 registers are slower
 #ifndef WALK_NT
-#define WALK_NT 128
+#define WALK_NT 64
 #endif
 #ifndef WALK_MINB
-#define WALK_MINB 4
+#define WALK_MINB 6
 #endif
 constexpr int WNT = WALK_NT;  // threads per block of walk_chunks_kernel
 
