@@ -17,6 +17,7 @@
 // here is launched with a fixed grid and returns at once when the list is empty.  They keep S, Q (16 B/sample) and t1, t2 (8 B/sample) in
 // an HBM scratch area, so they are NOT the roofline path.
 #include "kernels.cuh"
+#include "walk_core.cuh"
 
 namespace sgpu {
 
@@ -24,8 +25,14 @@ namespace sgpu {
 // compute_sum_sumsq: Sinc[base+i] = S[i+1], Qinc[base+i] = Q[i+1]  (S[0]=Q[0]=0 implied)
 __global__ void __launch_bounds__(128) gen_prefix_kernel(DevBatch b, WorkList wl, double* __restrict__ Sinc,
                                                          double* __restrict__ Qinc) {
+    // one WARP per read: lane 0 runs the two dependent chains of additions (the order IS the result), 32 samples at
+    // a time into shared memory; all lanes then store the tile coalesced (32 lanes walking 32 reads would issue 64
+    // store wavefronts per sample: measured 130 cycles per sample)
+    __shared__ double sS[4][32], sQ[4][32];
     const uint32_t n_list = *wl.count;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = warp; j < n_list; j += n_warps) {
         const uint32_t r = wl.list[j];
         const uint64_t base = wl.sbase[j];
         // reads start on 16-byte boundaries and the batch is padded to one: whole groups of 8 samples can be loaded
@@ -33,30 +40,43 @@ __global__ void __launch_bounds__(128) gen_prefix_kernel(DevBatch b, WorkList wl
         const uint32_t n = b.read_len[r], n8 = (n + 7u) >> 3;
         const float off = b.offset[r], unit = b.unit[r];
         double s = 0.0, q = 0.0;
-        constexpr int AHEAD = 4;  // groups in flight: the additions are one dependent chain, the loads must not be
-        int4 buf[AHEAD];
+        int4 buf[4];  // the next tile's samples (lane 0)
+        if (lane == 0) {
 #pragma unroll
-        for (int k = 0; k < AHEAD; k++) buf[k] = (uint32_t)k < n8 ? __ldg(raw8 + k) : make_int4(0, 0, 0, 0);
-        for (uint32_t g0 = 0; g0 < n8; g0 += AHEAD) {
+            for (int k = 0; k < 4; k++) buf[k] = (uint32_t)k < n8 ? __ldg(raw8 + k) : make_int4(0, 0, 0, 0);
+        }
+        for (uint32_t t0 = 0; t0 < n; t0 += 32) {
+            if (lane == 0) {
+                const uint32_t g0 = t0 >> 3;
 #pragma unroll
-            for (int k = 0; k < AHEAD; k++) {
-                const uint32_t g = g0 + k;
-                const int4 cur = buf[k];
-                buf[k] = g + AHEAD < n8 ? __ldg(raw8 + g + AHEAD) : make_int4(0, 0, 0, 0);
-                if (g >= n8) continue;
-                const int v[4] = {cur.x, cur.y, cur.z, cur.w};
+                for (int k = 0; k < 4; k++) {
+                    const int4 cur = buf[k];
+                    buf[k] = g0 + 4 + k < n8 ? __ldg(raw8 + g0 + 4 + k) : make_int4(0, 0, 0, 0);
+                    const int v[4] = {cur.x, cur.y, cur.z, cur.w};
+                    // everything that does not depend on the running sums first (conversions pipeline), then the chain
+                    float x[8];
+                    walk::cvt8(v, off, unit, x);   // misc.c:28 per sample (float add, float multiply)
+                    double xd[8], qd[8];
 #pragma unroll
-                for (int m = 0; m < 8; m++) {
-                    const uint32_t i = g * 8u + m;
-                    if (i >= n) break;
-                    const float x = pa_of((int16_t)((m & 1) ? (v[m >> 1] >> 16) : (v[m >> 1] & 0xffff)), off, unit);
-                    const float xx = __fmul_rn(x, x);  // float product, widened afterwards (events.c:301)
-                    s = __dadd_rn(s, (double)x);
-                    q = __dadd_rn(q, (double)xx);
-                    Sinc[base + i] = s;
-                    Qinc[base + i] = q;
+                    for (int m = 0; m < 8; m++) {
+                        xd[m] = (double)x[m];
+                        qd[m] = (double)__fmul_rn(x[m], x[m]);  // float product, widened afterwards (events.c:301)
+                    }
+#pragma unroll
+                    for (int m = 0; m < 8; m++) {  // (samples past the read's end only feed values nobody stores)
+                        s = __dadd_rn(s, xd[m]);
+                        q = __dadd_rn(q, qd[m]);
+                        sS[wib][8 * k + m] = s;
+                        sQ[wib][8 * k + m] = q;
+                    }
                 }
             }
+            __syncwarp();
+            if (t0 + lane < n) {
+                Sinc[base + t0 + lane] = sS[wib][lane];
+                Qinc[base + t0 + lane] = sQ[wib][lane];
+            }
+            __syncwarp();
         }
     }
 }
@@ -141,52 +161,119 @@ __device__ __forceinline__ int32_t det_step(DetState& d, DetState* other_long, b
     return -1;
 }
 
+// the detector of one read in the reference's own order (one thread): events.c:371-443
+__device__ void detect_read_in_order(const DetParams& p, const float* __restrict__ t1, const float* __restrict__ t2,
+                                     uint64_t base, uint64_t foff, uint32_t n, uint32_t* __restrict__ bitmap) {
+    clear_read_bits(bitmap, foff, foff + n);  // drop whatever was found for this read so far
+    atomicOr(&bitmap[foff >> 5], 1u << (foff & 31));  // event 0 starts at the first sample
+    DetState s, l;
+    det_reset(s);
+    det_reset(l);
+    // the detector is one dependent chain per read; its inputs are loaded 16 positions at a time, one group ahead
+    // (the scratch holds whole groups: every read's share is padded to 8 samples and the arrays to 16)
+    const float4* __restrict__ a1 = reinterpret_cast<const float4*>(t1 + base);
+    const float4* __restrict__ a2 = reinterpret_cast<const float4*>(t2 + base);
+    const uint32_t n4 = (n + 3u) >> 2;
+    float4 c1[4], c2[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        c1[k] = (uint32_t)k < n4 ? __ldg(a1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        c2[k] = (uint32_t)k < n4 ? __ldg(a2 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (uint32_t g0 = 0; g0 < n4; g0 += 4) {
+        float u1[16], u2[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u1[4 * k] = c1[k].x; u1[4 * k + 1] = c1[k].y; u1[4 * k + 2] = c1[k].z; u1[4 * k + 3] = c1[k].w;
+            u2[4 * k] = c2[k].x; u2[4 * k + 1] = c2[k].y; u2[4 * k + 2] = c2[k].z; u2[4 * k + 3] = c2[k].w;
+            const uint32_t g = g0 + 4 + k;
+            c1[k] = g < n4 ? __ldg(a1 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+            c2[k] = g < n4 ? __ldg(a2 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const uint32_t i = g0 * 4u + m;
+            if (i >= n) break;
+            const int32_t ps = det_step(s, &l, true, i, u1[m], p.thr1, p.w1, p.height);
+            if (ps > 0) { const uint64_t f = foff + (uint32_t)ps; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
+            const int32_t pl = det_step(l, nullptr, false, i, u2[m], p.thr2, p.w2, p.height);
+            if (pl > 0) { const uint64_t f = foff + (uint32_t)pl; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
+        }
+    }
+}
+
+// The detector over the stored t arrays, one WARP per read: the lanes walk 32 consecutive chunks of GD_CHUNK
+// positions at once, each from a cold state W positions early (the walker's warm-up, walk.cu), with the branch-free
+// detector step of walk_core.cuh; a chunk's state after its warm-up must equal its predecessor's end state
+// (compared through a shuffle; the group's last state is carried to the next group). Peaks are owned by the step
+// that emits them. Any mismatch in the read: lane 0 redoes the read in the reference's own order.
+constexpr int GD_CHUNK = 1024;
+template <int RNA>
+__device__ void detect_read_chunked(const float* __restrict__ t1, const float* __restrict__ t2, uint64_t base,
+                                    uint64_t foff, uint32_t n, uint32_t W, uint32_t* __restrict__ bitmap, int lane,
+                                    const DetParams& p) {
+    using namespace walk;
+    if (lane == 0) {
+        clear_read_bits(bitmap, foff, foff + n);
+        atomicOr(&bitmap[foff >> 5], 1u << (foff & 31));  // event 0 starts at the first sample
+    }
+    __syncwarp();
+    const uint32_t n_chunks = (n + GD_CHUNK - 1) / GD_CHUNK;
+    bool bad = false;
+    Canon carry = {};  // end state of the previous group's last chunk
+    auto on_emit = [&](int pos) { const uint64_t f = foff + (uint32_t)pos; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); };
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const bool have = c < n_chunks;
+        const uint32_t s0 = c * GD_CHUNK, s1 = min(n, s0 + GD_CHUNK);
+        WalkDet d;
+        Canon begin = {}, end = {};
+        if (have) {
+            uint32_t i = (c == 0) ? 1u : s0 - W;   // position 0 is never stepped (masked_to = 0, events.c:387)
+            det_cold(d, (int)i);
+            PeakAcc unused; unused.mk = 0u; unused.oldest = 0;
+            for (; i < s0; i++)   // warm-up: nothing is recorded
+                det_step<RNA>(d, 0, (int)i, __ldg(t1 + base + i), __ldg(t2 + base + i), unused, NoEmit());
+            begin = canon_of(d, (int)s0);
+            for (; i < s1; i++)
+                det_step<RNA>(d, 0, (int)i, __ldg(t1 + base + i), __ldg(t2 + base + i), unused, on_emit);
+            end = canon_of(d, (int)s1);
+        }
+        // chunk c must have reached the state chunk c-1 ended in
+        bool same = true;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            int prev = __shfl_up_sync(0xffffffffu, end.v[q], 1);
+            if (lane == 0) prev = carry.v[q];
+            same = same && (prev == begin.v[q]);
+        }
+        if (have && c > 0 && !same) bad = true;
+        const int last = (int)min(31u, n_chunks - 1u - c0);
+#pragma unroll
+        for (int q = 0; q < 5; q++) carry.v[q] = __shfl_sync(0xffffffffu, end.v[q], last);
+    }
+    if (__any_sync(0xffffffffu, bad)) {
+        __syncwarp();
+        if (lane == 0) detect_read_in_order(p, t1, t2, base, foff, n, bitmap);
+    }
+}
+
 __global__ void __launch_bounds__(128) gen_detect_kernel(DevBatch b, WorkList wl, const float* __restrict__ t1,
-                                                         const float* __restrict__ t2, uint32_t* __restrict__ bitmap) {
+                                                         const float* __restrict__ t2, uint32_t* __restrict__ bitmap,
+                                                         uint32_t W) {
     const uint32_t n_list = *wl.count;
     const DetParams p = det_params(b.rna);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_list; j += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t j = warp; j < n_list; j += n_warps) {
         const uint32_t r = wl.list[j];
-        const uint64_t base = wl.sbase[j];  // a multiple of 8: 16-byte aligned float4 loads
+        const uint64_t base = wl.sbase[j];
         const uint64_t foff = b.read_off[r];
         const uint32_t n = b.read_len[r];
         if (n == 0) continue;
-        clear_read_bits(bitmap, foff, foff + n);  // drop whatever the fast path found for this read
-        atomicOr(&bitmap[foff >> 5], 1u << (foff & 31));  // event 0 starts at the first sample
-        DetState s, l;
-        det_reset(s);
-        det_reset(l);
-        // the detector is one dependent chain per read; its inputs are loaded 16 positions at a time, one group ahead
-        // (the scratch holds whole groups: every read's share is padded to 8 samples and the arrays to 16)
-        const float4* __restrict__ a1 = reinterpret_cast<const float4*>(t1 + base);
-        const float4* __restrict__ a2 = reinterpret_cast<const float4*>(t2 + base);
-        const uint32_t n4 = (n + 3u) >> 2;
-        float4 c1[4], c2[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            c1[k] = (uint32_t)k < n4 ? __ldg(a1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            c2[k] = (uint32_t)k < n4 ? __ldg(a2 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (uint32_t g0 = 0; g0 < n4; g0 += 4) {
-            float u1[16], u2[16];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                u1[4 * k] = c1[k].x; u1[4 * k + 1] = c1[k].y; u1[4 * k + 2] = c1[k].z; u1[4 * k + 3] = c1[k].w;
-                u2[4 * k] = c2[k].x; u2[4 * k + 1] = c2[k].y; u2[4 * k + 2] = c2[k].z; u2[4 * k + 3] = c2[k].w;
-                const uint32_t g = g0 + 4 + k;
-                c1[k] = g < n4 ? __ldg(a1 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-                c2[k] = g < n4 ? __ldg(a2 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int m = 0; m < 16; m++) {
-                const uint32_t i = g0 * 4u + m;
-                if (i >= n) break;
-                const int32_t ps = det_step(s, &l, true, i, u1[m], p.thr1, p.w1, p.height);
-                if (ps > 0) { const uint64_t f = foff + (uint32_t)ps; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
-                const int32_t pl = det_step(l, nullptr, false, i, u2[m], p.thr2, p.w2, p.height);
-                if (pl > 0) { const uint64_t f = foff + (uint32_t)pl; atomicOr(&bitmap[f >> 5], 1u << (f & 31)); }
-            }
-        }
+        if (n >= (1u << 30)) { if (lane == 0) detect_read_in_order(p, t1, t2, base, foff, n, bitmap); continue; }
+        if (b.rna) detect_read_chunked<1>(t1, t2, base, foff, n, W, bitmap, lane, p);
+        else detect_read_chunked<0>(t1, t2, base, foff, n, W, bitmap, lane, p);
     }
 }
 
@@ -363,9 +450,9 @@ static inline int grid_for(uint64_t work, int block, int max_blocks) {
 }
 
 int launch_generic_detect(const DevBatch& b, const WorkList& wl, Scratch& sc, int sm_count, cudaStream_t st) {
-    gen_prefix_kernel<<<sm_count * 4, 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc);
+    gen_prefix_kernel<<<sm_count * 8, 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc);
     gen_tstat_kernel<<<sm_count * 8, 256, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.t1, sc.t2);
-    gen_detect_kernel<<<sm_count * 4, 128, 0, st>>>(b, wl, sc.t1, sc.t2, sc.bitmap);
+    gen_detect_kernel<<<sm_count * 8, 128, 0, st>>>(b, wl, sc.t1, sc.t2, sc.bitmap, b.rna ? 384u : 64u);
     return 3;
 }
 
