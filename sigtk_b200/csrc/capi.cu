@@ -319,7 +319,6 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     CUC(dev_alloc(&sc.tile_base, (uint64_t)sc.max_tiles + 1));
     CUC(dev_alloc(&sc.wit_min, max_reads));
     CUC(dev_alloc(&sc.wit_max, max_reads));
-    CUC(dev_alloc(&sc.nonpos, max_reads));
     CUC(dev_alloc(&ctx->dev_seq, max_reads));
     CUC(dev_alloc(&ctx->dev_fix, max_reads));
     CUC(dev_alloc(&sc.seq_list, max_reads));
@@ -391,7 +390,7 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     cudaFree(sc.Sinc); cudaFree(sc.Qinc); cudaFree(sc.t1); cudaFree(sc.t2); cudaFree(sc.bitmap);
     cudaFree(sc.wk_begin); cudaFree(sc.wk_end); cudaFree(sc.wk_cnt); cudaFree(sc.wk_ibase);
     cudaFree(sc.tile_cnt); cudaFree(sc.tile_base); cudaFree(sc.tile_read0);
-    cudaFree(sc.wit_min); cudaFree(sc.wit_max); cudaFree(sc.nonpos); cudaFree(ctx->dev_seq); cudaFree(ctx->dev_fix);
+    cudaFree(sc.wit_min); cudaFree(sc.wit_max); cudaFree(ctx->dev_seq); cudaFree(ctx->dev_fix);
     cudaFree(sc.seq_list); cudaFree(sc.seq_sbase); cudaFree(sc.seq_count); cudaFree(sc.cursor);
     cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status); cudaFree(sc.counters);
     for (int k = 0; k <= sgpu_ctx::MAX_STAGES; k++) if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);

@@ -50,10 +50,11 @@ __device__ __forceinline__ void add_raw(int raw, float off, float unit, double& 
     as = __dadd_rn(as, walk::widen_pos(x));
     aq = __dadd_rn(aq, walk::widen_pos(__fmul_rn(x, x)));
 }
-// the same for any sample (reads marked by the walker as holding samples with pA <= 0): real conversions
-__device__ __forceinline__ void add_raw_any(int raw, float off, float unit, double& as, double& aq) {
+// the same for any sample when `safe` (tiles marked by the walker as holding LOW samples): real conversions for the
+// values the shortcut does not cover
+__device__ __forceinline__ void add_raw_any(int raw, float off, float unit, double& as, double& aq, bool safe) {
     const float x = __fmul_rn(__fadd_rn((float)raw, off), unit);
-    if (x > 0.0f) {
+    if (!safe || x > 0.0f) {
         as = __dadd_rn(as, walk::widen_pos(x));
         aq = __dadd_rn(aq, walk::widen_pos(__fmul_rn(x, x)));
     } else {
@@ -91,8 +92,7 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                                                                   uint32_t* __restrict__ ev_start,
                                                                   float* __restrict__ ev_mean, float* __restrict__ ev_stdv,
                                                                   int* __restrict__ status,
-                                                                  const uint32_t* __restrict__ tile_read0,
-                                                                  const uint32_t* __restrict__ nonpos) {
+                                                                  const uint32_t* __restrict__ tile_read0) {
     __shared__ EmitWarp smem[EWARPS];
     const int lane = threadIdx.x & 31;
     EmitWarp& sm = smem[threadIdx.x >> 5];
@@ -127,7 +127,9 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
         for (int g = 0; g < 4; g++) rv[g] = rv_n[g];
         load_tile(wt + n_warps, word_n, rv_n);
         const uint64_t tbase = tile_base[tile];
-        const uint32_t tr0 = tile_read0[tile];
+        const uint32_t tr0_raw = tile_read0[tile];
+        const uint32_t tr0 = tr0_raw & 0x7fffffffu;
+        const bool tile_low = (tr0_raw >> 31) != 0u;  // the walker found LOW samples (pA <= 0 or barely above) in this tile
         uint32_t before = half ? (uint32_t)__popc(bitmap[(uint64_t)tile * (FAST_TILE / 32) + lane]) : 0u;
         before = __reduce_add_sync(0xffffffffu, before);  // FAST_TILE / EWT == 2: at most one warp tile before this one
         uint32_t incl = __popc(word);
@@ -156,9 +158,8 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
         const long long rs_first = (long long)b.read_off[r_first];
         const long long rend_first = rs_first + (long long)b.read_len[r_first];
         const float off_first = b.offset[r_first], unit_first = b.unit[r_first];
-        // (a read with non-positive samples takes the general path: its sums need real conversions)
-        const bool one_read = rs_first <= flat0 && flat0 + EWT <= rend_first && total <= (uint32_t)EFAST &&
-                              nonpos[r_first] == 0u;
+        // (a tile with LOW samples takes the general path: its sums need real conversions)
+        const bool one_read = rs_first <= flat0 && flat0 + EWT <= rend_first && total <= (uint32_t)EFAST && !tile_low;
         if (one_read) {
             // ---- fast path, step 2: the pieces of this lane's 32 samples ----------------------------------------------
             int slot = EFAST + lane;             // where the running piece goes: first the head of this word
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                         eq = __dadd_rn(eq, sm.Q[EFAST + l2]);
                     }
                     e = next_start(bitmap, (wt + 1) * 32, n_words, rend_first);
-                    for (long long i = flat0 + EWT; i < e; i++) add_raw((int)__ldg(b.samples + i), off_first, unit_first, es, eq);
+                    for (long long i = flat0 + EWT; i < e; i++) add_raw_any((int)__ldg(b.samples + i), off_first, unit_first, es, eq, true);
                 }
                 const uint64_t k = kbase + j;
                 if (k >= ev_cap) { atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
@@ -228,6 +229,9 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
         }
         // ---- general path: a read boundary inside the warp tile ---------------------------------------------------------
         __syncwarp();
+        // an event may run on into the next tile(s), whose marks are not known here: only a tile of one read that is
+        // itself unmarked keeps the shortcut for every sample
+        const bool safe = true;
         for (uint32_t j0 = 0; j0 < total; j0 += 32) {
             const uint32_t j = j0 + lane;
             const bool have = j < total;
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                 len = (uint32_t)(e - s);
                 i = s;
                 const long long stop = e - s > ELONG ? s + ELONG : e;
-                for (; i < stop; i++) add_raw_any((int)__ldg(b.samples + i), off, unit, as, aq);
+                for (; i < stop; i++) add_raw_any((int)__ldg(b.samples + i), off, unit, as, aq, safe);
             }
             // long events (rare): the whole warp sums the rest
             uint32_t longs = __ballot_sync(0xffffffffu, have && i < e);
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                 const long long li = __shfl_sync(0xffffffffu, i, src), le = __shfl_sync(0xffffffffu, e, src);
                 const float lo = __shfl_sync(0xffffffffu, off, src), lu = __shfl_sync(0xffffffffu, unit, src);
                 double ps = 0.0, pq = 0.0;
-                for (long long p = li + lane; p < le; p += 32) add_raw_any((int)__ldg(b.samples + p), lo, lu, ps, pq);
+                for (long long p = li + lane; p < le; p += 32) add_raw_any((int)__ldg(b.samples + p), lo, lu, ps, pq, safe);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) {
                     ps = __dadd_rn(ps, __shfl_xor_sync(0xffffffffu, ps, o));
@@ -297,7 +301,7 @@ int launch_fast_emit(const DevBatch& b, Scratch& sc, uint64_t ev_cap, uint32_t* 
     const uint32_t n_tiles = fast_tiles_for(b.span);
     const uint64_t n_wt = (uint64_t)n_tiles * (FAST_TILE / EWT);
     emit_events_kernel<<<grid_cap(n_wt, EWARPS, sm_count * EMIT_GRID), EWARPS * 32, 0, st>>>(
-        b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0, sc.nonpos);
+        b, n_tiles, sc.bitmap, sc.tile_base, ev_cap, ev_start, ev_mean, ev_stdv, sc.status, sc.tile_read0);
     sum_fixups_kernel<<<grid_cap(b.n_reads, 256, sm_count * 4), 256, 0, st>>>(b.n_reads, fixups, sc.counters);
     return 2;
 }

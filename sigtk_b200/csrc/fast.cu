@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(256) read_event_offsets_kernel(DevBatch b, con
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) init_reads_kernel(DevBatch b, uint32_t n_tiles, uint32_t* __restrict__ wit_min,
-                                                         uint32_t* __restrict__ wit_max, uint32_t* __restrict__ nonpos,
-                                                         uint32_t* __restrict__ seq_flag,
+                                                         uint32_t* __restrict__ wit_max, uint32_t* __restrict__ seq_flag,
                                                          uint32_t* __restrict__ fixups, uint32_t* __restrict__ seq_count,
                                                          unsigned long long* __restrict__ cursor,
                                                          uint32_t* __restrict__ tile_read0) {
@@ -118,7 +117,6 @@ __global__ void __launch_bounds__(256) init_reads_kernel(DevBatch b, uint32_t n_
     for (uint32_t r = g; r < n_reads; r += gridDim.x * blockDim.x) {
         wit_min[r] = 0xffffffffu;
         wit_max[r] = 0u;
-        nonpos[r] = 0u;
         seq_flag[r] = 0u;
         fixups[r] = 0u;
     }
@@ -137,7 +135,7 @@ int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32
                       cudaStream_t st) {
     const uint32_t n_tiles = fast_tiles_for(b.span);
     init_reads_kernel<<<grid_cap(max(b.n_reads, n_tiles), 256, sm_count * 8), 256, 0, st>>>(
-        b, n_tiles, sc.wit_min, sc.wit_max, sc.nonpos, seq_flag, fixups, sc.seq_count, sc.cursor, sc.tile_read0);
+        b, n_tiles, sc.wit_min, sc.wit_max, seq_flag, fixups, sc.seq_count, sc.cursor, sc.tile_read0);
     return 1;
 }
 

@@ -28,7 +28,8 @@ struct Scratch {
     uint32_t* bitmap; uint64_t bitmap_words;
     // per tile
     uint32_t* tile_cnt; uint64_t* tile_base;
-    uint32_t* tile_read0;            // first read that can intersect a 2048-sample tile (emit_events_kernel)
+    uint32_t* tile_read0;            // first read that can intersect a 2048-sample tile (emit_events_kernel); the
+                                     // walker sets the top bit of tiles that hold LOW samples (pA <= 0 or barely above)
     // chunk walker (walk.cu)
     uint32_t* wk_cnt;                // [max_reads] interior chunks per read
     uint64_t* wk_ibase;              // [max_reads+1] exclusive scan of wk_cnt
@@ -37,7 +38,6 @@ struct Scratch {
     uint32_t max_tiles;
     // per read
     uint32_t* wit_min; uint32_t* wit_max;  // exact-sum witness: min nonzero |pA| / max |pA| bit patterns
-    uint32_t* nonpos;                      // 1: the read has a sample with pA <= 0 (set by the walker)
     uint32_t* seq_list;     // compacted list of reads routed to the sequential-order kernels
     uint64_t* seq_sbase;
     uint32_t* seq_count;    // device scalar

@@ -45,7 +45,7 @@ struct WalkParams {
     int* st_end;                    // same indexing: state after the chunk's last step
     uint32_t* wit_min;
     uint32_t* wit_max;
-    uint32_t* nonpos;
+    uint32_t* tile_read0;
     uint32_t edge_blocks;
 };
 
@@ -58,7 +58,8 @@ struct DevIo {
     int* __restrict__ st_end;
     uint32_t* __restrict__ wit_min;   // this read's witness
     uint32_t* __restrict__ wit_max;
-    uint32_t* __restrict__ nonpos;    // this read's "has a sample with pA <= 0" mark
+    uint32_t* __restrict__ tile_read0;  // per 2048-sample tile; the top bit marks tiles with LOW samples
+    uint64_t base;                      // flat position of the read's first sample
     float off, unit;
 
     __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
@@ -93,23 +94,23 @@ struct DevIo {
     // build_seq_list_kernel), so the extreme pA sit at the ends of [rmin, rmax]. build_seq_list_kernel needs the
     // smallest NONZERO |pA| and the largest |pA| of the read. Samples with raw <= low_t (LOW: pA <= 0 or barely above;
     // walk_core.cuh) are not covered by the range's lower end: their blocks report their own magnitudes
-    // (witness_abs), so the minimum published here starts at pA(low_t + 1) > 0. A read with LOW samples is also
-    // marked for emit_events_kernel, whose widening shortcut needs positive samples.
+    // (low_samples), so the minimum published here starts at pA(low_t + 1) > 0.
     __device__ __forceinline__ void witness(int rmin, int rmax, int low_t) const {
         const float xh = __fmul_rn(__fadd_rn((float)rmax, off), unit);
         const float xa = __fmul_rn(__fadd_rn((float)rmin, off), unit);
         atomicMax(wit_max, max(__float_as_uint(xa) & 0x7fffffffu, __float_as_uint(xh) & 0x7fffffffu));
-        if (rmin <= low_t) *nonpos = 1u;
         const int gmin = rmin > low_t ? rmin : low_t + 1;  // smallest raw value that is not LOW
         if (gmin <= rmax) {
             const float xl = __fmul_rn(__fadd_rn((float)gmin, off), unit);
             atomicMin(wit_min, xl > 0.0f ? __float_as_uint(xl) : 1u);  // (xl > 0 by the definition of low_t)
         }
     }
-    __device__ __forceinline__ void witness_abs(uint32_t lo, uint32_t hi) const {
+    // LOW samples in the group of 8 that holds read index t: magnitudes to the witness, and the 2048-sample tile is
+    // marked (top bit of tile_read0) so that emit_events_kernel sums its events with real conversions
+    __device__ __forceinline__ void low_samples(int t, uint32_t lo, uint32_t hi) const {
         atomicMin(wit_min, lo);
         atomicMax(wit_max, hi);
-        *nonpos = 1u;
+        atomicOr(tile_read0 + ((base + (uint64_t)(uint32_t)t) / FAST_TILE), 0x80000000u);
     }
 };
 
@@ -124,7 +125,8 @@ __device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64
     io.st_end = p.st_end + sid * 8;
     io.wit_min = p.wit_min + r;
     io.wit_max = p.wit_max + r;
-    io.nonpos = p.nonpos + r;
+    io.tile_read0 = p.tile_read0;
+    io.base = base;
     io.off = p.b.offset[r];
     io.unit = p.b.unit[r];
     return io;
@@ -247,7 +249,7 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
     int n = 1 + launch_scan_u32(sc.wk_cnt, b.n_reads, sc.wk_ibase, nullptr, sc, st);
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
-    p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max; p.nonpos = sc.nonpos;
+    p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max; p.tile_read0 = sc.tile_read0;
     p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
     const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
     const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;

@@ -564,8 +564,9 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 //   peak(pos)          record one peak
 //   put_begin(c) / put_end(c)   the chunk's canonical detector state after the warm-up / after its last step
 //   witness(rmin, rmax, low_t)  extreme raw values of samples of the read (any superset of the owned samples);
-//                               samples with raw <= low_t are LOW (reported through witness_abs by their blocks)
-//   witness_abs(lo, hi)         smallest nonzero / largest |pA| bit patterns of a block with LOW samples
+//                               samples with raw <= low_t are LOW (reported through low_samples by their blocks)
+//   low_samples(t, lo, hi)      LOW samples in the group of 8 that holds read index t: their smallest nonzero /
+//                               largest |pA| bit patterns (lo > hi: all of them are zero)
 SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return (n + L - 1u) / L; }
 
 // int16 -> float without a conversion instruction: with the sign bit flipped, the 16 bits are raw + 32768 in
@@ -628,7 +629,7 @@ SGW_HD uint32_t pack_s16x2(int t) { return ((uint32_t)t & 0xffffu) * 0x10001u; }
 
 // the LOW samples of one group of 8: their magnitudes go to the witness, their values become 0 for the running sums
 template <class Io>
-SGW_HD void zero_low8(Io& io, const int (&v)[4], int low_t, float* x) {
+SGW_HD void zero_low8(Io& io, int t, const int (&v)[4], int low_t, float* x) {
     uint32_t lo = 0xffffffffu, hi = 0u;
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -639,7 +640,7 @@ SGW_HD void zero_low8(Io& io, const int (&v)[4], int low_t, float* x) {
             x[q] = 0.0f;
         }
     }
-    io.witness_abs(lo, hi);
+    io.low_samples(t, lo, hi);
 }
 
 // interior chunk k (1 <= k <= nch-2) of a read: every access is inside the read, no bounds checks.
@@ -685,7 +686,7 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
             if (pa && own) io.store_pa8(tau + 8 * h, x + 8 * h);
             if (can_low & any_le_s16x2(m8, low2)) {   // LOW samples in this group (rare)
                 dirty = DIRTY_BLOCKS;
-                zero_low8(io, v, low_t, x + 8 * h);
+                zero_low8(io, tau + 8 * h, v, low_t, x + 8 * h);
             }
         }
         vmin = min_s16x2(vmin, bmin);
@@ -743,7 +744,7 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
                 if (low) {
                     dirty = DIRTY_BLOCKS;
                     const uint32_t a = f_bits(y[q]) & 0x7fffffffu;
-                    if (a != 0u) io.witness_abs(a, a);
+                    io.low_samples(t8 + q, a != 0u ? a : 0xffffffffu, a);
                 }
                 if (own && in && t8 + q < s1) {
                     rmin = raw < rmin ? raw : rmin;

@@ -35,7 +35,7 @@ struct HostIo {
     void put_begin(const Canon& c) const { *begin = c; }
     void put_end(const Canon& c) const { *end = c; }
     void witness(int lo, int hi, int) const { if (lo < *rmin) *rmin = lo; if (hi > *rmax) *rmax = hi; }
-    void witness_abs(uint32_t, uint32_t) const {}
+    void low_samples(int, uint32_t, uint32_t) const {}
 };
 
 template <int RNA>
