@@ -152,7 +152,8 @@ struct Cfg {
     static constexpr int LAG = w2 - 1;        // detector position = newest sample index - LAG
     static constexpr int R1 = RNA ? 8 : 4;    // ring size of the depth-w1 rings (> w1, power of two)
     static constexpr int R2 = RNA ? 16 : 8;   // ring size of the depth-w2 rings (> w2, power of two)
-    static constexpr int U = RNA ? 16 : 8;    // samples per block (multiple of R2: every ring index is static)
+    static constexpr int U = RNA ? 16 : 8;    // samples per block (multiple of R2: every ring index is static;
+                                              // 16 for DNA measured 24 % slower: registers, and a shorter peak mask)
     static constexpr int FILL = 2;            // blocks that only fill the rings before the first detector step
     static_assert(FILL * U >= 2 * w2 - 1, "fill covers the look-back of the first step");
 };
@@ -346,7 +347,7 @@ struct NoEmit { SGW_HD void operator()(int) const {} };
 //   p2   : the (possibly moved) peak position with the PS_OPEN flag, valid when big2
 //   on_emit(pos) : called for an emitted peak (the fast path passes NoEmit and reads the mask instead)
 template <bool SHORT, int RNA, class E>
-SGW_HD void det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, bool& big2, int& p2, const E& on_emit) {
+SGW_HD int det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, bool& big2, int& p2, const E& on_emit) {
     constexpr int w = SHORT ? Cfg<RNA>::w1 : Cfg<RNA>::w2;
     const float h = peak_h<RNA>();
     const float thr = SHORT ? thr_short<RNA>() : thr_long<RNA>();
@@ -362,18 +363,18 @@ SGW_HD void det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, boo
     const int over = (u - (w / 2 + 1)) - p3;               // age of the peak beyond w/2 + 1; negative in CASE 1 and
     const bool emit = over >= 0;                           // while not valid (flag bits): events.c:429
     acc.mk |= shr_clamp(1u << (PkCfg<RNA>::LEAD + m - (w / 2 + 1)), over);  // no bit unless 0 <= over <= 31
-    acc.oldest = acc.oldest > over ? acc.oldest : over;
     if (emit) on_emit(p3);
     pv = (rise1 | emit) ? c : pvm;                         // 395 / 400 / 409 / 433
     ps = emit ? PS_NONE : p3;
     ps = rise1 ? (u | PS_OPEN) : ps;
+    return over;
 }
 
 // One position of both detectors, short first (events.c:385-440).
 template <int RNA, class E>
 SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc, const E& on_emit) {
     bool maskl, unused_b; int p2, unused_p;
-    det_one<true, RNA>(d.s_pv, d.s_ps, m, u, c1, acc, maskl, p2, on_emit);
+    const int over_s = det_one<true, RNA>(d.s_pv, d.s_ps, m, u, c1, acc, maskl, p2, on_emit);
     // the short detector dominates the long one while it holds a peak above its threshold (events.c:414-422)
     d.l_mt = maskl ? (p2 & ~PS_OPEN) + Cfg<RNA>::w1 : d.l_mt;
     d.l_ps = maskl ? PS_NONE : d.l_ps;
@@ -381,7 +382,9 @@ SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc,
     // a masked long detector is always in the reset state (masked_to is only ever set together with a reset, and
     // a masked detector is not stepped), and the reset state does not react to FLT_MAX: no gating needed
     const float c2m = d.l_mt < u ? c2 : FLT_MAX;
-    det_one<false, RNA>(d.l_pv, d.l_ps, m, u, c2m, acc, unused_b, unused_p, on_emit);
+    const int over_l = det_one<false, RNA>(d.l_pv, d.l_ps, m, u, c2m, acc, unused_b, unused_p, on_emit);
+    const int over = over_s > over_l ? over_s : over_l;   // (one three-input maximum)
+    acc.oldest = acc.oldest > over ? acc.oldest : over;
 }
 
 // a sample enters windows whose t-statistics are computed at most two blocks later
