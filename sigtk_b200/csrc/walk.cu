@@ -1,6 +1,6 @@
 // walk.cu -- walk_chunks_kernel: the first (and dominant) kernel of the fast path.
 //
-// Every read is cut into CHUNKS of L samples (the last chunk takes the remainder, L..2L-1 samples); ONE THREAD
+// Every read is cut into CHUNKS of L samples (the last chunk takes the remainder, 1..L samples); ONE THREAD
 // walks one chunk with the register-resident walker of walk_core.cuh. A chunk starts W samples early from a cold
 // detector state (plus two ring-fill blocks), so chunks are independent: no shared memory, no barriers, no
 // inter-thread communication. The detector state a chunk reaches at its first owned position (after the warm-up)

@@ -7,7 +7,8 @@
 //   (events.c:338-361, every rounding step written out) -> both peak detectors (events.c:387-437).
 //
 // Nothing per-sample is staged in shared or global memory: the only per-sample traffic is the 2-byte load (and
-// the optional 4-byte pA store); emitted peaks set bits of the event-start bitmap with fire-and-forget RED.OR.
+// the optional 4-byte pA store); emitted peaks are collected in a per-block register mask and set in the event-start
+// bitmap with fire-and-forget RED.OR.
 //
 // Timeline of one walker step (newest sample index j, all indices relative to the read):
 //     P(j+1)            = P(j) + x[j]                      running prefix sums (exact, see below)
@@ -24,7 +25,12 @@
 // build_seq_list_kernel) checks that sufficient condition; reads that fail are redone by the sequential-order
 // kernels (generic.cu).
 //
-// The file is `__host__ __device__` clean so that tests/tools/host_walk.cu can run the very same chunk logic on
+// Rare paths, all inside the walker (the read stays on the fast path): a t-statistic next to a float rounding
+// midpoint or a peak older than the block's mask -> redo_block (the block's t-statistics from the raw samples with
+// the reference's own operations); LOW samples (pA <= 0 or barely above: glitches) -> handed to the running sums as
+// 0, the three blocks around them redone (see walk_block).
+//
+// The file is `__host__ __device__` clean so that tests/tools/host_walk.cpp can run the very same chunk logic on
 // the CPU against the oracle (a checker for the chunking / ring / boundary logic; never part of the product).
 #pragma once
 #include <float.h>
@@ -412,16 +418,6 @@ struct Rings {
     }
 };
 
-// One block of U samples. Phase 1 computes the block's t-statistics without a single branch; phase 2 steps the
-// detector through them. The same code also fills the rings at the start of a chunk: the two blocks before the
-// first detector step run it with live == false (their t-statistics come from partly filled rings and are never
-// used, the detector state is reset afterwards), except that the last w1 values of t1 of the second of them ARE
-// the ones the first real steps read (live_t1).
-// EDGE: the block may touch positions outside the read [0, n): samples there count as 0, t is 0 outside
-// w <= i <= n-w (events.c:328-338), the detector only steps positions 1 <= p < n (position 0 is masked: 387).
-//   x[m]   : pA of sample tau0 + m (0 outside the read when EDGE)
-//   tau0   : read index of the block's first sample, a multiple of U
-//   sh     : read_off & 31
 // The rare path of a block: the t-statistics of the whole block from the raw samples with the reference's own
 // operations, then the block's detector steps again from the state the block started in; every emitted peak is
 // recorded on its own (io.peak), however old it is.
