@@ -2,40 +2,66 @@
 //
 // The reference accumulates in FLOAT, sequentially: the result depends on the
 // summation order, so a tree reduction cannot be bit-exact.
-// stat_moments_kernel therefore replays the float recurrence in order, one
-// thread per read ("exact emulation").  Medians are order-free: a two-level
+// stat_moments_kernel therefore replays the float recurrence in order ("exact
+// emulation"), one warp per read with the chains on two lanes.  Medians are order-free: a two-level
 // radix selection on the int16 samples, one CTA per read; pa_median follows
 // from raw_median because the pA map is monotone in raw.
 #include "kernels.cuh"
 
 namespace sgpu {
 
+// One WARP per read. The additions of a float accumulator form one dependent chain (4 cycles each): nothing can
+// shorten it, but everything around it can run beside it. All lanes load 32 consecutive samples (coalesced) and
+// compute the addends -- (float)raw and pA in the first pass, the squared deviations in the second -- into shared
+// memory; lanes 0 and 1 then run the two chains (raw / pA) side by side through the same instructions, while the
+// next tile's samples are already in flight.
 __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __restrict__ out) {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n_reads; r += gridDim.x * blockDim.x) {
+    __shared__ float add_all[4][2][32];
+    float (*add)[32] = add_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = warp; r < b.n_reads; r += n_warps) {
         const int16_t* __restrict__ raw = b.samples + b.read_off[r];
         const int n = (int)b.read_len[r];  // stat.h takes `int n`
         const float off = b.offset[r], unit = b.unit[r];
         const float nf = (float)n;
-        float acc_r = 0.0f, acc_p = 0.0f;  // meani16 / meanf: sum += x[i]
-        for (int i = 0; i < n; i++) {
-            const int16_t v = raw[i];
-            acc_r = __fadd_rn(acc_r, (float)v);
-            acc_p = __fadd_rn(acc_p, pa_of(v, off, unit));
+        float mean = 0.0f;  // lane 0: raw, lane 1: pA
+        for (int pass = 0; pass < 2; pass++) {
+            // pass 0: meani16 / meanf: sum += x[i]; pass 1: stdvi16 / stdvf: sum += (x[i]-m)*(x[i]-m)
+            const float mean_r = __shfl_sync(0xffffffffu, mean, 0), mean_p = __shfl_sync(0xffffffffu, mean, 1);
+            float acc = 0.0f;
+            int16_t nxt = lane < n ? raw[lane] : (int16_t)0;
+            for (int t0 = 0; t0 < n; t0 += 32) {
+                const int16_t v = nxt;
+                nxt = t0 + 32 + lane < n ? raw[t0 + 32 + lane] : (int16_t)0;
+                float ar = (float)v, ap = pa_of(v, off, unit);
+                if (pass) {
+                    const float dr = __fsub_rn(ar, mean_r), dp = __fsub_rn(ap, mean_p);
+                    ar = __fmul_rn(dr, dr);
+                    ap = __fmul_rn(dp, dp);
+                }
+                __syncwarp();  // the previous tile's chains are done with the shared tile
+                add[0][lane] = ar;
+                add[1][lane] = ap;
+                __syncwarp();
+                if (lane < 2) {
+                    const float* a = add[lane];
+                    const int cnt = n - t0 < 32 ? n - t0 : 32;
+                    if (cnt == 32) {
+#pragma unroll
+                        for (int k = 0; k < 32; k++) acc = __fadd_rn(acc, a[k]);
+                    } else {
+                        for (int k = 0; k < cnt; k++) acc = __fadd_rn(acc, a[k]);
+                    }
+                }
+            }
+            if (pass == 0) {
+                mean = __fdiv_rn(acc, nf);
+                if (lane < 2) out[(size_t)r * 6 + lane] = mean;
+            } else if (lane < 2) {
+                out[(size_t)r * 6 + 2 + lane] = __fsqrt_rn(__fdiv_rn(acc, nf));
+            }
         }
-        const float mean_r = __fdiv_rn(acc_r, nf), mean_p = __fdiv_rn(acc_p, nf);
-        float dev_r = 0.0f, dev_p = 0.0f;  // stdvi16 / stdvf: sum += (x[i]-m)*(x[i]-m)
-        for (int i = 0; i < n; i++) {
-            const int16_t v = raw[i];
-            const float dr = __fsub_rn((float)v, mean_r);
-            const float dp = __fsub_rn(pa_of(v, off, unit), mean_p);
-            dev_r = __fadd_rn(dev_r, __fmul_rn(dr, dr));
-            dev_p = __fadd_rn(dev_p, __fmul_rn(dp, dp));
-        }
-        float* o = out + (size_t)r * 6;
-        o[0] = mean_r;
-        o[1] = mean_p;
-        o[2] = __fsqrt_rn(__fdiv_rn(dev_r, nf));
-        o[3] = __fsqrt_rn(__fdiv_rn(dev_p, nf));
     }
 }
 
@@ -104,7 +130,7 @@ __global__ void __launch_bounds__(256) stat_median_kernel(DevBatch b, float* __r
 
 int launch_stat(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st) {
     if (b.n_reads == 0) return 0;
-    int g1 = (int)((b.n_reads + 127) / 128);
+    int g1 = (int)((b.n_reads + 3) / 4);  // one warp per read
     if (g1 > sm_count * 16) g1 = sm_count * 16;
     stat_moments_kernel<<<g1, 128, 0, st>>>(b, stat6);
     int g2 = (int)b.n_reads;
