@@ -412,3 +412,47 @@ def test_plateaus_emit_old_peaks_on_the_fast_path(ctx, orc, rna_flag, monkeypatc
     res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
     check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS)
     assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0
+
+
+def _fuzz_read(rng, k):
+    """a synthetic read with random adversarial features: glitches (zero / negative / barely positive pA), flat
+    stretches, ramps (plateaus of the t-statistic), steps, saturation"""
+    n = int(rng.choice([1, 2, 5, 13, 31, 200, 257, 1000, 1023, 1024, 1025, 3000, 6000, 12000]))
+    n = max(1, n + int(rng.integers(-3, 4)))
+    rd = synth.make_read(1000 + k, n, seed=int(rng.integers(1, 1 << 30)))
+    raw = rd[0].astype(np.int64)
+    off = int(rd[2])
+    for _ in range(int(rng.integers(0, 6))):
+        kind = int(rng.integers(0, 6))
+        p = int(rng.integers(0, n))
+        ln = int(rng.integers(1, max(2, min(n - p, 400))))
+        if kind == 0:      # single glitches like real data: raw + offset = -44, -376, ...
+            raw[p] = -off - int(rng.choice([0, 1, 44, 376, 3000]))
+        elif kind == 1:    # a run of low values around zero
+            raw[p:p + ln] = -off + rng.integers(-5, 70, min(ln, n - p))
+        elif kind == 2:    # flat stretch
+            raw[p:p + ln] = raw[p]
+        elif kind == 3:    # ramp
+            step = int(rng.choice([-7, -2, 3, 11, 30]))
+            raw[p:p + ln] = raw[p] + step * np.arange(min(ln, n - p))
+        elif kind == 4:    # big step
+            raw[p:] += int(rng.choice([-150, 200, 400]))
+        else:              # saturation
+            raw[p:p + ln] = int(rng.choice([32767, 4000]))
+    return np.clip(raw, -32768, 32767).astype(np.int16), rd[1], rd[2], rd[3]
+
+
+@pytest.mark.parametrize("rna_flag,chunk_len,seed", [(0, 128, 1), (0, 1024, 2), (1, 512, 3), (1, 4096, 4), (0, 4096, 5)])
+def test_fuzz_adversarial_reads(ctx, orc, rna_flag, chunk_len, seed, monkeypatch):
+    """random reads with glitches, flat stretches, ramps, steps and saturation: every output bit-exact, whichever
+    path (walker, its exact recompute, sequential-order kernels) a read takes"""
+    monkeypatch.setenv("SGPU_CHUNK_LEN", str(chunk_len))
+    rng = np.random.default_rng(seed)
+    reads = [_fuzz_read(rng, k) for k in range(300)]
+    res = ctx.run(reads, rna=rna_flag, want=ALL)
+    check_against_oracle(orc, res, reads, rna_flag)
+    # the same reads as svb-zd streams decoded on the GPU
+    sres = ctx.run_svbzd([(orc.svbzd_encode(r[0]), r[1], r[2], r[3]) for r in reads], rna=rna_flag, want=ALL)
+    assert np.array_equal(sres.ev_off, res.ev_off) and np.array_equal(sres.ev_start, res.ev_start)
+    assert np.array_equal(bits(sres.ev_mean), bits(res.ev_mean)) and np.array_equal(bits(sres.ev_stdv), bits(res.ev_stdv))
+    assert np.array_equal(bits(sres.stat), bits(res.stat))
