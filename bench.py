@@ -331,6 +331,23 @@ def run_ours(args):
     all_samples, all_events, all_reads = (float(x) for x in tot.tolist())
     value = all_samples / (ms_max * 1e-3) / 1e9
 
+    # ---- the siblings of the event path (`sigtk pa`, `sigtk stat`), device resident, on the first batch ----------------
+    siblings = {}
+    if not args.no_siblings:
+        p0 = pool[0]
+        for name, w_ in (("pa", sg.WANT_PA), ("stat", sg.WANT_STAT)):
+            tot_ms = 0.0
+            for k in range(4):
+                ctx.run_device(p0["samples"].data_ptr(), p0["read_off"].data_ptr(), p0["read_len"].data_ptr(),
+                               p0["offset"].data_ptr(), p0["unit"].data_ptr(), p0["n_reads"], p0["span"], rna, w_, stream)
+                ms = sum(m for _, m, _ in ctx.stage_times())
+                if k:
+                    tot_ms += ms
+            ms = tot_ms / 3.0
+            by = (6.0 if name == "pa" else 2.0) * p0["n_samples"]  # pa: 2 B in + 4 B out; stat: 2 B in (read 3 times)
+            siblings[name] = {"ms": ms, "value": p0["n_samples"] / (ms * 1e-3) / 1e9, "unit": UNIT,
+                              "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / measured_peak()[0]}
+
     # ---- end to end through the host C-ABI: pinned slots, H2D + kernels + D2H per step ----------------------------
     e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna)
     # ---- the same with svb-zd compressed records as input (decoded in HBM), and the decoder alone ------------------
@@ -385,6 +402,8 @@ def run_ours(args):
         }
         if svb:
             line["svbzd"] = svb
+        if siblings:
+            line["siblings"] = siblings
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:
@@ -506,6 +525,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=2000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-svbzd", action="store_true", help="skip the compressed-input (svb-zd) measurements")
+    ap.add_argument("--no-siblings", action="store_true", help="skip the pa / stat kernel timings")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -420,23 +420,26 @@ __global__ void __launch_bounds__(128) gen_emit_kernel(DevBatch b, WorkList wl, 
 // 16-byte group of 8 samples (groups never straddle reads: read starts are 8-aligned).
 __global__ void __launch_bounds__(256) pa_kernel(DevBatch b, float* __restrict__ pa) {
     const uint64_t n_groups = b.span >> 3;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
-         g += (uint64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    for (uint64_t g0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; g0 < n_groups;
+         g0 += (uint64_t)gridDim.x * blockDim.x) {
+        // one binary search per warp (its 32 groups are 256 consecutive samples), then a short walk per lane
+        uint32_t r = 0;
+        if (lane == 0) r = find_read(b.read_off, b.n_reads, g0 << 3);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        const uint64_t g = g0 + lane;
+        if (g >= n_groups) continue;
         const uint64_t p = g << 3;
-        const uint32_t r = find_read(b.read_off, b.n_reads, p);
+        while (r + 1 < b.n_reads && b.read_off[r + 1] <= p) r++;
         if (p - b.read_off[r] >= b.read_len[r]) continue;  // alignment gap
         const float off = b.offset[r], unit = b.unit[r];
         const int4 raw = __ldg(reinterpret_cast<const int4*>(b.samples + p));
         const int v[4] = {raw.x, raw.y, raw.z, raw.w};
         float o[8];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            o[2 * k] = pa_of((int16_t)(v[k] & 0xffff), off, unit);
-            o[2 * k + 1] = pa_of((int16_t)(v[k] >> 16), off, unit);
-        }
+        walk::cvt8(v, off, unit, o);   // misc.c:28 per sample: float add of the offset, float multiply by the unit
         float4* dst = reinterpret_cast<float4*>(pa + p);
-        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        __stcs(dst, make_float4(o[0], o[1], o[2], o[3]));      // streaming stores: the output is not read again here
+        __stcs(dst + 1, make_float4(o[4], o[5], o[6], o[7]));
     }
 }
 

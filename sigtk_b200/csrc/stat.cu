@@ -2,22 +2,105 @@
 //
 // The reference accumulates in FLOAT, sequentially: the result depends on the
 // summation order, so a tree reduction cannot be bit-exact.
-// stat_moments_kernel therefore replays the float recurrence in order ("exact
-// emulation"), one warp per read with the chains on two lanes.  Medians are order-free: a two-level
+// stat_moments_kernel therefore reproduces the float recurrence exactly ("exact
+// emulation"), one warp per read: runs of 32 values are summarised in parallel by
+// what they do to the accumulator for either parity of its last bit (see below).  Medians are order-free: a two-level
 // radix selection on the int16 samples, one CTA per read; pa_median follows
 // from raw_median because the pA map is monotone in raw.
 #include "kernels.cuh"
 
 namespace sgpu {
 
-// One WARP per read. The additions of a float accumulator form one dependent chain (4 cycles each): nothing can
-// shorten it, but everything around it can run beside it. All lanes load 32 consecutive samples (coalesced) and
-// compute the addends -- (float)raw and pA in the first pass, the squared deviations in the second -- into shared
-// memory; lanes 0 and 1 then run the two chains (raw / pA) side by side through the same instructions, while the
-// next tile's samples are already in flight.
+// ---- sequential float accumulation, in parallel ----------------------------------------------------------------------
+// The reference adds in float, one value after the other: s <- fl(s + v). While s stays in one binade [2^e, 2^(e+1))
+// every s is an integer multiple S of g = 2^(e-23), and for v >= 0
+//     fl(s + v) = g * RNE(S + v/g) = g * (S + a + c),   v/g = a + f,  a = floor, 0 <= f < 1,
+//     c = [f > 1/2], and on a tie (f == 1/2) c = parity of (S + a):
+// the only thing the step needs to know about the running sum is the PARITY of S. So a run of values is summarised by
+// two integers -- the total increment for an even and for an odd incoming S -- computed without knowing s, and runs
+// compose. One warp takes 1024 values: every lane summarises 32 consecutive ones (both parities), lane 0 walks the 32
+// summaries. A tile that would carry S to 2^24 (the binade ends there), holds a negative value or meets s <= 0 is
+// added value by value; the summaries after it are recomputed for the new binade. Bit-identical to the sequential
+// loop by construction (tests: every stat of every parity test and of the fuzz reads against the oracle).
+constexpr int SB = 1024;            // values per superblock
+constexpr int SB_STRIDE = 33;       // shared-memory row stride of a 32-value tile (conflict-free both ways)
+
+__device__ __forceinline__ float chain_superblock(const float* __restrict__ A, int ntiles, float s, int lane,
+                                                  int* __restrict__ sums, bool first) {
+    int tile = 0;
+    while (tile < ntiles) {  // (uniform across the warp)
+        const uint32_t sb = __float_as_uint(s);
+        const int e = (int)((sb >> 23) & 0xffu) - 127;
+        const bool s_ok = !first && s > 0.0f && e > -100 && e < 100;  // the first superblock starts from 0: binades fly by
+        int fail = tile;  // first tile that has to be added value by value
+        uint32_t S = (sb & 0x7fffffu) | 0x800000u;
+        if (s_ok) {
+            const float scale = __uint_as_float((uint32_t)(127 + 23 - e) << 23);
+            if (lane >= tile && lane < ntiles) {
+                const float* row = A + lane * SB_STRIDE;
+                int inc0 = 0, inc1 = 0;
+                uint32_t p0 = 0u, p1 = 1u;
+                bool ok = true;
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    const float v = row[k];
+                    const float x = __fmul_rn(v, scale);          // exact: a power of two
+                    ok = ok && ((__float_as_uint(v) >> 31) == 0u) && (x < 16777216.0f);
+                    const int a = __float2int_rd(x);
+                    const float f = __fsub_rn(x, (float)a);       // exact
+                    const bool tie = f == 0.5f;
+                    const uint32_t up = f > 0.5f ? 1u : 0u;
+                    const uint32_t t0 = p0 + (uint32_t)a, t1 = p1 + (uint32_t)a;
+                    const uint32_t c0 = tie ? (t0 & 1u) : up, c1 = tie ? (t1 & 1u) : up;
+                    inc0 += a + (int)c0;
+                    inc1 += a + (int)c1;
+                    p0 = (t0 + c0) & 1u;
+                    p1 = (t1 + c1) & 1u;
+                }
+                sums[3 * lane] = inc0;
+                sums[3 * lane + 1] = inc1;
+                sums[3 * lane + 2] = ok ? 1 : 0;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                int t = tile;
+                for (; t < ntiles; t++) {
+                    if (!sums[3 * t + 2]) break;
+                    const uint32_t Sn = S + (uint32_t)sums[3 * t + (S & 1u)];
+                    if (Sn >= 0x1000000u) break;  // the binade ends: this tile is added value by value
+                    S = Sn;
+                }
+                fail = t;
+            }
+            fail = __shfl_sync(0xffffffffu, fail, 0);
+            S = __shfl_sync(0xffffffffu, S, 0);
+            s = __uint_as_float(((uint32_t)(e + 127) << 23) | (S & 0x7fffffu));
+            __syncwarp();
+        }
+        if (fail < ntiles) {
+            if (lane == 0) {
+                const float* row = A + fail * SB_STRIDE;
+#pragma unroll
+                for (int k = 0; k < 32; k++) s = __fadd_rn(s, row[k]);
+            }
+            s = __shfl_sync(0xffffffffu, s, 0);
+            tile = fail + 1;
+        } else {
+            tile = ntiles;
+        }
+    }
+    return s;
+}
+
+// One WARP per read; per pass and superblock of 1024 samples all lanes load the samples (coalesced) and compute the
+// addends -- (float)raw and pA in the first pass (meani16 / meanf: sum += x[i]), the squared deviations in the
+// second (stdvi16 / stdvf: sum += (x[i]-m)*(x[i]-m)) -- into shared memory; chain_superblock adds them up in the
+// reference's order. Positions past the end of the read hold +0, which no float sum notices.
 __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __restrict__ out) {
-    __shared__ float add_all[4][2][32];
-    float (*add)[32] = add_all[threadIdx.x >> 5];
+    __shared__ float add_all[4][2][32 * SB_STRIDE];
+    __shared__ int sums_all[4][96];
+    float (*add)[32 * SB_STRIDE] = add_all[threadIdx.x >> 5];
+    int* sums = sums_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = warp; r < b.n_reads; r += n_warps) {
@@ -25,41 +108,46 @@ __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __
         const int n = (int)b.read_len[r];  // stat.h takes `int n`
         const float off = b.offset[r], unit = b.unit[r];
         const float nf = (float)n;
-        float mean = 0.0f;  // lane 0: raw, lane 1: pA
+        float mean_r = 0.0f, mean_p = 0.0f;
         for (int pass = 0; pass < 2; pass++) {
-            // pass 0: meani16 / meanf: sum += x[i]; pass 1: stdvi16 / stdvf: sum += (x[i]-m)*(x[i]-m)
-            const float mean_r = __shfl_sync(0xffffffffu, mean, 0), mean_p = __shfl_sync(0xffffffffu, mean, 1);
-            float acc = 0.0f;
-            int16_t nxt = lane < n ? raw[lane] : (int16_t)0;
-            for (int t0 = 0; t0 < n; t0 += 32) {
-                const int16_t v = nxt;
-                nxt = t0 + 32 + lane < n ? raw[t0 + 32 + lane] : (int16_t)0;
-                float ar = (float)v, ap = pa_of(v, off, unit);
-                if (pass) {
-                    const float dr = __fsub_rn(ar, mean_r), dp = __fsub_rn(ap, mean_p);
-                    ar = __fmul_rn(dr, dr);
-                    ap = __fmul_rn(dp, dp);
-                }
-                __syncwarp();  // the previous tile's chains are done with the shared tile
-                add[0][lane] = ar;
-                add[1][lane] = ap;
-                __syncwarp();
-                if (lane < 2) {
-                    const float* a = add[lane];
-                    const int cnt = n - t0 < 32 ? n - t0 : 32;
-                    if (cnt == 32) {
+            float acc_r = 0.0f, acc_p = 0.0f;
+            for (int t0 = 0; t0 < n; t0 += SB) {
+                __syncwarp();  // the previous superblock's readers are done
+                int vv[32];  // all 32 loads in flight before the first use (one warp per read: latency is everything)
 #pragma unroll
-                        for (int k = 0; k < 32; k++) acc = __fadd_rn(acc, a[k]);
-                    } else {
-                        for (int k = 0; k < cnt; k++) acc = __fadd_rn(acc, a[k]);
-                    }
+                for (int k = 0; k < 32; k++) {
+                    const int i = t0 + k * 32 + lane;
+                    vv[k] = i < n ? (int)raw[i] : 0;
                 }
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    const int i = t0 + k * 32 + lane;
+                    float ar = 0.0f, ap = 0.0f;
+                    if (i < n) {
+                        const int16_t v = (int16_t)vv[k];
+                        ar = (float)v;
+                        ap = pa_of(v, off, unit);
+                        if (pass) {
+                            const float dr = __fsub_rn(ar, mean_r), dp = __fsub_rn(ap, mean_p);
+                            ar = __fmul_rn(dr, dr);
+                            ap = __fmul_rn(dp, dp);
+                        }
+                    }
+                    add[0][k * SB_STRIDE + lane] = ar;
+                    add[1][k * SB_STRIDE + lane] = ap;
+                }
+                __syncwarp();
+                const int ntiles = (min(SB, n - t0) + 31) >> 5;
+                acc_r = chain_superblock(add[0], ntiles, acc_r, lane, sums, t0 == 0);
+                acc_p = chain_superblock(add[1], ntiles, acc_p, lane, sums, t0 == 0);
             }
             if (pass == 0) {
-                mean = __fdiv_rn(acc, nf);
-                if (lane < 2) out[(size_t)r * 6 + lane] = mean;
-            } else if (lane < 2) {
-                out[(size_t)r * 6 + 2 + lane] = __fsqrt_rn(__fdiv_rn(acc, nf));
+                mean_r = __fdiv_rn(acc_r, nf);
+                mean_p = __fdiv_rn(acc_p, nf);
+                if (lane == 0) { out[(size_t)r * 6] = mean_r; out[(size_t)r * 6 + 1] = mean_p; }
+            } else if (lane == 0) {
+                out[(size_t)r * 6 + 2] = __fsqrt_rn(__fdiv_rn(acc_r, nf));
+                out[(size_t)r * 6 + 3] = __fsqrt_rn(__fdiv_rn(acc_p, nf));
             }
         }
     }

@@ -69,8 +69,8 @@ struct DevIo {
     __device__ __forceinline__ bool want_pa() const { return pa != nullptr; }
     __device__ __forceinline__ void store_pa8(int t, const float* x) const {
         float4* dst = reinterpret_cast<float4*>(pa + t);
-        dst[0] = make_float4(x[0], x[1], x[2], x[3]);
-        dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+        __stcs(dst, make_float4(x[0], x[1], x[2], x[3]));      // streaming: nothing on the device reads pA back
+        __stcs(dst + 1, make_float4(x[4], x[5], x[6], x[7]));
     }
     __device__ __forceinline__ void store_pa1(int t, float x) const { pa[t] = x; }
     __device__ __forceinline__ void peak(int pos) const { atomicOr(bm + ((uint32_t)pos >> 5), 1u << (pos & 31)); }
