@@ -38,9 +38,12 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
             const float scale = __uint_as_float((uint32_t)(127 + 23 - e) << 23);
             if (lane >= tile && lane < ntiles) {
                 const float* row = A + lane * SB_STRIDE;
-                int inc0 = 0, inc1 = 0;
-                uint32_t p0 = 0u, p1 = 1u;
-                bool ok = true;
+                // A tie rounds to even: after the first tie of the run the parity is 0 whatever came in, so the two
+                // summaries differ only by the carry of that first tie (c and 1 - c). One chain (incoming S even)
+                // plus that difference.
+                int inc0 = 0, dif = 0;
+                uint32_t par = 0u;
+                bool seen = false, ok = true;
 #pragma unroll 8
                 for (int k = 0; k < 32; k++) {
                     const float v = row[k];
@@ -50,13 +53,13 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
                     const float f = __fsub_rn(x, (float)a);       // exact
                     const bool tie = f == 0.5f;
                     const uint32_t up = f > 0.5f ? 1u : 0u;
-                    const uint32_t t0 = p0 + (uint32_t)a, t1 = p1 + (uint32_t)a;
-                    const uint32_t c0 = tie ? (t0 & 1u) : up, c1 = tie ? (t1 & 1u) : up;
-                    inc0 += a + (int)c0;
-                    inc1 += a + (int)c1;
-                    p0 = (t0 + c0) & 1u;
-                    p1 = (t1 + c1) & 1u;
+                    const uint32_t t = par + (uint32_t)a;
+                    const uint32_t c = tie ? (t & 1u) : up;
+                    if (tie && !seen) { dif = 1 - 2 * (int)c; seen = true; }
+                    inc0 += a + (int)c;
+                    par = (t + c) & 1u;
                 }
+                const int inc1 = inc0 + dif;
                 sums[3 * lane] = inc0;
                 sums[3 * lane + 1] = inc1;
                 sums[3 * lane + 2] = ok ? 1 : 0;
