@@ -109,3 +109,43 @@ def test_cpu_decode_flag_gives_the_same_bytes(sp1):
     assert run(["stat", "--cpu-decode", "--batch-samples", "30000", sp1]).stdout == open(
         os.path.join(G, "ref_sp1_stat.txt"), "rb").read()
     assert run(["stat", "--batch-samples", "30000", sp1]).stdout == open(os.path.join(G, "ref_sp1_stat.txt"), "rb").read()
+
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "sigtk")
+WRITE = os.path.join(ROOT, "oracle", "_ref", "blow5_write")
+
+
+@pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(WRITE)), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kind", ["genomic_dna", "rna"])
+def test_adversarial_blow5_against_the_reference_binary(tmp_path, kind):
+    """a BLOW5 (zlib + svb-zd) of reads with glitches (pA <= 0), flat stretches, ramps, steps and saturation,
+    written with the reference's slow5lib; stdout of `event`, `event -c`, `stat` and `pa` must equal the stdout of
+    the compiled unmodified reference, byte for byte (reads on which the reference aborts are left out: n < 200,
+    constant chunks)"""
+    import struct
+    import numpy as np
+    from test_gpu_parity import _fuzz_read
+    rng = np.random.default_rng(11 if kind == "rna" else 7)
+    path = str(tmp_path / "fuzz.blow5")
+    p = subprocess.Popen([WRITE, path, kind], stdin=subprocess.PIPE)
+    k = n_written = 0
+    while n_written < 150:
+        raw, dig, off, rg = _fuzz_read(rng, k)
+        k += 1
+        if len(raw) < 1000:
+            continue
+        # the reference's dead trimming step asserts on chunk-wise constant signals (events.c:242): keep reads whose
+        # first and last 200 samples vary
+        if np.ptp(raw[:200]) < 20 or np.ptp(raw[-200:]) < 20:
+            continue
+        rid = f"fuzz-{k:05d}".encode()
+        p.stdin.write(struct.pack("<I", len(rid)) + rid + struct.pack("<Qddd", len(raw), dig, off, rg) + raw.tobytes())
+        n_written += 1
+    p.stdin.close()
+    assert p.wait() == 0
+    for args in (["event", "-c"], ["event"], ["stat"], ["pa"]):
+        ref = subprocess.run([REF_CLI] + args + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if ref.returncode != 0:
+            pytest.skip("the reference aborted on this input: " + ref.stderr.decode(errors="replace")[-200:])
+        ours = run(args + [path])
+        assert ours.stdout == ref.stdout, args
