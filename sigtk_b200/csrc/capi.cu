@@ -481,7 +481,7 @@ int64_t sgpu_slot_add_read_svbzd(sgpu_ctx_t* ctx, uint32_t slot, const uint8_t* 
     if (n_bytes) memcpy(&count, stream, 4);  // slow5_press.c:1093: the original length leads the stream
     const uint64_t n = count;                // (a record without signal stores no stream at all: n_bytes == 0)
     if (n_bytes && (4u + (n + 3u) / 4u + n > n_bytes || n_bytes > 4u + (n + 3u) / 4u + 4u * n)) return SGPU_E_STREAM;
-    if (n >= (1ull << 31)) return SGPU_E_TOOBIG;
+    if (n >= (1ull << 31) || n_bytes > 0xffffffffull) return SGPU_E_TOOBIG;
     const uint64_t need = align_up(n, SGPU_ALIGN), cneed = align_up(n_bytes, 16);
     if (need > ctx->max_samples || cneed > ctx->comp_cap) return SGPU_E_TOOBIG;
     sgpu_batch_t& b = sl.batch;
