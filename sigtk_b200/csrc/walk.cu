@@ -220,9 +220,9 @@ static inline int grid_cap(uint64_t work, int block, int max_blocks) {
 // a few waves of chunks
 uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count) {
     const uint32_t lmin = rna ? 512u : 128u;
-    // (measured: for DNA a little over one wave of resident threads is enough, the warm-up is what longer chunks save;
+    // (measured: for DNA one wave of resident threads is enough, the warm-up is what longer chunks save;
     //  the RNA instantiation (2 warps per scheduler, 416 warm-up samples) does better with four times as many)
-    const uint64_t want_chunks = (uint64_t)sm_count * (rna ? 2048ull : 512ull);
+    const uint64_t want_chunks = (uint64_t)sm_count * (rna ? 2048ull : 384ull);
     uint32_t L = rna ? 4096u : 1024u;
     while (L > lmin && span / L < want_chunks) L >>= 1;
     if (const char* e = getenv("SGPU_CHUNK_LEN")) {
