@@ -455,7 +455,7 @@ static inline int grid_for(uint64_t work, int block, int max_blocks) {
 int launch_generic_detect(const DevBatch& b, const WorkList& wl, Scratch& sc, int sm_count, cudaStream_t st) {
     gen_prefix_kernel<<<sm_count * 8, 128, 0, st>>>(b, wl, sc.Sinc, sc.Qinc);
     gen_tstat_kernel<<<sm_count * 8, 256, 0, st>>>(b, wl, sc.Sinc, sc.Qinc, sc.t1, sc.t2);
-    gen_detect_kernel<<<sm_count * 8, 128, 0, st>>>(b, wl, sc.t1, sc.t2, sc.bitmap, b.rna ? 384u : 64u);
+    gen_detect_kernel<<<sm_count * 8, 128, 0, st>>>(b, wl, sc.t1, sc.t2, sc.bitmap, b.rna ? 384u : 64u);  // (its own warm-up, longer than the walker's)
     return 3;
 }
 

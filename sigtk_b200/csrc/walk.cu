@@ -232,7 +232,10 @@ uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count) {
     return L;
 }
 uint32_t walk_warmup(int rna) {
-    uint32_t W = rna ? 384u : 64u;
+    // measured boundary mismatches per 10^6 chunk boundaries (bench batches): DNA W=24: 20, 32: 0.4, >= 40: 0 in
+    // 2.5 x 10^6; RNA W=192: 24, 256: 0.8, 320: 0 in 1.3 x 10^6. The rate falls by ~50x per 8 (DNA) / ~30x per 64 (RNA)
+    // samples; a mismatch only costs the read its place on the fast path.
+    uint32_t W = rna ? 384u : 48u;
     if (const char* e = getenv("SGPU_WARMUP")) {  // tests force short warm-ups to exercise the mismatch path
         const uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
         const uint32_t u = rna ? 16u : 8u;
