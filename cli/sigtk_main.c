@@ -1,4 +1,4 @@
-/* sigtk_main.c -- drop-in `sigtk event | pa | stat` on top of the B200 hot path (C99 host, links slow5lib).
+/* sigtk_main.c -- drop-in `sigtk event | pa | stat | ent` on top of the B200 hot path (C99 host, links slow5lib).
  *
  * Same command line, stdout bytes, stderr information lines and exit codes as the reference tool for the three
  * sub-commands of the raw-signal path:
@@ -7,6 +7,7 @@
  *                                    read-id random access)
  *     reference src/cfunc.c:16-159  (output formats of event / pa / stat)
  *     reference src/misc.c:34-101   (DNA/RNA and pore detection from the BLOW5 header)
+ *     reference src/ent.c:67-177    (`ent`: its own option set, usage text, header and "%f" line per record)
  * What changes is the execution model: instead of one record -> compute -> printf, decoded records are batched
  * into pinned slots of the CUDA library (include/sigtk_b200.h), several batches are in flight on one or more
  * GPUs, and the per-read results are printed in input order.  There is no CPU implementation of the path in
@@ -43,7 +44,7 @@
 #define ERROR(msg, ...) \
     fprintf(stderr, "[%s::ERROR]\033[1;31m " msg "\033[0m At %s:%d\n", __func__, __VA_ARGS__, __FILE__, __LINE__ - 1)
 
-enum { MODE_EVENT, MODE_PA, MODE_STAT };
+enum { MODE_EVENT, MODE_PA, MODE_STAT, MODE_ENT };
 
 typedef struct {
     int mode;
@@ -284,6 +285,8 @@ static void print_header(const opt_t *opt) {
         else printf("read_id\tevent_idx\traw_start\traw_end\tevent_mean\tevent_std\n");
     } else if (opt->mode == MODE_STAT) {
         printf("read_id\tlen_raw_signal\traw_mean\tpa_mean\traw_std\tpa_std\traw_median\tpa_median\n");
+    } else if (opt->mode == MODE_ENT) { /* ent.c:106 */
+        printf("read_id\traw_ent\tdelta_ent\tbyte_ent\n");
     } else {
         printf("read_id\tlen_raw_signal\tpa\n");
     }
@@ -353,6 +356,12 @@ static void format_read(const opt_t *opt, const sgpu_result_t *res, const sgpu_b
         }
         p = obuf_reserve(o, 1);
         *p++ = '\n';
+        o->len = (size_t)(p - o->p);
+    } else if (opt->mode == MODE_ENT) { /* ent.c:109,113,132,148,163: "%s\t" "%f" "\t%f" "\t%f" "\n" with doubles */
+        const double *h = res->ent + (size_t)r * 3;
+        p = obuf_reserve(o, idl + 256);
+        memcpy(p, rid, idl); p += idl;
+        p += snprintf(p, 200, "\t%f\t%f\t%f\n", h[0], h[1], h[2]);
         o->len = (size_t)(p - o->p);
     } else { /* cfunc.c:126-159: note the tab before the newline */
         const float *s = res->stat + (size_t)r * 6;
@@ -616,7 +625,8 @@ static struct option long_options[] = {{"verbose", required_argument, 0, 'v'},
                                        {0, 0, 0, 0}};
 
 static int cmain(int argc, char *argv[], const char *mode) {
-    const char *optstring = "o:hVnc";
+    const int is_ent = strcmp(mode, "ent") == 0;
+    const char *optstring = is_ent ? "hV" : "o:hVnc"; /* ent.c:70: `ent` only has -h, -V and --no-header */
     int longindex = 0, c = -1;
     FILE *fp_help = stderr;
     int hdr = 1, n_gpus = 1, n_threads = 0, cpu_decode = 0;
@@ -645,6 +655,15 @@ static int cmain(int argc, char *argv[], const char *mode) {
             cpu_decode = 1;
         }
     }
+    if (is_ent && (argc - optind != 1 || fp_help == stdout)) { /* ent.c:90-100 */
+        fprintf(fp_help, "Usage: sigtk ent a.blow5\n");
+        fprintf(fp_help, "\nbasic options:\n");
+        fprintf(fp_help, "   -h                         help\n");
+        fprintf(fp_help, "   -n                         suppress header\n");
+        fprintf(fp_help, "   --version                  print version\n");
+        if (fp_help == stdout) exit(EXIT_SUCCESS);
+        exit(EXIT_FAILURE);
+    }
     if (argc - optind < 1 || fp_help == stdout) {
         fprintf(fp_help, "Usage: sigtk %s reads.blow5 read_id1 read_id2 .. \n", mode);
         fprintf(fp_help, "       sigtk %s reads.blow5\n", mode);
@@ -658,12 +677,18 @@ static int cmain(int argc, char *argv[], const char *mode) {
     }
     slow5_file_t *sp = slow5_open(argv[optind], "r");
     if (!sp) {
-        ERROR("cannot open %s. \n", argv[optind]);
+        if (is_ent) fprintf(stderr, "Error in opening file\n"); /* ent.c:104 */
+        else ERROR("cannot open %s. \n", argv[optind]);
         exit(EXIT_FAILURE);
     }
-    eng.opt.rna = drna_detect(sp);
-    pore_detect(sp);
-    if (strcmp(mode, "event") == 0) {
+    if (!is_ent) { /* entmain does not look at the header (ent.c:102-107) */
+        eng.opt.rna = drna_detect(sp);
+        pore_detect(sp);
+    }
+    if (is_ent) {
+        eng.opt.mode = MODE_ENT;
+        eng.want = SGPU_WANT_ENT;
+    } else if (strcmp(mode, "event") == 0) {
         eng.opt.mode = MODE_EVENT;
         eng.want = SGPU_WANT_EVENTS;
     } else if (strcmp(mode, "stat") == 0) {
@@ -837,7 +862,8 @@ static int print_usage(FILE *fp_help) {
     fprintf(fp_help, "         pa        print raw signal in pico-amperes\n");
     fprintf(fp_help, "         event     segment raw signal into events\n");
     fprintf(fp_help, "         stat      print statistics of the raw signal\n");
-    fprintf(fp_help, "(B200 build: the raw-signal hot path only; sref, prefix, jnn, ss, ent and qts are served by the\n");
+    fprintf(fp_help, "         ent       entropy of the raw signal, its zig-zag deltas and their byte planes\n");
+    fprintf(fp_help, "(B200 build: the raw-signal hot path only; sref, prefix, jnn, ss and qts are served by the\n");
     fprintf(fp_help, " reference sigtk)\n");
     exit(fp_help == stderr ? EXIT_FAILURE : EXIT_SUCCESS);
 }
@@ -849,7 +875,8 @@ int main(int argc, char *argv[]) {
     setvbuf(stdout, outbuf, _IOFBF, sizeof outbuf);
     if (argc < 2) {
         return print_usage(stderr);
-    } else if (strcmp(argv[1], "event") == 0 || strcmp(argv[1], "stat") == 0 || strcmp(argv[1], "pa") == 0) {
+    } else if (strcmp(argv[1], "event") == 0 || strcmp(argv[1], "stat") == 0 || strcmp(argv[1], "pa") == 0 ||
+               strcmp(argv[1], "ent") == 0) {
         ret = cmain(argc - 1, argv + 1, argv[1]);
     } else if (strcmp(argv[1], "--version") == 0 || strcmp(argv[1], "-V") == 0) {
         fprintf(stdout, "sigtk %s\n", SIGTK_VERSION);
@@ -857,7 +884,7 @@ int main(int argc, char *argv[]) {
     } else if (strcmp(argv[1], "--help") == 0 || strcmp(argv[1], "-h") == 0) {
         print_usage(stdout);
     } else if (strcmp(argv[1], "sref") == 0 || strcmp(argv[1], "prefix") == 0 || strcmp(argv[1], "jnn") == 0 ||
-               strcmp(argv[1], "ss") == 0 || strcmp(argv[1], "ent") == 0 || strcmp(argv[1], "qts") == 0) {
+               strcmp(argv[1], "ss") == 0 || strcmp(argv[1], "qts") == 0) {
         fprintf(stderr, "[sigtk] command %s is outside the B200 raw-signal hot path; use the reference sigtk for it\n",
                 argv[1]);
         exit(EXIT_FAILURE);

@@ -9,6 +9,8 @@
  *   - event_table getevents(size_t, float*, int8_t rna)  src/sigtk.h:134, src/events.c:553-573
  *   - meanf/stdvf/medianf/meani16/stdvi16/mediani16      src/stat.h:17-73 (as used by stat_func,
  *                                                        src/cfunc.c:126-159)
+ *   - double entropy(int16_t*, uint64_t) and the zig-zag-delta / byte-plane loop of entmain
+ *                                                        src/ent.c:25-51, 56-65, 108-151
  * The reference calls those once per record from a callback
  * `void (*func)(slow5_rec_t*, opt_t)` (src/cmain.c:95-126).  Here the unit of
  * work is a BATCH of records: the host appends decoded records to a pinned
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SGPU_ABI_VERSION 2
+#define SGPU_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------- */
 #define SGPU_OK            0
@@ -50,6 +52,7 @@ extern "C" {
 #define SGPU_WANT_EVENTS   1u /* event table: getevents(), events.c:553-573 */
 #define SGPU_WANT_PA       2u /* materialise pA floats: signal_in_picoamps(), misc.c:15-32 */
 #define SGPU_WANT_STAT     4u /* the six numbers of stat_func, cfunc.c:126-159 */
+#define SGPU_WANT_ENT      8u /* the three entropies of `sigtk ent`, ent.c:108-151 */
 
 /* ---- context flags ------------------------------------------------------ */
 #define SGPU_F_DEFAULT       0u
@@ -95,6 +98,10 @@ typedef struct {
     uint32_t *fixups;      /* [n_reads] number of detector chunks whose warm-up state did not match (the read is then redone
                               by the sequential-order kernels) */
     uint64_t  n_events;    /* total events in the batch (host result only; 0 from sgpu_run_device) */
+    double   *ent;         /* [n_reads][3]: raw_ent, delta_ent, byte_ent in bits (ent.c:108-151); NULL unless
+                              SGPU_WANT_ENT. Histogram counts are exact and the terms are summed in the reference's
+                              order; log2 is CUDA's (<= 1 ulp), so the doubles agree to ~1e-15 and "%f" prints alike.
+                              An empty record (where the reference crashes) gives zeros. */
 } sgpu_result_t;
 
 /* ---- lifecycle ----------------------------------------------------------- */

@@ -231,6 +231,48 @@ static int cmp_float(const void *a, const void *b) {
 
 /* cfunc.c:126-159 + stat.h:17-73 (sequential float accumulators; the median
  * is the element of rank n/2, ksort.h:233-259) */
+/* Shannon entropy in bits of a table of bin counts taken over `total` symbols; terms are subtracted in
+ * ascending bin order like ent.c:38-46 (the order matters in the last bits). */
+static double bits_of_counts(const uint64_t *cnt, uint32_t bins, uint64_t total) {
+    double h = 0.0;
+    for (uint32_t k = 0; k < bins; k++) {
+        if (cnt[k] == 0) continue;
+        const double p = (double)cnt[k] / (double)total;
+        h -= p * log2(p);
+    }
+    return h;
+}
+
+/* ent.c:108-151. The reference materialises four arrays per record (int32 copy, zig-zag deltas, the deltas
+ * narrowed to int16, two byte planes) and calls entropy() on each; the same four count tables are filled
+ * here in one pass. Keys: (uint16)raw[i] for i < n; for i < n-1 the low 16 bits of zigzag32(raw[i]-raw[i-1])
+ * with raw[-1] = 0 (ent.c:62,124,128), and that key's high / low byte (ent.c:144-145). */
+void orc_ent(const int16_t *raw, uint64_t n, double *out3) {
+    out3[0] = out3[1] = out3[2] = 0.0;
+    if (n == 0) return;
+    uint64_t *tab = (uint64_t *)calloc(65536 * 2 + 512, sizeof(uint64_t));
+    uint64_t *c_raw = tab, *c_dlt = tab + 65536, *c_hi = tab + 131072, *c_lo = tab + 131072 + 256;
+    int32_t before = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const int32_t cur = raw[i];
+        c_raw[(uint16_t)raw[i]]++;
+        if (i + 1 < n) {
+            const int32_t d = cur - before;
+            const uint16_t key = (uint16_t)(((uint32_t)d << 1) ^ (uint32_t)(d >> 31));
+            c_dlt[key]++;
+            c_hi[key >> 8]++;
+            c_lo[key & 0xff]++;
+        }
+        before = cur;
+    }
+    out3[0] = bits_of_counts(c_raw, 65536, n);
+    if (n > 1) {
+        out3[1] = bits_of_counts(c_dlt, 65536, n - 1);
+        out3[2] = bits_of_counts(c_hi, 256, n - 1) + bits_of_counts(c_lo, 256, n - 1);
+    }
+    free(tab);
+}
+
 void orc_stat(const int16_t *raw, uint64_t n, double digitisation, double offset,
               double range, float *out6) {
     const int ni = (int)n;

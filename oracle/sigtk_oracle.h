@@ -73,6 +73,10 @@ int64_t orc_event_read(const int16_t *raw, uint64_t n, double digitisation,
 void orc_stat(const int16_t *raw, uint64_t n, double digitisation, double offset,
               double range, float *out6);
 
+/* `sigtk ent` numbers for one record (ent.c:25-51 entropy, 56-65 zig-zag delta, 108-151 the loop of entmain) in
+ * print order: raw_ent, delta_ent, byte_ent. n == 0 gives zeros (the reference crashes there: len-1 wraps). */
+void orc_ent(const int16_t *raw, uint64_t n, double *out3);
+
 /* svb-zd signal stream of a BLOW5 record (slow5_press.c:1055-1150, streamvbyte_decode.c:30-83,
  * streamvbyte_zigzag.c): encode returns the stream length in bytes (cap >= orc_svbzd_bound(n)), decode the
  * number of samples; -1 on a malformed stream. */

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (ALIGN, F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, F_STAGE_TIMERS, WANT_EVENTS, WANT_PA,
-                   WANT_STAT, SgpuError)
+                   WANT_STAT, WANT_ENT, SgpuError)
 
 Read = Tuple[np.ndarray, float, float, float]  # raw int16, digitisation, offset, range
 
@@ -47,6 +47,7 @@ class BatchResult:
     ev_stdv: Optional[np.ndarray] = None
     pa: Optional[List[np.ndarray]] = None
     stat: Optional[np.ndarray] = None
+    ent: Optional[np.ndarray] = None   # [n_reads][3] float64: raw_ent, delta_ent, byte_ent (ent.c:108-151)
     seq_order: Optional[np.ndarray] = None
     fixups: Optional[np.ndarray] = None
 
@@ -154,6 +155,8 @@ class Context:
             out.fixups = _np_from(res.fixups, np.uint32, n)
         if want & WANT_STAT:
             out.stat = _np_from(res.stat, np.float32, n * 6).reshape(n, 6)
+        if want & WANT_ENT:
+            out.ent = _np_from(res.ent, np.float64, n * 3).reshape(n, 3)
         if want & WANT_PA:
             span = int(read_off[n]) if n else 0
             flat = _np_from(res.pa, np.float32, span)
@@ -209,3 +212,8 @@ def getevents(ctx: Context, raw: np.ndarray, digitisation: float, offset: float,
 def stat(ctx: Context, raw: np.ndarray, digitisation: float, offset: float, range_: float) -> np.ndarray:
     """The six numbers of stat_func (cfunc.c:126-159) for one record."""
     return ctx.run([(raw, digitisation, offset, range_)], 0, WANT_STAT).stat[0]
+
+
+def ent(ctx: Context, raw: np.ndarray) -> np.ndarray:
+    """raw_ent, delta_ent, byte_ent of one record as `sigtk ent` prints them (ent.c:108-151)."""
+    return ctx.run([(raw, 8192.0, 0.0, 1.0)], 0, WANT_ENT).ent[0]

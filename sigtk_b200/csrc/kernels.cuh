@@ -98,4 +98,9 @@ int launch_svbzd_decode(const SvbBatch& s, SvbScratch& w, Scratch& sc, int16_t* 
 // stat.cu
 int launch_stat(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st);
 
+
+// ent.cu (`sigtk ent`: entropies of the raw samples, their zig-zag deltas and the deltas' byte planes)
+uint64_t ent_overflow_words(int sm_count);
+int launch_ent(const DevBatch& b, uint32_t* overflow, double* out3, int sm_count, cudaStream_t st);
+
 }  // namespace sgpu

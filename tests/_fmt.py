@@ -41,6 +41,12 @@ def stat_line(read_id, n, st) -> str:
                                                     int(st[4]), f6(st[5]))
 
 
+def ent_line(read_id, e3) -> str:
+    """entmain's per-record line (ent.c:108-163): three "%f" doubles"""
+    return "%s\t%s\t%s\t%s\n" % (read_id, f6(e3[0]), f6(e3[1]), f6(e3[2]))
+
+
+ENT_HDR = "read_id\traw_ent\tdelta_ent\tbyte_ent\n"
 EVENT_HDR_LONG = "read_id\tevent_idx\traw_start\traw_end\tevent_mean\tevent_std\n"
 EVENT_HDR_COMPACT = "read_id\tlen_raw_signal\traw_start\traw_end\tnum_event\tevents\n"
 PA_HDR = "read_id\tlen_raw_signal\tpa\n"

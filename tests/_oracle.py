@@ -136,6 +136,8 @@ class Oracle(_EventLib):
 
         self.Params, self.Det = Params, Det
         L.orc_params.argtypes = [C.c_int, C.POINTER(Params)]
+        L.orc_ent.argtypes = [_i16p, C.c_uint64, _f64p]
+        L.orc_ent.restype = None
         L.orc_prefix.argtypes = [_f32p, C.c_uint64, _f64p, _f64p]
         L.orc_tstat.argtypes = [_f64p, _f64p, C.c_uint64, C.c_uint32, _f32p]
         L.orc_det_init.argtypes = [C.POINTER(Det), C.POINTER(Det)]
@@ -143,6 +145,13 @@ class Oracle(_EventLib):
         L.orc_detect.restype = C.c_uint64
         L.orc_detect.argtypes = [_f32p, _f32p, C.c_uint64, C.c_uint64, C.POINTER(Params), C.POINTER(Det),
                                  C.POINTER(Det), _u64p, C.c_uint64]
+
+    def ent(self, raw):
+        """raw_ent, delta_ent, byte_ent of one record (ent.c:108-151) as float64[3]"""
+        raw = np.ascontiguousarray(raw, dtype=np.int16)
+        out = np.zeros(3, dtype=np.float64)
+        self.lib.orc_ent(_p(raw, _i16p), raw.shape[0], _p(out, _f64p))
+        return out
 
     def params(self, rna):
         p = self.Params()

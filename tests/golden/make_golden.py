@@ -11,6 +11,11 @@ Nothing here runs on the GPU box; the fixtures it writes are committed.
   synth_rna.blow5 / .npz            12 seeded synthetic RNA reads, experiment_type=rna (BASELINE config C2;
                                     the real test/sequin_rna.blow5 is a missing large blob)
   ref_rna_{event,event_c,stat}.txt* stdout of the compiled reference on synth_rna.blow5
+  ref_{sp1,rna}_ent.txt             stdout of `sigtk ent` (src/ent.c) on the two files
+  ent_adversarial.npz / ref_ent_adversarial.txt
+                                    seeded reads that leave the narrow value range of real signals (full-range noise,
+                                    negative values, +-32767 steps, constant, 1- and 2-sample records) and what the
+                                    compiled reference's `sigtk ent` prints for them   (`make_golden.py ent` makes only these)
 """
 import gzip
 import hashlib
@@ -68,7 +73,51 @@ def write_blow5(reads, ids, path, exp_type):
     subprocess.run([os.path.join(BIN, "blow5_write"), path, exp_type], input=bytes(blob), check=True)
 
 
+def ent_adversarial_reads():
+    """every |raw[i]-raw[i-1]| stays below 16,384: beyond that the reference aborts (assert c==out[i], ent.c:154)"""
+    rng = np.random.default_rng(20260017)
+    reads = []
+    reads.append(rng.integers(-8191, 8192, 70000).astype(np.int16))               # 16,383 keys; deltas up to 16,382
+    reads.append(rng.integers(-300, 300, 9000).astype(np.int16))                  # keys wrap around 0 / 65535
+    reads.append(np.where(rng.random(5000) < 0.5, 8000, -8000).astype(np.int16))  # deltas of +-16,000
+    reads.append(np.full(3000, 511, dtype=np.int16))                              # one raw bin: entropy 0
+    reads.append(np.array([1234], dtype=np.int16))                                # n = 1: no deltas
+    reads.append(np.array([-5, 17], dtype=np.int16))                              # n = 2: one delta
+    base = (600 + 80 * rng.standard_normal(40000)).astype(np.int16)
+    base[::997] = 8000                                                            # spikes leave the raw window
+    base[5::1999] = -7000
+    reads.append(base)
+    reads.append((rng.integers(0, 2, 20000) * 4096 + 100 + rng.integers(0, 40, 20000)).astype(np.int16))  # window edge
+    reads.append(np.arange(-8000, 8000, dtype=np.int32).astype(np.int16))         # 16,000 equal bins
+    reads.append((-9000 + rng.integers(-200, 200, 30000)).astype(np.int16))       # all negative (keys >= 32768)
+    return [(r, 8192.0, 3.0, 1402.882324) for r in reads]
+
+
+def ent_goldens():
+    sp1 = os.path.join(HERE, "sp1_dna.blow5")
+    rna = os.path.join(HERE, "synth_rna.blow5")
+    open(os.path.join(HERE, "ref_sp1_ent.txt"), "wb").write(run([SIGTK, "ent", sp1]))
+    open(os.path.join(HERE, "ref_rna_ent.txt"), "wb").write(run([SIGTK, "ent", rna]))
+    reads = ent_adversarial_reads()
+    ids = [f"ent-adv-{i:02d}" for i in range(len(reads))]
+    tmp = os.path.join(HERE, "_ent_adv.blow5")
+    write_blow5(reads, ids, tmp, "genomic_dna")
+    open(os.path.join(HERE, "ref_ent_adversarial.txt"), "wb").write(run([SIGTK, "ent", tmp]))
+    os.remove(tmp)
+    lens = [r[0].shape[0] for r in reads]
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    np.savez_compressed(os.path.join(HERE, "ent_adversarial.npz"), read_ids=np.array(ids),
+                        samples=np.concatenate([r[0] for r in reads]), read_off=off,
+                        digitisation=np.array([r[1] for r in reads]), offset=np.array([r[2] for r in reads]),
+                        range=np.array([r[3] for r in reads]))
+
+
 def main():
+    if sys.argv[1:] == ["ent"]:
+        ent_goldens()
+        print("ent fixtures written to", HERE)
+        return
     sha = {}
     shutil.copyfile(os.path.join(REF, "test", "sp1_dna.blow5"), os.path.join(HERE, "sp1_dna.blow5"))
     shutil.copyfile(os.path.join(REF, "test", "event_dna.exp"), os.path.join(HERE, "event_dna.exp"))
@@ -104,6 +153,7 @@ def main():
         f.write(full)
     full = run([SIGTK, "pa", rna])
     sha["rna_pa"] = hashlib.sha256(full).hexdigest()
+    ent_goldens()
     json.dump(sha, open(os.path.join(HERE, "sha256.json"), "w"), indent=1, sort_keys=True)
     print("golden fixtures written to", HERE)
 

@@ -89,6 +89,38 @@ def test_no_header_version_help_and_errors(sp1):
     assert r.returncode == 1
 
 
+def test_ent_equals_the_reference_stdout(sp1, tmp_path):
+    """`sigtk ent` (src/ent.c): stdout of the compiled reference on the DNA file, the synthetic RNA file and a BLOW5 of
+    reads with wide / wrapped / single-bin histograms (tests/golden/ent_adversarial.npz); its own option set"""
+    import struct
+    import numpy as np
+    exp = open(os.path.join(G, "ref_sp1_ent.txt"), "rb").read()
+    p = run(["ent", sp1])
+    assert p.stdout == exp
+    assert b"data detected" not in p.stderr and b"Real time:" in p.stderr  # entmain does not inspect the header
+    assert run(["ent", "--cpu-decode", "--batch-samples", "30000", sp1]).stdout == exp
+    assert run(["ent", "--no-header", sp1]).stdout == exp.split(b"\n", 1)[1]
+    assert run(["ent", RNA]).stdout == open(os.path.join(G, "ref_rna_ent.txt"), "rb").read()
+    assert run(["ent", "-h"]).stdout.startswith(b"Usage: sigtk ent a.blow5\n")
+    r = subprocess.run([CLI, "ent", sp1, "some-read-id"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and r.stderr.startswith(b"Usage: sigtk ent a.blow5\n")
+    r = subprocess.run([CLI, "ent", "/nonexistent.blow5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"Error in opening file" in r.stderr
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "blow5_write")):
+        return
+    d = np.load(os.path.join(G, "ent_adversarial.npz"))
+    path = str(tmp_path / "ent_adv.blow5")
+    w = subprocess.Popen([os.path.join(ROOT, "oracle", "_ref", "blow5_write"), path, "genomic_dna"], stdin=subprocess.PIPE)
+    for r in range(len(d["read_ids"])):
+        raw = d["samples"][int(d["read_off"][r]):int(d["read_off"][r + 1])]
+        rid = str(d["read_ids"][r]).encode()
+        w.stdin.write(struct.pack("<I", len(rid)) + rid + struct.pack("<Qddd", len(raw), float(d["digitisation"][r]),
+                      float(d["offset"][r]), float(d["range"][r])) + raw.tobytes())
+    w.stdin.close()
+    assert w.wait() == 0
+    assert run(["ent", path]).stdout == open(os.path.join(G, "ref_ent_adversarial.txt"), "rb").read()
+
+
 def test_two_gpus_same_bytes(sp1):
     import ctypes as C
     from sigtk_b200 import _lib

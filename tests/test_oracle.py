@@ -88,6 +88,40 @@ def test_rna_stat(orc, rna):
     assert got == exp
 
 
+# ---- `sigtk ent` ---------------------------------------------------------------
+@pytest.mark.parametrize("npz,txt", [("sp1_dna.npz", "ref_sp1_ent.txt"), ("synth_rna.npz", "ref_rna_ent.txt"),
+                                     ("ent_adversarial.npz", "ref_ent_adversarial.txt")])
+def test_ent_equals_reference_stdout(orc, npz, txt):
+    """orc_ent against the stdout of the compiled reference's `sigtk ent` (same libm: bit-identical doubles, so the
+    text must be identical), including reads with wrapped / wide / single-bin histograms and 1- and 2-sample records"""
+    reads = _fmt.load_npz(os.path.join(G, npz))
+    exp = open(os.path.join(G, txt)).read()
+    got = _fmt.ENT_HDR + "".join(_fmt.ent_line(rid, orc.ent(rd[0])) for rid, rd in reads)
+    assert got == exp
+
+
+def test_ent_against_numpy_histograms(orc):
+    """independent restatement with numpy (bincount + log2; pairwise instead of sequential summation, hence 1e-10);
+    also where the reference aborts (|delta| >= 16384)"""
+    rng = np.random.default_rng(5)
+    for raw in (rng.integers(-32768, 32768, 50000).astype(np.int16), rng.integers(300, 900, 777).astype(np.int16),
+                np.array([7], dtype=np.int16), np.zeros(0, dtype=np.int16)):
+        def H(keys, total):
+            c = np.bincount(keys, minlength=1)
+            p = c[c > 0] / float(total)
+            return float(-(p * np.log2(p)).sum()) if total else 0.0
+        n = raw.shape[0]
+        exp = np.zeros(3)
+        if n:
+            exp[0] = H(raw.view(np.uint16).astype(np.int64), n)
+        if n > 1:
+            d = np.diff(np.concatenate([[0], raw.astype(np.int64)]))[: n - 1]
+            z = (((d << 1) ^ (d >> 63)) & 0xffff)
+            exp[1] = H(z, n - 1)
+            exp[2] = H(z >> 8, n - 1) + H(z & 255, n - 1)
+        assert np.allclose(orc.ent(raw), exp, rtol=0, atol=1e-10)
+
+
 def _bits(a):
     return a.view(np.uint32) if a.dtype == np.float32 else a
 
