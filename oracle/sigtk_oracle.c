@@ -231,6 +231,69 @@ static int cmp_float(const void *a, const void *b) {
 
 /* cfunc.c:126-159 + stat.h:17-73 (sequential float accumulators; the median
  * is the element of rank n/2, ksort.h:233-259) */
+/* jnn.c:176-266 for the raw-sample entry point (jnn.c:269-282, 58-75). The thresholds are mean -/+ 0.75 standard
+ * deviations of the clamped signal, both accumulated in float in sample order (stat.h:17-24, 36-44). The segmenter is
+ * a counter machine over one bit per sample ("inside the band or not"); it is written here as a switch on that bit
+ * and on whether a stretch is open, with the reference's counters:
+ *   run   : samples in the open stretch, tolerated outliers included        (c)
+ *   grow  : 50 + every inside sample of the record so far                   (w; never reset)
+ *   bad   : tolerated outliers of the stretch (< 5)                         (err)
+ *   tail  : outliers at the very end of the stretch                         (prev_err)            */
+int64_t orc_jnn(const int16_t *raw, uint64_t n, int rna, uint64_t cap, int64_t *xy) {
+    if (n == 0) return 0;
+    const int ni = (int)n;
+    const int window = rna ? 1000 : 150;                 /* jnn.h:24-45 */
+    const float stall = rna ? 1.0f : 0.25f;
+    const float scale = 0.75f;
+    const int tolerated = 5, merge_dist = 50;
+    float *sig = (float *)malloc((size_t)ni * sizeof(float));
+    float acc = 0.0f;
+    for (int i = 0; i < ni; i++) {
+        const int v = raw[i];
+        sig[i] = v > 1200 ? 1200.0f : v < 0 ? 0.0f : (float)v;
+        acc = acc + sig[i];
+    }
+    const float mean = acc / (float)ni;
+    float dev = 0.0f;
+    for (int i = 0; i < ni; i++) {
+        const float d = sig[i] - mean;
+        dev = dev + d * d;
+    }
+    const float sd = sqrtf(dev / (float)ni);
+    const float band = sd * scale;
+    const float hi = mean + band, lo = mean - band;
+
+    int open = 0, run = 0, grow = 50, bad = 0, tail = 0, first = 0;
+    int64_t n_seg = 0, last_y = 0;
+    for (int i = 0; i < ni; i++) {
+        const int inside = sig[i] < hi && sig[i] > lo;
+        if (inside) {
+            if (!open) { open = 1; first = i; }
+            run++; grow++; tail = 0;
+            if (run >= window && run >= grow && run % grow == 0) bad--;
+        } else if (open) {
+            if (bad < tolerated) {
+                run++; bad++; tail++;
+                if (run >= window && run >= grow && run % grow == 0) bad--;
+            } else {
+                if (run >= window || (n_seg == 0 && (float)run >= (float)window * stall)) {
+                    const int stop = i - tail;
+                    if (n_seg && first - last_y < merge_dist) {
+                        if ((uint64_t)n_seg <= cap) xy[2 * (n_seg - 1) + 1] = stop;
+                    } else {
+                        if ((uint64_t)n_seg < cap) { xy[2 * n_seg] = first; xy[2 * n_seg + 1] = stop; }
+                        n_seg++;
+                    }
+                    last_y = stop;
+                }
+                open = 0; run = 0; bad = 0; tail = 0;
+            }
+        }
+    }
+    free(sig);
+    return (uint64_t)n_seg > cap ? -n_seg : n_seg;
+}
+
 /* Shannon entropy in bits of a table of bin counts taken over `total` symbols; terms are subtracted in
  * ascending bin order like ent.c:38-46 (the order matters in the last bits). */
 static double bits_of_counts(const uint64_t *cnt, uint32_t bins, uint64_t total) {

@@ -77,6 +77,12 @@ void orc_stat(const int16_t *raw, uint64_t n, double digitisation, double offset
  * print order: raw_ent, delta_ent, byte_ent. n == 0 gives zeros (the reference crashes there: len-1 wraps). */
 void orc_ent(const int16_t *raw, uint64_t n, double *out3);
 
+/* `sigtk jnn` segments of one record: jnn_raw (jnn.c:269-282) = rm_outlier (58-75: clamp to [0,1200]) + jnn_core
+ * (176-266) with the parameters jnn_print picks (305-312: JNNV1_DRNA_R9_PARAM for rna, JNNV1_CDNA_R9_PARAM
+ * otherwise, jnn.h:24-45). Writes up to cap pairs (x,y) to xy[2k], xy[2k+1]; returns the number of segments
+ * (or -(needed) when cap is too small). */
+int64_t orc_jnn(const int16_t *raw, uint64_t n, int rna, uint64_t cap, int64_t *xy);
+
 /* svb-zd signal stream of a BLOW5 record (slow5_press.c:1055-1150, streamvbyte_decode.c:30-83,
  * streamvbyte_zigzag.c): encode returns the stream length in bytes (cap >= orc_svbzd_bound(n)), decode the
  * number of samples; -1 on a malformed stream. */

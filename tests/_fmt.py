@@ -46,6 +46,35 @@ def ent_line(read_id, e3) -> str:
     return "%s\t%s\t%s\t%s\n" % (read_id, f6(e3[0]), f6(e3[1]), f6(e3[2]))
 
 
+def jnn_line(read_id, n, segs, compact=False, have_signal=True) -> str:
+    """jnn_func (cfunc.c:108-117) + jnn_print (jnn.c:303-343)"""
+    s = "%s\t%d\t" % (read_id, n)
+    if have_signal:
+        s += "%d\t" % len(segs)
+        if compact:
+            ci = 0
+            for x, y in segs:
+                mi = (int(x) - ci) & 0xFFFFFFFFFFFFFFFF
+                ci = (ci + mi) & 0xFFFFFFFFFFFFFFFF
+                if mi:
+                    s += "%dH" % _i32(mi)
+                mi = (int(y) - ci) & 0xFFFFFFFFFFFFFFFF
+                ci = (ci + mi) & 0xFFFFFFFFFFFFFFFF
+                if mi:
+                    s += "%d," % _i32(mi)
+        else:
+            s += "".join("%d,%d;" % (int(x), int(y)) for x, y in segs)
+        if len(segs) == 0:
+            s += "."
+    return s + "\n"
+
+
+def _i32(u):
+    u &= 0xFFFFFFFF
+    return u - (1 << 32) if u >= (1 << 31) else u
+
+
+JNN_HDR = "read_id\tlen_raw_signal\tnum_seg\tseg\n"
 ENT_HDR = "read_id\traw_ent\tdelta_ent\tbyte_ent\n"
 EVENT_HDR_LONG = "read_id\tevent_idx\traw_start\traw_end\tevent_mean\tevent_std\n"
 EVENT_HDR_COMPACT = "read_id\tlen_raw_signal\traw_start\traw_end\tnum_event\tevents\n"

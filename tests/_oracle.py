@@ -138,6 +138,8 @@ class Oracle(_EventLib):
         L.orc_params.argtypes = [C.c_int, C.POINTER(Params)]
         L.orc_ent.argtypes = [_i16p, C.c_uint64, _f64p]
         L.orc_ent.restype = None
+        L.orc_jnn.argtypes = [_i16p, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(C.c_int64)]
+        L.orc_jnn.restype = C.c_int64
         L.orc_prefix.argtypes = [_f32p, C.c_uint64, _f64p, _f64p]
         L.orc_tstat.argtypes = [_f64p, _f64p, C.c_uint64, C.c_uint32, _f32p]
         L.orc_det_init.argtypes = [C.POINTER(Det), C.POINTER(Det)]
@@ -152,6 +154,15 @@ class Oracle(_EventLib):
         out = np.zeros(3, dtype=np.float64)
         self.lib.orc_ent(_p(raw, _i16p), raw.shape[0], _p(out, _f64p))
         return out
+
+    def jnn(self, raw, rna=0):
+        """segments of `sigtk jnn` for one record (jnn.c:176-282) as int64[k][2]"""
+        raw = np.ascontiguousarray(raw, dtype=np.int16)
+        cap = raw.shape[0] // 32 + 2
+        xy = np.zeros(2 * cap, dtype=np.int64)
+        k = self.lib.orc_jnn(_p(raw, _i16p), raw.shape[0], int(rna), cap, xy.ctypes.data_as(C.POINTER(C.c_int64)))
+        assert k >= 0, k
+        return xy[:2 * k].reshape(k, 2).copy()
 
     def params(self, rna):
         p = self.Params()

@@ -16,6 +16,11 @@ Nothing here runs on the GPU box; the fixtures it writes are committed.
                                     seeded reads that leave the narrow value range of real signals (full-range noise,
                                     negative values, +-32767 steps, constant, 1- and 2-sample records) and what the
                                     compiled reference's `sigtk ent` prints for them   (`make_golden.py ent` makes only these)
+  ref_{sp1,rna}_jnn{,_c}.txt        stdout of `sigtk jnn` / `jnn -c` (src/jnn.c) on the two files
+  jnn_stalls_{dna,rna}.npz / ref_jnn_stalls_{dna,rna}{,_c}.txt
+                                    seeded reads with stalls (long stretches near the read's mean, a few outliers inside,
+                                    pairs closer than the merge distance, open stretches at the end, clipped spikes) and
+                                    the compiled reference's `sigtk jnn` stdout             (`make_golden.py jnn`)
 """
 import gzip
 import hashlib
@@ -113,7 +118,63 @@ def ent_goldens():
                         range=np.array([r[3] for r in reads]))
 
 
+def jnn_stall_reads(rna):
+    rng = np.random.default_rng(20260018 + int(rna))
+    win = 1000 if rna else 150
+    reads = []
+    for k in range(14):
+        n = int(rng.integers(6 * win, 60 * win))
+        raw = (500 + 90 * rng.standard_normal(n)).astype(np.int64)
+        level = np.repeat(rng.integers(-150, 150, n // 40 + 1), 40)[:n]
+        raw += level
+        pos = int(rng.integers(0, win))
+        while pos < n:
+            length = int(rng.integers(win // 5, 4 * win))
+            stop = min(n, pos + length)
+            raw[pos:stop] = 500 + rng.integers(-12, 13, stop - pos)          # a stall: inside the band
+            if k % 3 == 0 and stop - pos > 50:
+                bad = rng.integers(pos + 5, stop - 5, int(rng.integers(1, 8)))  # a few outliers inside (tolerated up to 5)
+                raw[bad] = 900
+            pos = stop + int(rng.integers(5, 60) if k % 2 else rng.integers(40, 6 * win))  # gaps around the merge distance
+        if k % 4 == 0:
+            raw[::1013] = 5000                                               # clipped to 1200 by rm_outlier
+            raw[7::2029] = -300                                              # clipped to 0
+        if k == 5:
+            raw[-2 * win:] = 500                                             # a stretch still open at the end
+        reads.append((np.clip(raw, -32768, 32767).astype(np.int16), 8192.0, 3.0, 1402.882324))
+    reads.append((np.full(5 * win, 480, dtype=np.int16), 8192.0, 3.0, 1402.882324))  # zero deviation: empty band
+    reads.append((np.array([5, 900, 20], dtype=np.int16), 8192.0, 3.0, 1402.882324))
+    return reads
+
+
+def jnn_goldens():
+    sp1 = os.path.join(HERE, "sp1_dna.blow5")
+    rna = os.path.join(HERE, "synth_rna.blow5")
+    for tag, path in (("sp1", sp1), ("rna", rna)):
+        open(os.path.join(HERE, f"ref_{tag}_jnn.txt"), "wb").write(run([SIGTK, "jnn", path]))
+        open(os.path.join(HERE, f"ref_{tag}_jnn_c.txt"), "wb").write(run([SIGTK, "jnn", "-c", path]))
+    for flag, kind in ((0, "dna"), (1, "rna")):
+        reads = jnn_stall_reads(flag)
+        ids = [f"jnn-{kind}-{i:02d}" for i in range(len(reads))]
+        tmp = os.path.join(HERE, "_jnn.blow5")
+        write_blow5(reads, ids, tmp, "rna" if flag else "genomic_dna")
+        open(os.path.join(HERE, f"ref_jnn_stalls_{kind}.txt"), "wb").write(run([SIGTK, "jnn", tmp]))
+        open(os.path.join(HERE, f"ref_jnn_stalls_{kind}_c.txt"), "wb").write(run([SIGTK, "jnn", "-c", tmp]))
+        os.remove(tmp)
+        lens = [r[0].shape[0] for r in reads]
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        np.savez_compressed(os.path.join(HERE, f"jnn_stalls_{kind}.npz"), read_ids=np.array(ids),
+                            samples=np.concatenate([r[0] for r in reads]), read_off=off,
+                            digitisation=np.array([r[1] for r in reads]), offset=np.array([r[2] for r in reads]),
+                            range=np.array([r[3] for r in reads]))
+
+
 def main():
+    if sys.argv[1:] == ["jnn"]:
+        jnn_goldens()
+        print("jnn fixtures written to", HERE)
+        return
     if sys.argv[1:] == ["ent"]:
         ent_goldens()
         print("ent fixtures written to", HERE)
@@ -154,6 +215,7 @@ def main():
     full = run([SIGTK, "pa", rna])
     sha["rna_pa"] = hashlib.sha256(full).hexdigest()
     ent_goldens()
+    jnn_goldens()
     json.dump(sha, open(os.path.join(HERE, "sha256.json"), "w"), indent=1, sort_keys=True)
     print("golden fixtures written to", HERE)
 

@@ -122,6 +122,20 @@ def test_ent_against_numpy_histograms(orc):
         assert np.allclose(orc.ent(raw), exp, rtol=0, atol=1e-10)
 
 
+# ---- `sigtk jnn` (the jnn half) ----------------------------------------------------
+@pytest.mark.parametrize("npz,txt,rna_flag", [("sp1_dna.npz", "ref_sp1_jnn", 0), ("synth_rna.npz", "ref_rna_jnn", 1),
+                                              ("jnn_stalls_dna.npz", "ref_jnn_stalls_dna", 0),
+                                              ("jnn_stalls_rna.npz", "ref_jnn_stalls_rna", 1)])
+def test_jnn_equals_reference_stdout(orc, npz, txt, rna_flag):
+    """orc_jnn against the stdout of the compiled reference's `sigtk jnn` and `jnn -c`: real DNA, synthetic RNA, and
+    reads with stalls (merged pairs, tolerated outliers, open stretches at the end, clipped spikes, empty band)"""
+    reads = _fmt.load_npz(os.path.join(G, npz))
+    for compact, suffix in ((False, ".txt"), (True, "_c.txt")):
+        exp = open(os.path.join(G, txt + suffix)).read()
+        got = _fmt.JNN_HDR + "".join(_fmt.jnn_line(rid, len(rd[0]), orc.jnn(rd[0], rna_flag), compact) for rid, rd in reads)
+        assert got == exp, suffix
+
+
 def _bits(a):
     return a.view(np.uint32) if a.dtype == np.float32 else a
 
