@@ -331,11 +331,11 @@ def run_ours(args):
     all_samples, all_events, all_reads = (float(x) for x in tot.tolist())
     value = all_samples / (ms_max * 1e-3) / 1e9
 
-    # ---- the siblings of the event path (`sigtk pa`, `sigtk stat`, `sigtk ent`), device resident, on the first batch ----------------
+    # ---- the siblings of the event path (`sigtk pa`, `sigtk stat`, `sigtk ent`, `sigtk jnn`), device resident, on the first batch ----------------
     siblings = {}
     if not args.no_siblings:
         p0 = pool[0]
-        for name, w_ in (("pa", sg.WANT_PA), ("stat", sg.WANT_STAT), ("ent", sg.WANT_ENT)):
+        for name, w_ in (("pa", sg.WANT_PA), ("stat", sg.WANT_STAT), ("ent", sg.WANT_ENT), ("jnn", sg.WANT_JNN)):
             tot_ms = 0.0
             for k in range(4):
                 ctx.run_device(p0["samples"].data_ptr(), p0["read_off"].data_ptr(), p0["read_len"].data_ptr(),
@@ -344,7 +344,7 @@ def run_ours(args):
                 if k:
                     tot_ms += ms
             ms = tot_ms / 3.0
-            by = (6.0 if name == "pa" else 2.0) * p0["n_samples"]  # pa: 2 B in + 4 B out; stat: 2 B in (read 3 times); ent: 2 B in
+            by = (6.0 if name == "pa" else 2.0) * p0["n_samples"]  # pa: 2 B in + 4 B out; stat: 2 B in (read 3 times); ent / jnn: 2 B in (jnn reads 3 times)
             siblings[name] = {"ms": ms, "value": p0["n_samples"] / (ms * 1e-3) / 1e9, "unit": UNIT,
                               "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / measured_peak()[0]}
 

@@ -1,4 +1,4 @@
-/* sigtk_main.c -- drop-in `sigtk event | pa | stat | ent` on top of the B200 hot path (C99 host, links slow5lib).
+/* sigtk_main.c -- drop-in `sigtk event | pa | stat | ent | jnn` on top of the B200 hot path (C99 host, links slow5lib).
  *
  * Same command line, stdout bytes, stderr information lines and exit codes as the reference tool for the three
  * sub-commands of the raw-signal path:
@@ -7,6 +7,7 @@
  *                                    read-id random access)
  *     reference src/cfunc.c:16-159  (output formats of event / pa / stat)
  *     reference src/misc.c:34-101   (DNA/RNA and pore detection from the BLOW5 header)
+ *     reference src/cfunc.c:108-120, src/jnn.c:303-343 (`jnn`: line format, long and -c compact)
  *     reference src/ent.c:67-177    (`ent`: its own option set, usage text, header and "%f" line per record)
  * What changes is the execution model: instead of one record -> compute -> printf, decoded records are batched
  * into pinned slots of the CUDA library (include/sigtk_b200.h), several batches are in flight on one or more
@@ -44,7 +45,7 @@
 #define ERROR(msg, ...) \
     fprintf(stderr, "[%s::ERROR]\033[1;31m " msg "\033[0m At %s:%d\n", __func__, __VA_ARGS__, __FILE__, __LINE__ - 1)
 
-enum { MODE_EVENT, MODE_PA, MODE_STAT, MODE_ENT };
+enum { MODE_EVENT, MODE_PA, MODE_STAT, MODE_ENT, MODE_JNN };
 
 typedef struct {
     int mode;
@@ -285,6 +286,8 @@ static void print_header(const opt_t *opt) {
         else printf("read_id\tevent_idx\traw_start\traw_end\tevent_mean\tevent_std\n");
     } else if (opt->mode == MODE_STAT) {
         printf("read_id\tlen_raw_signal\traw_mean\tpa_mean\traw_std\tpa_std\traw_median\tpa_median\n");
+    } else if (opt->mode == MODE_JNN) { /* cfunc.c:118-120 */
+        printf("read_id\tlen_raw_signal\tnum_seg\tseg\n");
     } else if (opt->mode == MODE_ENT) { /* ent.c:106 */
         printf("read_id\traw_ent\tdelta_ent\tbyte_ent\n");
     } else {
@@ -355,6 +358,32 @@ static void format_read(const opt_t *opt, const sgpu_result_t *res, const sgpu_b
             o->len = (size_t)(p - o->p);
         }
         p = obuf_reserve(o, 1);
+        *p++ = '\n';
+        o->len = (size_t)(p - o->p);
+    } else if (opt->mode == MODE_JNN) { /* cfunc.c:108-117 + jnn_print, jnn.c:303-343 */
+        const uint32_t ns = res->jnn_cnt[r];
+        const int32_t *sg = res->jnn_seg + 2 * SGPU_JNN_BASE(b->read_off[r], r);
+        p = obuf_reserve(o, idl + 96 + (size_t)ns * 44);
+        memcpy(p, rid, idl); p += idl; *p++ = '\t';
+        p = fmt_i64(p, n); *p++ = '\t';
+        if (n > 0) { /* jnn_raw returns NULL for an empty record and jnn_print then prints nothing */
+            p = fmt_i64(p, (long)ns); *p++ = '\t';
+            if (opt->compact) {
+                uint64_t ci = 0, mi = 0;
+                for (uint32_t k = 0; k < ns; k++) {
+                    ci += (mi = (uint64_t)(int64_t)sg[2 * k] - ci);
+                    if (mi) { p = fmt_i64(p, (int)mi); *p++ = 'H'; }
+                    ci += (mi = (uint64_t)(int64_t)sg[2 * k + 1] - ci);
+                    if (mi) { p = fmt_i64(p, (int)mi); *p++ = ','; }
+                }
+            } else {
+                for (uint32_t k = 0; k < ns; k++) {
+                    p = fmt_i64(p, (long)sg[2 * k]); *p++ = ',';
+                    p = fmt_i64(p, (long)sg[2 * k + 1]); *p++ = ';';
+                }
+            }
+            if (ns == 0) *p++ = '.';
+        }
         *p++ = '\n';
         o->len = (size_t)(p - o->p);
     } else if (opt->mode == MODE_ENT) { /* ent.c:109,113,132,148,163: "%s\t" "%f" "\t%f" "\t%f" "\n" with doubles */
@@ -688,6 +717,9 @@ static int cmain(int argc, char *argv[], const char *mode) {
     if (is_ent) {
         eng.opt.mode = MODE_ENT;
         eng.want = SGPU_WANT_ENT;
+    } else if (strcmp(mode, "jnn") == 0) {
+        eng.opt.mode = MODE_JNN;
+        eng.want = SGPU_WANT_JNN;
     } else if (strcmp(mode, "event") == 0) {
         eng.opt.mode = MODE_EVENT;
         eng.want = SGPU_WANT_EVENTS;
@@ -863,7 +895,8 @@ static int print_usage(FILE *fp_help) {
     fprintf(fp_help, "         event     segment raw signal into events\n");
     fprintf(fp_help, "         stat      print statistics of the raw signal\n");
     fprintf(fp_help, "         ent       entropy of the raw signal, its zig-zag deltas and their byte planes\n");
-    fprintf(fp_help, "(B200 build: the raw-signal hot path only; sref, prefix, jnn, ss and qts are served by the\n");
+    fprintf(fp_help, "         jnn       stall / homopolymer-stretch segments of the raw signal\n");
+    fprintf(fp_help, "(B200 build: the raw-signal hot path only; sref, prefix, ss and qts are served by the\n");
     fprintf(fp_help, " reference sigtk)\n");
     exit(fp_help == stderr ? EXIT_FAILURE : EXIT_SUCCESS);
 }
@@ -876,14 +909,14 @@ int main(int argc, char *argv[]) {
     if (argc < 2) {
         return print_usage(stderr);
     } else if (strcmp(argv[1], "event") == 0 || strcmp(argv[1], "stat") == 0 || strcmp(argv[1], "pa") == 0 ||
-               strcmp(argv[1], "ent") == 0) {
+               strcmp(argv[1], "ent") == 0 || strcmp(argv[1], "jnn") == 0) {
         ret = cmain(argc - 1, argv + 1, argv[1]);
     } else if (strcmp(argv[1], "--version") == 0 || strcmp(argv[1], "-V") == 0) {
         fprintf(stdout, "sigtk %s\n", SIGTK_VERSION);
         exit(EXIT_SUCCESS);
     } else if (strcmp(argv[1], "--help") == 0 || strcmp(argv[1], "-h") == 0) {
         print_usage(stdout);
-    } else if (strcmp(argv[1], "sref") == 0 || strcmp(argv[1], "prefix") == 0 || strcmp(argv[1], "jnn") == 0 ||
+    } else if (strcmp(argv[1], "sref") == 0 || strcmp(argv[1], "prefix") == 0 ||
                strcmp(argv[1], "ss") == 0 || strcmp(argv[1], "qts") == 0) {
         fprintf(stderr, "[sigtk] command %s is outside the B200 raw-signal hot path; use the reference sigtk for it\n",
                 argv[1]);

@@ -9,6 +9,7 @@
  *   - event_table getevents(size_t, float*, int8_t rna)  src/sigtk.h:134, src/events.c:553-573
  *   - meanf/stdvf/medianf/meani16/stdvi16/mediani16      src/stat.h:17-73 (as used by stat_func,
  *                                                        src/cfunc.c:126-159)
+ *   - jnn_pair_t *jnn_raw(const int16_t*, int64_t, jnn_param_t, int *n)   src/jnn.h:105, src/jnn.c:176-282
  *   - double entropy(int16_t*, uint64_t) and the zig-zag-delta / byte-plane loop of entmain
  *                                                        src/ent.c:25-51, 56-65, 108-151
  * The reference calls those once per record from a callback
@@ -34,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SGPU_ABI_VERSION 3
+#define SGPU_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------- */
 #define SGPU_OK            0
@@ -53,6 +54,8 @@ extern "C" {
 #define SGPU_WANT_PA       2u /* materialise pA floats: signal_in_picoamps(), misc.c:15-32 */
 #define SGPU_WANT_STAT     4u /* the six numbers of stat_func, cfunc.c:126-159 */
 #define SGPU_WANT_ENT      8u /* the three entropies of `sigtk ent`, ent.c:108-151 */
+#define SGPU_WANT_JNN     16u /* the segments of `sigtk jnn`: jnn_raw(), jnn.c:269-282 with the parameters of
+                                 jnn_print (jnn.c:305-312: JNNV1_DRNA_R9_PARAM when rna, else JNNV1_CDNA_R9_PARAM) */
 
 /* ---- context flags ------------------------------------------------------ */
 #define SGPU_F_DEFAULT       0u
@@ -102,7 +105,12 @@ typedef struct {
                               SGPU_WANT_ENT. Histogram counts are exact and the terms are summed in the reference's
                               order; log2 is CUDA's (<= 1 ulp), so the doubles agree to ~1e-15 and "%f" prints alike.
                               An empty record (where the reference crashes) gives zeros. */
+    uint32_t *jnn_cnt;     /* [n_reads] number of segments (jnn_raw's *n); NULL unless SGPU_WANT_JNN */
+    int32_t  *jnn_seg;     /* segment k of read r = (x, y) = jnn_seg[2*(SGPU_JNN_BASE(read_off[r], r) + k) + {0,1}]
+                              (jnn_pair_t, jnn.h:13-16; sample indices in the read). Bit-exact. */
 } sgpu_result_t;
+/* first segment slot of read r (a read of n samples has at most n/38 + 1 segments, jnn.c:232) */
+#define SGPU_JNN_BASE(read_off_r, r) (((uint64_t)(read_off_r) >> 5) + (uint64_t)(r))
 
 /* ---- lifecycle ----------------------------------------------------------- */
 int  sgpu_device_count(void);

@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsigtk_b200.so")
 
-WANT_EVENTS, WANT_PA, WANT_STAT, WANT_ENT = 1, 2, 4, 8
+WANT_EVENTS, WANT_PA, WANT_STAT, WANT_ENT, WANT_JNN = 1, 2, 4, 8, 16
 F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, F_STAGE_TIMERS = 0, 1, 2, 4
 ALIGN = 8
 
@@ -46,7 +46,7 @@ class Result(C.Structure):  # sgpu_result_t
     _fields_ = [
         ("ev_off", C.c_void_p), ("ev_start", C.c_void_p), ("ev_mean", C.c_void_p), ("ev_stdv", C.c_void_p),
         ("pa", C.c_void_p), ("stat", C.c_void_p), ("seq_order", C.c_void_p), ("fixups", C.c_void_p),
-        ("n_events", C.c_uint64), ("ent", C.c_void_p),
+        ("n_events", C.c_uint64), ("ent", C.c_void_p), ("jnn_cnt", C.c_void_p), ("jnn_seg", C.c_void_p),
     ]
 
 

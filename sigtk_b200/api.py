@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (ALIGN, F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, F_STAGE_TIMERS, WANT_EVENTS, WANT_PA,
-                   WANT_STAT, WANT_ENT, SgpuError)
+                   WANT_STAT, WANT_ENT, WANT_JNN, SgpuError)
 
 Read = Tuple[np.ndarray, float, float, float]  # raw int16, digitisation, offset, range
 
@@ -48,6 +48,7 @@ class BatchResult:
     pa: Optional[List[np.ndarray]] = None
     stat: Optional[np.ndarray] = None
     ent: Optional[np.ndarray] = None   # [n_reads][3] float64: raw_ent, delta_ent, byte_ent (ent.c:108-151)
+    jnn: Optional[List[np.ndarray]] = None  # per read int64[k][2]: the (x, y) pairs of jnn_raw (jnn.c:269-282)
     seq_order: Optional[np.ndarray] = None
     fixups: Optional[np.ndarray] = None
 
@@ -157,6 +158,14 @@ class Context:
             out.stat = _np_from(res.stat, np.float32, n * 6).reshape(n, 6)
         if want & WANT_ENT:
             out.ent = _np_from(res.ent, np.float64, n * 3).reshape(n, 3)
+        if want & WANT_JNN:
+            cnt = _np_from(res.jnn_cnt, np.uint32, n)
+            span = int(read_off[n]) if n else 0
+            seg = _np_from(res.jnn_seg, np.int32, 2 * ((span >> 5) + n + 1)).reshape(-1, 2)
+            out.jnn = []
+            for r in range(n):
+                base = (int(read_off[r]) >> 5) + r  # SGPU_JNN_BASE
+                out.jnn.append(seg[base: base + int(cnt[r])].astype(np.int64))
         if want & WANT_PA:
             span = int(read_off[n]) if n else 0
             flat = _np_from(res.pa, np.float32, span)
@@ -217,3 +226,8 @@ def stat(ctx: Context, raw: np.ndarray, digitisation: float, offset: float, rang
 def ent(ctx: Context, raw: np.ndarray) -> np.ndarray:
     """raw_ent, delta_ent, byte_ent of one record as `sigtk ent` prints them (ent.c:108-151)."""
     return ctx.run([(raw, 8192.0, 0.0, 1.0)], 0, WANT_ENT).ent[0]
+
+
+def jnn_raw(ctx: Context, raw: np.ndarray, rna: int = 0) -> np.ndarray:
+    """jnn_raw (jnn.c:269-282) with jnn_print's parameters for one record: int64[k][2] (x, y) pairs."""
+    return ctx.run([(raw, 8192.0, 0.0, 1.0)], rna, WANT_JNN).jnn[0]

@@ -25,6 +25,8 @@ struct DevOut {  // device-side outputs of one batch
     float* pa = nullptr;
     float* stat = nullptr;
     double* ent = nullptr;  // [max_reads][3], allocated on first use
+    uint32_t* jnn_cnt = nullptr;  // [max_reads], allocated on first use
+    int32_t* jnn_seg = nullptr;   // [2 * jnn_seg_capacity]
 };
 
 struct Slot {
@@ -48,6 +50,8 @@ struct Slot {
     float* h_pa = nullptr;
     float* h_stat = nullptr;
     double* h_ent = nullptr;
+    uint32_t* h_jnn_cnt = nullptr;
+    int32_t* h_jnn_seg = nullptr;
     uint32_t* h_seq = nullptr;
     uint32_t* h_fix = nullptr;
     unsigned long long* h_counters = nullptr;  // [4]
@@ -81,6 +85,7 @@ struct sgpu_ctx {
     uint32_t* dev_fix = nullptr;
     Slot* slots = nullptr;
     SvbScratch svb{};            // workspace of the svb-zd decoder (allocated on first use)
+    float* jnn_mom = nullptr;    // [max_reads][2] mean / stdv of the clamped signal (allocated on first use)
     uint32_t* ent_ovf = nullptr; // overflow histograms of ent_kernel (allocated on first use, kept all-zero)
     uint64_t comp_cap = 0;       // bytes of compressed input a slot can hold
     cudaStream_t compute = nullptr;
@@ -137,7 +142,7 @@ int alloc_dev_out(sgpu_ctx* ctx, DevOut& o) {
 
 void free_dev_out(DevOut& o) {
     cudaFree(o.ev_off); cudaFree(o.ev_start); cudaFree(o.ev_mean); cudaFree(o.ev_stdv);
-    cudaFree(o.pa); cudaFree(o.stat); cudaFree(o.ent);
+    cudaFree(o.pa); cudaFree(o.stat); cudaFree(o.ent); cudaFree(o.jnn_cnt); cudaFree(o.jnn_seg);
     o = DevOut{};
 }
 
@@ -206,6 +211,14 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
             CU(cudaMemsetAsync(ctx->ent_ovf, 0, (size_t)words * sizeof(uint32_t), st));
         }
         marks.done("ent", launch_ent(b, ctx->ent_ovf, o.ent, ctx->sm_count, st));
+    }
+    if (want & SGPU_WANT_JNN) {
+        if (!o.jnn_cnt) {
+            CU(dev_alloc(&o.jnn_cnt, ctx->max_reads));
+            CU(dev_alloc(&o.jnn_seg, 2 * jnn_seg_capacity(ctx->max_samples, ctx->max_reads)));
+        }
+        if (!ctx->jnn_mom) CU(dev_alloc(&ctx->jnn_mom, (uint64_t)ctx->max_reads * 2));
+        marks.done("jnn", launch_jnn(b, ctx->jnn_mom, o.jnn_cnt, o.jnn_seg, ctx->sm_count, st));
     }
     if (events) {
         const uint32_t n_tiles = fast_tiles_for(b.span);
@@ -407,7 +420,7 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     cudaFree(sc.scan_status); cudaFree(sc.scan_ticket); cudaFree(sc.status); cudaFree(sc.counters);
     for (int k = 0; k <= sgpu_ctx::MAX_STAGES; k++) if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
     free_dev_out(ctx->dev_out);
-    cudaFree(ctx->ent_ovf);
+    cudaFree(ctx->ent_ovf); cudaFree(ctx->jnn_mom);
     {
         SvbScratch& w = ctx->svb;
         cudaFree(w.cnt); cudaFree(w.base); cudaFree(w.blk_bytes); cudaFree(w.blk_gpos); cudaFree(w.blk_sum);
@@ -422,7 +435,7 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
             cudaFree(sl.d_unit); cudaFree(sl.d_seq); cudaFree(sl.d_fix);
             free_dev_out(sl.dout);
             cudaFreeHost(sl.h_ev_off); cudaFreeHost(sl.h_ev_start); cudaFreeHost(sl.h_ev_mean);
-            cudaFreeHost(sl.h_ev_stdv); cudaFreeHost(sl.h_pa); cudaFreeHost(sl.h_stat); cudaFreeHost(sl.h_ent); cudaFreeHost(sl.h_seq);
+            cudaFreeHost(sl.h_ev_stdv); cudaFreeHost(sl.h_pa); cudaFreeHost(sl.h_stat); cudaFreeHost(sl.h_ent); cudaFreeHost(sl.h_jnn_cnt); cudaFreeHost(sl.h_jnn_seg); cudaFreeHost(sl.h_seq);
             cudaFreeHost(sl.h_fix); cudaFreeHost(sl.h_counters); cudaFreeHost(sl.h_status);
             cudaFreeHost(sl.h_comp); cudaFreeHost(sl.h_comp_off); cudaFreeHost(sl.h_comp_len);
             cudaFree(sl.d_comp); cudaFree(sl.d_comp_off); cudaFree(sl.d_comp_len);
@@ -531,7 +544,7 @@ int64_t sgpu_slot_add_read_svbzd(sgpu_ctx_t* ctx, uint32_t slot, const uint8_t* 
 }
 
 int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
-    if (!ctx || slot >= ctx->n_slots || (want & ~15u) || want == 0) return SGPU_E_INVAL;
+    if (!ctx || slot >= ctx->n_slots || (want & ~31u) || want == 0) return SGPU_E_INVAL;
     Slot& sl = ctx->slots[slot];
     if (sl.submitted) return SGPU_E_STATE;
     CU(cudaSetDevice(ctx->device));
@@ -558,6 +571,10 @@ int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
     DevBatch b{sl.d_samples, sl.d_read_off, sl.d_read_len, sl.d_offset, sl.d_unit, nr, (int)hb.rna, sl.used};
     if ((want & SGPU_WANT_PA) && !sl.h_pa) CU(pin_alloc(&sl.h_pa, ctx->max_samples));
     if ((want & SGPU_WANT_ENT) && !sl.h_ent) CU(pin_alloc(&sl.h_ent, (uint64_t)ctx->max_reads * 3));
+    if ((want & SGPU_WANT_JNN) && !sl.h_jnn_cnt) {
+        CU(pin_alloc(&sl.h_jnn_cnt, ctx->max_reads));
+        CU(pin_alloc(&sl.h_jnn_seg, 2 * jnn_seg_capacity(ctx->max_samples, ctx->max_reads)));
+    }
     const int rc = run_pipeline(ctx, b, want, sl.dout, sl.d_seq, sl.d_fix, ctx->compute, compressed ? &svb : nullptr,
                                 sl.d_samples);
     if (rc) return rc;
@@ -576,6 +593,11 @@ int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
         CU(cudaMemcpyAsync(sl.h_stat, sl.dout.stat, (size_t)nr * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (want & SGPU_WANT_ENT)
         CU(cudaMemcpyAsync(sl.h_ent, sl.dout.ent, (size_t)nr * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want & SGPU_WANT_JNN) {
+        CU(cudaMemcpyAsync(sl.h_jnn_cnt, sl.dout.jnn_cnt, (size_t)nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sl.h_jnn_seg, sl.dout.jnn_seg, (size_t)2 * ((sl.used >> 5) + nr + 1) * sizeof(int32_t),
+                           cudaMemcpyDeviceToHost, st));
+    }
     if (want & SGPU_WANT_PA)
         CU(cudaMemcpyAsync(sl.h_pa, sl.dout.pa, (size_t)sl.used * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(sl.small_back, st));
@@ -614,12 +636,13 @@ int sgpu_wait(sgpu_ctx_t* ctx, uint32_t slot, sgpu_result_t* out) {
     if (sl.want & SGPU_WANT_STAT) out->stat = sl.h_stat;
     if (sl.want & SGPU_WANT_PA) out->pa = sl.h_pa;
     if (sl.want & SGPU_WANT_ENT) out->ent = sl.h_ent;
+    if (sl.want & SGPU_WANT_JNN) { out->jnn_cnt = sl.h_jnn_cnt; out->jnn_seg = sl.h_jnn_seg; }
     return SGPU_OK;
 }
 
 int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t want, void* stream,
                     sgpu_result_t* out) {
-    if (!ctx || !batch || !out || (want & ~15u) || want == 0) return SGPU_E_INVAL;
+    if (!ctx || !batch || !out || (want & ~31u) || want == 0) return SGPU_E_INVAL;
     CU(cudaSetDevice(ctx->device));
     DevBatch b{batch->samples, batch->read_off, batch->read_len, batch->offset_f, batch->raw_unit_f,
                batch->n_reads, (int)batch->rna, batch->span};
@@ -634,6 +657,8 @@ int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t wan
     out->pa = (want & SGPU_WANT_PA) ? ctx->dev_out.pa : nullptr;
     out->stat = ctx->dev_out.stat;
     out->ent = (want & SGPU_WANT_ENT) ? ctx->dev_out.ent : nullptr;
+    out->jnn_cnt = (want & SGPU_WANT_JNN) ? ctx->dev_out.jnn_cnt : nullptr;
+    out->jnn_seg = (want & SGPU_WANT_JNN) ? ctx->dev_out.jnn_seg : nullptr;
     out->seq_order = ctx->dev_seq;
     out->fixups = ctx->dev_fix;
     return SGPU_OK;

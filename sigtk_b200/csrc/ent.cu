@@ -2,10 +2,11 @@
 // deltas' byte planes (reference src/ent.c:25-51 `entropy`, 56-65 `zigzag_delta_encode`, 108-151 the per-record
 // loop of `entmain`). SURVEY 8f rank 4.
 //
-// One CTA per read, four histograms at once from ONE pass over the samples:
+// One CTA per read, four histograms from ONE pass over the samples:
 //   raw   : 65,536 bins keyed by (uint16)raw[i],                    i in [0, n)
 //   delta : 65,536 bins keyed by (uint16)zigzag32(raw[i]-raw[i-1]), i in [0, n-1), raw[-1] = 0  (ent.c:118-131)
-//   hi/lo : 256 bins each, the two bytes of the delta key                                      (ent.c:139-147)
+//   hi/lo : 256 bins each, the two bytes of the delta key (ent.c:139-147): not counted per sample but folded
+//           from the delta histogram's nonzero bins while it is swept (they are its marginals)
 // The two wide histograms live in SHARED memory as windows of ENT_WIN bins: raw keys within +-ENT_WIN/2 of the
 // read's first sample, delta keys below ENT_WIN (nanopore signals span ~1,000 ADC units, their deltas a few
 // hundred). A key outside its window goes to the CTA's 65,536-bin overflow histogram in HBM (L2 atomics) -- any
@@ -121,8 +122,6 @@ ent_kernel(DevBatch b, uint32_t* __restrict__ ovf_all, double* __restrict__ out)
                     dmin = min(dmin, z); dmax = max(dmax, z);
                     if (z < ENT_WIN) atomicAdd(&s.dlt[z], 1u);
                     else { atomicAdd(&ovf_dlt[z], 1u); dovf = true; }
-                    atomicAdd(&s.hi[z >> 8], 1u);     // ent.c:144
-                    atomicAdd(&s.lo[z & 255u], 1u);   // ent.c:145
                 }
                 prev = (int32_t)v[j];
             }
@@ -160,6 +159,10 @@ ent_kernel(DevBatch b, uint32_t* __restrict__ ovf_all, double* __restrict__ out)
                 if (k < ENT_WIN) { c = s.dlt[k]; s.dlt[k] = 0; }
                 else if (dov) { c = __ldcg(&ovf_dlt[k]); if (c) ovf_dlt[k] = 0; }
                 else c = 0;
+                if (c) {  // the byte planes' histograms are the marginals of this one (ent.c:144-145)
+                    atomicAdd(&s.hi[k >> 8], c);
+                    atomicAdd(&s.lo[k & 255u], c);
+                }
                 return c;
             });
             e_hi = entropy_sweep(s, 0u, 255u, len, [&](uint32_t k) -> uint32_t { const uint32_t c = s.hi[k]; s.hi[k] = 0; return c; });

@@ -99,8 +99,11 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
 // addends -- (float)raw and pA in the first pass (meani16 / meanf: sum += x[i]), the squared deviations in the
 // second (stdvi16 / stdvf: sum += (x[i]-m)*(x[i]-m)) -- into shared memory; chain_superblock adds them up in the
 // reference's order. Positions past the end of the read hold +0, which no float sum notices.
+// JNN = true: ONE channel, the samples clamped to [0, 1200] (rm_outlier, jnn.c:58-75), i.e. meanf / stdvf of the
+// signal jnn_core thresholds (jnn.c:181-185); out = [n_reads][2] (mean, stdv).
+template <bool JNN>
 __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __restrict__ out) {
-    __shared__ float add_all[4][2][32 * SB_STRIDE];
+    __shared__ float add_all[4][JNN ? 1 : 2][32 * SB_STRIDE];
     __shared__ int sums_all[4][96];
     float (*add)[32 * SB_STRIDE] = add_all[threadIdx.x >> 5];
     int* sums = sums_all[threadIdx.x >> 5];
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __
     for (uint32_t r = warp; r < b.n_reads; r += n_warps) {
         const int16_t* __restrict__ raw = b.samples + b.read_off[r];
         const int n = (int)b.read_len[r];  // stat.h takes `int n`
-        const float off = b.offset[r], unit = b.unit[r];
+        const float off = JNN ? 0.0f : b.offset[r], unit = JNN ? 0.0f : b.unit[r];
         const float nf = (float)n;
         float mean_r = 0.0f, mean_p = 0.0f;
         for (int pass = 0; pass < 2; pass++) {
@@ -128,8 +131,12 @@ __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __
                     float ar = 0.0f, ap = 0.0f;
                     if (i < n) {
                         const int16_t v = (int16_t)vv[k];
-                        ar = (float)v;
-                        ap = pa_of(v, off, unit);
+                        if (JNN) {
+                            ar = (float)min(max((int)v, 0), 1200);
+                        } else {
+                            ar = (float)v;
+                            ap = pa_of(v, off, unit);
+                        }
                         if (pass) {
                             const float dr = __fsub_rn(ar, mean_r), dp = __fsub_rn(ap, mean_p);
                             ar = __fmul_rn(dr, dr);
@@ -137,20 +144,26 @@ __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __
                         }
                     }
                     add[0][k * SB_STRIDE + lane] = ar;
-                    add[1][k * SB_STRIDE + lane] = ap;
+                    if (!JNN) add[JNN ? 0 : 1][k * SB_STRIDE + lane] = ap;
                 }
                 __syncwarp();
                 const int ntiles = (min(SB, n - t0) + 31) >> 5;
                 acc_r = chain_superblock(add[0], ntiles, acc_r, lane, sums, t0 == 0);
-                acc_p = chain_superblock(add[1], ntiles, acc_p, lane, sums, t0 == 0);
+                if (!JNN) acc_p = chain_superblock(add[JNN ? 0 : 1], ntiles, acc_p, lane, sums, t0 == 0);
             }
             if (pass == 0) {
                 mean_r = __fdiv_rn(acc_r, nf);
                 mean_p = __fdiv_rn(acc_p, nf);
-                if (lane == 0) { out[(size_t)r * 6] = mean_r; out[(size_t)r * 6 + 1] = mean_p; }
+                if (lane == 0) {
+                    if (JNN) out[(size_t)r * 2] = mean_r;
+                    else { out[(size_t)r * 6] = mean_r; out[(size_t)r * 6 + 1] = mean_p; }
+                }
             } else if (lane == 0) {
-                out[(size_t)r * 6 + 2] = __fsqrt_rn(__fdiv_rn(acc_r, nf));
-                out[(size_t)r * 6 + 3] = __fsqrt_rn(__fdiv_rn(acc_p, nf));
+                if (JNN) out[(size_t)r * 2 + 1] = __fsqrt_rn(__fdiv_rn(acc_r, nf));
+                else {
+                    out[(size_t)r * 6 + 2] = __fsqrt_rn(__fdiv_rn(acc_r, nf));
+                    out[(size_t)r * 6 + 3] = __fsqrt_rn(__fdiv_rn(acc_p, nf));
+                }
             }
         }
     }
@@ -223,11 +236,21 @@ int launch_stat(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st) 
     if (b.n_reads == 0) return 0;
     int g1 = (int)((b.n_reads + 3) / 4);  // one warp per read
     if (g1 > sm_count * 16) g1 = sm_count * 16;
-    stat_moments_kernel<<<g1, 128, 0, st>>>(b, stat6);
+    stat_moments_kernel<false><<<g1, 128, 0, st>>>(b, stat6);
     int g2 = (int)b.n_reads;
     if (g2 > sm_count * 8) g2 = sm_count * 8;
     stat_median_kernel<<<g2, 256, 0, st>>>(b, stat6);
     return 2;
+}
+
+// mean and standard deviation (float, in the reference's summation order) of the samples clamped to [0, 1200]:
+// what jnn_core derives its band from (jnn.c:58-75, 181-185). moments2 = [n_reads][2].
+int launch_jnn_moments(const DevBatch& b, float* moments2, int sm_count, cudaStream_t st) {
+    if (b.n_reads == 0) return 0;
+    int g1 = (int)((b.n_reads + 3) / 4);  // one warp per read
+    if (g1 > sm_count * 16) g1 = sm_count * 16;
+    stat_moments_kernel<true><<<g1, 128, 0, st>>>(b, moments2);
+    return 1;
 }
 
 }  // namespace sgpu

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sigtk_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names
-    assert lib.sgpu_abi_version() == 3
+    assert lib.sgpu_abi_version() == 4
 
 
 def test_strerror_and_argument_checks():

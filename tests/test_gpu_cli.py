@@ -86,7 +86,7 @@ def test_no_header_version_help_and_errors(sp1):
     r = subprocess.run([CLI, "event", "/nonexistent.blow5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and b"cannot open /nonexistent.blow5" in r.stderr
     r = subprocess.run([CLI, "prefix", sp1], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-    assert r.returncode == 1
+    assert r.returncode == 1 and b"outside the B200 raw-signal hot path" in r.stderr
 
 
 def test_ent_equals_the_reference_stdout(sp1, tmp_path):
@@ -119,6 +119,35 @@ def test_ent_equals_the_reference_stdout(sp1, tmp_path):
     w.stdin.close()
     assert w.wait() == 0
     assert run(["ent", path]).stdout == open(os.path.join(G, "ref_ent_adversarial.txt"), "rb").read()
+
+
+@pytest.mark.parametrize("kind", ["dna", "rna"])
+def test_jnn_equals_the_reference_stdout(sp1, tmp_path, kind):
+    """`sigtk jnn` and `jnn -c` (src/jnn.c): stdout of the compiled reference on the DNA file / the synthetic RNA file
+    and on a BLOW5 of reads with stalls (tests/golden/jnn_stalls_*.npz)"""
+    import struct
+    import numpy as np
+    path, tag = (sp1, "sp1") if kind == "dna" else (RNA, "rna")
+    p = run(["jnn", path])
+    assert p.stdout == open(os.path.join(G, f"ref_{tag}_jnn.txt"), "rb").read()
+    assert (b"RNA data detected." if kind == "rna" else b"DNA data detected.") in p.stderr
+    assert run(["jnn", "-c", "--batch-samples", "30000", path]).stdout == open(os.path.join(G, f"ref_{tag}_jnn_c.txt"), "rb").read()
+    assert run(["jnn", "--cpu-decode", "-n", path]).stdout == open(os.path.join(G, f"ref_{tag}_jnn.txt"), "rb").read().split(b"\n", 1)[1]
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "blow5_write")):
+        return
+    d = np.load(os.path.join(G, f"jnn_stalls_{kind}.npz"))
+    path = str(tmp_path / "stalls.blow5")
+    w = subprocess.Popen([os.path.join(ROOT, "oracle", "_ref", "blow5_write"), path, "rna" if kind == "rna" else "genomic_dna"],
+                         stdin=subprocess.PIPE)
+    for r in range(len(d["read_ids"])):
+        raw = d["samples"][int(d["read_off"][r]):int(d["read_off"][r + 1])]
+        rid = str(d["read_ids"][r]).encode()
+        w.stdin.write(struct.pack("<I", len(rid)) + rid + struct.pack("<Qddd", len(raw), float(d["digitisation"][r]),
+                      float(d["offset"][r]), float(d["range"][r])) + raw.tobytes())
+    w.stdin.close()
+    assert w.wait() == 0
+    assert run(["jnn", path]).stdout == open(os.path.join(G, f"ref_jnn_stalls_{kind}.txt"), "rb").read()
+    assert run(["jnn", "-c", path]).stdout == open(os.path.join(G, f"ref_jnn_stalls_{kind}_c.txt"), "rb").read()
 
 
 def test_two_gpus_same_bytes(sp1):
