@@ -340,12 +340,14 @@ def run_ours(args):
             for k in range(4):
                 ctx.run_device(p0["samples"].data_ptr(), p0["read_off"].data_ptr(), p0["read_len"].data_ptr(),
                                p0["offset"].data_ptr(), p0["unit"].data_ptr(), p0["n_reads"], p0["span"], rna, w_, stream)
-                ms = sum(m for _, m, _ in ctx.stage_times())
+                stages = ctx.stage_times()
+                ms = sum(m for _, m, _ in stages)
                 if k:
                     tot_ms += ms
             ms = tot_ms / 3.0
             by = (6.0 if name == "pa" else 2.0) * p0["n_samples"]  # pa: 2 B in + 4 B out; stat: 2 B in (read 3 times); ent / jnn: 2 B in (jnn reads 3 times)
-            siblings[name] = {"ms": ms, "value": p0["n_samples"] / (ms * 1e-3) / 1e9, "unit": UNIT,
+            siblings[name] = {"ms": ms, "kernels_ms": {n_: round(m_, 4) for n_, m_, _ in stages},
+                              "value": p0["n_samples"] / (ms * 1e-3) / 1e9, "unit": UNIT,
                               "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / measured_peak()[0]}
 
     # ---- end to end through the host C-ABI: pinned slots, H2D + kernels + D2H per step ----------------------------

@@ -218,7 +218,8 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
             CU(dev_alloc(&o.jnn_seg, 2 * jnn_seg_capacity(ctx->max_samples, ctx->max_reads)));
         }
         if (!ctx->jnn_mom) CU(dev_alloc(&ctx->jnn_mom, (uint64_t)ctx->max_reads * 2));
-        marks.done("jnn", launch_jnn(b, ctx->jnn_mom, o.jnn_cnt, o.jnn_seg, ctx->sm_count, st));
+        marks.done("jnn_moments", launch_jnn_moments(b, ctx->jnn_mom, ctx->sm_count, st));
+        marks.done("jnn_walk", launch_jnn(b, ctx->jnn_mom, o.jnn_cnt, o.jnn_seg, ctx->sm_count, st));
     }
     if (events) {
         const uint32_t n_tiles = fast_tiles_for(b.span);

@@ -101,7 +101,7 @@ int launch_jnn_moments(const DevBatch& b, float* moments2, int sm_count, cudaStr
 
 // jnn.cu (`sigtk jnn`: band from the clamped signal's mean / stdv, counter machine per read -> (start, end) pairs)
 uint64_t jnn_seg_capacity(uint64_t max_samples, uint32_t max_reads);
-int launch_jnn(const DevBatch& b, float* moments, uint32_t* seg_cnt, int32_t* seg, int sm_count, cudaStream_t st);
+int launch_jnn(const DevBatch& b, const float* moments, uint32_t* seg_cnt, int32_t* seg, int sm_count, cudaStream_t st);
 
 
 // ent.cu (`sigtk ent`: entropies of the raw samples, their zig-zag deltas and the deltas' byte planes)

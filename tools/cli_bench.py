@@ -3,7 +3,7 @@
 (oracle/_ref/sigtk, 1 thread) against the drop-in `cli/sigtk` on the same synthetic BLOW5 file. Checks that stdout is
 byte-identical (sha256) and prints one JSON line per sub-command with both wall times.
 
-  python tools/cli_bench.py [--reads 2000] [--mean 40000] [--modes event-c,event,pa,stat] [--gpus 1]
+  python tools/cli_bench.py [--reads 2000] [--mean 40000] [--modes event-c,event,pa,stat,jnn,ent] [--gpus 1]
 """
 import argparse
 import hashlib
@@ -59,7 +59,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=2000)
     ap.add_argument("--mean", type=float, default=40000.0)
-    ap.add_argument("--modes", default="event-c,event,stat,pa")
+    ap.add_argument("--modes", default="event-c,event,stat,pa,jnn,ent")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--threads", type=int, default=0)
     a = ap.parse_args()
@@ -70,7 +70,7 @@ def main():
         print(f"# {a.reads} reads, {n} samples, {os.path.getsize(f) / 1e6:.1f} MB BLOW5, made in {time.time() - t0:.1f} s",
               file=sys.stderr)
         for mode in a.modes.split(","):
-            args = {"event-c": ["event", "-c"], "event": ["event"], "stat": ["stat"], "pa": ["pa"]}[mode] + [f]
+            args = {"event-c": ["event", "-c"], "event": ["event"], "stat": ["stat"], "pa": ["pa"], "jnn": ["jnn"], "ent": ["ent"]}[mode] + [f]
             extra = ["--gpus", str(a.gpus)] + (["--threads", str(a.threads)] if a.threads else [])
             o = os.path.join(d, "out.txt")
             timed([CLI] + args + extra, o)  # warm-up: driver / file cache
