@@ -91,7 +91,7 @@ struct sgpu_ctx {
     cudaStream_t compute = nullptr;
     uint64_t last_launches = 0;
     // optional per-stage CUDA-event timers (SGPU_F_STAGE_TIMERS)
-    static constexpr int MAX_STAGES = 12;
+    static constexpr int MAX_STAGES = 16;
     cudaEvent_t stage_ev[MAX_STAGES + 1] = {};
     const char* stage_name[MAX_STAGES] = {};
     uint32_t stage_launches[MAX_STAGES] = {};
@@ -202,7 +202,10 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
         // with events on the fast path the pA store is fused into walk_chunks_kernel
         if (!events || force_generic) marks.done("pa", launch_pa(b, o.pa, ctx->sm_count, st));
     }
-    if (want & SGPU_WANT_STAT) marks.done("stat", launch_stat(b, o.stat, ctx->sm_count, st));
+    if (want & SGPU_WANT_STAT) {
+        marks.done("stat_moments", launch_stat_moments(b, o.stat, ctx->sm_count, st));
+        marks.done("stat_median", launch_stat_median(b, o.stat, ctx->sm_count, st));
+    }
     if (want & SGPU_WANT_ENT) {
         if (!o.ent) CU(dev_alloc(&o.ent, (uint64_t)ctx->max_reads * 3));
         if (!ctx->ent_ovf) {

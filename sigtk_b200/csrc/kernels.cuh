@@ -96,7 +96,8 @@ uint32_t svbzd_blocks_of(uint64_t n);
 int launch_svbzd_decode(const SvbBatch& s, SvbScratch& w, Scratch& sc, int16_t* samples, int sm_count, cudaStream_t st);
 
 // stat.cu
-int launch_stat(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st);
+int launch_stat_moments(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st);
+int launch_stat_median(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st);
 int launch_jnn_moments(const DevBatch& b, float* moments2, int sm_count, cudaStream_t st);
 
 // jnn.cu (`sigtk jnn`: band from the clamped signal's mean / stdv, counter machine per read -> (start, end) pairs)

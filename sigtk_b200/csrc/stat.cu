@@ -18,8 +18,8 @@ namespace sgpu {
 //     c = [f > 1/2], and on a tie (f == 1/2) c = parity of (S + a):
 // the only thing the step needs to know about the running sum is the PARITY of S. So a run of values is summarised by
 // two integers -- the total increment for an even and for an odd incoming S -- computed without knowing s, and runs
-// compose. One warp takes 1024 values: every lane summarises 32 consecutive ones (both parities), lane 0 walks the 32
-// summaries. A tile that would carry S to 2^24 (the binade ends there), holds a negative value or meets s <= 0 is
+// compose. One warp takes 1024 values: every lane summarises 32 consecutive ones (both parities), a shuffle scan
+// composes the 32 summaries (lane 0 used to walk them one by one: a quarter of the kernel's time). A tile that would carry S to 2^24 (the binade ends there), holds a negative value or meets s <= 0 is
 // added value by value; the summaries after it are recomputed for the new binade. Bit-identical to the sequential
 // loop by construction (tests: every stat of every parity test and of the fuzz reads against the oracle).
 constexpr int SB = 1024;            // values per superblock
@@ -36,6 +36,9 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
         uint32_t S = (sb & 0x7fffffu) | 0x800000u;
         if (s_ok) {
             const float scale = __uint_as_float((uint32_t)(127 + 23 - e) << 23);
+            // every lane summarises one tile: the increment of S for an even (u0) and for an odd (u1) incoming S
+            uint32_t u0 = 0u, u1 = 0u;  // lanes outside [tile, ntiles) are the identity
+            bool ok = true;
             if (lane >= tile && lane < ntiles) {
                 const float* row = A + lane * SB_STRIDE;
                 // A tie rounds to even: after the first tie of the run the parity is 0 whatever came in, so the two
@@ -43,7 +46,7 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
                 // plus that difference.
                 int inc0 = 0, dif = 0;
                 uint32_t par = 0u;
-                bool seen = false, ok = true;
+                bool seen = false;
 #pragma unroll 8
                 for (int k = 0; k < 32; k++) {
                     const float v = row[k];
@@ -59,24 +62,25 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
                     inc0 += a + (int)c;
                     par = (t + c) & 1u;
                 }
-                const int inc1 = inc0 + dif;
-                sums[3 * lane] = inc0;
-                sums[3 * lane + 1] = inc1;
-                sums[3 * lane + 2] = ok ? 1 : 0;
+                u0 = (uint32_t)inc0;
+                u1 = (uint32_t)(inc0 + dif);
             }
-            __syncwarp();
-            if (lane == 0) {
-                int t = tile;
-                for (; t < ntiles; t++) {
-                    if (!sums[3 * t + 2]) break;
-                    const uint32_t Sn = S + (uint32_t)sums[3 * t + (S & 1u)];
-                    if (Sn >= 0x1000000u) break;  // the binade ends: this tile is added value by value
-                    S = Sn;
+            // the summaries compose (the parity after a tile is the parity of S + its increment): an inclusive scan
+            // over the lanes gives the increment from tile `tile` through every tile for either incoming parity.
+            // (32-bit wrap-around can only happen after the first tile that ends the binade, which is all we need.)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t b0 = __shfl_up_sync(0xffffffffu, u0, d), b1 = __shfl_up_sync(0xffffffffu, u1, d);
+                if (lane >= d) {
+                    const uint32_t n0 = b0 + ((b0 & 1u) ? u1 : u0);
+                    const uint32_t n1 = b1 + ((b1 & 1u) ? u0 : u1);
+                    u0 = n0; u1 = n1;
                 }
-                fail = t;
             }
-            fail = __shfl_sync(0xffffffffu, fail, 0);
-            S = __shfl_sync(0xffffffffu, S, 0);
+            const uint32_t S_after = S + ((S & 1u) ? u1 : u0);
+            const uint32_t bad = __ballot_sync(0xffffffffu, !ok || S_after >= 0x1000000u);
+            fail = bad ? __ffs(bad) - 1 : ntiles;  // the first tile that has to be added value by value
+            if (fail > tile) S = __shfl_sync(0xffffffffu, S_after, fail - 1);
             s = __uint_as_float(((uint32_t)(e + 127) << 23) | (S & 0x7fffffu));
             __syncwarp();
         }
@@ -102,7 +106,7 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
 // JNN = true: ONE channel, the samples clamped to [0, 1200] (rm_outlier, jnn.c:58-75), i.e. meanf / stdvf of the
 // signal jnn_core thresholds (jnn.c:181-185); out = [n_reads][2] (mean, stdv).
 template <bool JNN>
-__global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __restrict__ out) {
+__global__ void __launch_bounds__(128, 4) stat_moments_kernel(DevBatch b, float* __restrict__ out) {
     __shared__ float add_all[4][JNN ? 1 : 2][32 * SB_STRIDE];
     __shared__ int sums_all[4][96];
     float (*add)[32 * SB_STRIDE] = add_all[threadIdx.x >> 5];
@@ -115,37 +119,58 @@ __global__ void __launch_bounds__(128) stat_moments_kernel(DevBatch b, float* __
         const float off = JNN ? 0.0f : b.offset[r], unit = JNN ? 0.0f : b.unit[r];
         const float nf = (float)n;
         float mean_r = 0.0f, mean_p = 0.0f;
+        // 128-bit loads: lane L takes the words q*32 + L of a superblock (4 per lane, 512 contiguous bytes per
+        // instruction); the next superblock's are in flight while this one is added up (the kernel is bound by the
+        // latency of these loads: one warp per read, profiles/r01_jnn_moments_ncu.md)
+        const uint4* __restrict__ src = reinterpret_cast<const uint4*>(raw);
+        const int n_words = (n + 7) >> 3;
+        uint4 cur[4], nxt[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int w = q * 32 + lane;
+            cur[q] = w < n_words ? __ldg(src + w) : make_uint4(0, 0, 0, 0);
+        }
         for (int pass = 0; pass < 2; pass++) {
             float acc_r = 0.0f, acc_p = 0.0f;
             for (int t0 = 0; t0 < n; t0 += SB) {
                 __syncwarp();  // the previous superblock's readers are done
-                int vv[32];  // all 32 loads in flight before the first use (one warp per read: latency is everything)
+                {
+                    const int tn = t0 + SB < n ? t0 + SB : 0;  // after the last superblock: the first one again (pass 2)
 #pragma unroll
-                for (int k = 0; k < 32; k++) {
-                    const int i = t0 + k * 32 + lane;
-                    vv[k] = i < n ? (int)raw[i] : 0;
-                }
-#pragma unroll
-                for (int k = 0; k < 32; k++) {
-                    const int i = t0 + k * 32 + lane;
-                    float ar = 0.0f, ap = 0.0f;
-                    if (i < n) {
-                        const int16_t v = (int16_t)vv[k];
-                        if (JNN) {
-                            ar = (float)min(max((int)v, 0), 1200);
-                        } else {
-                            ar = (float)v;
-                            ap = pa_of(v, off, unit);
-                        }
-                        if (pass) {
-                            const float dr = __fsub_rn(ar, mean_r), dp = __fsub_rn(ap, mean_p);
-                            ar = __fmul_rn(dr, dr);
-                            ap = __fmul_rn(dp, dp);
-                        }
+                    for (int q = 0; q < 4; q++) {
+                        const int w = (tn >> 3) + q * 32 + lane;
+                        nxt[q] = w < n_words ? __ldg(src + w) : make_uint4(0, 0, 0, 0);
                     }
-                    add[0][k * SB_STRIDE + lane] = ar;
-                    if (!JNN) add[JNN ? 0 : 1][k * SB_STRIDE + lane] = ap;
                 }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t wd[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
+#pragma unroll
+                    for (int h = 0; h < 8; h++) {
+                        const int j = q * 256 + lane * 8 + h;  // sample of the superblock: tile j/32, column j%32
+                        const int i = t0 + j;
+                        float ar = 0.0f, ap = 0.0f;
+                        if (i < n) {
+                            const int16_t v = (int16_t)(wd[h >> 1] >> ((h & 1) * 16));
+                            if (JNN) {
+                                ar = (float)min(max((int)v, 0), 1200);
+                            } else {
+                                ar = (float)v;
+                                ap = pa_of(v, off, unit);
+                            }
+                            if (pass) {
+                                const float dr = __fsub_rn(ar, mean_r), dp = __fsub_rn(ap, mean_p);
+                                ar = __fmul_rn(dr, dr);
+                                ap = __fmul_rn(dp, dp);
+                            }
+                        }
+                        const int at = (j >> 5) * SB_STRIDE + (j & 31);
+                        add[0][at] = ar;
+                        if (!JNN) add[JNN ? 0 : 1][at] = ap;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) cur[q] = nxt[q];
                 __syncwarp();
                 const int ntiles = (min(SB, n - t0) + 31) >> 5;
                 acc_r = chain_superblock(add[0], ntiles, acc_r, lane, sums, t0 == 0);
@@ -232,15 +257,20 @@ __global__ void __launch_bounds__(256) stat_median_kernel(DevBatch b, float* __r
     }
 }
 
-int launch_stat(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st) {
+int launch_stat_moments(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st) {
     if (b.n_reads == 0) return 0;
     int g1 = (int)((b.n_reads + 3) / 4);  // one warp per read
     if (g1 > sm_count * 16) g1 = sm_count * 16;
     stat_moments_kernel<false><<<g1, 128, 0, st>>>(b, stat6);
+    return 1;
+}
+
+int launch_stat_median(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st) {
+    if (b.n_reads == 0) return 0;
     int g2 = (int)b.n_reads;
     if (g2 > sm_count * 8) g2 = sm_count * 8;
     stat_median_kernel<<<g2, 256, 0, st>>>(b, stat6);
-    return 2;
+    return 1;
 }
 
 // mean and standard deviation (float, in the reference's summation order) of the samples clamped to [0, 1200]:
