@@ -194,17 +194,41 @@ __global__ void __launch_bounds__(128, 4) stat_moments_kernel(DevBatch b, float*
     }
 }
 
-// element of rank `rank` (0-based, ascending) of one read's int16 samples; all threads of the CTA call it
+// element of rank `rank` (0-based, ascending) of one read's int16 samples; all threads of the CTA call it.
+// Two levels over the order-preserving key raw + 32768: the upper 12 bits (4096 bins: the ~1,000 ADC units a signal
+// spans spread over ~60 bins, so the shared-memory atomics of a warp rarely meet; with 256 bins they met on 2-4 bins),
+// then the lower 4 bits among the samples of the selected bin. 128-bit loads (the read starts 16-byte aligned).
+constexpr int MED_BINS = 4096;
 __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint32_t rank, uint32_t* hist,
-                               uint32_t* sh) {
-    // level 1: high byte of the order-preserving key (raw + 32768)
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[k] = 0;
+                               uint32_t* part, uint32_t* sh) {
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(raw);
+    const uint32_t n_words = (n + 7u) >> 3;
+    for (int k = threadIdx.x; k < MED_BINS; k += blockDim.x) hist[k] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[((uint32_t)(raw[i] + 32768)) >> 8], 1u);
+    for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+        const uint4 q = __ldg(src + w);
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+            const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
+            if (w * 8u + h < n) atomicAdd(&hist[key >> 4], 1u);
+        }
+    }
+    __syncthreads();
+    {   // 256 threads x 16 bins, then one thread over the 256 partial sums and the 16 bins of the group
+        uint32_t sum = 0;
+        for (int k = 0; k < MED_BINS / 256; k++) sum += hist[threadIdx.x * (MED_BINS / 256) + k];
+        part[threadIdx.x] = sum;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t seen = 0, k = 0;
-        for (; k < 256; k++) {
+        uint32_t seen = 0, g = 0;
+        for (; g < 256; g++) {
+            if (seen + part[g] > rank) break;
+            seen += part[g];
+        }
+        uint32_t k = g * (MED_BINS / 256);
+        for (;; k++) {
             if (seen + hist[k] > rank) break;
             seen += hist[k];
         }
@@ -214,41 +238,47 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
     __syncthreads();
     const uint32_t hi = sh[0], rank2 = sh[1];
     __syncthreads();
-    // level 2: low byte among the samples whose high byte matched
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[k] = 0;
+    // level 2: the low 4 bits among the samples whose upper 12 bits matched
+    if (threadIdx.x < 16) part[threadIdx.x] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t key = (uint32_t)(raw[i] + 32768);
-        if ((key >> 8) == hi) atomicAdd(&hist[key & 255u], 1u);
+    for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+        const uint4 q = __ldg(src + w);
+        const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+            const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
+            if ((key >> 4) == hi && w * 8u + h < n) atomicAdd(&part[key & 15u], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t seen = 0, k = 0;
-        for (; k < 256; k++) {
-            if (seen + hist[k] > rank2) break;
-            seen += hist[k];
+        for (; k < 16; k++) {
+            if (seen + part[k] > rank2) break;
+            seen += part[k];
         }
         sh[2] = k;
     }
     __syncthreads();
-    const int med = (int)((hi << 8) | sh[2]) - 32768;
+    const int med = (int)((hi << 4) | sh[2]) - 32768;
     __syncthreads();
     return med;
 }
 
 __global__ void __launch_bounds__(256) stat_median_kernel(DevBatch b, float* __restrict__ out) {
-    __shared__ uint32_t hist[256];
+    __shared__ uint32_t hist[MED_BINS];
+    __shared__ uint32_t part[256];
     __shared__ uint32_t sh[4];
     for (uint32_t r = blockIdx.x; r < b.n_reads; r += gridDim.x) {
         const int16_t* __restrict__ raw = b.samples + b.read_off[r];
         const uint32_t n = b.read_len[r];
         if (n == 0) continue;
         const uint32_t rank = (uint32_t)((int)n / 2);  // ks_ksmall(n, copy, n/2), stat.h:60,70
-        const int med_r = select_rank_i16(raw, n, rank, hist, sh);
+        const int med_r = select_rank_i16(raw, n, rank, hist, part, sh);
         const float off = b.offset[r], unit = b.unit[r];
         // pA is non-decreasing in raw for unit >= 0 and non-increasing for unit < 0
         int med_for_pa = med_r;
-        if (unit < 0.0f) med_for_pa = select_rank_i16(raw, n, n - 1 - rank, hist, sh);
+        if (unit < 0.0f) med_for_pa = select_rank_i16(raw, n, n - 1 - rank, hist, part, sh);
         if (threadIdx.x == 0) {
             float* o = out + (size_t)r * 6;
             o[4] = (float)med_r;
