@@ -53,20 +53,22 @@ __device__ double entropy_sweep(EntShared& s, uint32_t kmin, uint32_t kmax, doub
             const double p = __ddiv_rn((double)c, len);       // ent.c:41
             t = __dmul_rn(p, log2(p));                        // ent.c:42
         }
-        s.term[threadIdx.x] = t;
+        // the nonzero terms of the chunk, packed in key order, so that the ordered subtraction below is one
+        // dependent FP64 operation per term and nothing else
         const uint32_t m = __ballot_sync(0xffffffffu, c != 0);
         if (lane == 0) s.mask[warp] = m;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 0; w < ENT_THREADS / 32; w++) {
-                uint32_t mm = s.mask[w];
-                while (mm) {
-                    const int b = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    ent = __dsub_rn(ent, s.term[w * 32 + b]);  // ent.c:42, ascending key order
-                }
-            }
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < ENT_THREADS / 32; w++) {
+            const uint32_t pc = __popc(s.mask[w]);
+            if (w < warp) before += pc;
+            total += pc;
         }
+        if (c) s.term[before + __popc(m & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (uint32_t q = 0; q < total; q++) ent = __dsub_rn(ent, s.term[q]);  // ent.c:42, ascending key order
         __syncthreads();
     }
     return ent;

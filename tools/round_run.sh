@@ -10,6 +10,7 @@ ncu --set full --clock-control none --import-source on -k regex:emit_events -s 3
 ncu --set full --clock-control none --import-source on -k regex:svb_write -s 1 -c 1 -f -o gpurun_out/r01_svb_write python bench.py --steps 1 --warmup 3 --no-cpu --reads-per-step 1024 --e2e-reads 16384 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ent_kernel -s 1 -c 1 -f -o gpurun_out/r01_ent_kernel python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:jnn_walk -s 1 -c 1 -f -o gpurun_out/r01_jnn_walk python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stat_moments -s 1 -c 1 -f -o gpurun_out/r01_stat_moments python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
 python tools/fallback_cost.py 2>&1 | tail -2 | tee gpurun_out/r01_glitch_cost.jsonl
 python tools/cli_bench.py --reads 8000 2>gpurun_out/cli_bench_err.log | tee gpurun_out/r01_cli_bench.jsonl | cut -c1-200
 python tools/stat_time.py 2>&1 | tail -3 | tee gpurun_out/r01_stat_pa_time.jsonl
