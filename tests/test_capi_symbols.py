@@ -27,6 +27,20 @@ def test_library_exports_every_declared_symbol():
     assert lib.sgpu_abi_version() == 4
 
 
+def test_python_mirror_matches_the_header():
+    """the WANT_* / F_* constants and the result struct of the ctypes mirror follow include/sigtk_b200.h"""
+    hdr = open(os.path.join(ROOT, "include", "sigtk_b200.h")).read()
+    defs = {k: int(v.rstrip("u"), 0) for k, v in re.findall(r"#define\s+(SGPU_[A-Z_]+)\s+(-?\d+u?)\b", hdr)}
+    for name in ("EVENTS", "PA", "STAT", "ENT", "JNN"):
+        assert getattr(_lib, "WANT_" + name) == defs["SGPU_WANT_" + name]
+    for name in ("DEFAULT", "FORCE_GENERIC", "NO_HOST_SLOTS", "STAGE_TIMERS"):
+        assert getattr(_lib, "F_" + name) == defs["SGPU_F_" + name]
+    assert _lib.ALIGN == defs["SGPU_ALIGN"] and _lib.E_FULL == defs["SGPU_E_FULL"] and _lib.E_TOOBIG == defs["SGPU_E_TOOBIG"]
+    body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    fields = re.findall(r"\*?\s*(\w+);", re.search(r"typedef struct \{([^}]*)\} sgpu_result_t;", body).group(1))
+    assert fields == [f[0] for f in _lib.Result._fields_]
+
+
 def test_strerror_and_argument_checks():
     lib = _lib.load()
     assert lib.sgpu_strerror(0) == b"success"
