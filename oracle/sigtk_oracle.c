@@ -294,6 +294,139 @@ int64_t orc_jnn(const int16_t *raw, uint64_t n, int rna, uint64_t cap, int64_t *
     return (uint64_t)n_seg > cap ? -n_seg : n_seg;
 }
 
+/* float mean / stdv in sample order (stat.h:17-24, 36-44) and the n/2-th smallest (stat.h:55-63) of x[0..n) */
+static float seq_meanf(const float *x, int n) {
+    float acc = 0.0f;
+    for (int i = 0; i < n; i++) acc = acc + x[i];
+    return acc / (float)n;
+}
+static float seq_stdvf(const float *x, int n) {
+    const float m = seq_meanf(x, n);
+    float acc = 0.0f;
+    for (int i = 0; i < n; i++) {
+        const float d = x[i] - m;
+        acc = acc + d * d;
+    }
+    return sqrtf(acc / (float)n);
+}
+static float rank_half(const float *x, int n) {
+    float *tmp = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+    memcpy(tmp, x, (size_t)n * sizeof(float));
+    qsort(tmp, (size_t)n, sizeof(float), cmp_float);
+    const float v = n > 0 ? tmp[n / 2] : 0.0f;
+    free(tmp);
+    return v;
+}
+
+/* jnn.c:103-175 (jnnv2) with JNNV2_RNA_R9_ADAPTOR: the band's lower edge over a 2000-sample rolling mean of the
+ * clamped signal, runs below it, first run of a plausible length */
+static void adaptor_r9(const int16_t *raw, int64_t n, int64_t *x, int64_t *y) {
+    const int w = 2000, merge = 1500, longest = 200000, shortest = 2000;
+    if (n <= w) { *x = -1; *y = -1; return; }
+    const int nt = (int)n - w;
+    float *t = (float *)malloc((size_t)nt * sizeof(float));
+    #define CLAMPED(i) (raw[i] > 1200 ? 1200.0f : raw[i] < 0 ? 0.0f : (float)raw[i])
+    float run = 0.0f;
+    for (int i = 0; i < w; i++) run = run + CLAMPED(i);
+    t[0] = run / (float)w;
+    for (int i = 1; i < nt; i++) {
+        run = run - CLAMPED(i - 1);
+        run = run + CLAMPED(i + w - 1);
+        t[i] = run / (float)w;
+    }
+    #undef CLAMPED
+    const float mn = seq_meanf(t, nt), sd = seq_stdvf(t, nt);
+    const float floor_ = mn - sd * 0.5f;
+    int below = 0, first = 0, last = 0;
+    int64_t n_seg = 0, cap = 64;
+    int64_t *sx = (int64_t *)malloc((size_t)cap * 2 * sizeof(int64_t));
+    for (int j = 0; j < nt; j++) {
+        const float v = t[j];
+        if (v < floor_) {
+            if (!below) { first = j; below = 1; } else last = j;
+        } else if (v > floor_ && below) {
+            if (n_seg && first - sx[2 * (n_seg - 1) + 1] < merge) {
+                sx[2 * (n_seg - 1) + 1] = last;
+            } else {
+                if (n_seg == cap) { cap *= 2; sx = (int64_t *)realloc(sx, (size_t)cap * 2 * sizeof(int64_t)); }
+                sx[2 * n_seg] = first; sx[2 * n_seg + 1] = last;
+                n_seg++;
+            }
+            first = 0; last = 0; below = 0;
+        }
+    }
+    *x = 0; *y = 0;
+    for (int64_t k = 0; k < n_seg; k++) {
+        const int64_t len = sx[2 * k + 1] - sx[2 * k];
+        if (len > longest || len < shortest) continue;
+        *x = sx[2 * k] + w / 2 - 1;
+        *y = sx[2 * k + 1] + w / 2 - 1;
+        break;
+    }
+    free(sx); free(t);
+}
+
+/* jnn.c:176-266 on pA clamped to [0,1200] (jnn_pa, jnn.c:284-297) with a given band and JNNV1_R9_POLYA
+ * (window 250, 30 tolerated outliers, merge distance 200, stall_len 1): only the FIRST segment is wanted (jnn.c:360) */
+static void polya_r9(const float *pa, int64_t n, float top, float bot, int64_t *x, int64_t *y) {
+    const int window = 250, tolerated = 30, merge = 200;
+    const float stall = 1.0f;
+    *x = -1; *y = -1;
+    int open = 0, run = 0, grow = 50, bad = 0, tail = 0, first = 0;
+    int64_t n_seg = 0, sx0 = 0, sy0 = 0, last_y = 0;
+    for (int i = 0; i < (int)n; i++) {
+        const float v = pa[i] > 1200.0f ? 1200.0f : pa[i] < 0.0f ? 0.0f : pa[i];
+        if (v < top && v > bot) {
+            if (!open) { open = 1; first = i; }
+            run++; grow++; tail = 0;
+            if (run >= window && run >= grow && run % grow == 0) bad--;
+        } else if (open) {
+            if (bad < tolerated) {
+                run++; bad++; tail++;
+                if (run >= window && run >= grow && run % grow == 0) bad--;
+            } else {
+                if (run >= window || (n_seg == 0 && (float)run >= (float)window * stall)) {
+                    const int stop = i - tail;
+                    if (n_seg && first - last_y < merge) {
+                        if (n_seg == 1) sy0 = stop;
+                    } else {
+                        if (n_seg == 0) { sx0 = first; sy0 = stop; }
+                        n_seg++;
+                    }
+                    last_y = stop;
+                }
+                open = 0; run = 0; bad = 0; tail = 0;
+            }
+        }
+    }
+    if (n_seg > 0) { *x = sx0; *y = sy0; }
+}
+
+void orc_adaptor_polya(const int16_t *raw, uint64_t n, double digitisation, double offset, double range, int rna,
+                int64_t *pos4, float *st6) {
+    for (int k = 0; k < 6; k++) st6[k] = 0.0f;
+    pos4[2] = -1; pos4[3] = -1;
+    adaptor_r9(raw, (int64_t)n, &pos4[0], &pos4[1]);
+    if (pos4[1] <= 0) return;                                  /* cfunc.c:173 */
+    float *pa = (float *)malloc((n ? n : 1) * sizeof(float));
+    orc_pa(raw, n, digitisation, offset, range, pa);
+    const int64_t ax = pos4[0], ay = pos4[1];
+    st6[0] = seq_meanf(pa + ax, (int)(ay - ax));
+    st6[1] = seq_stdvf(pa + ax, (int)(ay - ax));
+    st6[2] = rank_half(pa + ax, (int)(ay - ax));
+    if (rna) {                                                  /* cfunc.c:189-190: m_a+30+20, m_a+30-20 in float */
+        const float top = (st6[0] + 30) + 20, bot = (st6[0] + 30) - 20;
+        polya_r9(pa + ay, (int64_t)n - ay, top, bot, &pos4[2], &pos4[3]);
+        if (pos4[3] > 0) {
+            const int64_t px = pos4[2] + ay, len = pos4[3] - pos4[2];
+            st6[3] = seq_meanf(pa + px, (int)len);
+            st6[4] = seq_stdvf(pa + px, (int)len);
+            st6[5] = rank_half(pa + px, (int)len);
+        }
+    }
+    free(pa);
+}
+
 /* Shannon entropy in bits of a table of bin counts taken over `total` symbols; terms are subtracted in
  * ascending bin order like ent.c:38-46 (the order matters in the last bits). */
 static double bits_of_counts(const uint64_t *cnt, uint32_t bins, uint64_t total) {

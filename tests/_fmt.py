@@ -74,6 +74,22 @@ def _i32(u):
     return u - (1 << 32) if u >= (1 << 31) else u
 
 
+def prefix_line(read_id, n, pos, st, p_stat=False) -> str:
+    """prefix_func (cfunc.c:169-234)"""
+    s = "%s\t%d\t" % (read_id, n)
+    if pos[1] > 0:
+        s += "%d\t%d\t" % (pos[0], pos[1])
+        s += "%d\t%d" % (pos[2] + pos[1], pos[3] + pos[1]) if pos[3] > 0 else ".\t."
+        if p_stat:
+            s += "\t%s\t%s\t%s\t" % (f6(st[0]), f6(st[1]), f6(st[2]))
+            s += "\t%s\t%s\t%s\t" % (f6(st[3]), f6(st[4]), f6(st[5])) if pos[3] > 0 else "\t.\t.\t."
+    else:
+        s += ".\t.\t.\t."
+    return s + "\n"
+
+
+PREFIX_HDR = "read_id\tlen_raw_signal\tadapt_start\tadapt_end\tpolya_start\tpolya_end"
+PREFIX_HDR_STAT = "\tadapt_mean\tadapt_std\tadapt_median\tpolya_mean\tpolya_std\tpolya_median"
 JNN_HDR = "read_id\tlen_raw_signal\tnum_seg\tseg\n"
 ENT_HDR = "read_id\traw_ent\tdelta_ent\tbyte_ent\n"
 EVENT_HDR_LONG = "read_id\tevent_idx\traw_start\traw_end\tevent_mean\tevent_std\n"

@@ -21,6 +21,10 @@ Nothing here runs on the GPU box; the fixtures it writes are committed.
                                     seeded reads with stalls (long stretches near the read's mean, a few outliers inside,
                                     pairs closer than the merge distance, open stretches at the end, clipped spikes) and
                                     the compiled reference's `sigtk jnn` stdout             (`make_golden.py jnn`)
+  prefix_dna.exp                    the reference's own golden for `sigtk prefix test/sp1_dna.blow5` (scripts/test.sh:54-56)
+  ref_{sp1,rna}_prefix_stat.txt, prefix_adaptor_{dna,rna}.npz / ref_prefix_adaptor_{dna,rna}{,_stat}.txt
+                                    `sigtk prefix [--print-stat]` of the compiled reference on the two files and on seeded
+                                    reads with an adaptor and a poly-A-like stretch      (`make_golden.py prefix`)
 """
 import gzip
 import hashlib
@@ -170,7 +174,57 @@ def jnn_goldens():
                             range=np.array([r[3] for r in reads]))
 
 
+def prefix_adaptor_reads(rna):
+    """reads with a low-current adaptor stretch near the start, a flat poly-A-like stretch behind it, then signal"""
+    rng = np.random.default_rng(20260019 + int(rna))
+    reads = []
+    for k in range(12):
+        n = int(rng.integers(20000, 90000))
+        raw = (525 + 70 * rng.standard_normal(n)).astype(np.int64)
+        lead = int(rng.integers(200, 3000))
+        alen = int(rng.integers(3500, 12000)) if k != 3 else 0        # read 3: no adaptor at all
+        raw[lead:lead + alen] = 380 + 25 * rng.standard_normal(alen)
+        plen = int(rng.integers(300, 4000)) if k % 4 != 1 else 0       # every fourth read: no poly-A stretch
+        a = lead + alen
+        raw[a:a + plen] = 575 + 12 * rng.standard_normal(plen)
+        if k % 5 == 0:
+            raw[::1501] = 4000                                          # clipped spikes
+        if k == 7:
+            raw[n // 2: n // 2 + 5000] = 370 + 20 * rng.standard_normal(5000)   # a second low stretch
+        reads.append((np.clip(raw, -32768, 32767).astype(np.int16), 8192.0, 3.0, 1402.882324))
+    reads.append(((525 + 70 * rng.standard_normal(1500)).astype(np.int16), 8192.0, 3.0, 1402.882324))  # n <= window
+    return reads
+
+
+def prefix_goldens():
+    sp1 = os.path.join(HERE, "sp1_dna.blow5")
+    rna = os.path.join(HERE, "synth_rna.blow5")
+    shutil.copyfile(os.path.join(REF, "test", "prefix_dna.exp"), os.path.join(HERE, "prefix_dna.exp"))
+    os.chmod(os.path.join(HERE, "prefix_dna.exp"), 0o644)
+    for tag, path in (("sp1", sp1), ("rna", rna)):
+        open(os.path.join(HERE, f"ref_{tag}_prefix_stat.txt"), "wb").write(run([SIGTK, "prefix", "--print-stat", path]))
+    for flag, kind in ((0, "dna"), (1, "rna")):
+        reads = prefix_adaptor_reads(flag)
+        ids = [f"adaptor-{kind}-{i:02d}" for i in range(len(reads))]
+        tmp = os.path.join(HERE, "_prefix.blow5")
+        write_blow5(reads, ids, tmp, "rna" if flag else "genomic_dna")
+        open(os.path.join(HERE, f"ref_prefix_adaptor_{kind}.txt"), "wb").write(run([SIGTK, "prefix", tmp]))
+        open(os.path.join(HERE, f"ref_prefix_adaptor_{kind}_stat.txt"), "wb").write(run([SIGTK, "prefix", "--print-stat", tmp]))
+        os.remove(tmp)
+        lens = [r[0].shape[0] for r in reads]
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        np.savez_compressed(os.path.join(HERE, f"prefix_adaptor_{kind}.npz"), read_ids=np.array(ids),
+                            samples=np.concatenate([r[0] for r in reads]), read_off=off,
+                            digitisation=np.array([r[1] for r in reads]), offset=np.array([r[2] for r in reads]),
+                            range=np.array([r[3] for r in reads]))
+
+
 def main():
+    if sys.argv[1:] == ["prefix"]:
+        prefix_goldens()
+        print("prefix fixtures written to", HERE)
+        return
     if sys.argv[1:] == ["jnn"]:
         jnn_goldens()
         print("jnn fixtures written to", HERE)
@@ -216,6 +270,7 @@ def main():
     sha["rna_pa"] = hashlib.sha256(full).hexdigest()
     ent_goldens()
     jnn_goldens()
+    prefix_goldens()
     json.dump(sha, open(os.path.join(HERE, "sha256.json"), "w"), indent=1, sort_keys=True)
     print("golden fixtures written to", HERE)
 

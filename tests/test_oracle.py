@@ -136,6 +136,31 @@ def test_jnn_equals_reference_stdout(orc, npz, txt, rna_flag):
         assert got == exp, suffix
 
 
+# ---- `sigtk prefix` (prefix half): oracle only, the CUDA path is next round's --------------------
+@pytest.mark.parametrize("npz,txt,rna_flag", [("sp1_dna.npz", "ref_sp1_prefix_stat.txt", 0),
+                                              ("synth_rna.npz", "ref_rna_prefix_stat.txt", 1),
+                                              ("prefix_adaptor_dna.npz", "ref_prefix_adaptor_dna_stat.txt", 0),
+                                              ("prefix_adaptor_rna.npz", "ref_prefix_adaptor_rna_stat.txt", 1)])
+def test_prefix_equals_reference_stdout(orc, npz, txt, rna_flag):
+    """orc_adaptor_polya against `sigtk prefix --print-stat` (and, without the statistics, `sigtk prefix`) of the
+    compiled reference: adaptor by jnnv2 on the rolling mean, poly-A by jnn_core on pA, float statistics of both"""
+    reads = _fmt.load_npz(os.path.join(G, npz))
+    rows = [(rid, len(rd[0])) + orc.adaptor_polya(*rd, rna=rna_flag) for rid, rd in reads]
+    got = _fmt.PREFIX_HDR + _fmt.PREFIX_HDR_STAT + "\n" + "".join(_fmt.prefix_line(r, n, p, s, True) for r, n, p, s in rows)
+    assert got == open(os.path.join(G, txt)).read()
+    plain = txt.replace("_stat.txt", ".txt")
+    if os.path.exists(os.path.join(G, plain)):
+        got = _fmt.PREFIX_HDR + "\n" + "".join(_fmt.prefix_line(r, n, p, s, False) for r, n, p, s in rows)
+        assert got == open(os.path.join(G, plain)).read()
+
+
+def test_prefix_dna_exp(orc, sp1):
+    """the reference's own golden test/prefix_dna.exp (scripts/test.sh:54-56)"""
+    got = _fmt.PREFIX_HDR + "\n" + "".join(_fmt.prefix_line(rid, len(rd[0]), *orc.adaptor_polya(*rd, rna=0))
+                                           for rid, rd in sp1)
+    assert got == open(os.path.join(G, "prefix_dna.exp")).read()
+
+
 def _bits(a):
     return a.view(np.uint32) if a.dtype == np.float32 else a
 
