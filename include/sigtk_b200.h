@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SGPU_ABI_VERSION 4
+#define SGPU_ABI_VERSION 5
 
 /* ---- error codes ------------------------------------------------------- */
 #define SGPU_OK            0
@@ -62,6 +62,8 @@ extern "C" {
 #define SGPU_F_FORCE_GENERIC 1u /* run every read through the sequential-order (reference-order) kernels */
 #define SGPU_F_NO_HOST_SLOTS 2u /* device-resident use only: do not allocate pinned slots */
 #define SGPU_F_STAGE_TIMERS  4u /* record CUDA events between the kernel groups of a run (sgpu_stage_times) */
+#define SGPU_F_FULL_SEQ_SCRATCH 8u /* size the sequential-order scratch for the whole batch (a context opened for one
+                                      huge read: the reference handles any read < 2^31 samples, misc.c:20) */
 
 typedef struct sgpu_ctx sgpu_ctx_t;
 
@@ -190,8 +192,18 @@ typedef struct {
     uint64_t n_fixups;            /* detector chunks with a boundary-state mismatch */
     uint64_t n_kernel_launches;   /* kernels launched by the last run */
     int32_t  status;              /* 0 or SGPU_E_EVCAP / SGPU_E_SCRATCH reported by the device */
+    uint64_t n_long_jobs;         /* stretches of the long peak detector (events.c:414-437) that were replayed with the
+                                     reference's own operations because their t-statistic may exceed its threshold */
 } sgpu_counters_t;
 int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
+
+/* Development / test parameters of a context (take effect from the next run; nothing reads the environment).
+ * They never change results -- except SGPU_PARAM_THR_LONG, which replaces the reference's constant 9.0
+ * (events.c:46,53) so that tests can make the long detector emit. */
+#define SGPU_PARAM_CHUNK_LEN 1 /* samples per detector chunk (power of two >= 128 DNA / 512 RNA); 0 = automatic */
+#define SGPU_PARAM_WARMUP    2 /* detector warm-up in samples (multiple of 8 DNA / 16 RNA, <= default); 0 = default */
+#define SGPU_PARAM_THR_LONG  3 /* threshold of the long detector */
+int  sgpu_set_param(sgpu_ctx_t *ctx, int key, double value);
 
 /* Device time of every kernel group of the last run, measured with CUDA events on the stream the kernels were
  * launched on (needs SGPU_F_STAGE_TIMERS). Returns the number of entries written, or a negative code. */

@@ -24,8 +24,9 @@ EXPORTS = (
     "sgpu_abi_version", "sgpu_device_count", "sgpu_create", "sgpu_destroy", "sgpu_strerror",
     "sgpu_last_error", "sgpu_slot_batch", "sgpu_slot_reset", "sgpu_slot_add_read", "sgpu_submit",
     "sgpu_wait", "sgpu_run_device", "sgpu_counters", "sgpu_memcpy_d2h", "sgpu_stage_times",
-    "sgpu_slot_add_read_svbzd", "sgpu_decode_svbzd_device",
+    "sgpu_slot_add_read_svbzd", "sgpu_decode_svbzd_device", "sgpu_set_param",
 )
+PARAM_CHUNK_LEN, PARAM_WARMUP, PARAM_THR_LONG = 1, 2, 3  # sgpu_set_param keys (development / test parameters)
 
 
 class SgpuError(RuntimeError):
@@ -67,7 +68,7 @@ class SvbDevBatch(C.Structure):  # sgpu_svb_dev_batch_t
 class Counters(C.Structure):  # sgpu_counters_t
     _fields_ = [
         ("n_events", C.c_uint64), ("n_seq_order_reads", C.c_uint64), ("n_fixups", C.c_uint64),
-        ("n_kernel_launches", C.c_uint64), ("status", C.c_int32),
+        ("n_kernel_launches", C.c_uint64), ("status", C.c_int32), ("n_long_jobs", C.c_uint64),
     ]
 
 
@@ -121,5 +122,7 @@ def load() -> C.CDLL:
     lib.sgpu_stage_times.restype = i32
     lib.sgpu_memcpy_d2h.argtypes = [vp, vp, vp, u64]
     lib.sgpu_memcpy_d2h.restype = i32
+    lib.sgpu_set_param.argtypes = [vp, i32, C.c_double]
+    lib.sgpu_set_param.restype = i32
     _lib = lib
     return lib

@@ -203,7 +203,12 @@ class Context:
         c = _lib.Counters()
         self._check(self._lib.sgpu_counters(self._h, C.byref(c)))
         return {"n_events": int(c.n_events), "n_seq_order_reads": int(c.n_seq_order_reads),
-                "n_fixups": int(c.n_fixups), "n_kernel_launches": int(c.n_kernel_launches), "status": int(c.status)}
+                "n_fixups": int(c.n_fixups), "n_kernel_launches": int(c.n_kernel_launches), "status": int(c.status),
+                "n_long_jobs": int(c.n_long_jobs)}
+
+    def set_param(self, key: int, value: float) -> None:
+        """development / test parameters (_lib.PARAM_*): chunk length, detector warm-up, the long detector's threshold"""
+        self._check(self._lib.sgpu_set_param(self._h, int(key), float(value)))
 
 
 # ---- per-record conveniences mirroring the reference's function names --------

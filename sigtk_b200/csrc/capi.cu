@@ -290,7 +290,7 @@ const char* sgpu_last_error(const sgpu_ctx_t* ctx) { return ctx ? ctx->err : "no
 
 int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max_reads, uint32_t n_slots,
                 uint32_t flags) {
-    if (!out || max_samples == 0 || max_reads == 0 || (flags & ~7u)) return SGPU_E_INVAL;
+    if (!out || max_samples == 0 || max_reads == 0 || (flags & ~15u)) return SGPU_E_INVAL;
     *out = nullptr;
     if (flags & SGPU_F_NO_HOST_SLOTS) n_slots = 0; else if (n_slots == 0) n_slots = 2;
     sgpu_ctx* ctx = new (std::nothrow) sgpu_ctx();
@@ -329,8 +329,9 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     Scratch& sc = ctx->sc;
     // scratch of the sequential-order kernels (24 B/sample): everything for small contexts or when forced,
     // one eighth of the batch otherwise (reads that fail the fast path's checks are rare)
-    sc.gen_cap = (max_samples <= (64ull << 20) || (flags & SGPU_F_FORCE_GENERIC)) ? max_samples : max_samples / 8;
-    if (const char* e = getenv("SGPU_GEN_CAP")) { uint64_t v = strtoull(e, nullptr, 10); if (v) sc.gen_cap = v; }
+    // (SGPU_F_FULL_SEQ_SCRATCH: a context opened for one huge read must be able to redo that read in order)
+    sc.gen_cap = (max_samples <= (64ull << 20) || (flags & (SGPU_F_FORCE_GENERIC | SGPU_F_FULL_SEQ_SCRATCH)))
+                     ? max_samples : max_samples / 8;
     CUC(dev_alloc(&sc.Sinc, sc.gen_cap));
     CUC(dev_alloc(&sc.Qinc, sc.gen_cap));
     CUC(dev_alloc(&sc.t1, sc.gen_cap));
@@ -343,6 +344,10 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     CUC(dev_alloc(&sc.wk_end, sc.wk_slots * 8));
     CUC(dev_alloc(&sc.wk_cnt, max_reads));
     CUC(dev_alloc(&sc.wk_ibase, (uint64_t)max_reads + 1));
+    sc.job_cap = walk_job_capacity(max_samples);
+    CUC(dev_alloc(&sc.jobs, (uint64_t)sc.job_cap * 4));
+    CUC(dev_alloc(&sc.job_count, 1));
+    sc.tune_chunk_len = 0; sc.tune_warmup = 0; sc.tune_thr_long = 9.0f;  // events.c:46,53: threshold of the long detector
     CUC(dev_alloc(&sc.tile_cnt, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_read0, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_base, (uint64_t)sc.max_tiles + 1));
@@ -418,6 +423,7 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
     Scratch& sc = ctx->sc;
     cudaFree(sc.Sinc); cudaFree(sc.Qinc); cudaFree(sc.t1); cudaFree(sc.t2); cudaFree(sc.bitmap);
     cudaFree(sc.wk_begin); cudaFree(sc.wk_end); cudaFree(sc.wk_cnt); cudaFree(sc.wk_ibase);
+    cudaFree(sc.jobs); cudaFree(sc.job_count);
     cudaFree(sc.tile_cnt); cudaFree(sc.tile_base); cudaFree(sc.tile_read0);
     cudaFree(sc.wit_min); cudaFree(sc.wit_max); cudaFree(ctx->dev_seq); cudaFree(ctx->dev_fix);
     cudaFree(sc.seq_list); cudaFree(sc.seq_sbase); cudaFree(sc.seq_count); cudaFree(sc.cursor);
@@ -697,7 +703,28 @@ int sgpu_counters(sgpu_ctx_t* ctx, sgpu_counters_t* out) {
     out->n_fixups = c[2];
     out->n_kernel_launches = ctx->last_launches;
     out->status = map_dev_status(status);
+    out->n_long_jobs = c[3];
     return SGPU_OK;
+}
+
+int sgpu_set_param(sgpu_ctx_t* ctx, int key, double value) {
+    if (!ctx) return SGPU_E_INVAL;
+    Scratch& sc = ctx->sc;
+    switch (key) {
+        case SGPU_PARAM_CHUNK_LEN:
+            if (value < 0 || value > (double)(1u << 20)) return SGPU_E_INVAL;
+            sc.tune_chunk_len = (uint32_t)value;
+            return SGPU_OK;
+        case SGPU_PARAM_WARMUP:
+            if (value < 0 || value > 4096) return SGPU_E_INVAL;
+            sc.tune_warmup = (uint32_t)value;
+            return SGPU_OK;
+        case SGPU_PARAM_THR_LONG:
+            if (!(value > 0 && value < 1e6)) return SGPU_E_INVAL;
+            sc.tune_thr_long = (float)value;
+            return SGPU_OK;
+        default: return SGPU_E_INVAL;
+    }
 }
 
 int sgpu_stage_times(sgpu_ctx_t* ctx, sgpu_stage_time_t* out, uint32_t cap) {

@@ -226,18 +226,17 @@ __device__ void detect_read_chunked(const float* __restrict__ t1, const float* _
         const uint32_t c = c0 + lane;
         const bool have = c < n_chunks;
         const uint32_t s0 = c * GD_CHUNK, s1 = min(n, s0 + GD_CHUNK);
-        WalkDet d;
+        DualDet d;
         Canon begin = {}, end = {};
         if (have) {
             uint32_t i = (c == 0) ? 1u : s0 - W;   // position 0 is never stepped (masked_to = 0, events.c:387)
-            det_cold(d, (int)i);
-            PeakAcc unused; unused.mk = 0u; unused.oldest = 0;
+            dual_cold(d, (int)i);
             for (; i < s0; i++)   // warm-up: nothing is recorded
-                det_step<RNA>(d, 0, (int)i, __ldg(t1 + base + i), __ldg(t2 + base + i), unused, NoEmit());
-            begin = canon_of(d, (int)s0);
+                dual_step<RNA>(d, (int)i, __ldg(t1 + base + i), __ldg(t2 + base + i), NoEmit());
+            begin = dual_canon(d, (int)s0);
             for (; i < s1; i++)
-                det_step<RNA>(d, 0, (int)i, __ldg(t1 + base + i), __ldg(t2 + base + i), unused, on_emit);
-            end = canon_of(d, (int)s1);
+                dual_step<RNA>(d, (int)i, __ldg(t1 + base + i), __ldg(t2 + base + i), on_emit);
+            end = dual_canon(d, (int)s1);
         }
         // chunk c must have reached the state chunk c-1 ended in
         bool same = true;

@@ -35,6 +35,12 @@ struct Scratch {
     uint64_t* wk_ibase;              // [max_reads+1] exclusive scan of wk_cnt
     int* wk_begin; int* wk_end;      // [wk_slots*8] detector state after the warm-up / after the last step of a chunk
     uint64_t wk_slots;
+    int* jobs;                       // [job_cap * 4] lives of the long detector to replay: {read, chunk, l_start, end}
+    uint32_t* job_count;             // device scalar
+    uint32_t job_cap;
+    // development / test parameters (sgpu_set_param): 0 = automatic
+    uint32_t tune_chunk_len, tune_warmup;
+    float tune_thr_long;             // the long detector's threshold (9.0)
     uint32_t max_tiles;
     // per read
     uint32_t* wit_min; uint32_t* wit_max;  // exact-sum witness: min nonzero |pA| / max |pA| bit patterns
@@ -63,8 +69,9 @@ int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32
 int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
                 cudaStream_t st);
 uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads);
-uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count);
-uint32_t walk_warmup(int rna);
+uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced);
+uint32_t walk_warmup(int rna, uint32_t forced);
+uint32_t walk_job_capacity(uint64_t max_samples);
 int launch_build_seq_list(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int force_all, int sm_count,
                           cudaStream_t st);
 int launch_rank_events(const DevBatch& b, Scratch& sc, uint64_t* ev_off, int sm_count, cudaStream_t st);

@@ -12,6 +12,11 @@
 // Peaks are owned by the STEP that emits them (not by position): every detector step belongs to exactly one
 // chunk, so every peak of the true trajectory is recorded exactly once, with a RED.OR into the event-start bitmap.
 //
+// The LONG detector is not stepped by the walker (walk_core.cuh): a chunk only tracks where the long detector's
+// current life starts and whether one of its stepped positions MAY exceed the long threshold (a conservative float
+// test on exact integer window sums). Such lives -- about one per 10,000 samples -- are written to a job list and
+// replayed by long_jobs_kernel with the reference's own operations; what they emit is ORed into the same bitmap.
+//
 // Thread blocks [0, edge_blocks) walk the first / last chunks of the reads (bounds-checked variant, they take
 // longest and start first); the remaining blocks walk the interior chunks with the unchecked variant.
 #include <cstdlib>
@@ -47,6 +52,12 @@ struct WalkParams {
     uint32_t* wit_max;
     uint32_t* tile_read0;
     uint32_t edge_blocks;
+    float thr_long;                 // the long detector's threshold (9.0; a context parameter for tests)
+    int4* jobs;                     // [job_cap] {read, chunk, l_start, end}: lives of the long detector to replay
+    uint32_t* job_count;
+    uint32_t job_cap;
+    uint32_t* seq_flag;             // a read whose job does not fit the list goes to the sequential-order kernels
+    unsigned long long* counters;   // [3] = number of replayed lives
 };
 
 // the memory side of one chunk walk (see walk_core.cuh)
@@ -61,6 +72,11 @@ struct DevIo {
     uint32_t* __restrict__ tile_read0;  // per 2048-sample tile; the top bit marks tiles with LOW samples
     uint64_t base;                      // flat position of the read's first sample
     float off, unit;
+    int4* __restrict__ jobs;            // job list (walk_core.cuh: lives of the long detector that may emit)
+    uint32_t* __restrict__ job_count;
+    uint32_t job_cap;
+    uint32_t* __restrict__ seq_flag;
+    int read, chunk;
 
     __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
         const int4 w = __ldg(reinterpret_cast<const int4*>(sp + t));
@@ -105,6 +121,11 @@ struct DevIo {
             atomicMin(wit_min, xl > 0.0f ? __float_as_uint(xl) : 1u);  // (xl > 0 by the definition of low_t)
         }
     }
+    __device__ __forceinline__ void job(int l_start, int end) const {
+        const uint32_t k = atomicAdd(job_count, 1u);
+        if (k < job_cap) jobs[k] = make_int4(read, chunk, l_start, end);
+        else seq_flag[read] = 1u;       // (list full: the read is redone in order)
+    }
     // LOW samples in the group of 8 that holds read index t: magnitudes to the witness, and the 2048-sample tile is
     // marked (top bit of tile_read0) so that emit_events_kernel sums its events with real conversions
     __device__ __forceinline__ void low_samples(int t, uint32_t lo, uint32_t hi) const {
@@ -114,7 +135,7 @@ struct DevIo {
     }
 };
 
-__device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64_t sid, int* sh) {
+__device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64_t sid, int chunk, int* sh) {
     const uint64_t base = p.b.read_off[r];
     *sh = (int)(base & 31u);
     DevIo io;
@@ -129,14 +150,17 @@ __device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64
     io.base = base;
     io.off = p.b.offset[r];
     io.unit = p.b.unit[r];
+    io.jobs = p.jobs; io.job_count = p.job_count; io.job_cap = p.job_cap; io.seq_flag = p.seq_flag;
+    io.read = (int)r; io.chunk = chunk;
     return io;
 }
 
 template <int RNA>
 __device__ __noinline__ void walk_edge_dev(const WalkParams& p, uint32_t r, int last) {
     int sh;
-    DevIo io = make_io(p, r, 2ull * r + (uint64_t)last, &sh);
-    walk_edge<RNA>(io, (int)p.b.read_len[r], io.off, io.unit, sh, p.L, p.W, last);
+    const int n = (int)p.b.read_len[r];
+    DevIo io = make_io(p, r, 2ull * r + (uint64_t)last, last ? (int)n_chunks((uint32_t)n, (uint32_t)p.L) - 1 : 0, &sh);
+    walk_edge<RNA>(io, n, io.off, io.unit, sh, p.L, p.W, last, p.thr_long);
 }
 
 // largest r with ibase[r] <= i (ibase is non-decreasing, ibase[n_reads] > i)
@@ -162,8 +186,54 @@ __global__ void __launch_bounds__(WNT, RNA ? 1 : WALK_MINB) walk_chunks_kernel(c
     if (i >= p.ibase[p.b.n_reads]) return;
     const uint32_t r = find_chunk_read(p.ibase, p.b.n_reads, i);
     int sh;
-    DevIo io = make_io(p, r, 2ull * p.b.n_reads + i, &sh);
-    walk_interior<RNA>(io, (int)p.b.read_len[r], io.off, io.unit, sh, p.L, p.W, (int)(i - p.ibase[r]) + 1);
+    const int k = (int)(i - p.ibase[r]) + 1;
+    DevIo io = make_io(p, r, 2ull * p.b.n_reads + i, k, &sh);
+    walk_interior<RNA>(io, (int)p.b.read_len[r], io.off, io.unit, sh, p.L, p.W, k, p.thr_long);
+}
+
+// ---- the lives of the long detector that may emit -------------------------------------------------------------------
+// One thread per job: long_job() of walk_core.cuh replays the long detector over the life with the reference's own
+// operations from the raw samples and ORs what it emits into the bitmap. It reads the END records of the read's
+// chunks (where an earlier chunk's life started; the short detector's state at the end of the job's chunk).
+struct JobIo {
+    const int16_t* __restrict__ sp;
+    uint32_t* __restrict__ bm;
+    const int* __restrict__ st_end;    // all END records
+    uint64_t sid_first, sid_last, sid_int0;   // slots of the read's first / last / first interior chunk
+    int nch;
+    __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
+        const int4 w = __ldg(reinterpret_cast<const int4*>(sp + t));
+        v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+    }
+    __device__ __forceinline__ void peak(int pos) const { atomicOr(bm + ((uint32_t)pos >> 5), 1u << (pos & 31)); }
+    __device__ __forceinline__ const int* rec(int kk) const {
+        const uint64_t sid = kk == 0 ? sid_first : kk == nch - 1 ? sid_last : sid_int0 + (uint64_t)(kk - 1);
+        return st_end + sid * 8;
+    }
+    __device__ __forceinline__ int end_lstart(int kk) const { return rec(kk)[6]; }
+    __device__ __forceinline__ void end_short(int kk, float* pv, int* ps) const {
+        const int* q = rec(kk);
+        *pv = __int_as_float(q[0]); *ps = q[1];
+    }
+};
+
+template <int RNA>
+__global__ void __launch_bounds__(128) long_jobs_kernel(const WalkParams p) {
+    const uint32_t nj = min(*p.job_count, p.job_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[3] = nj;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nj; j += gridDim.x * blockDim.x) {
+        const int4 job = p.jobs[j];
+        const uint32_t r = (uint32_t)job.x;
+        const uint64_t base = p.b.read_off[r];
+        const int n = (int)p.b.read_len[r];
+        JobIo io;
+        io.sp = p.b.samples + base;
+        io.bm = p.bitmap + (base >> 5);
+        io.st_end = p.st_end;
+        io.sid_first = 2ull * r; io.sid_last = 2ull * r + 1; io.sid_int0 = 2ull * p.b.n_reads + p.ibase[r];
+        io.nch = (int)n_chunks((uint32_t)n, (uint32_t)p.L);
+        long_job<RNA>(io, n, (int)(base & 31u), p.b.offset[r], p.b.unit[r], p.L, job.y, job.z, job.w, p.thr_long);
+    }
 }
 
 // ---- chunk counts and verification ----------------------------------------------------------------------------------
@@ -217,62 +287,55 @@ static inline int grid_cap(uint64_t work, int block, int max_blocks) {
 }  // namespace
 
 // chunk length for a batch: as long as possible (the warm-up is amortised over it) while the batch still yields
-// a few waves of chunks
-uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count) {
+// a few waves of chunks. `forced` != 0: the context's development parameter SGPU_PARAM_CHUNK_LEN.
+uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced) {
     const uint32_t lmin = rna ? 512u : 128u;
     // (measured: for DNA one wave of resident threads is enough, the warm-up is what longer chunks save;
-    //  the RNA instantiation (2 warps per scheduler, 416 warm-up samples) does better with four times as many)
+    //  the RNA instantiation does better with four times as many)
     const uint64_t want_chunks = (uint64_t)sm_count * (rna ? 2048ull : 384ull);
     uint32_t L = rna ? 4096u : 1024u;
     while (L > lmin && span / L < want_chunks) L >>= 1;
-    if (const char* e = getenv("SGPU_CHUNK_LEN")) {
-        const uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
-        if (v >= lmin && (v & (v - 1)) == 0u) L = v;
-    }
+    if (forced >= lmin && (forced & (forced - 1)) == 0u) L = forced;
     return L;
 }
-uint32_t walk_warmup(int rna) {
+uint32_t walk_warmup(int rna, uint32_t forced) {
     // measured boundary mismatches per 10^6 chunk boundaries (bench batches): DNA W=24: 20, 32: 0.4, >= 40: 0 in
     // 2.5 x 10^6; RNA W=192: 24, 256: 0.8, 320: 0 in 1.3 x 10^6. The rate falls by ~50x per 8 (DNA) / ~30x per 64 (RNA)
     // samples; a mismatch only costs the read its place on the fast path.
+    // `forced` != 0: SGPU_PARAM_WARMUP (tests force short warm-ups to exercise the mismatch path).
     uint32_t W = rna ? 384u : 48u;
-    if (const char* e = getenv("SGPU_WARMUP")) {  // tests force short warm-ups to exercise the mismatch path
-        const uint32_t v = (uint32_t)strtoul(e, nullptr, 10);
-        const uint32_t u = rna ? 16u : 8u;
-        if (v % u == 0u && v <= W) W = v;
-    }
+    const uint32_t u = rna ? 16u : 8u;
+    if (forced != 0u && forced % u == 0u && forced <= W) W = forced;
     return W;
 }
 uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads) { return 2ull * max_reads + max_samples / 128u + 1u; }
+uint32_t walk_job_capacity(uint64_t max_samples) { return (uint32_t)(max_samples / 512u + 4096u); }
 
 int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
                 cudaStream_t st) {
-    const uint32_t L = walk_chunk_len(b.span, b.rna, sm_count), W = walk_warmup(b.rna);
+    const uint32_t L = walk_chunk_len(b.span, b.rna, sm_count, sc.tune_chunk_len), W = walk_warmup(b.rna, sc.tune_warmup);
     const uint64_t words = (uint64_t)fast_tiles_for(b.span) * (FAST_TILE / 32);
     cudaMemsetAsync(sc.bitmap, 0, (size_t)words * sizeof(uint32_t), st);
+    cudaMemsetAsync(sc.job_count, 0, sizeof(uint32_t), st);
     chunk_count_kernel<<<grid_cap(b.n_reads, 256, sm_count * 8), 256, 0, st>>>(b, L, sc.wk_cnt);
     int n = 1 + launch_scan_u32(sc.wk_cnt, b.n_reads, sc.wk_ibase, nullptr, sc, st);
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
     p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max; p.tile_read0 = sc.tile_read0;
     p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
+    p.thr_long = sc.tune_thr_long;
+    p.jobs = reinterpret_cast<int4*>(sc.jobs); p.job_count = sc.job_count; p.job_cap = sc.job_cap; p.seq_flag = seq_flag;
+    p.counters = sc.counters;
     const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
     const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;
-    // development knob: unused dynamic shared memory caps the resident blocks per SM (occupancy experiments)
-    static int dyn_smem = -1;
-    if (dyn_smem < 0) {
-        const char* e = getenv("SGPU_WALK_SMEM");
-        dyn_smem = e ? atoi(e) : 0;
-        if (dyn_smem > 0) {
-            cudaFuncSetAttribute(walk_chunks_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
-            cudaFuncSetAttribute(walk_chunks_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem);
-        }
-    }
-    if (b.rna) walk_chunks_kernel<1><<<(unsigned)grid, WNT, dyn_smem, st>>>(p);
-    else walk_chunks_kernel<0><<<(unsigned)grid, WNT, dyn_smem, st>>>(p);
+    if (b.rna) walk_chunks_kernel<1><<<(unsigned)grid, WNT, 0, st>>>(p);
+    else walk_chunks_kernel<0><<<(unsigned)grid, WNT, 0, st>>>(p);
+    // the lives of the long detector that may emit (a few per 100,000 samples), replayed exactly
+    if (b.rna) long_jobs_kernel<1><<<sm_count * 4, 128, 0, st>>>(p);
+    else long_jobs_kernel<0><<<sm_count * 4, 128, 0, st>>>(p);
     verify_chunks_kernel<<<grid_cap(max_interior + b.n_reads, 256, sm_count * 8), 256, 0, st>>>(
         b, L, sc.wk_ibase, sc.wk_begin, sc.wk_end, seq_flag, fixups);
-    return n + 2;
+    return n + 3;
 }
 
 }  // namespace sgpu

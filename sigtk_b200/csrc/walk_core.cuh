@@ -233,18 +233,21 @@ SGW_HD void window_terms(double D, double E, float& A, double& Lq, float& B, dou
     Vd = widen_pos(bv.hi);
     B2d = widen_pos(fmul(B, B));                          // (double)(mean2*mean2)
 }
-// both t-statistics of one step: the windows' terms -> combined variance (events.c:349-353) -> tail
-template <int W1, int W2>
-SGW_HD void tstat_pair(float A1l, double L1l, float B1, double V1, double B1sq, float A2l, double L2l, float B2,
-                       double V2, double B2sq, float& t1, bool& ok1, float& t2, bool& ok2) {
-    const double acc1 = dsub(dadd(L1l, V1), B1sq);        // ((.. - m1sq) + v2) - m2sq, left to right in double
-    const double acc2 = dsub(dadd(L2l, V2), B2sq);
-    const F2 cv = {fmaxf(d2f(acc1), FLT_MIN), fmaxf(d2f(acc2), FLT_MIN)};   // events.c:353
-    const F2 sc = fdivw2<W1, W2>(cv);                     // cv / w (float); cv >= FLT_MIN, shortcut valid for cv >= 1e-36
+// the short-window t-statistics of TWO consecutive positions: the windows' terms -> combined variance
+// (events.c:349-353) -> tail; the float divisions and halvings of the two positions share packed instructions.
+// No fmaxf(cv, FLT_MIN) (events.c:353) here: `tail` clears ok for every cv below 2e-29 (NaN included), and such a
+// block is recomputed with the reference's own operations, floor included.
+template <int W>
+SGW_HD void tstat_two(float A0, double L0, float B0, double V0, double B0sq, float A1, double L1, float B1, double V1,
+                      double B1sq, float& t0, bool& ok0, float& t1, bool& ok1) {
+    const double acc0 = dsub(dadd(L0, V0), B0sq);         // ((.. - m1sq) + v2) - m2sq, left to right in double
+    const double acc1 = dsub(dadd(L1, V1), B1sq);
+    const F2 cv = {d2f(acc0), d2f(acc1)};
+    const F2 sc = fdivw2<W, W>(cv);                       // cv / w (float); shortcut valid for cv >= 1e-36
     const F2 half = {0.5f, 0.5f};
     const F2 sh = f2mul(sc, half);
-    t1 = tail(fsub(B1, A1l), sc.lo, sh.lo, cv.lo, ok1);   // delta = mean2 - mean1
-    t2 = tail(fsub(B2, A2l), sc.hi, sh.hi, cv.hi, ok2);
+    t0 = tail(fsub(B0, A0), sc.lo, sh.lo, cv.lo, ok0);    // delta = mean2 - mean1
+    t1 = tail(fsub(B1, A1), sc.hi, sh.hi, cv.hi, ok1);
 }
 
 // ---- the reference's own operation sequence, from the raw samples (rare path) ---------------------------------------
@@ -300,7 +303,7 @@ void exact_block(const Io& io, int tau0, int n, float off, float unit, int m1, i
         for (int m = 0; m < C::U; m++) t2v[m] = tstat_exact(io, tau0 + m - C::w2 + 1, C::w2, n, off, unit);
 }
 
-// ---- the dual peak detector (events.c:371-443) --------------------------------------------------------------------
+// ---- the peak detectors (events.c:371-443) ------------------------------------------------------------------------
 // Positions are "shifted" read indices: index in the read + (read_off & 31), so that position >> 5 is a word of the
 // read's part of the event-start bitmap; they stay below 2^30 (reads of 2^30 samples or more take the
 // sequential-order kernels). One word `ps` per detector packs peak_pos and valid_peak of the reference's Detector
@@ -308,25 +311,47 @@ void exact_block(const Io& io, int tau0, int n, float off, float unit, int m1, i
 //                       ps = peak_pos | PS_OPEN   CASE 2, valid_peak == false
 //                       ps = peak_pos             CASE 2, valid_peak == true
 // so that "valid_peak && i - peak_pos > w/2" (events.c:429) is the single comparison  i - ps > w/2.
+//
+// THE LONG DETECTOR IS NOT STEPPED ON THE FAST PATH (round 2). The short detector is autonomous; the long one is
+// driven by it: every step at which the short detector holds a peak above its threshold resets the long detector
+// and masks it up to peak_pos + w_short (events.c:414-422). Call the steps between two such resets a LIFE of the
+// long detector. Within a life its peak_value is FLT_MAX (CASE 1, before its first step) or the t-statistic of
+// one of the life's stepped positions, and valid_peak needs peak_value > threshold (events.c:424): a life in which
+// no stepped position has t2 > thr_long emits nothing, and the state it ends in is wiped by the next reset. On
+// real R9.4 reads and on the synthetic sets the long detector never emits at all (0 of 92,935 events of
+// sp1_dna.blow5) and about 2 steps in 10,000 are stepped with t2 > 9.
+//   The walker therefore only tracks, per step, where the current life's steps start (`l_start`: a function of the
+// short detector alone) and whether a stepped position of the life MAY have t2 > thr_long -- decided by a
+// conservative float test on exact integer window sums of the raw samples (long_candidate below; the bound is
+// proved in oracle/proofs/long_filter.md and checked by oracle/proofs/long_filter_check.c). A life that may be
+// hot becomes a JOB: long_job() replays the long detector over exactly that life with the reference's own
+// operations (tstat_exact) and records whatever it emits (long_jobs_kernel in walk.cu; OR into the bitmap is
+// idempotent). Everything else about the long window -- its t-statistic chain and its detector -- is gone from
+// the per-sample path.
 constexpr int PS_NONE = 0x7fff0000;  // (room below INT_MAX: position - PS_NONE must not wrap for positions >= -2^16)
 constexpr int PS_OPEN = 0x40000000;
+constexpr int LS_PRED = -0x40000000;  // l_start: the life began before this chunk's first owned step (see long_job)
+constexpr int LS_CONT = 0x7fffffff;   // job end: the life runs past the chunk's last owned step
 struct WalkDet {
     float s_pv; int s_ps;               // short detector (never masked after the read's first sample)
-    float l_pv; int l_ps; int l_mt;     // long detector; l_mt = masked_to
+    int l_start;                        // first step of the long detector's current life that is not masked:
+                                        // max(reset step, masked_to + 1); LS_PRED while unknown to this chunk
+    int l_hot;                          // != 0: a stepped position of the current life may have t2 > thr_long
 };
 SGW_HD void det_cold(WalkDet& d, int first_step) {  // both detectors start at `first_step` from the reset state
     d.s_pv = FLT_MAX; d.s_ps = PS_NONE;
-    d.l_pv = FLT_MAX; d.l_ps = PS_NONE; d.l_mt = first_step - 1;
+    d.l_start = first_step; d.l_hot = 0;
 }
 
-// canonical form at boundary b (state before step b): 8 words, bit-comparable between the chunk that ends at b
-// and the chunk that starts there
+// canonical form at boundary b (state before step b): the first 6 words are bit-compared between the chunk that
+// ends at b and the chunk that starts there (the short detector; the long one has no state on the fast path);
+// word 6 of an END record carries l_start for the jobs of later chunks (not compared).
 struct Canon { int v[8]; };
 SGW_HD Canon canon_of(const WalkDet& d, int b) {
     Canon c;
-    c.v[0] = (int)f_bits(d.s_pv); c.v[1] = d.s_ps; c.v[2] = (int)f_bits(d.l_pv); c.v[3] = d.l_ps;
-    c.v[4] = d.l_mt >= b ? d.l_mt : -1;
-    c.v[5] = 0; c.v[6] = 0; c.v[7] = 0;
+    (void)b;
+    c.v[0] = (int)f_bits(d.s_pv); c.v[1] = d.s_ps; c.v[2] = 0; c.v[3] = 0; c.v[4] = 0; c.v[5] = 0;
+    c.v[6] = d.l_start; c.v[7] = 0;
     return c;
 }
 
@@ -340,23 +365,25 @@ template <int RNA> struct PkCfg {
 #if defined(WALK_TEST_FAR)  // host tests: treat every peak older than w/2 + 2 as too old for the mask
     static constexpr int FAR = 0;
 #else
-    static constexpr int FAR = LEAD - (Cfg<RNA>::w2 / 2 + 1);  // largest (age - w/2 - 1) that always fits the mask
+    static constexpr int FAR = LEAD - (Cfg<RNA>::w1 / 2 + 1);  // largest (age - w/2 - 1) that always fits the mask
 #endif
 };
-struct PeakAcc { uint32_t mk; int oldest; };
+// (`jobs`, `job_ls`, `job_end`: the fast path does not call io.job() from inside a block, because the block may
+// still be redone with exact values; it parks the block's first job here and a second one sends the block to redo_block)
+struct PeakAcc { uint32_t mk; int oldest; int jobs, job_ls, job_end; };
 struct NoEmit { SGW_HD void operator()(int) const {} };
 
 // One detector, one position (events.c:393-437); the detector is not masked at u (events.c:387).
 //   m    : index of the step within its block (compile-time), u : its position
-//   c    : the t-statistic at u
+//   c    : the t-statistic at u, thr : the detector's threshold
 //   big2 : CASE 2 and the running maximum is above the threshold (the short detector then masks the long one)
 //   p2   : the (possibly moved) peak position with the PS_OPEN flag, valid when big2
 //   on_emit(pos) : called for an emitted peak (the fast path passes NoEmit and reads the mask instead)
 template <bool SHORT, int RNA, class E>
-SGW_HD int det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, bool& big2, int& p2, const E& on_emit) {
+SGW_HD int det_one(float& pv, int& ps, int m, int u, float c, float thr, PeakAcc& acc, bool& big2, int& p2,
+                   const E& on_emit) {
     constexpr int w = SHORT ? Cfg<RNA>::w1 : Cfg<RNA>::w2;
     const float h = peak_h<RNA>();
-    const float thr = SHORT ? thr_short<RNA>() : thr_long<RNA>();
     const bool none = ps == PS_NONE;
     const float df = fsub(c, pv);                          // > 0: above the running value, < 0: below
     const float pvm = none ? fminf(pv, c) : fmaxf(pv, c);  // CASE 1: running minimum (394); CASE 2: running maximum (408)
@@ -376,11 +403,28 @@ SGW_HD int det_one(float& pv, int& ps, int m, int u, float c, PeakAcc& acc, bool
     return over;
 }
 
-// One position of both detectors, short first (events.c:385-440).
+// Both detectors stepped together, short first (events.c:385-440): the sequential-order kernels (generic.cu) walk
+// stored t arrays with this; the fast path does not step the long detector (see above).
+struct DualDet {
+    float s_pv; int s_ps;               // short detector
+    float l_pv; int l_ps; int l_mt;     // long detector; l_mt = masked_to
+};
+SGW_HD void dual_cold(DualDet& d, int first_step) {
+    d.s_pv = FLT_MAX; d.s_ps = PS_NONE;
+    d.l_pv = FLT_MAX; d.l_ps = PS_NONE; d.l_mt = first_step - 1;
+}
+SGW_HD Canon dual_canon(const DualDet& d, int b) {
+    Canon c;
+    c.v[0] = (int)f_bits(d.s_pv); c.v[1] = d.s_ps; c.v[2] = (int)f_bits(d.l_pv); c.v[3] = d.l_ps;
+    c.v[4] = d.l_mt >= b ? d.l_mt : -1;
+    c.v[5] = 0; c.v[6] = 0; c.v[7] = 0;
+    return c;
+}
 template <int RNA, class E>
-SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc, const E& on_emit) {
+SGW_HD void dual_step(DualDet& d, int u, float c1, float c2, const E& on_emit) {
     bool maskl, unused_b; int p2, unused_p;
-    const int over_s = det_one<true, RNA>(d.s_pv, d.s_ps, m, u, c1, acc, maskl, p2, on_emit);
+    PeakAcc unused; unused.mk = 0u; unused.oldest = 0;
+    det_one<true, RNA>(d.s_pv, d.s_ps, 0, u, c1, thr_short<RNA>(), unused, maskl, p2, on_emit);
     // the short detector dominates the long one while it holds a peak above its threshold (events.c:414-422)
     d.l_mt = maskl ? (p2 & ~PS_OPEN) + Cfg<RNA>::w1 : d.l_mt;
     d.l_ps = maskl ? PS_NONE : d.l_ps;
@@ -388,9 +432,54 @@ SGW_HD void det_step(WalkDet& d, int m, int u, float c1, float c2, PeakAcc& acc,
     // a masked long detector is always in the reset state (masked_to is only ever set together with a reset, and
     // a masked detector is not stepped), and the reset state does not react to FLT_MAX: no gating needed
     const float c2m = d.l_mt < u ? c2 : FLT_MAX;
-    const int over_l = det_one<false, RNA>(d.l_pv, d.l_ps, m, u, c2m, acc, unused_b, unused_p, on_emit);
-    const int over = over_s > over_l ? over_s : over_l;   // (one three-input maximum)
-    acc.oldest = acc.oldest > over ? acc.oldest : over;
+    det_one<false, RNA>(d.l_pv, d.l_ps, 0, u, c2m, thr_long<RNA>(), unused, unused_b, unused_p, on_emit);
+}
+
+// ---- the long window on the fast path: a conservative test on exact integer sums -----------------------------------
+// z = raw - c0 (c0: an integer pivot of the chunk, |z| <= ZMAX so that every sum below is an exact integer in
+// float). For the windows L = [p - w, p), R = [p, p + w) of position p, w = w_long:
+//     S = sum z,  V = w * sum z^2 - S^2      (V / w^2 = the window's variance in raw units; pivot-free)
+//     the t-statistic of events.c:338-361 in exact arithmetic is  sqrt(w) * |S_R - S_L| / sqrt(V_L + V_R)
+// and the reference's rounded value t2(p) obeys (oracle/proofs/long_filter.md)
+//     t2(p) > thr   ==>   w (|S_R - S_L| + a)^2 (1 + 2^-12)  >=  thr^2 (V_L + V_R) - B,
+//     a = 8 u w M,  B = thr^2 48 u w^2 M^2,  u = 2^-24,  M >= max |raw + offset| over both windows.
+// long_candidate() evaluates the right-hand condition; a false result PROVES t2(p) <= thr.
+constexpr int ZMAX = 1023;
+struct LongK {
+    float c0;      // pivot (integer valued)
+    float ca;      // a
+    float cw;      // w (1 + 2^-12)
+    float thr2;    // thr^2
+    float cB;      // B
+    float thr;     // thr_long (9.0 for DNA and RNA; a context parameter so that tests can make the long detector fire)
+};
+template <int RNA>
+SGW_HD LongK long_consts(int c0, float off, float thr_long) {
+    constexpr float w = (float)Cfg<RNA>::w2;
+    const float u = 5.9604644775390625e-08f;  // 2^-24
+    LongK k;
+    k.c0 = (float)c0;
+    const float M = fmul(fadd(fabsf(fadd(k.c0, off)), (float)(ZMAX + 2)), 1.0001f);  // >= |raw + offset| while |z| <= ZMAX
+    k.ca = fmul(fmul(8.0f * u * w, M), 1.0001f);
+    k.cw = w * (1.0f + 0.000244140625f);
+    k.thr = thr_long;
+    k.thr2 = fmul(thr_long, thr_long);
+    k.cB = fmul(fmul(fmul(k.thr2, 48.0f * u * w * w), fmul(M, M)), 1.0001f);
+    return k;
+}
+SGW_HD bool long_candidate(float SL, float VL, float SR, float VR, const LongK& k) {
+    const float g = fadd(fabsf(fsub(SR, SL)), k.ca);
+    const float lhs = fmul(fmul(g, k.cw), g);
+    const float rhs = ffma(fadd(VL, VR), k.thr2, -k.cB);
+    return !(lhs < rhs);  // (NaN / infinity anywhere: candidate)
+}
+// V = w * Q - S * S for exact integers S, Q in float: S*S = p + e exactly (e from the FMA), one rounding of the
+// result's own size at most (covered by the 2^-12 slack of the test)
+template <int W>
+SGW_HD float long_var(float S, float Q) {
+    const float p = fmul(S, S);
+    const float e = ffma(S, S, -p);
+    return fsub(ffma((float)W, Q, -p), e);
 }
 
 // a sample enters windows whose t-statistics are computed at most two blocks later
@@ -402,21 +491,45 @@ template <int RNA>
 struct Rings {
     using C = Cfg<RNA>;
     double P[C::R1], PQ[C::R1];    // P[j & (R1-1)] = sum of x over the walked samples before j
-    double D1[C::R1], E1[C::R1];   // short-window sums by window start
     float A1[C::R1];               // left-window terms of the short window by window start
     double L1[C::R1];
     float T1c[C::w1];              // t1 of the last w1 positions of the previous block
-    float A2[C::R2];               // left-window terms of the long window by window start
-    double L2[C::R2];
+    // integer side (z = raw - pivot, exact in float)
+    F2 ZC[C::w1];                  // {z, z*z} of the last w1 samples of the previous block
+    F2 ZSc;                        // running {sum z, sum z*z} over the last w1 samples
+    F2 ZS[C::R1];                  // short-window sums by window start
+    float S2[C::R2], V2[C::R2];    // long-window S and V by window start
     SGW_HD void clear() {
 #pragma unroll
-        for (int k = 0; k < C::R1; k++) { P[k] = 0.0; PQ[k] = 0.0; D1[k] = 0.0; E1[k] = 0.0; A1[k] = 0.0f; L1[k] = 0.0; }
+        for (int k = 0; k < C::R1; k++) { P[k] = 0.0; PQ[k] = 0.0; A1[k] = 0.0f; L1[k] = 0.0; ZS[k].lo = 0.0f; ZS[k].hi = 0.0f; }
 #pragma unroll
-        for (int k = 0; k < C::w1; k++) T1c[k] = 0.0f;
+        for (int k = 0; k < C::w1; k++) { T1c[k] = 0.0f; ZC[k].lo = 0.0f; ZC[k].hi = 0.0f; }
 #pragma unroll
-        for (int k = 0; k < C::R2; k++) { A2[k] = 0.0f; L2[k] = 0.0; }
+        for (int k = 0; k < C::R2; k++) { S2[k] = 0.0f; V2[k] = 0.0f; }
+        ZSc.lo = 0.0f; ZSc.hi = 0.0f;
     }
 };
+
+// One position of the fast path: the short detector (events.c:385-440 for the short one) and the bookkeeping of the
+// long detector's lives.
+//   cand : long_candidate() of position u (false proves t2(u) <= thr_long)
+//   rec  : the step is owned by this chunk (jobs are only created for owned steps)
+template <int RNA, bool DIRECT, class E, class Io>
+SGW_HD void det_step(WalkDet& d, int m, int u, float c1, bool cand, bool rec, PeakAcc& acc, const E& on_emit, Io& io) {
+    bool maskl; int p2;
+    const int over = det_one<true, RNA>(d.s_pv, d.s_ps, m, u, c1, thr_short<RNA>(), acc, maskl, p2, on_emit);
+    acc.oldest = acc.oldest > over ? acc.oldest : over;
+    // the short detector holds a peak above its threshold: the long detector is reset and masked up to
+    // peak_pos + w_short (events.c:414-422) -- the current life ends before this step, a new one starts with it
+    if (maskl & (d.l_hot != 0) & rec) {                       // rare: the life that ends here may have emitted
+        if (DIRECT) io.job(d.l_start, u);
+        else { if (acc.jobs == 0) { acc.job_ls = d.l_start; acc.job_end = u; } acc.jobs++; }
+    }
+    const int ls = (p2 & ~PS_OPEN) + Cfg<RNA>::w1 + 1;
+    d.l_hot = maskl ? 0 : d.l_hot;
+    d.l_start = maskl ? (ls > u ? ls : u) : d.l_start;
+    d.l_hot |= (int)((u >= d.l_start) & cand);               // the long detector is stepped at u (events.c:387)
+}
 
 // The rare path of a block: the t-statistics of the whole block from the raw samples with the reference's own
 // operations, then the block's detector steps again from the state the block started in; every emitted peak is
@@ -428,13 +541,13 @@ __host__ __device__ __noinline__
 #else
 inline
 #endif
-Redo<RNA> redo_block(const Io& io, Redo<RNA> in, int tau0, int n, int sh, bool rec, float off, float unit) {
+Redo<RNA> redo_block(Io& io, Redo<RNA> in, int tau0, int n, int sh, bool rec, float off, float unit, float thr_long) {
     using C = Cfg<RNA>;
     constexpr int w1 = C::w1, w2 = C::w2, U = C::U;
     float e1[U], e2[U];
     exact_block<RNA>(io, tau0, n, off, unit, 0, 1, e1, e2);
     Redo<RNA> r;
-    r.d = in.d; r.acc.mk = 0u; r.acc.oldest = 0;
+    r.d = in.d; r.acc.mk = 0u; r.acc.oldest = 0; r.acc.jobs = 0;
     const int u0 = tau0 - w2 + 1 + sh;
     for (int m = 0; m < U; m++) {
         const int j1 = tau0 + m - w1 + 1, j2 = tau0 + m - w2 + 1;
@@ -444,25 +557,28 @@ Redo<RNA> redo_block(const Io& io, Redo<RNA> in, int tau0, int n, int sh, bool r
         }
         const float c1 = m >= w1 ? e1[m - w1] : in.t1c[m];
         if (!EDGE || (j2 >= 1 && j2 < n)) {
-            PeakAcc unused; unused.mk = 0u; unused.oldest = 0;   // the mask is not used here
-            det_step<RNA>(r.d, 0, u0 + m, c1, e2[m], unused, [&](int pos) { if (rec) io.peak(pos); });
+            PeakAcc unused; unused.mk = 0u; unused.oldest = 0; unused.jobs = 0;   // the mask is not used here
+            det_step<RNA, true>(r.d, 0, u0 + m, c1, e2[m] > thr_long, rec, unused, [&](int pos) { if (rec) io.peak(pos); }, io);
         }
     }
     for (int k = 0; k < w1; k++) r.t1c[k] = e1[U - w1 + k];
     return r;
 }
 
-// One block of U samples, one sample at a time: window terms -> both t-statistics -> one step of both detectors,
-// in one straight line of code (the scheduler overlaps the FP64 chains of sample m+1 with the detector's
-// dependent chain of sample m). The same code also fills the rings at the start of a chunk: the two blocks before
-// the first detector step run it with live == false (their t-statistics come from partly filled rings and are
-// never used, the detector state is reset afterwards), except that the last w1 values of t1 of the second of
-// them ARE the ones the first real steps read (live_t1).
+// One block of U samples, two samples at a time: window terms -> the short t-statistic -> the exact integer sums
+// of the long windows and their candidate test -> one step of the short detector, in one straight line of code.
+// The same code also fills the rings at the start of a chunk: the two blocks before the first detector step run
+// it with live == false (their t-statistics come from partly filled rings and are never used, the detector state
+// is reset afterwards), except that the last w1 values of t1 of the second of them ARE the ones the first real
+// steps read (live_t1).
 // EDGE: the block may touch positions outside the read [0, n): samples there count as 0, t is 0 outside
 // w <= i <= n-w (events.c:328-338), the detector only steps positions 1 <= p < n (position 0 is masked: 387).
 //   x[m]   : pA of sample tau0 + m (0 outside the read when EDGE)
+//   z[m]   : raw - pivot of the same sample (0 outside the read when EDGE)
 //   tau0   : read index of the block's first sample, a multiple of U
 //   sh     : read_off & 31
+//   zdirty : > 0 when a window of this block holds a sample with |z| > ZMAX (its sums may be inexact): every
+//            position of the block is a candidate
 // dirty > 0: a window of this block holds a LOW sample (pA <= 0 or barely above: a glitch; about 3 reads in 100 of
 // real R9.4 data have one). widen_pos does not apply to such a value, so the chunk drivers hand it to this code as
 // 0 (it then adds nothing to the running sums), and this block and the next two -- every window that contains the
@@ -470,85 +586,108 @@ Redo<RNA> redo_block(const Io& io, Redo<RNA> in, int tau0, int n, int sh, bool r
 // operations. Every other window holds unmodified positive samples only, and its sums are differences of running
 // sums that miss the same samples on both sides: nothing else changes and the read stays on the fast path.
 template <int RNA, bool EDGE, class Io>
-SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U], int tau0, int n, int sh, bool rec,
-                       bool live, bool live_t1, int dirty, float off, float unit, Io& io) {
+SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U], const float (&z)[Cfg<RNA>::U], int tau0,
+                       int n, int sh, bool rec, bool live, bool live_t1, int dirty, int zdirty, float off, float unit,
+                       const LongK& lk, Io& io) {
     using C = Cfg<RNA>;
     constexpr int w1 = C::w1, w2 = C::w2, M1 = C::R1 - 1, M2 = C::R2 - 1, U = C::U;
     float t1v[U];
     bool ok = true, ok_t1 = true;  // ok_t1: among the last w1 values of t1
     const WalkDet d0 = d;
     PeakAcc acc;
-    acc.mk = 0u; acc.oldest = 0;
+    acc.mk = 0u; acc.oldest = 0; acc.jobs = 0;
     const int u0 = tau0 - w2 + 1 + sh;                              // position of the block's first step
     float xq[U];                                                    // float squares (events.c:301), two per instruction
+    F2 zz[U];                                                       // {z, z*z}: exact integers
 #pragma unroll
     for (int m = 0; m < U; m += 2) {
         const F2 p = {x[m], x[m + 1]};
         const F2 q = f2sq(p);
         xq[m] = q.lo; xq[m + 1] = q.hi;
+        const F2 zp = {z[m], z[m + 1]};
+        const F2 zq = f2sq(zp);
+        zz[m].lo = zp.lo; zz[m].hi = zq.lo;
+        zz[m + 1].lo = zp.hi; zz[m + 1].hi = zq.hi;
     }
+    F2 zs = g.ZSc;
 #pragma unroll
-    for (int m = 0; m < U; m++) {
-        // static ring slots: every index below is (m + const) & mask because tau0 is a multiple of U
-        const double xd = widen_pos(x[m]);                          // (a sample handed over as 0 widens to 2^-127: it is
-        const double qd = widen_pos(xq[m]);                         //  absorbed by the first addition to a real sum)
-        const double pn = dadd(g.P[m & M1], EDGE ? (x[m] > 0.0f ? xd : 0.0) : xd);
-        const double pqn = dadd(g.PQ[m & M1], EDGE ? (x[m] > 0.0f ? qd : 0.0) : qd);
-        g.P[(m + 1) & M1] = pn;
-        g.PQ[(m + 1) & M1] = pqn;
-        // short window [j1, j1+w1), j1 = tau0 + m - w1 + 1
-        const int s1 = (m - w1 + 1) & M1;                           // slot of j1
-        const int s1l = (m - 2 * w1 + 1) & M1;                      // slot of j1 - w1
-        const double d1 = dsub(pn, g.P[s1]), e1 = dsub(pqn, g.PQ[s1]);
-        float a1, b1; double l1, v1, b1sq;
-        window_terms<w1>(d1, e1, a1, l1, b1, v1, b1sq);
-        // long window [j2, j2+w2) = short(j2) + short(j1), j2 = j1 - w1
-        const int s2 = (m - 2 * w1 + 1) & M2;                       // slot of j2
-        const int s2l = (m - 2 * w1 + 1 - w2) & M2;                 // slot of j2 - w2
-        const double d2 = dadd(g.D1[s1l], d1), e2 = dadd(g.E1[s1l], e1);
-        float a2, b2; double l2, v2, b2sq;
-        window_terms<w2>(d2, e2, a2, l2, b2, v2, b2sq);
-        float t2m;
-        const int j2 = tau0 + m - w2 + 1;
-        if (EDGE) {  // positions whose windows leave the read do not count: their t is 0
-            bool k1 = true, k2 = true;
-            tstat_pair<w1, w2>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, g.A2[s2l], g.L2[s2l], b2, v2, b2sq, t1v[m], k1, t2m, k2);
-            const int j1 = tau0 + m - w1 + 1;
-            const bool in1 = (j1 >= w1) & (j1 + w1 <= n), in2 = (j2 >= w2) & (j2 + w2 <= n);
-            k1 = k1 | !in1;
-            k2 = k2 | !in2;
-            if (m >= U - w1) ok_t1 = ok_t1 & k1; else ok = ok & k1;
-            ok = ok & k2;
-            t1v[m] = in1 ? t1v[m] : 0.0f;
-            t2m = in2 ? t2m : 0.0f;
-        } else {
-            if (m >= U - w1)
-                tstat_pair<w1, w2>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, g.A2[s2l], g.L2[s2l], b2, v2, b2sq, t1v[m], ok_t1, t2m, ok);
-            else
-                tstat_pair<w1, w2>(g.A1[s1l], g.L1[s1l], b1, v1, b1sq, g.A2[s2l], g.L2[s2l], b2, v2, b2sq, t1v[m], ok, t2m, ok);
+    for (int m0 = 0; m0 < U; m0 += 2) {
+        // ---- the short t-statistic of the two positions j1 = tau0 + m - w1 + 1, m = m0, m0 + 1 ----
+        float a1[2], b1[2]; double l1[2], v1[2], b1sq[2];
+        float al[2]; double ll[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = m0 + h;
+            // static ring slots: every index below is (m + const) & mask because tau0 is a multiple of U
+            const double xd = widen_pos(x[m]);                      // (a sample handed over as 0 widens to 2^-127: it is
+            const double qd = widen_pos(xq[m]);                     //  absorbed by the first addition to a real sum)
+            const double pn = dadd(g.P[m & M1], EDGE ? (x[m] > 0.0f ? xd : 0.0) : xd);
+            const double pqn = dadd(g.PQ[m & M1], EDGE ? (x[m] > 0.0f ? qd : 0.0) : qd);
+            g.P[(m + 1) & M1] = pn;
+            g.PQ[(m + 1) & M1] = pqn;
+            const int s1 = (m - w1 + 1) & M1;                       // slot of j1 (short window [j1, j1+w1))
+            const int s1l = (m - 2 * w1 + 1) & M1;                  // slot of j1 - w1
+            const double d1 = dsub(pn, g.P[s1]), e1 = dsub(pqn, g.PQ[s1]);
+            window_terms<w1>(d1, e1, a1[h], l1[h], b1[h], v1[h], b1sq[h]);
+            al[h] = g.A1[s1l]; ll[h] = g.L1[s1l];
         }
-        g.D1[s1] = d1; g.E1[s1] = e1;
-        g.A1[s1] = a1; g.L1[s1] = l1;
-        g.A2[s2] = a2; g.L2[s2] = l2;
-        const float c1 = m >= w1 ? t1v[m - w1] : g.T1c[m];         // t1(j2), computed w1 samples ago
-        if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA>(d, m, u0 + m, c1, t2m, acc, NoEmit());
+        bool k0 = true, k1 = true;
+        tstat_two<w1>(al[0], ll[0], b1[0], v1[0], b1sq[0], al[1], ll[1], b1[1], v1[1], b1sq[1], t1v[m0], k0, t1v[m0 + 1], k1);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = m0 + h;
+            bool kh = h ? k1 : k0;
+            const int j1 = tau0 + m - w1 + 1;
+            if (EDGE) {  // positions whose windows leave the read do not count: their t is 0
+                const bool in1 = (j1 >= w1) & (j1 + w1 <= n);
+                kh = kh | !in1;
+                t1v[m] = in1 ? t1v[m] : 0.0f;
+            }
+            if (m >= U - w1) ok_t1 = ok_t1 & kh; else ok = ok & kh;
+            const int s1 = (m - w1 + 1) & M1;
+            g.A1[s1] = a1[h]; g.L1[s1] = l1[h];
+        }
+        // ---- the long window's exact integer sums, the candidate test, the detector steps ----
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = m0 + h;
+            const int s1 = (m - w1 + 1) & M1, s1l = (m - 2 * w1 + 1) & M1;
+            const int s2 = (m - 2 * w1 + 1) & M2;                   // slot of j2 = j1 - w1 (long window [j2, j2+w2))
+            const int s2l = (m - 2 * w1 + 1 - w2) & M2;             // slot of j2 - w2
+            const F2 zold = m >= w1 ? zz[m - w1 >= 0 ? m - w1 : 0] : g.ZC[m];
+            zs = f2add(zs, f2sub(zz[m], zold));                     // sums over [j1, j1+w1)
+            const F2 zl = f2add(g.ZS[s1l], zs);                     // long window = short(j2) + short(j1)
+            g.ZS[s1] = zs;
+            const float vr = long_var<w2>(zl.lo, zl.hi);
+            bool cand = long_candidate(g.S2[s2l], g.V2[s2l], zl.lo, vr, lk);
+            g.S2[s2] = zl.lo; g.V2[s2] = vr;
+            const int j2 = tau0 + m - w2 + 1;
+            if (EDGE) cand = cand & (j2 >= w2) & (j2 + w2 <= n);    // t2 is 0 there (events.c:328-338)
+            cand = cand | (zdirty > 0);
+            const float c1 = m >= w1 ? t1v[m >= w1 ? m - w1 : 0] : g.T1c[m < w1 ? m : 0];  // t1(j2), computed w1 samples ago
+            if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA, false>(d, m, u0 + m, c1, cand, rec, acc, NoEmit(), io);
+        }
     }
+    g.ZSc = zs;
+#pragma unroll
+    for (int k = 0; k < w1; k++) g.ZC[k] = zz[U - w1 + k];
 #if defined(WALK_TEST_REDO)  // host tests: take the rare path on every third block
     ok = ok & ((tau0 / U) % 3 != 0);
 #endif
     if (dirty > 0) { ok = false; ok_t1 = false; }  // a window of this block holds a LOW sample
     // rare (about 3 blocks in 100,000): a t-statistic next to a rounding midpoint, or a peak too old for the mask
-    if ((!ok & live) | (!ok_t1 & live_t1) | (rec & (acc.oldest > PkCfg<RNA>::FAR))) {
+    if ((!ok & live) | (!ok_t1 & live_t1) | (rec & ((acc.oldest > PkCfg<RNA>::FAR) | (acc.jobs > 1)))) {
         Redo<RNA> in;
         in.d = d0; in.acc = acc;
 #pragma unroll
         for (int k = 0; k < w1; k++) in.t1c[k] = g.T1c[k];
-        const Redo<RNA> r = redo_block<RNA, EDGE>(io, in, tau0, n, sh, rec, off, unit);
+        const Redo<RNA> r = redo_block<RNA, EDGE>(io, in, tau0, n, sh, rec, off, unit, lk.thr);
         d = r.d; acc = r.acc;
 #pragma unroll
         for (int k = 0; k < w1; k++) t1v[U - w1 + k] = r.t1c[k];
     }
     if (rec && acc.mk) io.peaks32(u0 - PkCfg<RNA>::LEAD, acc.mk);  // peaks are owned by the step that emits them
+    if (acc.jobs == 1) io.job(acc.job_ls, acc.job_end);            // (0 after redo_block: it creates its jobs itself)
 #pragma unroll
     for (int k = 0; k < w1; k++) g.T1c[k] = t1v[U - w1 + k];
 }
@@ -562,6 +701,8 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 //   peaks32(ub, mk)    record the emitted peaks of a block: bit k of mk (nonzero) <=> a peak at shifted position ub + k
 //   peak(pos)          record one peak
 //   put_begin(c) / put_end(c)   the chunk's canonical detector state after the warm-up / after its last step
+//   job(l_start, end)  a life of the long detector that may emit: its steps [l_start, end) (shifted positions;
+//                      l_start == LS_PRED: the life began in an earlier chunk, end == LS_CONT: it runs past this one)
 //   witness(rmin, rmax, low_t)  extreme raw values of samples of the read (any superset of the owned samples);
 //                               samples with raw <= low_t are LOW (reported through low_samples by their blocks)
 //   low_samples(t, lo, hi)      LOW samples in the group of 8 that holds read index t: their smallest nonzero /
@@ -571,8 +712,25 @@ SGW_HD uint32_t n_chunks(uint32_t n, uint32_t L) { return (n + L - 1u) / L; }
 // int16 -> float without a conversion instruction: with the sign bit flipped, the 16 bits are raw + 32768 in
 // [0, 65535]; placed under the exponent of 2^23 they read as the float 2^23 + raw + 32768, and subtracting
 // 2^23 + 32768 is exact. Then misc.c:28: float add of the offset, float multiply by the unit (two samples per
-// instruction).
-SGW_HD void cvt8(const int (&v)[4], float off, float unit, float* x) {
+// instruction); z = raw - pivot from the same exact float (one more packed subtraction).
+SGW_HD void cvt8(const int (&v)[4], float off, float unit, float c0, float* x, float* z) {
+    const F2 bias = {8421376.0f, 8421376.0f}, off2 = {off, off}, unit2 = {unit, unit}, c2 = {c0, c0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t w = (uint32_t)v[k] ^ 0x80008000u;
+        F2 r;
+        r.lo = bits_f(0x4b000000u | (w & 0xffffu));
+        r.hi = bits_f(0x4b000000u | (w >> 16));
+        r = f2sub(r, bias);
+        const F2 zz = f2sub(r, c2);
+        r = f2mul(f2add(r, off2), unit2);
+        x[2 * k] = r.lo;
+        x[2 * k + 1] = r.hi;
+        z[2 * k] = zz.lo;
+        z[2 * k + 1] = zz.hi;
+    }
+}
+SGW_HD void cvt8(const int (&v)[4], float off, float unit, float* x) {  // pA only (sequential-order kernels, pa_kernel)
     const F2 bias = {8421376.0f, 8421376.0f}, off2 = {off, off}, unit2 = {unit, unit};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -625,6 +783,14 @@ SGW_HD int low_threshold(float off, bool* can) {
     return t > 32767 ? 32767 : t < -32768 ? -32768 : t;
 }
 SGW_HD uint32_t pack_s16x2(int t) { return ((uint32_t)t & 0xffffu) * 0x10001u; }
+SGW_HD int s16_lo(uint32_t v) { return (int)(int16_t)(v & 0xffffu); }
+SGW_HD int s16_hi(uint32_t v) { return (int)v >> 16; }
+
+// the pivot of a chunk: the median of the first three samples it walks (one glitch sample cannot drag it away)
+SGW_HD int pivot_of(int a, int b, int c) {
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    return c < lo ? lo : c > hi ? hi : c;
+}
 
 // the LOW samples of one group of 8: their magnitudes go to the witness, their values become 0 for the running sums
 template <class Io>
@@ -646,7 +812,7 @@ SGW_HD void zero_low8(Io& io, int t, const int (&v)[4], int low_t, float* x) {
 // ONE loop (one copy of the block code in the instruction cache) runs the two ring-fill blocks, the detector
 // warm-up and the owned samples.
 template <int RNA, class Io>
-SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, int W, int k) {
+SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, int W, int k, float thr_long) {
     using C = Cfg<RNA>;
     constexpr int U = C::U;
     const int s0 = k * L, s1 = s0 + L;               // the samples this chunk owns
@@ -655,24 +821,33 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
     g.clear();
     WalkDet d;
     det_cold(d, 0);
-    float x[U];
+    float x[U], z[U];
     int v[4];
     uint32_t vmin = 0x7fff7fffu, vmax = 0x80008000u;  // packed int16 min / max (over warm-up and owned samples)
     bool can_low;
     const int low_t = low_threshold(off, &can_low);
     const uint32_t low2 = pack_s16x2(low_t);
-    int dirty = 0;
+    int dirty = 0, zdirty = 0;
     const bool pa = io.want_pa();
     int vn[U / 8][4];                                 // the next block's samples, loaded one block ahead
 #pragma unroll
     for (int h = 0; h < U / 8; h++) io.load8(t_live - C::FILL * U + 8 * h, vn[h]);
+    const int c0 = pivot_of(s16_lo((uint32_t)vn[0][0]), s16_hi((uint32_t)vn[0][0]), s16_lo((uint32_t)vn[0][1]));
+    const LongK lk = long_consts<RNA>(c0, off, thr_long);
+    // |z| <= ZMAX  <=>  c0 - ZMAX <= raw <= c0 + ZMAX (clamped so that the packed comparisons cannot wrap)
+    const uint32_t zlo2 = pack_s16x2(c0 - ZMAX - 1 < -32768 ? -32768 : c0 - ZMAX - 1);
+    const uint32_t zhi2 = pack_s16x2(c0 + ZMAX + 1 > 32767 ? 32767 : c0 + ZMAX + 1);
+    const bool zlo_on = c0 - ZMAX - 1 >= -32768, zhi_on = c0 + ZMAX + 1 <= 32767;
 #pragma unroll 1
     for (int tau = t_live - C::FILL * U; tau < s1; tau += U) {
         const bool own = tau >= s0;
         if (tau == t_live) det_cold(d, t_live - C::LAG + sh);   // forget the steps taken on partly filled rings
-        if (tau == s0) io.put_begin(canon_of(d, s0 - C::LAG + sh));
+        if (tau == s0) {
+            io.put_begin(canon_of(d, s0 - C::LAG + sh));
+            d.l_start = LS_PRED; d.l_hot = 0;                   // the running life began before this chunk's steps
+        }
         const int tn = tau + U < s1 ? tau + U : tau;  // (the last block is simply loaded again)
-        uint32_t bmin = 0x7fff7fffu;                  // packed minimum of this block's samples
+        uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;  // packed extremes of this block's samples
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {
 #pragma unroll
@@ -680,8 +855,8 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
             io.load8(tn + 8 * h, vn[h]);
             const uint32_t m8 = min_s16x2(min_s16x2((uint32_t)v[0], (uint32_t)v[1]), min_s16x2((uint32_t)v[2], (uint32_t)v[3]));
             bmin = min_s16x2(bmin, m8);
-            vmax = max_s16x2(max_s16x2(vmax, (uint32_t)v[0]), max_s16x2((uint32_t)v[1], max_s16x2((uint32_t)v[2], (uint32_t)v[3])));
-            cvt8(v, off, unit, x + 8 * h);
+            bmax = max_s16x2(max_s16x2(bmax, (uint32_t)v[0]), max_s16x2((uint32_t)v[1], max_s16x2((uint32_t)v[2], (uint32_t)v[3])));
+            cvt8(v, off, unit, lk.c0, x + 8 * h, z + 8 * h);
             if (pa && own) io.store_pa8(tau + 8 * h, x + 8 * h);
             if (can_low & any_le_s16x2(m8, low2)) {   // LOW samples in this group (rare)
                 dirty = DIRTY_BLOCKS;
@@ -689,18 +864,27 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
             }
         }
         vmin = min_s16x2(vmin, bmin);
-        walk_block<RNA, false>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, off, unit, io);
+        vmax = max_s16x2(vmax, bmax);
+        if ((zlo_on & any_le_s16x2(bmin, zlo2)) | (zhi_on & any_le_s16x2(zhi2, bmax))) {  // |z| > ZMAX (rare)
+            zdirty = DIRTY_BLOCKS;                    // every window that holds the sample is a candidate, and the
+#pragma unroll
+            for (int q = 0; q < U; q++)               // running integer sums stay exact: the sample enters them clamped
+                z[q] = z[q] > (float)(ZMAX + 1) ? (float)(ZMAX + 1) : z[q] < -(float)(ZMAX + 1) ? -(float)(ZMAX + 1) : z[q];
+        }
+        walk_block<RNA, false>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
         dirty = dirty > 0 ? dirty - 1 : 0;
+        zdirty = zdirty > 0 ? zdirty - 1 : 0;
     }
+    if (d.l_hot) io.job(d.l_start, LS_CONT);
     io.put_end(canon_of(d, s1 - C::LAG + sh));
-    const int rmin0 = (int)(int16_t)(vmin & 0xffffu), rmin1 = (int)vmin >> 16;
-    const int rmax0 = (int)(int16_t)(vmax & 0xffffu), rmax1 = (int)vmax >> 16;
+    const int rmin0 = s16_lo(vmin), rmin1 = s16_hi(vmin);
+    const int rmax0 = s16_lo(vmax), rmax1 = s16_hi(vmax);
     io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1, can_low ? low_t : -32769);
 }
 
 // first chunk (last == 0) or last chunk (last == 1; only when the read has >= 2 chunks) of a read: bounds-checked
 template <int RNA, class Io>
-SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W, int last) {
+SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W, int last, float thr_long) {
     using C = Cfg<RNA>;
     constexpr int U = C::U;
     const uint32_t nch = n_chunks((uint32_t)n, (uint32_t)L);
@@ -715,31 +899,46 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
     g.clear();
     WalkDet d;
     det_cold(d, sh + 1);  // first chunk: the reference's initial state, masked_to = 0: position 0 is skipped (events.c:516-536, 387)
-    float x[U];
+    float x[U], z[U];
     int rmin = 32767, rmax = -32768;
     bool can_low;
     const int low_t0 = low_threshold(off, &can_low);
     const int low_t = can_low ? low_t0 : -32769;
-    int dirty = 0;
+    int dirty = 0, zdirty = 0;
     const bool pa = io.want_pa();
+    const int t_first = last ? t_live - C::FILL * U : 0;
+    int c0;
+    {
+        int v0[4] = {0, 0, 0, 0};
+        io.load8(t_first, v0);                        // t_first < n: inside the read's padded span
+        const int a = s16_lo((uint32_t)v0[0]), b = t_first + 1 < n ? s16_hi((uint32_t)v0[0]) : a;
+        c0 = pivot_of(a, b, t_first + 2 < n ? s16_lo((uint32_t)v0[1]) : a);
+    }
+    const LongK lk = long_consts<RNA>(c0, off, thr_long);
 #pragma unroll 1
-    for (int tau = last ? t_live - C::FILL * U : 0; tau - C::LAG < step_end; tau += U) {
+    for (int tau = t_first; tau - C::LAG < step_end; tau += U) {
         const bool own = tau >= s0;
         if (last && tau == t_live) det_cold(d, t_live - C::LAG + sh);
-        if (last && tau == s0) io.put_begin(canon_of(d, s0 - C::LAG + sh));
+        if (last && tau == s0) {
+            io.put_begin(canon_of(d, s0 - C::LAG + sh));
+            d.l_start = LS_PRED; d.l_hot = 0;
+        }
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {
             const int t8 = tau + 8 * h;
             int v[4] = {0, 0, 0, 0};
             if (t8 < n) io.load8(t8, v);  // t8 < n: inside the read's padded span
-            float y[8];
-            cvt8(v, off, unit, y);
+            float y[8], zy[8];
+            cvt8(v, off, unit, lk.c0, y, zy);
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 const bool in = t8 + q < n;
                 const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
                 const bool low = in & (raw <= low_t);   // rare: handed to the block as 0, its windows are dirty
                 x[8 * h + q] = (in & !low) ? y[q] : 0.0f;
+                const bool zbad = in & ((raw - c0 > ZMAX) | (c0 - raw > ZMAX));  // rare: enters the integer sums clamped
+                z[8 * h + q] = !in ? 0.0f : !zbad ? zy[q] : raw > c0 ? (float)(ZMAX + 1) : -(float)(ZMAX + 1);
+                if (zbad) zdirty = DIRTY_BLOCKS;
                 if (low) {
                     dirty = DIRTY_BLOCKS;
                     const uint32_t a = f_bits(y[q]) & 0x7fffffffu;
@@ -752,12 +951,56 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
                 }
             }
         }
-        walk_block<RNA, true>(g, d, x, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, off, unit, io);
+        walk_block<RNA, true>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
         dirty = dirty > 0 ? dirty - 1 : 0;
+        zdirty = zdirty > 0 ? zdirty - 1 : 0;
     }
-    if (!to_end) io.put_end(canon_of(d, s1 - C::LAG + sh));
+    if (to_end) {
+        if (d.l_hot) io.job(d.l_start, n + sh);      // the life ends with the read
+    } else {
+        if (d.l_hot) io.job(d.l_start, LS_CONT);
+        io.put_end(canon_of(d, s1 - C::LAG + sh));
+    }
     if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)
     if (rmin <= rmax) io.witness(rmin, rmax, low_t);
+}
+
+// ---- a life of the long detector, replayed with the reference's own operations --------------------------------------
+// Steps [l_start, end) of the long detector from its reset state (shifted positions; chunk k of the read created
+// the job). `Jo` supplies, besides load8 / peak:
+//   end_lstart(kk)     word 6 of the END record of chunk kk (its l_start after its last owned step)
+//   end_short(kk, pv, ps)   the short detector's state in the same record
+// l_start == LS_PRED: the life began in an earlier chunk -- the END records of the chunks before k are searched
+// backwards for the last reset (the first chunk always knows: the reference's initial state). end == LS_CONT: the
+// life runs past chunk k's last owned step -- from there on the short detector is replayed as well (from chunk
+// k's END record, with exact t1) until it resets the long one, which ends the life.
+template <int RNA, class Jo>
+SGW_HD void long_job(Jo& io, int n, int sh, float off, float unit, int L, int k, int l_start, int end, float thr_long) {
+    using C = Cfg<RNA>;
+    constexpr int w1 = C::w1, w2 = C::w2;
+    for (int kk = k - 1; l_start == LS_PRED && kk >= 0; kk--) l_start = io.end_lstart(kk);
+    if (l_start == LS_PRED) return;  // (cannot happen: chunk 0 starts from a concrete state)
+    const int stop = n + sh;         // steps exist for positions 1 .. n-1
+    const int own_end = end == LS_CONT ? (k + 1) * L - C::LAG + sh : (end < stop ? end : stop);
+    float pv = FLT_MAX; int ps = PS_NONE;
+    PeakAcc unused; unused.mk = 0u; unused.oldest = 0;
+    bool b2; int p2;
+    auto t_at = [&](int u, int w) -> float {
+        const int i = u - sh;
+        return (i >= w && i + w <= n) ? tstat_exact(io, i, w, n, off, unit) : 0.0f;
+    };
+    int u = l_start;
+    for (; u < own_end; u++)
+        det_one<false, RNA>(pv, ps, 0, u, t_at(u, w2), thr_long, unused, b2, p2, [&](int pos) { io.peak(pos); });
+    if (end != LS_CONT) return;
+    float spv; int sps;
+    io.end_short(k, &spv, &sps);
+    u = own_end;                     // (l_start <= own_end: the life was alive at the chunk's last owned step)
+    for (; u < stop; u++) {
+        det_one<true, RNA>(spv, sps, 0, u, t_at(u, w1), thr_short<RNA>(), unused, b2, p2, NoEmit());
+        if (b2) return;              // reset: the life ended before the long detector's step at u
+        det_one<false, RNA>(pv, ps, 0, u, t_at(u, w2), thr_long, unused, b2, p2, [&](int pos) { io.peak(pos); });
+    }
 }
 
 }  // namespace walk

@@ -194,7 +194,20 @@ class Oracle(_EventLib):
         self.lib.orc_tstat(_p(S, _f64p), _p(Q, _f64p), n, w, _p(t, _f32p))
         return t[:n]
 
-    def detect(self, t1, t2, rna, start=0, stop=None, cold=False):
+    def event_starts(self, raw, dig, off, rng, rna=0, thr_long=None):
+        """event start positions of one read through the stage-level entry points, optionally with another
+        threshold for the long detector (the reference's is 9.0 and its long detector hardly ever emits; tests lower
+        it to exercise the code that handles long-detector peaks)"""
+        pa = self.pa(raw, dig, off, rng)
+        S, Q = self.prefix(pa)
+        p = self.params(rna)
+        t1, t2 = self.tstat(S, Q, p.w_short), self.tstat(S, Q, p.w_long)
+        peaks = self.detect(t1, t2, rna, thr_long=thr_long)[0].astype(np.int64)
+        n = len(raw)
+        peaks = peaks[(peaks > 0) & (peaks < n)]
+        return np.concatenate([np.zeros(1, np.int64), peaks]) if n else np.zeros(0, np.int64)
+
+    def detect(self, t1, t2, rna, start=0, stop=None, cold=False, thr_long=None):
         """run the dual detector over [start, stop); -> (peaks, short_state, long_state)"""
         n = t1.shape[0]
         stop = n if stop is None else stop
@@ -204,6 +217,8 @@ class Oracle(_EventLib):
         else:
             self.lib.orc_det_init(C.byref(s), C.byref(l))
         p = self.params(rna)
+        if thr_long is not None:
+            p.thr_long = float(thr_long)
         peaks = np.empty(max(n, 1), dtype=np.uint64)
         t1 = np.ascontiguousarray(t1, dtype=np.float32)
         t2 = np.ascontiguousarray(t2, dtype=np.float32)

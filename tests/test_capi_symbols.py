@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sigtk_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names
-    assert lib.sgpu_abi_version() == 4
+    assert lib.sgpu_abi_version() == 5
 
 
 def test_python_mirror_matches_the_header():
@@ -39,6 +39,10 @@ def test_python_mirror_matches_the_header():
     body = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     fields = re.findall(r"\*?\s*(\w+);", re.search(r"typedef struct \{([^}]*)\} sgpu_result_t;", body).group(1))
     assert fields == [f[0] for f in _lib.Result._fields_]
+    fields = re.findall(r"\*?\s*(\w+);", re.search(r"typedef struct \{([^}]*)\} sgpu_counters_t;", body).group(1))
+    assert fields == [f[0] for f in _lib.Counters._fields_]
+    for name in ("CHUNK_LEN", "WARMUP", "THR_LONG"):
+        assert getattr(_lib, "PARAM_" + name) == defs["SGPU_PARAM_" + name]
 
 
 def test_strerror_and_argument_checks():

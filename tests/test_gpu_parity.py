@@ -1,5 +1,6 @@
 """GPU parity tests: the CUDA path (through the C-ABI, include/sigtk_b200.h) against the CPU oracle and
 against the committed stdout of the compiled reference. Bit-exact for boundaries, pA, means, stdv and stat."""
+import contextlib
 import gzip
 import os
 
@@ -9,11 +10,26 @@ import pytest
 import _fmt
 from _oracle import Oracle
 import sigtk_b200 as sg
+from sigtk_b200 import _lib as _sl
 from sigtk_b200 import synth
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALL = sg.WANT_EVENTS | sg.WANT_PA | sg.WANT_STAT
+
+
+@contextlib.contextmanager
+def tuned(ctx, chunk_len=0, warmup=0, thr_long=9.0):
+    """development parameters of the context (sgpu_set_param), restored afterwards"""
+    ctx.set_param(_sl.PARAM_CHUNK_LEN, chunk_len)
+    ctx.set_param(_sl.PARAM_WARMUP, warmup)
+    ctx.set_param(_sl.PARAM_THR_LONG, thr_long)
+    try:
+        yield ctx
+    finally:
+        ctx.set_param(_sl.PARAM_CHUNK_LEN, 0)
+        ctx.set_param(_sl.PARAM_WARMUP, 0)
+        ctx.set_param(_sl.PARAM_THR_LONG, 9.0)
 
 
 @pytest.fixture(scope="module")
@@ -209,24 +225,23 @@ def test_flat_stretch_inside_a_read(ctx, orc):
 
 
 @pytest.mark.parametrize("chunk_len", [128, 256, 512, 1024])
-def test_chunk_lengths(ctx, orc, chunk_len, monkeypatch):
+def test_chunk_lengths(ctx, orc, chunk_len):
     """the chunk length is chosen from the batch size; force every value the DNA path can take"""
-    monkeypatch.setenv("SGPU_CHUNK_LEN", str(chunk_len))
     reads = synth.make_reads(24, mean=9000.0, seed=61)
     reads.append(synth.make_read(99, 3 * chunk_len, seed=61))       # exact multiple of the chunk length
     reads.append(synth.make_read(98, 2 * chunk_len + 1, seed=61))   # one-sample last chunk
-    res = ctx.run(reads, rna=0, want=ALL)
+    with tuned(ctx, chunk_len=chunk_len):
+        res = ctx.run(reads, rna=0, want=ALL)
     check_against_oracle(orc, res, reads, 0)
     assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0
 
 
-def test_short_warmup_falls_back(ctx, orc, monkeypatch):
+def test_short_warmup_falls_back(ctx, orc):
     """an 8-sample detector warm-up leaves many chunks in a wrong state: the boundary-state check must catch every
     one of them (fixups > 0), route those reads to the sequential-order kernels, and the results stay bit-exact"""
-    monkeypatch.setenv("SGPU_WARMUP", "8")
-    monkeypatch.setenv("SGPU_CHUNK_LEN", "128")
     reads = synth.make_reads(40, mean=12000.0, seed=62)
-    res = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)
+    with tuned(ctx, chunk_len=128, warmup=8):
+        res = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)
     check_against_oracle(orc, res, reads, 0, want=sg.WANT_EVENTS)
     assert int(res.fixups.sum()) > 0
     assert np.all(res.seq_order[res.fixups > 0] == 1)
@@ -402,14 +417,14 @@ def test_full_size_batch(orc):
 
 
 @pytest.mark.parametrize("rna_flag", [0, 1])
-def test_plateaus_emit_old_peaks_on_the_fast_path(ctx, orc, rna_flag, monkeypatch):
+def test_plateaus_emit_old_peaks_on_the_fast_path(ctx, orc, rna_flag):
     """linear ramps keep the t-statistic within peak_height of its maximum: the peak is emitted dozens of samples
     after its position, too old for the walker's per-block register mask; the block then records its peaks one by
     one (redo_block) and the read stays on the fast path"""
     from test_host_walk import ramp_read
-    monkeypatch.setenv("SGPU_CHUNK_LEN", "4096")
     reads = [ramp_read(12000, seed=3), ramp_read(15000, seed=4)] + synth.make_reads(6, mean=9000.0, seed=63)
-    res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
+    with tuned(ctx, chunk_len=4096):
+        res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
     check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS)
     assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0
 
@@ -443,16 +458,74 @@ def _fuzz_read(rng, k):
 
 
 @pytest.mark.parametrize("rna_flag,chunk_len,seed", [(0, 128, 1), (0, 1024, 2), (1, 512, 3), (1, 4096, 4), (0, 4096, 5)])
-def test_fuzz_adversarial_reads(ctx, orc, rna_flag, chunk_len, seed, monkeypatch):
+def test_fuzz_adversarial_reads(ctx, orc, rna_flag, chunk_len, seed):
     """random reads with glitches, flat stretches, ramps, steps and saturation: every output bit-exact, whichever
     path (walker, its exact recompute, sequential-order kernels) a read takes"""
-    monkeypatch.setenv("SGPU_CHUNK_LEN", str(chunk_len))
     rng = np.random.default_rng(seed)
     reads = [_fuzz_read(rng, k) for k in range(300)]
-    res = ctx.run(reads, rna=rna_flag, want=ALL)
-    check_against_oracle(orc, res, reads, rna_flag)
-    # the same reads as svb-zd streams decoded on the GPU
-    sres = ctx.run_svbzd([(orc.svbzd_encode(r[0]), r[1], r[2], r[3]) for r in reads], rna=rna_flag, want=ALL)
+    with tuned(ctx, chunk_len=chunk_len):
+        res = ctx.run(reads, rna=rna_flag, want=ALL)
+        check_against_oracle(orc, res, reads, rna_flag)
+        # the same reads as svb-zd streams decoded on the GPU
+        sres = ctx.run_svbzd([(orc.svbzd_encode(r[0]), r[1], r[2], r[3]) for r in reads], rna=rna_flag, want=ALL)
     assert np.array_equal(sres.ev_off, res.ev_off) and np.array_equal(sres.ev_start, res.ev_start)
     assert np.array_equal(bits(sres.ev_mean), bits(res.ev_mean)) and np.array_equal(bits(sres.ev_stdv), bits(res.ev_stdv))
     assert np.array_equal(bits(sres.stat), bits(res.stat))
+
+
+# ---- round 2: the long detector's lives (not stepped by the walker, replayed as jobs) ----------------------------
+@pytest.mark.parametrize("rna_flag,chunk_len", [(0, 128), (0, 1024), (1, 512), (1, 4096)])
+@pytest.mark.parametrize("thr", [0.3, 1.0, 2.5])
+def test_long_detector_lives_are_replayed(ctx, orc, rna_flag, chunk_len, thr):
+    """with the reference's threshold (9.0) the long detector never emits on these reads; lowered through the
+    context's test parameter it emits all the time: every life that may emit is replayed by long_jobs_kernel
+    (lives inside a chunk, lives inherited from an earlier chunk, lives that run past their chunk)"""
+    from test_host_walk import ramp_read
+    reads = synth.make_reads(24, mean=9000.0, seed=171 + rna_flag, rna=bool(rna_flag))
+    rd = synth.make_read(11, 30000, seed=3)
+    raw = rd[0].copy()
+    raw[6000:14000] = raw[5999]                              # no short peak for thousands of samples: one long life
+    raw[14000:20000] = raw[5999] + (np.arange(6000) // 40)
+    reads += [(raw, rd[1], rd[2], rd[3]), ramp_read(12000, seed=3)]
+    with tuned(ctx, chunk_len=chunk_len, thr_long=thr):
+        res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS)
+        jobs = ctx.counters()["n_long_jobs"]
+    extra = 0
+    for r, rd in enumerate(reads):
+        if res.seq_order[r]:
+            continue  # (the sequential-order kernels keep the reference's constant)
+        st = orc.event_starts(*rd, rna=rna_flag, thr_long=thr)
+        assert np.array_equal(res.events(r).start.astype(np.int64), st), f"read {r}"
+        extra += len(np.setdiff1d(st, orc.events(*rd, rna=rna_flag)[0].astype(np.int64)))
+    assert int(res.seq_order.sum()) <= 2 and jobs > 0
+    if thr <= 1.0:
+        assert extra > 0
+
+
+def test_far_from_the_pivot(ctx, orc):
+    """samples more than 1023 raw units from a chunk's pivot (level jumps, spikes): every window that holds one is a
+    candidate of the long detector's test; results stay bit-exact"""
+    rd = synth.make_read(21, 40000, seed=8)
+    raw = rd[0].astype(np.int32)
+    raw[3000:5000] += 3000
+    raw[7000] = 30000
+    raw[7001] = -20000
+    raw[9000:9100] += np.arange(100) * 40
+    raw[20000:] += 1500
+    raw = np.clip(raw, -32768, 32767).astype(np.int16)
+    reads = [(raw, rd[1], rd[2], rd[3])] + synth.make_reads(4, mean=9000.0, seed=8)
+    for rna_flag in (0, 1):
+        res = ctx.run(reads, rna=rna_flag, want=ALL)
+        check_against_oracle(orc, res, reads, rna_flag)
+        assert ctx.counters()["n_long_jobs"] > 0
+
+
+# ---- BASELINE configs[4]: 2,000,000-sample reads (the reference's width limits: int32_t nsample misc.c:20,
+# int peak_pos events.c:277) --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rna_flag", [0, 1])
+def test_two_million_sample_reads(ctx, orc, rna_flag):
+    reads = [synth.make_read(7000 + k, 2_000_000 + 3 * k, seed=9, p_change=0.025 if rna_flag else 0.1) for k in range(2)]
+    reads.append(synth.make_read(7002, 50_001, seed=9))
+    res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS | sg.WANT_STAT)
+    check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS | sg.WANT_STAT)
+    assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0

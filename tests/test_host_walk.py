@@ -130,3 +130,72 @@ def test_non_positive_samples_stay_on_the_walker(lib, orc, rna, L, W):
     check(lib, orc, ((-rd[0] - 100).astype(np.int16), rd[1], rd[2], rd[3]), rna, L, W, 8, must_verify=False)
     raw = rd[0].copy(); raw[1500] = -int(rd[2])
     check(lib, orc, (raw, rd[1], rd[2], rd[3]), rna, L, W, 8)
+
+
+# ---- the long detector: not stepped on the fast path, its lives replayed as jobs (walk_core.cuh) ------------------
+def check_thr(lib, orc, rd, rna, L, W, sh, thr, jobs):
+    raw, dig, off, rng = rd
+    st = orc.event_starts(raw, dig, off, rng, rna=rna, thr_long=thr)
+    mism, starts, _, _ = _hostwalk.walk(lib, raw, dig, off, rng, rna, L, W, sh, thr_long=thr, jobs_out=jobs)
+    if mism == 0:
+        assert np.array_equal(starts, st), f"n={len(raw)} L={L} W={W} sh={sh} thr={thr}"
+    return mism, st
+
+
+def test_event_starts_helper_equals_event_read(orc):
+    rd = synth.make_read(2, 9000, seed=4)
+    assert np.array_equal(orc.event_starts(*rd), orc.events(*rd)[0].astype(np.int64))
+
+
+@pytest.mark.parametrize("rna,L,W", [(0, 128, 64), (0, 256, 64), (0, 1024, 64), (1, 512, 384), (1, 2048, 384)])
+@pytest.mark.parametrize("thr", [0.3, 1.0, 2.5, 5.0])
+def test_long_detector_lives_are_replayed(lib, orc, rna, L, W, thr):
+    """with the reference's threshold (9.0) the long detector never emits on these reads; lowered, it emits all the
+    time: lives inside a chunk, lives that began in an earlier chunk (LS_PRED), lives that run past the chunk (LS_CONT)"""
+    reads = synth.make_reads(5, mean=9000.0, seed=141 + rna, rna=bool(rna))
+    jobs, extra = [], 0
+    for k, rd in enumerate(reads):
+        mism, st = check_thr(lib, orc, rd, rna, L, W, (0, 8, 16, 24)[k % 4], thr, jobs)
+        assert mism == 0
+        extra += len(np.setdiff1d(st, orc.events(*rd, rna=rna)[0].astype(np.int64)))
+    assert sum(jobs) > 0
+    if thr <= 2.5:
+        assert extra > 0   # the long detector did emit peaks the short one does not
+
+
+def test_long_detector_quiet_stretches(lib, orc):
+    """long lives (no short peak for thousands of samples: a flat stretch, a slow ramp) across many chunk boundaries"""
+    rd = synth.make_read(11, 30000, seed=3)
+    raw = rd[0].copy()
+    raw[6000:14000] = raw[5999]
+    raw[14000:20000] = raw[5999] + (np.arange(6000) // 40)
+    jobs = []
+    for rna, L, W in ((0, 128, 64), (0, 1024, 64), (1, 512, 384)):
+        for thr in (0.05, 0.5, 9.0):
+            check_thr(lib, orc, (raw, rd[1], rd[2], rd[3]), rna, L, W, 8, thr, jobs)
+
+
+def test_long_detector_ragged_and_edges(lib, orc):
+    base = synth.make_read(3, 3 * 128 + 40, seed=9)
+    jobs = []
+    for n in [1, 5, 13, 14, 27, 28, 29, 33, 127, 128, 129, 135, 136, 137, 255, 256, 257, 3 * 128, 3 * 128 + 5]:
+        for thr in (0.3, 1.5):
+            for rna in (0, 1):
+                check_thr(lib, orc, (base[0][:n].copy(), base[1], base[2], base[3]), rna, 128 if not rna else 512,
+                          64 if not rna else 384, 8, thr, jobs)
+
+
+def test_far_from_the_pivot(lib, orc):
+    """samples more than ZMAX raw units from the chunk's pivot (level jumps of thousands of units, spikes): the
+    integer sums are clamped there and every window that holds such a sample is a candidate"""
+    rd = synth.make_read(21, 12000, seed=8)
+    raw = rd[0].astype(np.int32)
+    raw[3000:5000] += 3000
+    raw[7000] = 30000
+    raw[7001] = -20000
+    raw[9000:9100] += np.arange(100) * 40
+    raw = np.clip(raw, -32768, 32767).astype(np.int16)
+    jobs = []
+    for rna, L, W in ((0, 128, 64), (0, 1024, 64), (1, 512, 384)):
+        for thr in (1.0, 9.0):
+            mism, _ = check_thr(lib, orc, (raw, rd[1], rd[2], rd[3]), rna, L, W, 0, thr, jobs)

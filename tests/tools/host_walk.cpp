@@ -36,21 +36,42 @@ struct HostIo {
     void put_end(const Canon& c) const { *end = c; }
     void witness(int lo, int hi, int) const { if (lo < *rmin) *rmin = lo; if (hi > *rmax) *rmax = hi; }
     void low_samples(int, uint32_t, uint32_t) const {}
+    // a life of the long detector that may emit (walk_core.cuh): replayed after all chunks have been walked
+    struct Job { int k, l_start, end; };
+    std::vector<Job>* jobs;
+    int k;
+    void job(int l_start, int end) const { jobs->push_back(Job{k, l_start, end}); }
+};
+
+// the memory side of long_job(): the END records of the read's chunks
+struct HostJobIo {
+    const int16_t* sp;
+    uint32_t* bm;
+    const std::vector<Canon>* end;
+    void load8(int t, int (&v)[4]) const { memcpy(v, sp + t, 16); }
+    void peak(int pos) const { bm[pos >> 5] |= 1u << (pos & 31); }
+    int end_lstart(int kk) const { return (*end)[kk].v[6]; }
+    void end_short(int kk, float* pv, int* ps) const { *pv = bits_f((uint32_t)(*end)[kk].v[0]); *ps = (*end)[kk].v[1]; }
 };
 
 template <int RNA>
 int run(const int16_t* raw_padded, int n, float off, float unit, int L, int W, int sh, uint32_t* bitmap, float* pa,
-        int* rminmax) {
+        int* rminmax, float thr_long, int* n_jobs) {
     const uint32_t nch = n_chunks((uint32_t)n, (uint32_t)L);
     if (nch == 0) return 0;
     std::vector<Canon> begin(nch), end(nch);
     int rmin = 32767, rmax = -32768;
+    std::vector<HostIo::Job> jobs;
     for (uint32_t k = 0; k < nch; k++) {
-        HostIo io{raw_padded, pa, bitmap, &begin[k], &end[k], &rmin, &rmax};
-        if (k == 0) walk_edge<RNA>(io, n, off, unit, sh, L, W, 0);
-        else if (k == nch - 1) walk_edge<RNA>(io, n, off, unit, sh, L, W, 1);
-        else walk_interior<RNA>(io, n, off, unit, sh, L, W, (int)k);
+        HostIo io{raw_padded, pa, bitmap, &begin[k], &end[k], &rmin, &rmax, &jobs, (int)k};
+        if (k == 0) walk_edge<RNA>(io, n, off, unit, sh, L, W, 0, thr_long);
+        else if (k == nch - 1) walk_edge<RNA>(io, n, off, unit, sh, L, W, 1, thr_long);
+        else walk_interior<RNA>(io, n, off, unit, sh, L, W, (int)k, thr_long);
     }
+    // second pass: the lives of the long detector that may emit, with the reference's own operations
+    HostJobIo jo{raw_padded, bitmap, &end};
+    for (const HostIo::Job& j : jobs) long_job<RNA>(jo, n, sh, off, unit, L, j.k, j.l_start, j.end, thr_long);
+    *n_jobs = (int)jobs.size();
     int mism = 0;
     for (uint32_t k = 1; k < nch; k++) {
         bool same = true;
@@ -66,8 +87,10 @@ int run(const int16_t* raw_padded, int n, float off, float unit, int L, int W, i
 // raw_padded: the read's samples followed by enough padding for 16-byte loads up to the 8-aligned length.
 // bitmap: ((n + sh + 31) / 32 + 1) zeroed words; bit (i + sh) set <=> an event starts at sample i.
 // Returns the number of chunk boundaries whose warm-up state differed from the predecessor's end state.
+// thr_long: the long detector's threshold (9.0 in the reference; tests lower it so that the long detector emits).
+// n_jobs: number of lives of the long detector that were replayed.
 extern "C" int host_walk_read(const int16_t* raw_padded, int n, float off, float unit, int rna, int L, int W, int sh,
-                              uint32_t* bitmap, float* pa, int* rminmax) {
-    return rna ? run<1>(raw_padded, n, off, unit, L, W, sh, bitmap, pa, rminmax)
-               : run<0>(raw_padded, n, off, unit, L, W, sh, bitmap, pa, rminmax);
+                              uint32_t* bitmap, float* pa, int* rminmax, float thr_long, int* n_jobs) {
+    return rna ? run<1>(raw_padded, n, off, unit, L, W, sh, bitmap, pa, rminmax, thr_long, n_jobs)
+               : run<0>(raw_padded, n, off, unit, L, W, sh, bitmap, pa, rminmax, thr_long, n_jobs);
 }
