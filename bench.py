@@ -45,7 +45,8 @@ WORKLOAD = "synthetic 1M DNA reads, int16, lognormal length mean 40k samples (si
 WORKLOADS = {"dna40k": WORKLOAD,
              "dna178k": "synthetic DNA reads, int16, fixed 178,000 samples (20 kb-equivalent), {mode}",
              "ultralong": "synthetic ultra-long DNA reads, int16, 2,000,000 samples each, {mode}",
-             "rna40k": "synthetic RNA-parameter reads, int16, lognormal length mean 40k samples, {mode}"}
+             "rna40k": "synthetic RNA-parameter reads, int16, lognormal length mean 40k samples, {mode}",
+             "real": "the 100 R9.4 DNA reads of test/sp1_dna.blow5 (tests/golden/sp1_dna.npz) tiled to >= 300 M samples, {mode}"}
 
 
 def alg_bytes(n_samples: int, n_reads: int, n_events: int, pa: bool) -> int:
@@ -160,8 +161,77 @@ def host_reads_of(batch, n_first: int):
     off, lens = batch["host_off"], batch["host_len"]
     n_first = min(n_first, len(lens))
     flat = batch["samples"][: int(off[n_first])].cpu().numpy()
-    return [(flat[int(off[r]): int(off[r]) + int(lens[r])].copy(), synth.DIGITISATION, float(batch["host_offset"][r]),
-             synth.RANGE) for r in range(n_first)]
+    dig, rng = batch.get("host_dig"), batch.get("host_range")
+    return [(flat[int(off[r]): int(off[r]) + int(lens[r])].copy(), synth.DIGITISATION if dig is None else float(dig[r]),
+             float(batch["host_offset"][r]), synth.RANGE if rng is None else float(rng[r])) for r in range(n_first)]
+
+
+def real_batch(torch, dev, target_samples: int = 300_000_000):
+    """The reference's own fixture (100 real R9.4 reads, 472,511 samples) repeated until the batch holds
+    target_samples: real glitches, stalls and reads whose sums are order dependent (1 in 100 fails the exact-sum
+    witness and takes the sequential-order kernels) -- what the synthetic model does not have."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "sp1_dna.npz"), allow_pickle=True)
+    roff = z["read_off"].astype(np.int64)
+    lens1 = np.diff(roff)
+    copies = int(-(-target_samples // int(lens1.sum())))
+    lens = np.tile(lens1, copies)
+    n = len(lens)
+    al = (lens + 7) // 8 * 8
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum(al)
+    one = np.zeros(int(al[:len(lens1)].sum()), dtype=np.int16)
+    for r in range(len(lens1)):
+        one[int(off[r]): int(off[r]) + int(lens1[r])] = z["samples"][int(roff[r]): int(roff[r + 1])]
+    samples = torch.from_numpy(one).to(dev).repeat(copies)
+    offsets = np.tile(z["offset"].astype(np.float32), copies)
+    unit1 = (z["range"].astype(np.float32) / z["digitisation"].astype(np.float32)).astype(np.float32)  # misc.c:17-19,26
+    unit = np.tile(unit1, copies)
+    return {
+        "samples": samples, "read_off": torch.from_numpy(off).to(dev), "read_len": torch.from_numpy(lens.astype(np.int32)).to(dev),
+        "offset": torch.from_numpy(offsets).to(dev), "unit": torch.from_numpy(unit).to(dev),
+        "span": int(off[-1]), "n_samples": int(lens.sum()), "n_reads": n, "host_off": off, "host_len": lens,
+        "host_offset": offsets, "copies": copies,
+        "host_dig": np.tile(z["digitisation"], copies), "host_range": np.tile(z["range"], copies),
+    }
+
+
+def short_run(torch, sg, local, batches, rna, want, steps=3, warmup=3):
+    """a short device-resident timing of one workload (the extra sub-lines of the default bench line):
+    -> dict(value Gsamples/s, ms_per_step, stage ms, counters of the last step)"""
+    max_span = max(p["span"] for p in batches)
+    max_reads = max(p["n_reads"] for p in batches)
+    ctx = sg.Context(device=local, max_samples=max_span, max_reads=max_reads, flags=sg.F_NO_HOST_SLOTS | sg.F_STAGE_TIMERS)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(p):
+        ctx.run_device(p["samples"].data_ptr(), p["read_off"].data_ptr(), p["read_len"].data_ptr(), p["offset"].data_ptr(),
+                       p["unit"].data_ptr(), p["n_reads"], p["span"], rna, want, stream)
+
+    for w in range(warmup):
+        step(batches[w % len(batches)])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = {}
+    ns = 0
+    ev0.record()
+    for k in range(steps):
+        p = batches[(warmup + k) % len(batches)]
+        step(p)
+        for name, ms, _ in ctx.stage_times():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+        ns += p["n_samples"]
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    c = ctx.counters()
+    ctx.close()
+    last = batches[(warmup + steps - 1) % len(batches)]
+    return {"value": ns / (ms * 1e-3) / 1e9, "unit": UNIT, "steps": steps, "ms_per_step": ms / steps,
+            "samples_per_step": ns // steps, "reads_per_step": last["n_reads"],
+            "stage_ms_per_step": {k: round(v / steps, 4) for k, v in stage_ms.items()},
+            "sequential_order_reads": c["n_seq_order_reads"], "detector_fixups": c["n_fixups"],
+            "long_detector_replays": c["n_long_jobs"], "events_per_sample": c["n_events"] / max(last["n_samples"], 1),
+            "status": c["status"]}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -263,7 +333,10 @@ def run_ours(args):
     pool_n = max(1, min(args.pool, args.steps + args.warmup))
     from sigtk_b200.shard import shard_ranges
     pool = []
-    for j in range(pool_n):
+    if args.workload == "real":
+        pool_n = 1
+        pool.append(real_batch(torch, dev))
+    for j in range(pool_n if args.workload != "real" else 0):
         # step j works on the next world*B reads of the set, split into contiguous read ranges balanced by samples
         g0 = (j * world * B) % (N_SET - world * B)
         lo, hi = shard_ranges(lens_all[g0:g0 + world * B], world)[rank]
@@ -317,7 +390,8 @@ def run_ours(args):
         step(p)
         torch.cuda.synchronize()
         c = ctx.counters()
-        ev_per_batch.append((c["n_events"], c["n_seq_order_reads"], c["n_fixups"], c["n_kernel_launches"], c["status"]))
+        ev_per_batch.append((c["n_events"], c["n_seq_order_reads"], c["n_fixups"], c["n_kernel_launches"], c["status"],
+                             c["n_long_jobs"]))
     for k in range(args.steps):
         e = ev_per_batch[(args.warmup + k) % pool_n]
         n_events += e[0]
@@ -349,6 +423,27 @@ def run_ours(args):
             siblings[name] = {"ms": ms, "kernels_ms": {n_: round(m_, 4) for n_, m_, _ in stages},
                               "value": p0["n_samples"] / (ms * 1e-3) / 1e9, "unit": UNIT,
                               "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / measured_peak()[0]}
+
+    # ---- the other BASELINE configs as short sub-lines of the default line (N = 1 only) ---------------------------------
+    others = {}
+    if world == 1 and args.workload == "dna40k" and not args.no_others:
+        del pool[1:]          # (HBM: keep batch 0 for the e2e / svb-zd legs)
+        torch.cuda.empty_cache()
+        ul = [device_batch(torch, dev, np.full(160, 2_000_000, dtype=np.int64), 0, synth.SEED + 11, 0.1)]
+        others["ultralong"] = dict(short_run(torch, sg, local, ul, 0, want),
+                                   workload=WORKLOADS["ultralong"].format(mode=args.mode) + " (BASELINE configs[4])")
+        del ul
+        torch.cuda.empty_cache()
+        rn = [device_batch(torch, dev, lens_all[:8192], 0, synth.SEED + 13, 0.025)]
+        others["rna40k"] = dict(short_run(torch, sg, local, rn, 1, want),
+                                workload=WORKLOADS["rna40k"].format(mode=args.mode) + " (RNA detector parameters, BASELINE configs[1])")
+        del rn
+        torch.cuda.empty_cache()
+        rb = [real_batch(torch, dev)]
+        others["real"] = dict(short_run(torch, sg, local, rb, 0, want), workload=WORKLOADS["real"].format(mode=args.mode),
+                              copies=rb[0]["copies"])
+        del rb
+        torch.cuda.empty_cache()
 
     # ---- end to end through the host C-ABI: pinned slots, H2D + kernels + D2H per step ----------------------------
     e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna)
@@ -399,13 +494,16 @@ def run_ours(args):
                        "events_per_sample": all_events / max(all_samples, 1.0),
                        "l2": f"inputs {2 * max_span / 1e6:.0f} MB per step > 126 MB L2; pool of {pool_n} distinct batches",
                        "sequential_order_reads": sum(e[1] for e in ev_per_batch),
-                       "detector_fixups": sum(e[2] for e in ev_per_batch)},
+                       "detector_fixups": sum(e[2] for e in ev_per_batch),
+                       "long_detector_replays": sum(e[5] for e in ev_per_batch)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if svb:
             line["svbzd"] = svb
         if siblings:
             line["siblings"] = siblings
+        if others:
+            line["other_workloads"] = others
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist:
@@ -519,7 +617,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="event+pa", choices=["event+pa", "event"])
-    ap.add_argument("--workload", default="dna40k", choices=["dna40k", "dna178k", "ultralong", "rna40k"],
+    ap.add_argument("--workload", default="dna40k", choices=["dna40k", "dna178k", "ultralong", "rna40k", "real"],
                     help="dna40k = BASELINE.json configs[2] (the headline); the others are reported in DESIGN.md")
     ap.add_argument("--reads-per-step", type=int, default=16384)
     ap.add_argument("--pool", type=int, default=4, help="distinct device-resident batches cycled through")
@@ -528,6 +626,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-svbzd", action="store_true", help="skip the compressed-input (svb-zd) measurements")
     ap.add_argument("--no-siblings", action="store_true", help="skip the pa / stat / ent kernel timings")
+    ap.add_argument("--no-others", action="store_true", help="skip the ultralong / rna40k / real sub-lines")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -336,11 +336,11 @@ struct WalkDet {
     float s_pv; int s_ps;               // short detector (never masked after the read's first sample)
     int l_start;                        // first step of the long detector's current life that is not masked:
                                         // max(reset step, masked_to + 1); LS_PRED while unknown to this chunk
-    int l_hot;                          // != 0: a stepped position of the current life may have t2 > thr_long
+    bool l_hot;                         // a stepped position of the current life may have t2 > thr_long
 };
 SGW_HD void det_cold(WalkDet& d, int first_step) {  // both detectors start at `first_step` from the reset state
     d.s_pv = FLT_MAX; d.s_ps = PS_NONE;
-    d.l_start = first_step; d.l_hot = 0;
+    d.l_start = first_step; d.l_hot = false;
 }
 
 // canonical form at boundary b (state before step b): the first 6 words are bit-compared between the chunk that
@@ -514,6 +514,21 @@ struct Rings {
 // long detector's lives.
 //   cand : long_candidate() of position u (false proves t2(u) <= thr_long)
 //   rec  : the step is owned by this chunk (jobs are only created for owned steps)
+// (kept out of line, everything by value, so that the compiler neither if-converts it into every step nor moves
+// the block's state to memory for it: it runs about once per 10,000 steps)
+struct Parked { int jobs, ls, end; };
+#if defined(__CUDACC__) && defined(WALK_PARK_CALL)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+Parked park_job(int jobs, int ls, int end, int l_start, int u) {
+    Parked p;
+    p.ls = jobs == 0 ? l_start : ls;
+    p.end = jobs == 0 ? u : end;
+    p.jobs = jobs + 1;
+    return p;
+}
 template <int RNA, bool DIRECT, class E, class Io>
 SGW_HD void det_step(WalkDet& d, int m, int u, float c1, bool cand, bool rec, PeakAcc& acc, const E& on_emit, Io& io) {
     bool maskl; int p2;
@@ -521,14 +536,15 @@ SGW_HD void det_step(WalkDet& d, int m, int u, float c1, bool cand, bool rec, Pe
     acc.oldest = acc.oldest > over ? acc.oldest : over;
     // the short detector holds a peak above its threshold: the long detector is reset and masked up to
     // peak_pos + w_short (events.c:414-422) -- the current life ends before this step, a new one starts with it
-    if (maskl & (d.l_hot != 0) & rec) {                       // rare: the life that ends here may have emitted
+    bool hot = d.l_hot != 0;
+    if (maskl & hot & rec) {                                 // rare: the life that ends here may have emitted
         if (DIRECT) io.job(d.l_start, u);
-        else { if (acc.jobs == 0) { acc.job_ls = d.l_start; acc.job_end = u; } acc.jobs++; }
+        else { const Parked k = park_job(acc.jobs, acc.job_ls, acc.job_end, d.l_start, u); acc.jobs = k.jobs; acc.job_ls = k.ls; acc.job_end = k.end; }
     }
     const int ls = (p2 & ~PS_OPEN) + Cfg<RNA>::w1 + 1;
-    d.l_hot = maskl ? 0 : d.l_hot;
     d.l_start = maskl ? (ls > u ? ls : u) : d.l_start;
-    d.l_hot |= (int)((u >= d.l_start) & cand);               // the long detector is stepped at u (events.c:387)
+    hot = (hot & !maskl) | ((u >= d.l_start) & cand);        // the long detector is stepped at u (events.c:387)
+    d.l_hot = hot;
 }
 
 // The rare path of a block: the t-statistics of the whole block from the raw samples with the reference's own
@@ -844,7 +860,7 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
         if (tau == t_live) det_cold(d, t_live - C::LAG + sh);   // forget the steps taken on partly filled rings
         if (tau == s0) {
             io.put_begin(canon_of(d, s0 - C::LAG + sh));
-            d.l_start = LS_PRED; d.l_hot = 0;                   // the running life began before this chunk's steps
+            d.l_start = LS_PRED; d.l_hot = false;                   // the running life began before this chunk's steps
         }
         const int tn = tau + U < s1 ? tau + U : tau;  // (the last block is simply loaded again)
         uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;  // packed extremes of this block's samples
@@ -921,7 +937,7 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
         if (last && tau == t_live) det_cold(d, t_live - C::LAG + sh);
         if (last && tau == s0) {
             io.put_begin(canon_of(d, s0 - C::LAG + sh));
-            d.l_start = LS_PRED; d.l_hot = 0;
+            d.l_start = LS_PRED; d.l_hot = false;
         }
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {
