@@ -233,8 +233,9 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
             marks.done("init", n);
         } else {
             marks.done("init", n);
-            marks.done("walk_chunks", launch_walk(b, sc, (want & SGPU_WANT_PA) ? o.pa : nullptr, d_seq, d_fix,
-                                                   ctx->sm_count, st));
+            marks.done("walk_chunks", launch_walk(b, sc, (want & SGPU_WANT_PA) ? o.pa : nullptr, d_seq, ctx->sm_count, st));
+            marks.done("long_jobs", launch_long_jobs(b, sc, d_seq, ctx->sm_count, st));
+            marks.done("verify_chunks", launch_verify_chunks(b, sc, d_seq, d_fix, ctx->sm_count, st));
         }
         n = launch_build_seq_list(b, sc, d_seq, force_generic ? 1 : 0, ctx->sm_count, st);
         WorkList wl{sc.seq_list, sc.seq_sbase, sc.seq_count};

@@ -66,8 +66,9 @@ uint32_t fast_tiles_for(uint64_t span);
 int launch_init_reads(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
                       cudaStream_t st);
 // walk.cu (chunk walker: pA, t-statistics, peak detector -> event-start bitmap)
-int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
-                cudaStream_t st);
+int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, int sm_count, cudaStream_t st);
+int launch_long_jobs(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int sm_count, cudaStream_t st);
+int launch_verify_chunks(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count, cudaStream_t st);
 uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads);
 uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced);
 uint32_t walk_warmup(int rna, uint32_t forced);

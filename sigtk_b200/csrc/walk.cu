@@ -309,16 +309,10 @@ uint32_t walk_warmup(int rna, uint32_t forced) {
     return W;
 }
 uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads) { return 2ull * max_reads + max_samples / 128u + 1u; }
-uint32_t walk_job_capacity(uint64_t max_samples) { return (uint32_t)(max_samples / 512u + 4096u); }
+uint32_t walk_job_capacity(uint64_t max_samples) { return (uint32_t)(max_samples / 64u + 4096u); }  // (16 B each)
 
-int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, uint32_t* fixups, int sm_count,
-                cudaStream_t st) {
+static WalkParams walk_params(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, int sm_count) {
     const uint32_t L = walk_chunk_len(b.span, b.rna, sm_count, sc.tune_chunk_len), W = walk_warmup(b.rna, sc.tune_warmup);
-    const uint64_t words = (uint64_t)fast_tiles_for(b.span) * (FAST_TILE / 32);
-    cudaMemsetAsync(sc.bitmap, 0, (size_t)words * sizeof(uint32_t), st);
-    cudaMemsetAsync(sc.job_count, 0, sizeof(uint32_t), st);
-    chunk_count_kernel<<<grid_cap(b.n_reads, 256, sm_count * 8), 256, 0, st>>>(b, L, sc.wk_cnt);
-    int n = 1 + launch_scan_u32(sc.wk_cnt, b.n_reads, sc.wk_ibase, nullptr, sc, st);
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
     p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max; p.tile_read0 = sc.tile_read0;
@@ -326,16 +320,37 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
     p.thr_long = sc.tune_thr_long;
     p.jobs = reinterpret_cast<int4*>(sc.jobs); p.job_count = sc.job_count; p.job_cap = sc.job_cap; p.seq_flag = seq_flag;
     p.counters = sc.counters;
-    const uint64_t max_interior = b.span / L;  // every interior chunk covers L distinct samples
+    return p;
+}
+
+int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, int sm_count, cudaStream_t st) {
+    const WalkParams p = walk_params(b, sc, pa_out, seq_flag, sm_count);
+    const uint64_t words = (uint64_t)fast_tiles_for(b.span) * (FAST_TILE / 32);
+    cudaMemsetAsync(sc.bitmap, 0, (size_t)words * sizeof(uint32_t), st);
+    cudaMemsetAsync(sc.job_count, 0, sizeof(uint32_t), st);
+    chunk_count_kernel<<<grid_cap(b.n_reads, 256, sm_count * 8), 256, 0, st>>>(b, (uint32_t)p.L, sc.wk_cnt);
+    int n = 1 + launch_scan_u32(sc.wk_cnt, b.n_reads, sc.wk_ibase, nullptr, sc, st);
+    const uint64_t max_interior = b.span / (uint32_t)p.L;  // every interior chunk covers L distinct samples
     const uint64_t grid = (uint64_t)p.edge_blocks + (max_interior + WNT - 1) / WNT;
     if (b.rna) walk_chunks_kernel<1><<<(unsigned)grid, WNT, 0, st>>>(p);
     else walk_chunks_kernel<0><<<(unsigned)grid, WNT, 0, st>>>(p);
-    // the lives of the long detector that may emit (a few per 100,000 samples), replayed exactly
+    return n + 1;
+}
+
+// the lives of the long detector that may emit (a few per 100,000 samples), replayed exactly
+int launch_long_jobs(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int sm_count, cudaStream_t st) {
+    const WalkParams p = walk_params(b, sc, nullptr, seq_flag, sm_count);
     if (b.rna) long_jobs_kernel<1><<<sm_count * 4, 128, 0, st>>>(p);
     else long_jobs_kernel<0><<<sm_count * 4, 128, 0, st>>>(p);
+    return 1;
+}
+
+int launch_verify_chunks(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count, cudaStream_t st) {
+    const uint32_t L = walk_chunk_len(b.span, b.rna, sm_count, sc.tune_chunk_len);
+    const uint64_t max_interior = b.span / L;
     verify_chunks_kernel<<<grid_cap(max_interior + b.n_reads, 256, sm_count * 8), 256, 0, st>>>(
         b, L, sc.wk_ibase, sc.wk_begin, sc.wk_end, seq_flag, fixups);
-    return n + 3;
+    return 1;
 }
 
 }  // namespace sgpu

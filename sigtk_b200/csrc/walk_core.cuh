@@ -270,13 +270,9 @@ SGW_HD void window_sums(const Io& io, int a, int w, int n, float off, float unit
         Q = dadd(Q, (double)fmul(x, x));
     }
 }
-// events.c:338-361 for position i with window length w (the sums are exact, so forming them per window is the
-// same as the reference's prefix differences)
-template <class Io>
-SGW_HD float tstat_exact(const Io& io, int i, int w, int n, float off, float unit) {
-    double sum1, ssq1, sum2d, ssq2d;
-    window_sums(io, i - w, w, n, off, unit, sum1, ssq1);
-    window_sums(io, i, w, n, off, unit, sum2d, ssq2d);
+// events.c:338-361 from the four window sums of one position (sum1 / ssq1: the left window, kept in double;
+// sum2d / ssq2d: the right window, narrowed to float at once), every operation the reference's own
+SGW_HD float tstat_from_sums(double sum1, double ssq1, double sum2d, double ssq2d, int w) {
     const float wf = (float)w;
     const float sum2 = d2f(sum2d), ssq2 = d2f(ssq2d);
     const float mean1 = d2f(ddiv(sum1, (double)wf));
@@ -289,6 +285,41 @@ SGW_HD float tstat_exact(const Io& io, int i, int w, int n, float off, float uni
     const float delta = fsub(mean2, mean1);
     return d2f(ddiv(fabs((double)delta), dsqrt((double)fdiv(cv, wf))));
 }
+// the same for position i with window length w from the raw samples (the sums are exact, so forming them per
+// window is the same as the reference's prefix differences)
+template <class Io>
+SGW_HD float tstat_exact(const Io& io, int i, int w, int n, float off, float unit) {
+    double sum1, ssq1, sum2d, ssq2d;
+    window_sums(io, i - w, w, n, off, unit, sum1, ssq1);
+    window_sums(io, i, w, n, off, unit, sum2d, ssq2d);
+    return tstat_from_sums(sum1, ssq1, sum2d, ssq2d, w);
+}
+// t-statistics of CONSECUTIVE positions: the four window sums slide by one sample per step (three samples touched
+// instead of 2w; exact like every other grouping of these sums). next(i) must be called with i increasing by one;
+// positions whose windows leave the read give 0 (events.c:328-338).
+template <class Io>
+struct SlidingT {
+    double s1, q1, s2, q2;
+    int at;   // the position the sums belong to, -1: none
+    SGW_HD SlidingT() : s1(0.0), q1(0.0), s2(0.0), q2(0.0), at(-1) {}
+    SGW_HD float next(const Io& io, int i, int w, int n, float off, float unit) {
+        if (!(i >= w && i + w <= n)) { at = -1; return 0.0f; }
+        if (at != i - 1) {
+            window_sums(io, i - w, w, n, off, unit, s1, q1);
+            window_sums(io, i, w, n, off, unit, s2, q2);
+        } else {
+            const float xa = sample_pa(io, i - 1 - w, n, off, unit);   // leaves the left window
+            const float xb = sample_pa(io, i - 1, n, off, unit);       // moves from the right window to the left one
+            const float xc = sample_pa(io, i - 1 + w, n, off, unit);   // enters the right window
+            const double da = (double)xa, db = (double)xb, dc = (double)xc;
+            const double qa = (double)fmul(xa, xa), qb = (double)fmul(xb, xb), qc = (double)fmul(xc, xc);
+            s1 = dadd(dsub(s1, da), db); q1 = dadd(dsub(q1, qa), qb);
+            s2 = dadd(dsub(s2, db), dc); q2 = dadd(dsub(q2, qb), qc);
+        }
+        at = i;
+        return tstat_from_sums(s1, q1, s2, q2, w);
+    }
+};
 // recompute the t-statistics of one block: t1v[m] (m >= m1) belongs to position tau0+m-w1+1, t2v[m] to tau0+m-w2+1
 template <int RNA, class Io>
 #if defined(__CUDACC__)
@@ -519,6 +550,8 @@ struct Rings {
 struct Parked { int jobs, ls, end; };
 #if defined(__CUDACC__) && defined(WALK_PARK_CALL)
 static __host__ __device__ __noinline__
+#elif defined(__CUDACC__)
+static __host__ __device__ __forceinline__
 #else
 static inline
 #endif
@@ -824,6 +857,49 @@ SGW_HD void zero_low8(Io& io, int t, const int (&v)[4], int low_t, float* x) {
     io.low_samples(t, lo, hi);
 }
 
+// what a chunk driver needs to turn the packed samples of one block into x[] / z[] on the unchecked path
+struct BlockCvt {
+    bool can_low, zlo_on, zhi_on, pa;
+    int low_t;
+    uint32_t low2, zlo2, zhi2;
+};
+SGW_HD BlockCvt block_cvt(float off, int c0, bool want_pa) {
+    BlockCvt k;
+    k.low_t = low_threshold(off, &k.can_low);
+    k.low2 = pack_s16x2(k.low_t);
+    // |z| <= ZMAX  <=>  c0 - ZMAX <= raw <= c0 + ZMAX (clamped so that the packed comparisons cannot wrap)
+    k.zlo2 = pack_s16x2(c0 - ZMAX - 1 < -32768 ? -32768 : c0 - ZMAX - 1);
+    k.zhi2 = pack_s16x2(c0 + ZMAX + 1 > 32767 ? 32767 : c0 + ZMAX + 1);
+    k.zlo_on = c0 - ZMAX - 1 >= -32768; k.zhi_on = c0 + ZMAX + 1 <= 32767;
+    k.pa = want_pa;
+    return k;
+}
+// one group of 8 samples (all inside the read): pA, z, the optional pA store, LOW samples, packed extremes
+template <class Io>
+SGW_HD void cvt_group(Io& io, const BlockCvt& k, const LongK& lk, const int (&v)[4], int t8, bool own, float off, float unit,
+                      float* x, float* z, uint32_t& bmin, uint32_t& bmax, int& dirty) {
+    const uint32_t m8 = min_s16x2(min_s16x2((uint32_t)v[0], (uint32_t)v[1]), min_s16x2((uint32_t)v[2], (uint32_t)v[3]));
+    bmin = min_s16x2(bmin, m8);
+    bmax = max_s16x2(max_s16x2(bmax, (uint32_t)v[0]), max_s16x2((uint32_t)v[1], max_s16x2((uint32_t)v[2], (uint32_t)v[3])));
+    cvt8(v, off, unit, lk.c0, x, z);
+    if (k.pa && own) io.store_pa8(t8, x);
+    if (k.can_low & any_le_s16x2(m8, k.low2)) {   // LOW samples in this group (rare)
+        dirty = DIRTY_BLOCKS;
+        zero_low8(io, t8, v, k.low_t, x);
+    }
+}
+// after the groups of a block: samples far from the pivot (rare) enter the integer sums clamped, and every window
+// that holds one is a candidate of the long detector's test
+template <int U>
+SGW_HD void clamp_far(const BlockCvt& k, uint32_t bmin, uint32_t bmax, float* z, int& zdirty) {
+    if ((k.zlo_on & any_le_s16x2(bmin, k.zlo2)) | (k.zhi_on & any_le_s16x2(k.zhi2, bmax))) {  // |z| > ZMAX
+        zdirty = DIRTY_BLOCKS;
+#pragma unroll
+        for (int q = 0; q < U; q++)
+            z[q] = z[q] > (float)(ZMAX + 1) ? (float)(ZMAX + 1) : z[q] < -(float)(ZMAX + 1) ? -(float)(ZMAX + 1) : z[q];
+    }
+}
+
 // interior chunk k (1 <= k <= nch-2) of a read: every access is inside the read, no bounds checks.
 // ONE loop (one copy of the block code in the instruction cache) runs the two ring-fill blocks, the detector
 // warm-up and the owned samples.
@@ -840,27 +916,20 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
     float x[U], z[U];
     int v[4];
     uint32_t vmin = 0x7fff7fffu, vmax = 0x80008000u;  // packed int16 min / max (over warm-up and owned samples)
-    bool can_low;
-    const int low_t = low_threshold(off, &can_low);
-    const uint32_t low2 = pack_s16x2(low_t);
     int dirty = 0, zdirty = 0;
-    const bool pa = io.want_pa();
     int vn[U / 8][4];                                 // the next block's samples, loaded one block ahead
 #pragma unroll
     for (int h = 0; h < U / 8; h++) io.load8(t_live - C::FILL * U + 8 * h, vn[h]);
     const int c0 = pivot_of(s16_lo((uint32_t)vn[0][0]), s16_hi((uint32_t)vn[0][0]), s16_lo((uint32_t)vn[0][1]));
     const LongK lk = long_consts<RNA>(c0, off, thr_long);
-    // |z| <= ZMAX  <=>  c0 - ZMAX <= raw <= c0 + ZMAX (clamped so that the packed comparisons cannot wrap)
-    const uint32_t zlo2 = pack_s16x2(c0 - ZMAX - 1 < -32768 ? -32768 : c0 - ZMAX - 1);
-    const uint32_t zhi2 = pack_s16x2(c0 + ZMAX + 1 > 32767 ? 32767 : c0 + ZMAX + 1);
-    const bool zlo_on = c0 - ZMAX - 1 >= -32768, zhi_on = c0 + ZMAX + 1 <= 32767;
+    const BlockCvt bc = block_cvt(off, c0, io.want_pa());
 #pragma unroll 1
     for (int tau = t_live - C::FILL * U; tau < s1; tau += U) {
         const bool own = tau >= s0;
         if (tau == t_live) det_cold(d, t_live - C::LAG + sh);   // forget the steps taken on partly filled rings
         if (tau == s0) {
             io.put_begin(canon_of(d, s0 - C::LAG + sh));
-            d.l_start = LS_PRED; d.l_hot = false;                   // the running life began before this chunk's steps
+            d.l_start = LS_PRED; d.l_hot = false;               // the running life began before this chunk's steps
         }
         const int tn = tau + U < s1 ? tau + U : tau;  // (the last block is simply loaded again)
         uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;  // packed extremes of this block's samples
@@ -869,24 +938,11 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
 #pragma unroll
             for (int q = 0; q < 4; q++) v[q] = vn[h][q];
             io.load8(tn + 8 * h, vn[h]);
-            const uint32_t m8 = min_s16x2(min_s16x2((uint32_t)v[0], (uint32_t)v[1]), min_s16x2((uint32_t)v[2], (uint32_t)v[3]));
-            bmin = min_s16x2(bmin, m8);
-            bmax = max_s16x2(max_s16x2(bmax, (uint32_t)v[0]), max_s16x2((uint32_t)v[1], max_s16x2((uint32_t)v[2], (uint32_t)v[3])));
-            cvt8(v, off, unit, lk.c0, x + 8 * h, z + 8 * h);
-            if (pa && own) io.store_pa8(tau + 8 * h, x + 8 * h);
-            if (can_low & any_le_s16x2(m8, low2)) {   // LOW samples in this group (rare)
-                dirty = DIRTY_BLOCKS;
-                zero_low8(io, tau + 8 * h, v, low_t, x + 8 * h);
-            }
+            cvt_group(io, bc, lk, v, tau + 8 * h, own, off, unit, x + 8 * h, z + 8 * h, bmin, bmax, dirty);
         }
         vmin = min_s16x2(vmin, bmin);
         vmax = max_s16x2(vmax, bmax);
-        if ((zlo_on & any_le_s16x2(bmin, zlo2)) | (zhi_on & any_le_s16x2(zhi2, bmax))) {  // |z| > ZMAX (rare)
-            zdirty = DIRTY_BLOCKS;                    // every window that holds the sample is a candidate, and the
-#pragma unroll
-            for (int q = 0; q < U; q++)               // running integer sums stay exact: the sample enters them clamped
-                z[q] = z[q] > (float)(ZMAX + 1) ? (float)(ZMAX + 1) : z[q] < -(float)(ZMAX + 1) ? -(float)(ZMAX + 1) : z[q];
-        }
+        clamp_far<U>(bc, bmin, bmax, z, zdirty);
         walk_block<RNA, false>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
         dirty = dirty > 0 ? dirty - 1 : 0;
         zdirty = zdirty > 0 ? zdirty - 1 : 0;
@@ -895,7 +951,7 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
     io.put_end(canon_of(d, s1 - C::LAG + sh));
     const int rmin0 = s16_lo(vmin), rmin1 = s16_hi(vmin);
     const int rmax0 = s16_lo(vmax), rmax1 = s16_hi(vmax);
-    io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1, can_low ? low_t : -32769);
+    io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1, bc.can_low ? bc.low_t : -32769);
 }
 
 // first chunk (last == 0) or last chunk (last == 1; only when the read has >= 2 chunks) of a read: bounds-checked
@@ -931,6 +987,10 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
         c0 = pivot_of(a, b, t_first + 2 < n ? s16_lo((uint32_t)v0[1]) : a);
     }
     const LongK lk = long_consts<RNA>(c0, off, thr_long);
+    const BlockCvt bc = block_cvt(off, c0, pa);
+    // blocks whose samples and windows all lie inside the read take the unchecked code of the interior chunks
+    // (reads of a few thousand samples are mostly edge chunks); only the first and the last blocks are bounds-checked
+    constexpr int INNER_MIN = (2 * C::w2 - 1 + U - 1) / U * U;
 #pragma unroll 1
     for (int tau = t_first; tau - C::LAG < step_end; tau += U) {
         const bool own = tau >= s0;
@@ -939,35 +999,52 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
             io.put_begin(canon_of(d, s0 - C::LAG + sh));
             d.l_start = LS_PRED; d.l_hot = false;
         }
+        if (tau >= INNER_MIN && tau + U <= n) {
+            uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;
 #pragma unroll
-        for (int h = 0; h < U / 8; h++) {
-            const int t8 = tau + 8 * h;
-            int v[4] = {0, 0, 0, 0};
-            if (t8 < n) io.load8(t8, v);  // t8 < n: inside the read's padded span
-            float y[8], zy[8];
-            cvt8(v, off, unit, lk.c0, y, zy);
+            for (int h = 0; h < U / 8; h++) {
+                int v[4];
+                io.load8(tau + 8 * h, v);
+                cvt_group(io, bc, lk, v, tau + 8 * h, own, off, unit, x + 8 * h, z + 8 * h, bmin, bmax, dirty);
+            }
+            if (own) {  // (an owned inner block lies inside [s0, s1): s1 is n or a multiple of U)
+                const int b0 = s16_lo(bmin), b1 = s16_hi(bmin), c0x = s16_lo(bmax), c1x = s16_hi(bmax);
+                rmin = b0 < rmin ? b0 : rmin; rmin = b1 < rmin ? b1 : rmin;
+                rmax = c0x > rmax ? c0x : rmax; rmax = c1x > rmax ? c1x : rmax;
+            }
+            clamp_far<U>(bc, bmin, bmax, z, zdirty);
+            walk_block<RNA, false>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
+        } else {
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const bool in = t8 + q < n;
-                const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
-                const bool low = in & (raw <= low_t);   // rare: handed to the block as 0, its windows are dirty
-                x[8 * h + q] = (in & !low) ? y[q] : 0.0f;
-                const bool zbad = in & ((raw - c0 > ZMAX) | (c0 - raw > ZMAX));  // rare: enters the integer sums clamped
-                z[8 * h + q] = !in ? 0.0f : !zbad ? zy[q] : raw > c0 ? (float)(ZMAX + 1) : -(float)(ZMAX + 1);
-                if (zbad) zdirty = DIRTY_BLOCKS;
-                if (low) {
-                    dirty = DIRTY_BLOCKS;
-                    const uint32_t a = f_bits(y[q]) & 0x7fffffffu;
-                    io.low_samples(t8 + q, a != 0u ? a : 0xffffffffu, a);
-                }
-                if (own && in && t8 + q < s1) {
-                    rmin = raw < rmin ? raw : rmin;
-                    rmax = raw > rmax ? raw : rmax;
-                    if (pa) io.store_pa1(t8 + q, y[q]);
+            for (int h = 0; h < U / 8; h++) {
+                const int t8 = tau + 8 * h;
+                int v[4] = {0, 0, 0, 0};
+                if (t8 < n) io.load8(t8, v);  // t8 < n: inside the read's padded span
+                float y[8], zy[8];
+                cvt8(v, off, unit, lk.c0, y, zy);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const bool in = t8 + q < n;
+                    const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
+                    const bool low = in & (raw <= low_t);   // rare: handed to the block as 0, its windows are dirty
+                    x[8 * h + q] = (in & !low) ? y[q] : 0.0f;
+                    const bool zbad = in & ((raw - c0 > ZMAX) | (c0 - raw > ZMAX));  // rare: enters the integer sums clamped
+                    z[8 * h + q] = !in ? 0.0f : !zbad ? zy[q] : raw > c0 ? (float)(ZMAX + 1) : -(float)(ZMAX + 1);
+                    if (zbad) zdirty = DIRTY_BLOCKS;
+                    if (low) {
+                        dirty = DIRTY_BLOCKS;
+                        const uint32_t a = f_bits(y[q]) & 0x7fffffffu;
+                        io.low_samples(t8 + q, a != 0u ? a : 0xffffffffu, a);
+                    }
+                    if (own && in && t8 + q < s1) {
+                        rmin = raw < rmin ? raw : rmin;
+                        rmax = raw > rmax ? raw : rmax;
+                        if (pa) io.store_pa1(t8 + q, y[q]);
+                    }
                 }
             }
+            walk_block<RNA, true>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
         }
-        walk_block<RNA, true>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
         dirty = dirty > 0 ? dirty - 1 : 0;
         zdirty = zdirty > 0 ? zdirty - 1 : 0;
     }
@@ -1005,9 +1082,11 @@ SGW_HD void long_job(Jo& io, int n, int sh, float off, float unit, int L, int k,
         const int i = u - sh;
         return (i >= w && i + w <= n) ? tstat_exact(io, i, w, n, off, unit) : 0.0f;
     };
+    SlidingT<Jo> slide;
     int u = l_start;
     for (; u < own_end; u++)
-        det_one<false, RNA>(pv, ps, 0, u, t_at(u, w2), thr_long, unused, b2, p2, [&](int pos) { io.peak(pos); });
+        det_one<false, RNA>(pv, ps, 0, u, slide.next(io, u - sh, w2, n, off, unit), thr_long, unused, b2, p2,
+                            [&](int pos) { io.peak(pos); });
     if (end != LS_CONT) return;
     float spv; int sps;
     io.end_short(k, &spv, &sps);

@@ -207,6 +207,34 @@ class Oracle(_EventLib):
         peaks = peaks[(peaks > 0) & (peaks < n)]
         return np.concatenate([np.zeros(1, np.int64), peaks]) if n else np.zeros(0, np.int64)
 
+    def hot_lives(self, raw, dig, off, rng, rna=0, thr_long=None):
+        """number of LIVES of the long detector (stretches between two resets by the short detector,
+        events.c:414-422) that contain a stepped position with t2 > thr_long -- the only lives in which the long
+        detector can emit (its peak_value must exceed the threshold, events.c:424). The detector is stepped one
+        position at a time so that its masking can be observed. A walker that does not step the long detector must
+        replay at least these lives."""
+        pa = self.pa(raw, dig, off, rng)
+        S, Q = self.prefix(pa)
+        p = self.params(rna)
+        if thr_long is not None:
+            p.thr_long = float(thr_long)
+        t1 = np.ascontiguousarray(self.tstat(S, Q, p.w_short), dtype=np.float32)
+        t2 = np.ascontiguousarray(self.tstat(S, Q, p.w_long), dtype=np.float32)
+        n = len(raw)
+        s, l = self.Det(), self.Det()
+        self.lib.orc_det_init(C.byref(s), C.byref(l))
+        peaks = np.empty(4, dtype=np.uint64)
+        lives, hot = 0, False
+        for i in range(n):
+            reset = s.peak_pos >= 0 and max(s.peak_value, float(t1[i])) > p.thr_short
+            if reset:
+                lives += int(hot)
+                hot = False
+            self.lib.orc_detect(_p(t1, _f32p), _p(t2, _f32p), i, i + 1, C.byref(p), C.byref(s), C.byref(l), _p(peaks, _u64p), 4)
+            if l.masked_to < i and float(t2[i]) > p.thr_long:
+                hot = True
+        return lives + int(hot)
+
     def detect(self, t1, t2, rna, start=0, stop=None, cold=False, thr_long=None):
         """run the dual detector over [start, stop); -> (peaks, short_state, long_state)"""
         n = t1.shape[0]

@@ -481,7 +481,7 @@ def test_long_detector_lives_are_replayed(ctx, orc, rna_flag, chunk_len, thr):
     context's test parameter it emits all the time: every life that may emit is replayed by long_jobs_kernel
     (lives inside a chunk, lives inherited from an earlier chunk, lives that run past their chunk)"""
     from test_host_walk import ramp_read
-    reads = synth.make_reads(24, mean=9000.0, seed=171 + rna_flag, rna=bool(rna_flag))
+    reads = synth.make_reads(12, mean=9000.0, seed=171 + rna_flag, rna=bool(rna_flag))
     rd = synth.make_read(11, 30000, seed=3)
     raw = rd[0].copy()
     raw[6000:14000] = raw[5999]                              # no short peak for thousands of samples: one long life
@@ -500,6 +500,20 @@ def test_long_detector_lives_are_replayed(ctx, orc, rna_flag, chunk_len, thr):
     assert int(res.seq_order.sum()) <= 2 and jobs > 0
     if thr <= 1.0:
         assert extra > 0
+
+
+def test_every_hot_life_is_replayed(ctx, orc):
+    """at the reference's threshold the long detector never emits, so parity cannot tell whether its lives are looked
+    at: the number of replayed lives must reach the number of lives in which a stepped position has t2 > 9 (oracle,
+    stepped position by position). (A build that silently dropped the job bookkeeping passed every parity test.)"""
+    reads = [synth.make_read(k, 12000, seed=77) for k in range(3)]
+    for thr in (9.0, 6.0):
+        need = sum(orc.hot_lives(*rd, rna=0, thr_long=thr) for rd in reads)
+        with tuned(ctx, chunk_len=1024, thr_long=thr):
+            res = ctx.run(reads, rna=0, want=sg.WANT_EVENTS)
+            jobs = ctx.counters()["n_long_jobs"]
+        assert need > 0 and jobs >= need and int(res.seq_order.sum()) == 0, (thr, need, jobs)
+        assert jobs <= 60 * need + 60
 
 
 def test_far_from_the_pivot(ctx, orc):

@@ -199,3 +199,17 @@ def test_far_from_the_pivot(lib, orc):
     for rna, L, W in ((0, 128, 64), (0, 1024, 64), (1, 512, 384)):
         for thr in (1.0, 9.0):
             mism, _ = check_thr(lib, orc, (raw, rd[1], rd[2], rd[3]), rna, L, W, 0, thr, jobs)
+
+
+def test_every_hot_life_is_replayed(lib, orc):
+    """the filter that replaces the long detector on the fast path is conservative: the walker replays at least the
+    lives in which a stepped position has t2 > thr_long (counted with the oracle, stepping its detector position by
+    position) -- at the reference's threshold, where the long detector never emits and parity alone could not tell"""
+    reads = [synth.make_read(k, 12000, seed=77) for k in range(3)]
+    for thr in (9.0, 6.0):
+        jobs, need = [], 0
+        for rd in reads:
+            need += orc.hot_lives(*rd, rna=0, thr_long=thr)
+            check_thr(lib, orc, rd, 0, 32768, 64, 0, thr, jobs)   # one chunk per read: one job per life
+        assert need > 0 and sum(jobs) >= need, (thr, need, sum(jobs))
+        assert sum(jobs) <= 40 * need + 40                        # ... and not wildly more
