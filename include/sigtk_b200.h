@@ -57,6 +57,9 @@ extern "C" {
 #define SGPU_WANT_JNN     16u /* the segments of `sigtk jnn`: jnn_raw(), jnn.c:269-282 with the parameters of
                                  jnn_print (jnn.c:305-312: JNNV1_DRNA_R9_PARAM when rna, else JNNV1_CDNA_R9_PARAM) */
 
+#define SGPU_WANT_PREFIX  32u /* `sigtk prefix` (prefix_func, cfunc.c:169-234): find_adaptor (jnnv2, jnn.c:99-188), the
+                                 adaptor's pA statistics, find_polya (jnn.c:352-374) when rna, its statistics */
+
 /* ---- context flags ------------------------------------------------------ */
 #define SGPU_F_DEFAULT       0u
 #define SGPU_F_FORCE_GENERIC 1u /* run every read through the sequential-order (reference-order) kernels */
@@ -110,6 +113,11 @@ typedef struct {
     uint32_t *jnn_cnt;     /* [n_reads] number of segments (jnn_raw's *n); NULL unless SGPU_WANT_JNN */
     int32_t  *jnn_seg;     /* segment k of read r = (x, y) = jnn_seg[2*(SGPU_JNN_BASE(read_off[r], r) + k) + {0,1}]
                               (jnn_pair_t, jnn.h:13-16; sample indices in the read). Bit-exact. */
+    int32_t  *prefix_pos;  /* [n_reads][4]: adaptor x, y as find_adaptor returns them ((0,0): none found, (-1,-1): record not
+                              longer than the 2,000-sample window), poly-A x, y as find_polya returns them, i.e. relative
+                              to the adaptor's end ((-1,-1): none / DNA); NULL unless SGPU_WANT_PREFIX. Bit-exact. */
+    float    *prefix_stat; /* [n_reads][6]: meanf, stdvf, medianf of the adaptor's pA (valid when its y > 0), then of the
+                              poly-A's (valid when its y > 0): cfunc.c:178-180, 202-204. Bit-exact. */
 } sgpu_result_t;
 /* first segment slot of read r (a read of n samples has at most n/38 + 1 segments, jnn.c:232) */
 #define SGPU_JNN_BASE(read_off_r, r) (((uint64_t)(read_off_r) >> 5) + (uint64_t)(r))
@@ -203,6 +211,9 @@ int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
 #define SGPU_PARAM_CHUNK_LEN 1 /* samples per detector chunk (power of two >= 128 DNA / 512 RNA); 0 = automatic */
 #define SGPU_PARAM_WARMUP    2 /* detector warm-up in samples (multiple of 8 DNA / 16 RNA, <= default); 0 = default */
 #define SGPU_PARAM_THR_LONG  3 /* threshold of the long detector */
+#define SGPU_PARAM_PORE      4 /* 0: R9 (JNNV2_RNA_R9_ADAPTOR), 1: RNA004 (JNNV2_RNA_RNA004_ADAPTOR), jnn.h:88-102: the
+                                  host picks it from the BLOW5 header like pore_detect (misc.c:74-101); used by
+                                  SGPU_WANT_PREFIX only (not a test parameter) */
 int  sgpu_set_param(sgpu_ctx_t *ctx, int key, double value);
 
 /* Device time of every kernel group of the last run, measured with CUDA events on the stream the kernels were

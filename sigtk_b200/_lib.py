@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsigtk_b200.so")
 
-WANT_EVENTS, WANT_PA, WANT_STAT, WANT_ENT, WANT_JNN = 1, 2, 4, 8, 16
+WANT_EVENTS, WANT_PA, WANT_STAT, WANT_ENT, WANT_JNN, WANT_PREFIX = 1, 2, 4, 8, 16, 32
 F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, F_STAGE_TIMERS = 0, 1, 2, 4
 ALIGN = 8
 
@@ -26,7 +26,7 @@ EXPORTS = (
     "sgpu_wait", "sgpu_run_device", "sgpu_counters", "sgpu_memcpy_d2h", "sgpu_stage_times",
     "sgpu_slot_add_read_svbzd", "sgpu_decode_svbzd_device", "sgpu_set_param",
 )
-PARAM_CHUNK_LEN, PARAM_WARMUP, PARAM_THR_LONG = 1, 2, 3  # sgpu_set_param keys (development / test parameters)
+PARAM_CHUNK_LEN, PARAM_WARMUP, PARAM_THR_LONG, PARAM_PORE = 1, 2, 3, 4  # sgpu_set_param keys (development / test parameters)
 
 
 class SgpuError(RuntimeError):
@@ -48,6 +48,7 @@ class Result(C.Structure):  # sgpu_result_t
         ("ev_off", C.c_void_p), ("ev_start", C.c_void_p), ("ev_mean", C.c_void_p), ("ev_stdv", C.c_void_p),
         ("pa", C.c_void_p), ("stat", C.c_void_p), ("seq_order", C.c_void_p), ("fixups", C.c_void_p),
         ("n_events", C.c_uint64), ("ent", C.c_void_p), ("jnn_cnt", C.c_void_p), ("jnn_seg", C.c_void_p),
+        ("prefix_pos", C.c_void_p), ("prefix_stat", C.c_void_p),
     ]
 
 

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (ALIGN, F_DEFAULT, F_FORCE_GENERIC, F_NO_HOST_SLOTS, F_STAGE_TIMERS, WANT_EVENTS, WANT_PA,
-                   WANT_STAT, WANT_ENT, WANT_JNN, SgpuError)
+                   WANT_STAT, WANT_ENT, WANT_JNN, WANT_PREFIX, SgpuError)
 
 Read = Tuple[np.ndarray, float, float, float]  # raw int16, digitisation, offset, range
 
@@ -49,11 +49,16 @@ class BatchResult:
     stat: Optional[np.ndarray] = None
     ent: Optional[np.ndarray] = None   # [n_reads][3] float64: raw_ent, delta_ent, byte_ent (ent.c:108-151)
     jnn: Optional[List[np.ndarray]] = None  # per read int64[k][2]: the (x, y) pairs of jnn_raw (jnn.c:269-282)
+    prefix_pos: Optional[np.ndarray] = None   # [n_reads][4] int32: adaptor (x, y), poly-A (x, y) (cfunc.c:169-234)
+    prefix_stat: Optional[np.ndarray] = None  # [n_reads][6] float32: mean, stdv, median of both stretches' pA
     seq_order: Optional[np.ndarray] = None
     fixups: Optional[np.ndarray] = None
 
     def events(self, r: int) -> EventTable:
         a, b = int(self.ev_off[r]), int(self.ev_off[r + 1])
+        if a == b:  # an empty record has no event
+            e = np.empty(0, np.float32)
+            return EventTable(np.empty(0, np.uint64), e, e.copy(), e.copy())
         start = self.ev_start[a:b].astype(np.uint64)
         end = np.empty_like(start)
         end[:-1] = start[1:]
@@ -166,6 +171,9 @@ class Context:
             for r in range(n):
                 base = (int(read_off[r]) >> 5) + r  # SGPU_JNN_BASE
                 out.jnn.append(seg[base: base + int(cnt[r])].astype(np.int64))
+        if want & WANT_PREFIX:
+            out.prefix_pos = _np_from(res.prefix_pos, np.int32, n * 4).reshape(n, 4)
+            out.prefix_stat = _np_from(res.prefix_stat, np.float32, n * 6).reshape(n, 6)
         if want & WANT_PA:
             span = int(read_off[n]) if n else 0
             flat = _np_from(res.pa, np.float32, span)

@@ -27,6 +27,8 @@ struct DevOut {  // device-side outputs of one batch
     double* ent = nullptr;  // [max_reads][3], allocated on first use
     uint32_t* jnn_cnt = nullptr;  // [max_reads], allocated on first use
     int32_t* jnn_seg = nullptr;   // [2 * jnn_seg_capacity]
+    int32_t* prefix_pos = nullptr;   // [max_reads][4], allocated on first use
+    float* prefix_stat = nullptr;    // [max_reads][6]
 };
 
 struct Slot {
@@ -52,6 +54,8 @@ struct Slot {
     double* h_ent = nullptr;
     uint32_t* h_jnn_cnt = nullptr;
     int32_t* h_jnn_seg = nullptr;
+    int32_t* h_prefix_pos = nullptr;
+    float* h_prefix_stat = nullptr;
     uint32_t* h_seq = nullptr;
     uint32_t* h_fix = nullptr;
     unsigned long long* h_counters = nullptr;  // [4]
@@ -86,6 +90,7 @@ struct sgpu_ctx {
     Slot* slots = nullptr;
     SvbScratch svb{};            // workspace of the svb-zd decoder (allocated on first use)
     float* jnn_mom = nullptr;    // [max_reads][2] mean / stdv of the clamped signal (allocated on first use)
+    int pore_rna004 = 0;         // SGPU_PARAM_PORE: jnnv2 parameters of `prefix` (misc.c:74-101 picks them from the header)
     uint32_t* ent_ovf = nullptr; // overflow histograms of ent_kernel (allocated on first use, kept all-zero)
     uint64_t comp_cap = 0;       // bytes of compressed input a slot can hold
     cudaStream_t compute = nullptr;
@@ -143,6 +148,7 @@ int alloc_dev_out(sgpu_ctx* ctx, DevOut& o) {
 void free_dev_out(DevOut& o) {
     cudaFree(o.ev_off); cudaFree(o.ev_start); cudaFree(o.ev_mean); cudaFree(o.ev_stdv);
     cudaFree(o.pa); cudaFree(o.stat); cudaFree(o.ent); cudaFree(o.jnn_cnt); cudaFree(o.jnn_seg);
+    cudaFree(o.prefix_pos); cudaFree(o.prefix_stat);
     o = DevOut{};
 }
 
@@ -223,6 +229,13 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
         if (!ctx->jnn_mom) CU(dev_alloc(&ctx->jnn_mom, (uint64_t)ctx->max_reads * 2));
         marks.done("jnn_moments", launch_jnn_moments(b, ctx->jnn_mom, ctx->sm_count, st));
         marks.done("jnn_walk", launch_jnn(b, ctx->jnn_mom, o.jnn_cnt, o.jnn_seg, ctx->sm_count, st));
+    }
+    if (want & SGPU_WANT_PREFIX) {
+        if (!o.prefix_pos) {
+            CU(dev_alloc(&o.prefix_pos, (uint64_t)ctx->max_reads * 4));
+            CU(dev_alloc(&o.prefix_stat, (uint64_t)ctx->max_reads * 6));
+        }
+        marks.done("prefix", launch_prefix(b, ctx->pore_rna004, o.prefix_pos, o.prefix_stat, ctx->sm_count, st));
     }
     if (events) {
         const uint32_t n_tiles = fast_tiles_for(b.span);
@@ -446,7 +459,7 @@ void sgpu_destroy(sgpu_ctx_t* ctx) {
             cudaFree(sl.d_unit); cudaFree(sl.d_seq); cudaFree(sl.d_fix);
             free_dev_out(sl.dout);
             cudaFreeHost(sl.h_ev_off); cudaFreeHost(sl.h_ev_start); cudaFreeHost(sl.h_ev_mean);
-            cudaFreeHost(sl.h_ev_stdv); cudaFreeHost(sl.h_pa); cudaFreeHost(sl.h_stat); cudaFreeHost(sl.h_ent); cudaFreeHost(sl.h_jnn_cnt); cudaFreeHost(sl.h_jnn_seg); cudaFreeHost(sl.h_seq);
+            cudaFreeHost(sl.h_ev_stdv); cudaFreeHost(sl.h_pa); cudaFreeHost(sl.h_stat); cudaFreeHost(sl.h_ent); cudaFreeHost(sl.h_jnn_cnt); cudaFreeHost(sl.h_jnn_seg); cudaFreeHost(sl.h_prefix_pos); cudaFreeHost(sl.h_prefix_stat); cudaFreeHost(sl.h_seq);
             cudaFreeHost(sl.h_fix); cudaFreeHost(sl.h_counters); cudaFreeHost(sl.h_status);
             cudaFreeHost(sl.h_comp); cudaFreeHost(sl.h_comp_off); cudaFreeHost(sl.h_comp_len);
             cudaFree(sl.d_comp); cudaFree(sl.d_comp_off); cudaFree(sl.d_comp_len);
@@ -555,7 +568,7 @@ int64_t sgpu_slot_add_read_svbzd(sgpu_ctx_t* ctx, uint32_t slot, const uint8_t* 
 }
 
 int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
-    if (!ctx || slot >= ctx->n_slots || (want & ~31u) || want == 0) return SGPU_E_INVAL;
+    if (!ctx || slot >= ctx->n_slots || (want & ~63u) || want == 0) return SGPU_E_INVAL;
     Slot& sl = ctx->slots[slot];
     if (sl.submitted) return SGPU_E_STATE;
     CU(cudaSetDevice(ctx->device));
@@ -586,6 +599,10 @@ int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
         CU(pin_alloc(&sl.h_jnn_cnt, ctx->max_reads));
         CU(pin_alloc(&sl.h_jnn_seg, 2 * jnn_seg_capacity(ctx->max_samples, ctx->max_reads)));
     }
+    if ((want & SGPU_WANT_PREFIX) && !sl.h_prefix_pos) {
+        CU(pin_alloc(&sl.h_prefix_pos, (uint64_t)ctx->max_reads * 4));
+        CU(pin_alloc(&sl.h_prefix_stat, (uint64_t)ctx->max_reads * 6));
+    }
     const int rc = run_pipeline(ctx, b, want, sl.dout, sl.d_seq, sl.d_fix, ctx->compute, compressed ? &svb : nullptr,
                                 sl.d_samples);
     if (rc) return rc;
@@ -608,6 +625,10 @@ int sgpu_submit(sgpu_ctx_t* ctx, uint32_t slot, uint32_t want) {
         CU(cudaMemcpyAsync(sl.h_jnn_cnt, sl.dout.jnn_cnt, (size_t)nr * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(sl.h_jnn_seg, sl.dout.jnn_seg, (size_t)2 * ((sl.used >> 5) + nr + 1) * sizeof(int32_t),
                            cudaMemcpyDeviceToHost, st));
+    }
+    if (want & SGPU_WANT_PREFIX) {
+        CU(cudaMemcpyAsync(sl.h_prefix_pos, sl.dout.prefix_pos, (size_t)nr * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(sl.h_prefix_stat, sl.dout.prefix_stat, (size_t)nr * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     if (want & SGPU_WANT_PA)
         CU(cudaMemcpyAsync(sl.h_pa, sl.dout.pa, (size_t)sl.used * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -648,12 +669,13 @@ int sgpu_wait(sgpu_ctx_t* ctx, uint32_t slot, sgpu_result_t* out) {
     if (sl.want & SGPU_WANT_PA) out->pa = sl.h_pa;
     if (sl.want & SGPU_WANT_ENT) out->ent = sl.h_ent;
     if (sl.want & SGPU_WANT_JNN) { out->jnn_cnt = sl.h_jnn_cnt; out->jnn_seg = sl.h_jnn_seg; }
+    if (sl.want & SGPU_WANT_PREFIX) { out->prefix_pos = sl.h_prefix_pos; out->prefix_stat = sl.h_prefix_stat; }
     return SGPU_OK;
 }
 
 int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t want, void* stream,
                     sgpu_result_t* out) {
-    if (!ctx || !batch || !out || (want & ~31u) || want == 0) return SGPU_E_INVAL;
+    if (!ctx || !batch || !out || (want & ~63u) || want == 0) return SGPU_E_INVAL;
     CU(cudaSetDevice(ctx->device));
     DevBatch b{batch->samples, batch->read_off, batch->read_len, batch->offset_f, batch->raw_unit_f,
                batch->n_reads, (int)batch->rna, batch->span};
@@ -670,6 +692,8 @@ int sgpu_run_device(sgpu_ctx_t* ctx, const sgpu_dev_batch_t* batch, uint32_t wan
     out->ent = (want & SGPU_WANT_ENT) ? ctx->dev_out.ent : nullptr;
     out->jnn_cnt = (want & SGPU_WANT_JNN) ? ctx->dev_out.jnn_cnt : nullptr;
     out->jnn_seg = (want & SGPU_WANT_JNN) ? ctx->dev_out.jnn_seg : nullptr;
+    out->prefix_pos = (want & SGPU_WANT_PREFIX) ? ctx->dev_out.prefix_pos : nullptr;
+    out->prefix_stat = (want & SGPU_WANT_PREFIX) ? ctx->dev_out.prefix_stat : nullptr;
     out->seq_order = ctx->dev_seq;
     out->fixups = ctx->dev_fix;
     return SGPU_OK;
@@ -719,6 +743,10 @@ int sgpu_set_param(sgpu_ctx_t* ctx, int key, double value) {
         case SGPU_PARAM_WARMUP:
             if (value < 0 || value > 4096) return SGPU_E_INVAL;
             sc.tune_warmup = (uint32_t)value;
+            return SGPU_OK;
+        case SGPU_PARAM_PORE:
+            if (value != 0 && value != 1) return SGPU_E_INVAL;
+            ctx->pore_rna004 = (int)value;
             return SGPU_OK;
         case SGPU_PARAM_THR_LONG:
             if (!(value > 0 && value < 1e6)) return SGPU_E_INVAL;

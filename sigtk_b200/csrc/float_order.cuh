@@ -1,0 +1,183 @@
+// float_order.cuh -- sequential FLOAT accumulation (the reference's meanf / stdvf loops, stat.h:17-44) reproduced
+// bit for bit by a whole warp: shared by stat.cu (`sigtk stat`, the jnn band) and prefix.cu (`sigtk prefix`).
+#pragma once
+#include "common.cuh"
+
+namespace sgpu {
+
+// ---- sequential float accumulation, in parallel ----------------------------------------------------------------------
+// The reference adds in float, one value after the other: s <- fl(s + v). While s stays in one binade [2^e, 2^(e+1))
+// every s is an integer multiple S of g = 2^(e-23), and for v >= 0
+//     fl(s + v) = g * RNE(S + v/g) = g * (S + a + c),   v/g = a + f,  a = floor, 0 <= f < 1,
+//     c = [f > 1/2], and on a tie (f == 1/2) c = parity of (S + a):
+// the only thing the step needs to know about the running sum is the PARITY of S. So a run of values is summarised by
+// two integers -- the total increment for an even and for an odd incoming S -- computed without knowing s, and runs
+// compose. One warp takes 1024 values: every lane summarises 32 consecutive ones (both parities), a shuffle scan
+// composes the 32 summaries (lane 0 used to walk them one by one: a quarter of the kernel's time). A tile that would carry S to 2^24 (the binade ends there), holds a negative value or meets s <= 0 is
+// added value by value; the summaries after it are recomputed for the new binade. Bit-identical to the sequential
+// loop by construction (tests: every stat of every parity test and of the fuzz reads against the oracle).
+constexpr int SB = 1024;            // values per superblock
+constexpr int SB_STRIDE = 33;       // shared-memory row stride of a 32-value tile (conflict-free both ways)
+
+__device__ __forceinline__ float chain_superblock(const float* __restrict__ A, int ntiles, float s, int lane,
+                                                  int* __restrict__ sums, bool first) {
+    int tile = 0;
+    while (tile < ntiles) {  // (uniform across the warp)
+        const uint32_t sb = __float_as_uint(s);
+        const int e = (int)((sb >> 23) & 0xffu) - 127;
+        const bool s_ok = !first && s > 0.0f && e > -100 && e < 100;  // the first superblock starts from 0: binades fly by
+        int fail = tile;  // first tile that has to be added value by value
+        uint32_t S = (sb & 0x7fffffu) | 0x800000u;
+        if (s_ok) {
+            const float scale = __uint_as_float((uint32_t)(127 + 23 - e) << 23);
+            // every lane summarises one tile: the increment of S for an even (u0) and for an odd (u1) incoming S
+            uint32_t u0 = 0u, u1 = 0u;  // lanes outside [tile, ntiles) are the identity
+            bool ok = true;
+            if (lane >= tile && lane < ntiles) {
+                const float* row = A + lane * SB_STRIDE;
+                // A tie rounds to even: after the first tie of the run the parity is 0 whatever came in, so the two
+                // summaries differ only by the carry of that first tie (c and 1 - c). One chain (incoming S even)
+                // plus that difference.
+                int inc0 = 0, dif = 0;
+                uint32_t par = 0u;
+                bool seen = false;
+#pragma unroll 8
+                for (int k = 0; k < 32; k++) {
+                    const float v = row[k];
+                    const float x = __fmul_rn(v, scale);          // exact: a power of two
+                    ok = ok && ((__float_as_uint(v) >> 31) == 0u) && (x < 16777216.0f);
+                    const int a = __float2int_rd(x);
+                    const float f = __fsub_rn(x, (float)a);       // exact
+                    const bool tie = f == 0.5f;
+                    const uint32_t up = f > 0.5f ? 1u : 0u;
+                    const uint32_t t = par + (uint32_t)a;
+                    const uint32_t c = tie ? (t & 1u) : up;
+                    if (tie && !seen) { dif = 1 - 2 * (int)c; seen = true; }
+                    inc0 += a + (int)c;
+                    par = (t + c) & 1u;
+                }
+                u0 = (uint32_t)inc0;
+                u1 = (uint32_t)(inc0 + dif);
+            }
+            // the summaries compose (the parity after a tile is the parity of S + its increment): an inclusive scan
+            // over the lanes gives the increment from tile `tile` through every tile for either incoming parity.
+            // (32-bit wrap-around can only happen after the first tile that ends the binade, which is all we need.)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t b0 = __shfl_up_sync(0xffffffffu, u0, d), b1 = __shfl_up_sync(0xffffffffu, u1, d);
+                if (lane >= d) {
+                    const uint32_t n0 = b0 + ((b0 & 1u) ? u1 : u0);
+                    const uint32_t n1 = b1 + ((b1 & 1u) ? u0 : u1);
+                    u0 = n0; u1 = n1;
+                }
+            }
+            const uint32_t S_after = S + ((S & 1u) ? u1 : u0);
+            const uint32_t bad = __ballot_sync(0xffffffffu, !ok || S_after >= 0x1000000u);
+            fail = bad ? __ffs(bad) - 1 : ntiles;  // the first tile that has to be added value by value
+            if (fail > tile) S = __shfl_sync(0xffffffffu, S_after, fail - 1);
+            s = __uint_as_float(((uint32_t)(e + 127) << 23) | (S & 0x7fffffu));
+            __syncwarp();
+        }
+        if (fail < ntiles) {
+            if (lane == 0) {
+                const float* row = A + fail * SB_STRIDE;
+#pragma unroll
+                for (int k = 0; k < 32; k++) s = __fadd_rn(s, row[k]);
+            }
+            s = __shfl_sync(0xffffffffu, s, 0);
+            tile = fail + 1;
+        } else {
+            tile = ntiles;
+        }
+    }
+    return s;
+}
+
+
+constexpr int MED_BINS = 4096;
+// element of rank `rank` (0-based, ascending) of the int16 samples raw[0..n); all threads of the CTA call it.
+// ALIGNED: raw is 16-byte aligned (a read's first sample: 128-bit loads); otherwise any sub-range of a read.
+// Two levels over the order-preserving key raw + 32768: the upper 12 bits (4096 bins: the ~1,000 ADC units a signal
+// spans spread over ~60 bins, so the shared-memory atomics of a warp rarely meet; with 256 bins they met on 2-4 bins),
+// then the lower 4 bits among the samples of the selected bin. 128-bit loads (the read starts 16-byte aligned).
+template <bool ALIGNED>
+__device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint32_t rank, uint32_t* hist,
+                               uint32_t* part, uint32_t* sh) {
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(raw);
+    const uint32_t n_words = (n + 7u) >> 3;
+    for (int k = threadIdx.x; k < MED_BINS; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    if (ALIGNED) {
+        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+            const uint4 q = __ldg(src + w);
+            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int h = 0; h < 8; h++) {
+                const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
+                if (w * 8u + h < n) atomicAdd(&hist[key >> 4], 1u);
+            }
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            atomicAdd(&hist[(uint32_t)((int)__ldg(raw + i) + 32768) >> 4], 1u);
+    }
+    __syncthreads();
+    {   // 256 threads x 16 bins, then one thread over the 256 partial sums and the 16 bins of the group
+        uint32_t sum = 0;
+        for (int k = 0; k < MED_BINS / 256; k++) sum += hist[threadIdx.x * (MED_BINS / 256) + k];
+        part[threadIdx.x] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t seen = 0, g = 0;
+        for (; g < 256; g++) {
+            if (seen + part[g] > rank) break;
+            seen += part[g];
+        }
+        uint32_t k = g * (MED_BINS / 256);
+        for (;; k++) {
+            if (seen + hist[k] > rank) break;
+            seen += hist[k];
+        }
+        sh[0] = k;
+        sh[1] = rank - seen;
+    }
+    __syncthreads();
+    const uint32_t hi = sh[0], rank2 = sh[1];
+    __syncthreads();
+    // level 2: the low 4 bits among the samples whose upper 12 bits matched
+    if (threadIdx.x < 16) part[threadIdx.x] = 0;
+    __syncthreads();
+    if (ALIGNED) {
+        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+            const uint4 q = __ldg(src + w);
+            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int h = 0; h < 8; h++) {
+                const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
+                if ((key >> 4) == hi && w * 8u + h < n) atomicAdd(&part[key & 15u], 1u);
+            }
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t key = (uint32_t)((int)__ldg(raw + i) + 32768);
+            if ((key >> 4) == hi) atomicAdd(&part[key & 15u], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t seen = 0, k = 0;
+        for (; k < 16; k++) {
+            if (seen + part[k] > rank2) break;
+            seen += part[k];
+        }
+        sh[2] = k;
+    }
+    __syncthreads();
+    const int med = (int)((hi << 4) | sh[2]) - 32768;
+    __syncthreads();
+    return med;
+}
+
+
+}  // namespace sgpu

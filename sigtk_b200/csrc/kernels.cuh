@@ -113,6 +113,9 @@ uint64_t jnn_seg_capacity(uint64_t max_samples, uint32_t max_reads);
 int launch_jnn(const DevBatch& b, const float* moments, uint32_t* seg_cnt, int32_t* seg, int sm_count, cudaStream_t st);
 
 
+// prefix.cu (`sigtk prefix`: adaptor by jnnv2 on the rolling mean, poly-A by jnn_core on pA, statistics of both)
+int launch_prefix(const DevBatch& b, int rna004, int32_t* pos4, float* st6, int sm_count, cudaStream_t st);
+
 // ent.cu (`sigtk ent`: entropies of the raw samples, their zig-zag deltas and the deltas' byte planes)
 uint64_t ent_overflow_words(int sm_count);
 int launch_ent(const DevBatch& b, uint32_t* overflow, double* out3, int sm_count, cudaStream_t st);

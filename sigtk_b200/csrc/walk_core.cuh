@@ -545,23 +545,6 @@ struct Rings {
 // long detector's lives.
 //   cand : long_candidate() of position u (false proves t2(u) <= thr_long)
 //   rec  : the step is owned by this chunk (jobs are only created for owned steps)
-// (kept out of line, everything by value, so that the compiler neither if-converts it into every step nor moves
-// the block's state to memory for it: it runs about once per 10,000 steps)
-struct Parked { int jobs, ls, end; };
-#if defined(__CUDACC__) && defined(WALK_PARK_CALL)
-static __host__ __device__ __noinline__
-#elif defined(__CUDACC__)
-static __host__ __device__ __forceinline__
-#else
-static inline
-#endif
-Parked park_job(int jobs, int ls, int end, int l_start, int u) {
-    Parked p;
-    p.ls = jobs == 0 ? l_start : ls;
-    p.end = jobs == 0 ? u : end;
-    p.jobs = jobs + 1;
-    return p;
-}
 template <int RNA, bool DIRECT, class E, class Io>
 SGW_HD void det_step(WalkDet& d, int m, int u, float c1, bool cand, bool rec, PeakAcc& acc, const E& on_emit, Io& io) {
     bool maskl; int p2;
@@ -572,7 +555,7 @@ SGW_HD void det_step(WalkDet& d, int m, int u, float c1, bool cand, bool rec, Pe
     bool hot = d.l_hot != 0;
     if (maskl & hot & rec) {                                 // rare: the life that ends here may have emitted
         if (DIRECT) io.job(d.l_start, u);
-        else { const Parked k = park_job(acc.jobs, acc.job_ls, acc.job_end, d.l_start, u); acc.jobs = k.jobs; acc.job_ls = k.ls; acc.job_end = k.end; }
+        else { acc.job_ls = d.l_start; acc.job_end = u; acc.jobs++; }   // (parked; a second one redoes the block)
     }
     const int ls = (p2 & ~PS_OPEN) + Cfg<RNA>::w1 + 1;
     d.l_start = maskl ? (ls > u ? ls : u) : d.l_start;
