@@ -1,4 +1,4 @@
-/* sigtk_main.c -- drop-in `sigtk event | pa | stat | ent | jnn` on top of the B200 hot path (C99 host, links slow5lib).
+/* sigtk_main.c -- drop-in `sigtk event | pa | stat | ent | jnn | prefix` on top of the B200 hot path (C99 host, links slow5lib).
  *
  * Same command line, stdout bytes, stderr information lines and exit codes as the reference tool for the three
  * sub-commands of the raw-signal path:
@@ -24,6 +24,7 @@
 #include <inttypes.h>
 #include <pthread.h>
 #include <stdint.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -45,12 +46,14 @@
 #define ERROR(msg, ...) \
     fprintf(stderr, "[%s::ERROR]\033[1;31m " msg "\033[0m At %s:%d\n", __func__, __VA_ARGS__, __FILE__, __LINE__ - 1)
 
-enum { MODE_EVENT, MODE_PA, MODE_STAT, MODE_ENT, MODE_JNN };
+enum { MODE_EVENT, MODE_PA, MODE_STAT, MODE_ENT, MODE_JNN, MODE_PREFIX };
 
 typedef struct {
     int mode;
     int compact;
     int rna;
+    int p_stat; /* --print-stat (prefix) */
+    int rna004; /* the pore picks jnnv2's parameters for `prefix` (jnn.c:181-188) */
 } opt_t;
 
 /* ---- timing footer (reference src/misc.h:19-43) ------------------------------------------------------------- */
@@ -70,50 +73,78 @@ static long peakrss(void) {
     return r.ru_maxrss * 1024;
 }
 
-/* ---- header inspection (reference src/misc.c:34-101) ---------------------------------------------------------- */
-static int drna_detect(slow5_file_t *sp) {
-    const slow5_hdr_t *hdr = sp->header;
-    int rna = 0;
-    char *exp = slow5_hdr_get("experiment_type", 0, hdr);
-    if (exp == NULL) {
-        WARNING("%s", "experiment_type not found in SLOW5 header. Assuming genomic_dna");
-        return 0;
-    }
-    if (strcmp(exp, "genomic_dna") == 0) {
-        INFO("%s", "DNA data detected.");
-    } else if (strcmp(exp, "rna") == 0) {
-        rna = 1;
-        INFO("%s", "RNA data detected.");
-    } else {
-        WARNING("Unknown experiment type: %s. Assuming genomic_dna", exp);
-    }
-    for (uint32_t i = 1; i < hdr->num_read_groups; i++) {
-        char *curr = slow5_hdr_get("experiment_type", i, hdr);
-        if (curr && strcmp(curr, exp))
-            WARNING("Experiment type mismatch: %s != %s in read group %d. Defaulted to %s", curr, exp, (int)i, exp);
-    }
-    return rna;
+/* ---- header inspection (reference src/misc.c:34-101) ----------------------------------------------------------
+ * Both questions the reference asks of the BLOW5 header -- DNA or RNA, which pore -- have the same shape: one
+ * attribute of read group 0 decides, a list of substrings maps its value to an answer and an INFO line, the other
+ * read groups are only compared with it. The stderr lines are the reference's. */
+typedef struct {
+    const char *needle; /* substring (pore) or whole value (experiment type) looked for in the attribute */
+    int value;
+    const char *info;   /* INFO line printed on a match */
+} hdr_rule_t;
+typedef struct {
+    const char *attr;
+    const char *missing;      /* WARNING when read group 0 has no such attribute */
+    int whole;                /* rules must match the whole value */
+    const hdr_rule_t *rules;
+    int n_rules;
+    int fallback;             /* answer when no rule matches */
+    const char *fallback_info;    /* INFO line for the fallback, or NULL: */
+    const char *fallback_warning; /* WARNING format taking the value */
+    const char *mismatch;     /* WARNING format: other value, first value, group, first value */
+} hdr_query_t;
+
+/* the reference's WARNING line (error.h:60-66) for a format that is not a string literal */
+static void warn_fmt(const char *func, int line, const char *fmt, ...) {
+    va_list ap;
+    fprintf(stderr, "[%s::WARNING]\033[1;33m ", func);
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "\033[0m At %s:%d\n", __FILE__, line);
 }
 
-static void pore_detect(slow5_file_t *sp) { /* only `prefix` uses the pore; the messages are kept */
+static int hdr_ask(slow5_file_t *sp, const hdr_query_t *q) {
     const slow5_hdr_t *hdr = sp->header;
-    char *kit = slow5_hdr_get("sequencing_kit", 0, hdr);
-    if (kit == NULL) {
-        WARNING("%s", "sequencing_kit not found in SLOW5 header. Assuming R9.4.1");
-        return;
+    char *first = slow5_hdr_get(q->attr, 0, hdr);
+    if (first == NULL) {
+        warn_fmt(__func__, __LINE__, "%s", q->missing);
+        return 0;
     }
-    if (strstr(kit, "114") != NULL) {
-        INFO("%s", "R10 data detected.");
-    } else if (strstr(kit, "rna004") != NULL) {
-        INFO("%s", "RNA004 data detected.");
-    } else {
-        INFO("%s", "R9 data detected.");
+    int answer = q->fallback, hit = 0;
+    for (int k = 0; k < q->n_rules && !hit; k++) {
+        const hdr_rule_t *r = &q->rules[k];
+        if (q->whole ? strcmp(first, r->needle) == 0 : strstr(first, r->needle) != NULL) {
+            answer = r->value;
+            INFO("%s", r->info);
+            hit = 1;
+        }
     }
-    for (uint32_t i = 1; i < hdr->num_read_groups; i++) {
-        char *curr = slow5_hdr_get("sequencing_kit", i, hdr);
-        if (curr && strcmp(curr, kit))
-            WARNING("sequencing_kit type mismatch: %s != %s in read group %d. Defaulted to %s", curr, kit, (int)i, kit);
+    if (!hit) {
+        if (q->fallback_info) INFO("%s", q->fallback_info);
+        else warn_fmt(__func__, __LINE__, q->fallback_warning, first);
     }
+    for (uint32_t g = 1; g < hdr->num_read_groups; g++) {
+        char *other = slow5_hdr_get(q->attr, g, hdr);
+        if (other && strcmp(other, first)) warn_fmt(__func__, __LINE__, q->mismatch, other, first, (int)g, first);
+    }
+    return answer;
+}
+
+enum { PORE_R9 = 0, PORE_R10 = 1, PORE_RNA004 = 2 }; /* sigtk.h:107-109 */
+static int drna_detect(slow5_file_t *sp) { /* misc.c:34-60 */
+    static const hdr_rule_t rules[] = {{"genomic_dna", 0, "DNA data detected."}, {"rna", 1, "RNA data detected."}};
+    static const hdr_query_t q = {"experiment_type", "experiment_type not found in SLOW5 header. Assuming genomic_dna", 1,
+                                  rules, 2, 0, NULL, "Unknown experiment type: %s. Assuming genomic_dna",
+                                  "Experiment type mismatch: %s != %s in read group %d. Defaulted to %s"};
+    return hdr_ask(sp, &q);
+}
+static int pore_detect(slow5_file_t *sp) { /* misc.c:74-101; only `prefix` uses the answer */
+    static const hdr_rule_t rules[] = {{"114", PORE_R10, "R10 data detected."}, {"rna004", PORE_RNA004, "RNA004 data detected."}};
+    static const hdr_query_t q = {"sequencing_kit", "sequencing_kit not found in SLOW5 header. Assuming R9.4.1", 0,
+                                  rules, 2, PORE_R9, "R9 data detected.", NULL,
+                                  "sequencing_kit type mismatch: %s != %s in read group %d. Defaulted to %s"};
+    return hdr_ask(sp, &q);
 }
 
 /* optional wall-clock breakdown of the host side (SIGTK_PROFILE=1): read, decode, add, wait, format, write */
@@ -256,6 +287,7 @@ static void engine_open(engine_t *e, int n_gpus, uint64_t cap_samples) {
         sgpu_ctx_t *ctx = NULL;
         int rc = sgpu_create(&ctx, g, cap_samples, e->cap_reads, 2, SGPU_F_DEFAULT);
         if (rc) die_sgpu(NULL, rc, "sgpu_create");
+        if (e->opt.rna004) sgpu_set_param(ctx, SGPU_PARAM_PORE, 1.0);
         for (uint32_t s = 0; s < 2; s++) {
             lane_t *l = &e->lanes[s * n_gpus + g]; /* consecutive lanes alternate between the GPUs */
             l->ctx = ctx;
@@ -290,6 +322,10 @@ static void print_header(const opt_t *opt) {
         printf("read_id\tlen_raw_signal\tnum_seg\tseg\n");
     } else if (opt->mode == MODE_ENT) { /* ent.c:106 */
         printf("read_id\traw_ent\tdelta_ent\tbyte_ent\n");
+    } else if (opt->mode == MODE_PREFIX) { /* cfunc.c:161-167 */
+        printf("read_id\tlen_raw_signal\tadapt_start\tadapt_end\tpolya_start\tpolya_end");
+        if (opt->p_stat) printf("\tadapt_mean\tadapt_std\tadapt_median\tpolya_mean\tpolya_std\tpolya_median");
+        printf("\n");
     } else {
         printf("read_id\tlen_raw_signal\tpa\n");
     }
@@ -383,6 +419,37 @@ static void format_read(const opt_t *opt, const sgpu_result_t *res, const sgpu_b
                 }
             }
             if (ns == 0) *p++ = '.';
+        }
+        *p++ = '\n';
+        o->len = (size_t)(p - o->p);
+    } else if (opt->mode == MODE_PREFIX) { /* prefix_func, cfunc.c:169-234 */
+        const int32_t *q = res->prefix_pos + (size_t)r * 4;
+        const float *st = res->prefix_stat + (size_t)r * 6;
+        p = obuf_reserve(o, idl + 640);
+        memcpy(p, rid, idl); p += idl; *p++ = '\t';
+        p = fmt_i64(p, n); *p++ = '\t';
+        if (q[1] > 0) {
+            p = fmt_i64(p, (long)q[0]); *p++ = '\t';
+            p = fmt_i64(p, (long)q[1]); *p++ = '\t';
+            if (q[3] > 0) {
+                p = fmt_i64(p, (long)q[2] + q[1]); *p++ = '\t';
+                p = fmt_i64(p, (long)q[3] + q[1]);
+            } else {
+                memcpy(p, ".\t.", 3); p += 3;
+            }
+            if (opt->p_stat) {
+                *p++ = '\t';
+                for (int k = 0; k < 3; k++) { p = fmt_f6(p, st[k]); *p++ = '\t'; }
+                if (q[3] > 0) {
+                    *p++ = '\t';
+                    for (int k = 3; k < 6; k++) { p = fmt_f6(p, st[k]); *p++ = '\t'; }
+                } else {
+                    memcpy(p, "\t.\t.\t.", 6); p += 6;
+                }
+            }
+        } else {
+            if (q[1] < 0) WARNING("%s", "Not enough data to trim\n"); /* jnnv2, jnn.c:173 */
+            memcpy(p, ".\t.\t.\t.", 7); p += 7;
         }
         *p++ = '\n';
         o->len = (size_t)(p - o->p);
@@ -673,6 +740,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
             hdr = 0;
         } else if (c == 'c') {
             eng.opt.compact = 1;
+        } else if (c == 0 && longindex == 4) { /* cmain.c:63-64 */
+            eng.opt.p_stat = 1;
         } else if (c == 0 && longindex == 7) {
             n_gpus = atoi(optarg);
             if (n_gpus < 1) n_gpus = 1;
@@ -712,7 +781,7 @@ static int cmain(int argc, char *argv[], const char *mode) {
     }
     if (!is_ent) { /* entmain does not look at the header (ent.c:102-107) */
         eng.opt.rna = drna_detect(sp);
-        pore_detect(sp);
+        eng.opt.rna004 = pore_detect(sp) == PORE_RNA004;
     }
     if (is_ent) {
         eng.opt.mode = MODE_ENT;
@@ -720,6 +789,9 @@ static int cmain(int argc, char *argv[], const char *mode) {
     } else if (strcmp(mode, "jnn") == 0) {
         eng.opt.mode = MODE_JNN;
         eng.want = SGPU_WANT_JNN;
+    } else if (strcmp(mode, "prefix") == 0) {
+        eng.opt.mode = MODE_PREFIX;
+        eng.want = SGPU_WANT_PREFIX;
     } else if (strcmp(mode, "event") == 0) {
         eng.opt.mode = MODE_EVENT;
         eng.want = SGPU_WANT_EVENTS;
@@ -896,7 +968,8 @@ static int print_usage(FILE *fp_help) {
     fprintf(fp_help, "         stat      print statistics of the raw signal\n");
     fprintf(fp_help, "         ent       entropy of the raw signal, its zig-zag deltas and their byte planes\n");
     fprintf(fp_help, "         jnn       stall / homopolymer-stretch segments of the raw signal\n");
-    fprintf(fp_help, "(B200 build: the raw-signal hot path only; sref, prefix, ss and qts are served by the\n");
+    fprintf(fp_help, "         prefix    adaptor and poly-A stretch at the start of a read\n");
+    fprintf(fp_help, "(B200 build: the raw-signal hot path only; sref, ss and qts are served by the\n");
     fprintf(fp_help, " reference sigtk)\n");
     exit(fp_help == stderr ? EXIT_FAILURE : EXIT_SUCCESS);
 }
@@ -909,15 +982,14 @@ int main(int argc, char *argv[]) {
     if (argc < 2) {
         return print_usage(stderr);
     } else if (strcmp(argv[1], "event") == 0 || strcmp(argv[1], "stat") == 0 || strcmp(argv[1], "pa") == 0 ||
-               strcmp(argv[1], "ent") == 0 || strcmp(argv[1], "jnn") == 0) {
+               strcmp(argv[1], "ent") == 0 || strcmp(argv[1], "jnn") == 0 || strcmp(argv[1], "prefix") == 0) {
         ret = cmain(argc - 1, argv + 1, argv[1]);
     } else if (strcmp(argv[1], "--version") == 0 || strcmp(argv[1], "-V") == 0) {
         fprintf(stdout, "sigtk %s\n", SIGTK_VERSION);
         exit(EXIT_SUCCESS);
     } else if (strcmp(argv[1], "--help") == 0 || strcmp(argv[1], "-h") == 0) {
         print_usage(stdout);
-    } else if (strcmp(argv[1], "sref") == 0 || strcmp(argv[1], "prefix") == 0 ||
-               strcmp(argv[1], "ss") == 0 || strcmp(argv[1], "qts") == 0) {
+    } else if (strcmp(argv[1], "sref") == 0 || strcmp(argv[1], "ss") == 0 || strcmp(argv[1], "qts") == 0) {
         fprintf(stderr, "[sigtk] command %s is outside the B200 raw-signal hot path; use the reference sigtk for it\n",
                 argv[1]);
         exit(EXIT_FAILURE);

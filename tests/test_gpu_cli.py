@@ -85,7 +85,7 @@ def test_no_header_version_help_and_errors(sp1):
     assert r.returncode == 1 and r.stderr.startswith(b"Usage: sigtk event")
     r = subprocess.run([CLI, "event", "/nonexistent.blow5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and b"cannot open /nonexistent.blow5" in r.stderr
-    r = subprocess.run([CLI, "prefix", sp1], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = subprocess.run([CLI, "sref", sp1], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and b"outside the B200 raw-signal hot path" in r.stderr
 
 
@@ -148,6 +148,38 @@ def test_jnn_equals_the_reference_stdout(sp1, tmp_path, kind):
     assert w.wait() == 0
     assert run(["jnn", path]).stdout == open(os.path.join(G, f"ref_jnn_stalls_{kind}.txt"), "rb").read()
     assert run(["jnn", "-c", path]).stdout == open(os.path.join(G, f"ref_jnn_stalls_{kind}_c.txt"), "rb").read()
+
+
+@pytest.mark.parametrize("kind", ["dna", "rna"])
+def test_prefix_equals_the_reference_stdout(sp1, tmp_path, kind):
+    """`sigtk prefix` and `prefix --print-stat` (src/cfunc.c:169-234): the reference's own golden test/prefix_dna.exp,
+    the stdout of the compiled reference on the DNA file / the synthetic RNA file and on a BLOW5 of reads with adaptor
+    and poly-A like stretches (tests/golden/prefix_adaptor_*.npz)"""
+    import struct
+    import numpy as np
+    path, tag = (sp1, "sp1") if kind == "dna" else (RNA, "rna")
+    exp_stat = open(os.path.join(G, f"ref_{tag}_prefix_stat.txt"), "rb").read()
+    p = run(["prefix", "--print-stat", path])
+    assert p.stdout == exp_stat
+    assert (b"RNA data detected." if kind == "rna" else b"DNA data detected.") in p.stderr
+    if kind == "dna":
+        assert run(["prefix", path]).stdout == open(os.path.join(G, "prefix_dna.exp"), "rb").read()
+    assert run(["prefix", "--print-stat", "--cpu-decode", "--batch-samples", "60000", "-n", path]).stdout == exp_stat.split(b"\n", 1)[1]
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "blow5_write")):
+        return
+    d = np.load(os.path.join(G, f"prefix_adaptor_{kind}.npz"))
+    path = str(tmp_path / "adaptor.blow5")
+    w = subprocess.Popen([os.path.join(ROOT, "oracle", "_ref", "blow5_write"), path, "rna" if kind == "rna" else "genomic_dna"],
+                         stdin=subprocess.PIPE)
+    for r in range(len(d["read_ids"])):
+        raw = d["samples"][int(d["read_off"][r]):int(d["read_off"][r + 1])]
+        rid = str(d["read_ids"][r]).encode()
+        w.stdin.write(struct.pack("<I", len(rid)) + rid + struct.pack("<Qddd", len(raw), float(d["digitisation"][r]),
+                      float(d["offset"][r]), float(d["range"][r])) + raw.tobytes())
+    w.stdin.close()
+    assert w.wait() == 0
+    assert run(["prefix", path]).stdout == open(os.path.join(G, f"ref_prefix_adaptor_{kind}.txt"), "rb").read()
+    assert run(["prefix", "--print-stat", path]).stdout == open(os.path.join(G, f"ref_prefix_adaptor_{kind}_stat.txt"), "rb").read()
 
 
 def test_two_gpus_same_bytes(sp1):
