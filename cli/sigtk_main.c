@@ -148,7 +148,7 @@ static int pore_detect(slow5_file_t *sp) { /* misc.c:74-101; only `prefix` uses 
 }
 
 /* optional wall-clock breakdown of the host side (SIGTK_PROFILE=1): read, decode, add, wait, format, write */
-static double g_prof[8];
+static double g_prof[10];
 
 /* ---- fork-join thread pool ---------------------------------------------------------------------------------------- */
 typedef void (*task_fn)(void *arg, int item);
@@ -260,6 +260,7 @@ typedef struct {
     uint32_t cap_reads;
     opt_t opt;
     uint32_t want;
+    uint32_t ctx_flags; /* SGPU_F_* of the contexts */
     uint64_t n_seq_order, n_fixups, n_reads_total;
     pool_t pool;
     obuf_t *obufs;   /* one per formatting chunk */
@@ -269,6 +270,23 @@ typedef struct {
 static void die_sgpu(sgpu_ctx_t *ctx, int rc, const char *what) {
     ERROR("%s failed: %s (%s)", what, sgpu_strerror(rc), ctx ? sgpu_last_error(ctx) : "-");
     exit(EXIT_FAILURE);
+}
+
+/* one context (CUDA context on first use + pinned slots) per GPU, created concurrently: on a cold box this is the
+ * largest single cost of the whole command (seconds), and it does not depend on the input */
+typedef struct {
+    int device;
+    uint64_t cap_samples;
+    uint32_t cap_reads, flags;
+    int rna004;
+    sgpu_ctx_t *ctx;
+    int rc;
+} ctx_job_t;
+static void *ctx_create_thread(void *arg) {
+    ctx_job_t *j = (ctx_job_t *)arg;
+    j->rc = sgpu_create(&j->ctx, j->device, j->cap_samples, j->cap_reads, 2, j->flags);
+    if (j->rc == 0 && j->rna004) sgpu_set_param(j->ctx, SGPU_PARAM_PORE, 1.0);
+    return NULL;
 }
 
 static void engine_open(engine_t *e, int n_gpus, uint64_t cap_samples) {
@@ -283,22 +301,59 @@ static void engine_open(engine_t *e, int n_gpus, uint64_t cap_samples) {
     e->cap_reads = (uint32_t)(cap_samples / 256 + 1024);
     e->n_lanes = 2 * n_gpus;
     e->lanes = (lane_t *)calloc((size_t)e->n_lanes, sizeof(lane_t));
+    ctx_job_t *jobs = (ctx_job_t *)calloc((size_t)n_gpus, sizeof(ctx_job_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_gpus, sizeof(pthread_t));
     for (int g = 0; g < n_gpus; g++) {
-        sgpu_ctx_t *ctx = NULL;
-        int rc = sgpu_create(&ctx, g, cap_samples, e->cap_reads, 2, SGPU_F_DEFAULT);
-        if (rc) die_sgpu(NULL, rc, "sgpu_create");
-        if (e->opt.rna004) sgpu_set_param(ctx, SGPU_PARAM_PORE, 1.0);
+        jobs[g].device = g; jobs[g].cap_samples = cap_samples; jobs[g].cap_reads = e->cap_reads;
+        jobs[g].flags = e->ctx_flags; jobs[g].rna004 = e->opt.rna004;
+        if (g == 0 || pthread_create(&th[g], NULL, ctx_create_thread, &jobs[g]) != 0) {
+            if (g) { ctx_create_thread(&jobs[g]); th[g] = 0; }
+        }
+    }
+    ctx_create_thread(&jobs[0]); /* the caller creates the first one itself */
+    for (int g = 0; g < n_gpus; g++) {
+        if (g && th[g]) pthread_join(th[g], NULL);
+        if (jobs[g].rc) die_sgpu(NULL, jobs[g].rc, "sgpu_create");
         for (uint32_t s = 0; s < 2; s++) {
             lane_t *l = &e->lanes[s * n_gpus + g]; /* consecutive lanes alternate between the GPUs */
-            l->ctx = ctx;
+            l->ctx = jobs[g].ctx;
             l->slot = s;
         }
     }
+    free(jobs);
+    free(th);
     e->cur = 0;
     e->oldest = 0;
     e->n_busy = 0;
     int rc = sgpu_slot_reset(e->lanes[0].ctx, e->lanes[0].slot, (uint32_t)e->opt.rna);
     if (rc) die_sgpu(e->lanes[0].ctx, rc, "sgpu_slot_reset");
+}
+
+/* engine_open on a helper thread while the caller opens the file, reads and inflates the first records */
+typedef struct { engine_t *e; int n_gpus; uint64_t cap; double seconds; } open_job_t;
+static open_job_t g_open_job;
+static pthread_t g_open_thread;
+static int g_open_pending;
+static void *engine_open_thread(void *arg) {
+    open_job_t *j = (open_job_t *)arg;
+    const double t0 = realtime();
+    engine_open(j->e, j->n_gpus, j->cap);
+    j->seconds = realtime() - t0;
+    return NULL;
+}
+static void engine_open_async(engine_t *e, int n_gpus, uint64_t cap_samples) {
+    g_open_job.e = e; g_open_job.n_gpus = n_gpus; g_open_job.cap = cap_samples; g_open_job.seconds = 0.0;
+    if (pthread_create(&g_open_thread, NULL, engine_open_thread, &g_open_job) == 0) g_open_pending = 1;
+    else engine_open_thread(&g_open_job);
+}
+static void engine_ready(void) { /* before the first use of the engine */
+    if (g_open_pending) {
+        const double t0 = realtime();
+        pthread_join(g_open_thread, NULL);
+        g_open_pending = 0;
+        g_prof[6] = g_open_job.seconds;   /* the open itself ... */
+        g_prof[8] = realtime() - t0;      /* ... and how long the main thread still had to wait for it */
+    }
 }
 
 static void engine_close(engine_t *e) {
@@ -542,6 +597,7 @@ static void print_lane(engine_t *e, lane_t *l) {
 }
 
 static void engine_submit_current(engine_t *e) {
+    engine_ready();
     lane_t *l = &e->lanes[e->cur];
     if (l->n_reads == 0) return;
     int rc = sgpu_submit(l->ctx, l->slot, e->want);
@@ -584,6 +640,7 @@ typedef struct {
 } rec_view_t;
 
 static void engine_add_view(engine_t *e, const rec_view_t *v) {
+    engine_ready();
     for (int attempt = 0; attempt < 3; attempt++) {
         lane_t *l = &e->lanes[e->cur];
         int64_t rc = v->raw || !v->svb
@@ -620,6 +677,7 @@ static void engine_add_view(engine_t *e, const rec_view_t *v) {
             uint64_t cap = e->cap_samples;
             while (cap < v->len_raw_signal + 64 || 2 * cap < v->svb_bytes + 64) cap *= 2;
             engine_close(e);
+            e->ctx_flags |= SGPU_F_FULL_SEQ_SCRATCH; /* a read this long must be able to take the sequential-order kernels */
             engine_open(e, n_gpus, cap);
             continue;
         }
@@ -818,11 +876,7 @@ static int cmain(int argc, char *argv[], const char *mode) {
     }
     pool_open(&eng.pool, n_threads);
     if (eng.opt.mode == MODE_PA && batch_samples > (1ull << 23)) batch_samples = 1ull << 23; /* 13 text bytes per sample */
-    {
-        const double t0 = realtime();
-        engine_open(&eng, n_gpus, batch_samples);
-        g_prof[6] = realtime() - t0;
-    }
+    engine_open_async(&eng, n_gpus, batch_samples); /* joined by the first engine_add / engine_drain */
 
     slow5_rec_t *rec = NULL;
     int ret = 0;
@@ -862,6 +916,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
             t0 = realtime();
             for (int i = 0; i < n; i++) {
                 if (job.err[i] < 0) {
+                    engine_drain(&eng); /* the reference has printed every record before this one */
+                    fflush(stdout);
                     fprintf(stderr, "Error in slow5_get_next. Error code %d\n", job.err[i]);
                     exit(EXIT_FAILURE);
                 }
@@ -872,6 +928,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
             g_prof[2] += realtime() - t0;
         }
         if (ret != SLOW5_ERR_EOF) {
+            engine_drain(&eng);
+            fflush(stdout);
             fprintf(stderr, "Error in slow5_get_next. Error code %d\n", ret);
             exit(EXIT_FAILURE);
         }
@@ -907,6 +965,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
             t0 = realtime();
             for (int i = 0; i < n; i++) {
                 if (job.err[i] < 0) {
+                    engine_drain(&eng);
+                    fflush(stdout);
                     fprintf(stderr, "Error in slow5_get_next. Error code %d\n", job.err[i]);
                     exit(EXIT_FAILURE);
                 }
@@ -915,6 +975,8 @@ static int cmain(int argc, char *argv[], const char *mode) {
             g_prof[2] += realtime() - t0; /* includes the submits and prints that engine_add triggers */
         }
         if (ret != SLOW5_ERR_EOF) {
+            engine_drain(&eng);
+            fflush(stdout);
             fprintf(stderr, "Error in slow5_get_next. Error code %d\n", ret);
             exit(EXIT_FAILURE);
         }
@@ -949,9 +1011,10 @@ static int cmain(int argc, char *argv[], const char *mode) {
     if (getenv("SIGTK_PROFILE"))
         fprintf(stderr, "[%s] signal decode: %s\n", __func__, gpu_decode ? "GPU (svb-zd)" : "host threads (slow5_decode)");
     if (getenv("SIGTK_PROFILE"))
-        fprintf(stderr, "[%s] host wall clock: open (CUDA context, pinned slots) %.3f s, read %.3f s, decode %.3f s (%d threads), "
+        fprintf(stderr, "[%s] host wall clock: open (CUDA context, pinned slots) %.3f s on a helper thread, of which the main "
+                        "thread waited %.3f s, read %.3f s, decode %.3f s (%d threads), "
                         "add+submit+print %.3f s of which wait %.3f s, format %.3f s, write %.3f s, close %.3f s\n", __func__,
-                g_prof[6], g_prof[0], g_prof[1], eng.pool.n_threads + 1, g_prof[2], g_prof[3], g_prof[4], g_prof[5], g_prof[7]);
+                g_prof[6], g_prof[8], g_prof[0], g_prof[1], eng.pool.n_threads + 1, g_prof[2], g_prof[3], g_prof[4], g_prof[5], g_prof[7]);
     pool_close(&eng.pool);
     for (int c = 0; c < eng.n_obufs; c++) free(eng.obufs[c].p);
     free(eng.obufs);
