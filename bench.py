@@ -110,6 +110,73 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def pin_to_gpu_numa(torch, local: int, world: int) -> dict:
+    """Run this rank on the cores of the NUMA node its GPU hangs off (pinned host buffers are then allocated there:
+    first touch), the node's cores shared evenly by the ranks on it. The end-to-end number is a PCIe number; a DMA
+    that crosses the socket interconnect runs at a fraction of the link rate."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return info
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return info
+        # ranks whose GPUs share this node split its cores
+        peers = []
+        for g in range(world):
+            q = torch.cuda.get_device_properties(g)
+            b2 = f"{q.pci_domain_id:04x}:{q.pci_bus_id:02x}:{q.pci_device_id:02x}.0"
+            try:
+                if int(open(f"/sys/bus/pci/devices/{b2}/numa_node").read().strip()) == node:
+                    peers.append(g)
+            except Exception:
+                pass
+        k, m = peers.index(local) if local in peers else 0, max(len(peers), 1)
+        share = allowed[k * len(allowed) // m:(k + 1) * len(allowed) // m] or allowed
+        os.sched_setaffinity(0, share)
+        info = {"numa_node": node, "cpus": f"{share[0]}-{share[-1]} ({len(share)})"}
+    except Exception as e:  # no sysfs / no permission: run unpinned
+        info["error"] = str(e)[:80]
+    return info
+
+
+def copy_only_ceiling(torch, dev, h2d_bytes: int, d2h_bytes: int, steps: int, dist):
+    """The PCIe ceiling of the end-to-end path: the same bytes per step as run_e2e moves, pinned host memory, H2D
+    and D2H on two streams at once, NO kernels. seconds (max over ranks) for `steps` steps."""
+    hin = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8).pin_memory()
+    hout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8).pin_memory()
+    din = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=dev)
+    dout = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    for _ in range(2):
+        with torch.cuda.stream(s_in):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hout.copy_(dout, non_blocking=True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        with torch.cuda.stream(s_in):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hout.copy_(dout, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def device_batch(torch, dev, lens: np.ndarray, first_index: int, seed: int, p_change: float = 0.1):
     """One batch of synthetic reads generated on the device (signal model of sigtk_b200/synth.py).
     -> dict(samples i16[span], read_off i64[n+1], read_len i32[n], offset f32[n], unit f32[n], span, n_samples)"""
@@ -310,6 +377,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the sigtk_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa(torch, local, world) if not args.no_affinity else {"numa_node": None, "cpus": "unpinned"}
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -446,7 +514,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     # ---- end to end through the host C-ABI: pinned slots, H2D + kernels + D2H per step ----------------------------
-    e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna)
+    e2e = run_e2e(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna, ceiling=True)
+    e2e["affinity"] = affinity
     # ---- the same with svb-zd compressed records as input (decoded in HBM), and the decoder alone ------------------
     svb = run_svbzd(args, sg, torch, dev, local, pool[0], want, pa_mode, dist, rna) if not args.no_svbzd else None
     if svb and pa_mode:
@@ -510,7 +579,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0, n_reads=None):
+def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0, n_reads=None, ceiling=False):
     """K steps of (pinned slot -> H2D -> kernels -> D2H -> host-visible event table), two slots in flight."""
     B = min(n_reads or args.e2e_reads, batch["n_reads"])
     off, lens = batch["host_off"], batch["host_len"]
@@ -547,9 +616,20 @@ def run_e2e(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0, n_re
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     h2d = 2 * span + 20 * B
     d2h = 12 * ne + 8 * (B + 1) + 8 * B + (4 * span if pa_mode else 0)
-    return {"value": float(tot.item()) / float(t.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h, "reads_per_step_per_gpu": B, "samples_per_step_per_gpu": n_samp,
-            "timing": "host wall clock around submit/wait of K steps, 2 pinned slots in flight, max over ranks"}
+    value = float(tot.item()) / float(t.item()) / 1e9
+    out = {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "reads_per_step_per_gpu": B, "samples_per_step_per_gpu": n_samp,
+           "timing": "host wall clock around submit/wait of K steps, 2 pinned slots in flight, max over ranks; the "
+                     "slots are filled once before the timed region (the batch loader's decode into pinned memory is "
+                     "not part of this number)"}
+    if ceiling:
+        # the same bytes, both directions at once, no kernels: what the PCIe links of this box give N ranks
+        dt_c = copy_only_ceiling(torch, dev, h2d, d2h, steps, dist)
+        cval = float(tot.item()) / dt_c / 1e9
+        out["copy_only_ceiling"] = {"value": cval, "unit": UNIT, "frac": value / cval,
+                                    "gbs_h2d_plus_d2h": (h2d + d2h) * steps * (int(dist.get_world_size()) if dist else 1) / dt_c / 1e9,
+                                    "what": "same h2d/d2h bytes per step from/to pinned memory on two streams, no kernels, max over ranks"}
+    return out
 
 
 def run_svbzd(args, sg, torch, dev, local, batch, want, pa_mode, dist, rna=0):
@@ -627,6 +707,7 @@ def main():
     ap.add_argument("--no-svbzd", action="store_true", help="skip the compressed-input (svb-zd) measurements")
     ap.add_argument("--no-siblings", action="store_true", help="skip the pa / stat / ent kernel timings")
     ap.add_argument("--no-others", action="store_true", help="skip the ultralong / rna40k / real sub-lines")
+    ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -38,6 +38,9 @@ using namespace walk;
 #ifndef WALK_MINB
 #define WALK_MINB 6
 #endif
+#ifndef WALK_MINB_RNA
+#define WALK_MINB_RNA 1
+#endif
 constexpr int WNT = WALK_NT;  // threads per block of walk_chunks_kernel
 
 struct WalkParams {
@@ -174,7 +177,7 @@ __device__ __forceinline__ uint32_t find_chunk_read(const uint64_t* __restrict__
 }
 
 template <int RNA>
-__global__ void __launch_bounds__(WNT, RNA ? 1 : WALK_MINB) walk_chunks_kernel(const WalkParams p) {
+__global__ void __launch_bounds__(WNT, RNA ? WALK_MINB_RNA : WALK_MINB) walk_chunks_kernel(const WalkParams p) {
     if (blockIdx.x < p.edge_blocks) {
         // first chunks of all reads, then last chunks: the lanes of a warp walk chunks of the same kind
         const uint64_t e = (uint64_t)blockIdx.x * WNT + threadIdx.x;

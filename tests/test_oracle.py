@@ -258,3 +258,20 @@ def test_synthetic_svbzd_encoder_equals_oracle(orc):
         for scale in (5, 300, 50000):
             raw = np.clip(np.cumsum(rng.integers(-scale, scale + 1, n)), -32768, 32767).astype(np.int16)
             assert np.array_equal(synth.svbzd_encode(raw), orc.svbzd_encode(raw)), (n, scale)
+
+
+def test_long_filter_checker_finds_no_violation(tmp_path):
+    """oracle/proofs/long_filter_check.cpp: the float test that replaces the long window's t-statistic on the fast
+    path (walk_core.cuh: long_candidate) never misses a position whose reference t2 exceeds the threshold
+    (2,000,000 random / adversarial windows here; 10^9 in profiles/r02_long_filter_check.json)"""
+    import subprocess
+    exe = str(tmp_path / "long_filter_check")
+    here = os.path.dirname(os.path.abspath(__file__))
+    proofs = os.path.join(os.path.dirname(here), "oracle", "proofs")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-x", "c++",
+                           os.path.join(proofs, "long_filter_check.cpp"), "-x", "c",
+                           os.path.join(proofs, "..", "sigtk_oracle.c"), "-lm", "-o", exe], stderr=subprocess.DEVNULL)
+    out = subprocess.run([exe, "2000000", "7"], check=True, stdout=subprocess.PIPE).stdout
+    import json
+    d = json.loads(out)
+    assert d["violations"] == 0 and d["t_above_threshold"] > 500000
