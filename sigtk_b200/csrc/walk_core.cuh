@@ -320,20 +320,6 @@ struct SlidingT {
         return tstat_from_sums(s1, q1, s2, q2, w);
     }
 };
-// recompute the t-statistics of one block: t1v[m] (m >= m1) belongs to position tau0+m-w1+1, t2v[m] to tau0+m-w2+1
-template <int RNA, class Io>
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#else
-inline
-#endif
-void exact_block(const Io& io, int tau0, int n, float off, float unit, int m1, int want_t2, float* t1v, float* t2v) {
-    using C = Cfg<RNA>;
-    for (int m = m1; m < C::U; m++) t1v[m] = tstat_exact(io, tau0 + m - C::w1 + 1, C::w1, n, off, unit);
-    if (want_t2)
-        for (int m = 0; m < C::U; m++) t2v[m] = tstat_exact(io, tau0 + m - C::w2 + 1, C::w2, n, off, unit);
-}
-
 // ---- the peak detectors (events.c:371-443) ------------------------------------------------------------------------
 // Positions are "shifted" read indices: index in the read + (read_off & 31), so that position >> 5 is a word of the
 // read's part of the event-start bitmap; they stay below 2^30 (reads of 2^30 samples or more take the
@@ -576,21 +562,22 @@ inline
 Redo<RNA> redo_block(Io& io, Redo<RNA> in, int tau0, int n, int sh, bool rec, float off, float unit, float thr_long) {
     using C = Cfg<RNA>;
     constexpr int w1 = C::w1, w2 = C::w2, U = C::U;
-    float e1[U], e2[U];
-    exact_block<RNA>(io, tau0, n, off, unit, 0, 1, e1, e2);
+    (void)thr_long;
+    // the short t-statistic of the block's U positions with the reference's own operations; the window sums slide
+    // (three samples per position instead of 2 w1). The long window is not evaluated at all: every position of a
+    // redone block simply counts as a candidate (a life that holds one is replayed by long_job, which is exact).
+    float e1[U];
+    SlidingT<Io> slide;
+    for (int m = 0; m < U; m++) e1[m] = slide.next(io, tau0 + m - w1 + 1, w1, n, off, unit);   // (0 where the windows leave the read)
     Redo<RNA> r;
     r.d = in.d; r.acc.mk = 0u; r.acc.oldest = 0; r.acc.jobs = 0;
     const int u0 = tau0 - w2 + 1 + sh;
     for (int m = 0; m < U; m++) {
-        const int j1 = tau0 + m - w1 + 1, j2 = tau0 + m - w2 + 1;
-        if (EDGE) {
-            e1[m] = (j1 >= w1 && j1 + w1 <= n) ? e1[m] : 0.0f;
-            e2[m] = (j2 >= w2 && j2 + w2 <= n) ? e2[m] : 0.0f;
-        }
+        const int j2 = tau0 + m - w2 + 1;
         const float c1 = m >= w1 ? e1[m - w1] : in.t1c[m];
         if (!EDGE || (j2 >= 1 && j2 < n)) {
             PeakAcc unused; unused.mk = 0u; unused.oldest = 0; unused.jobs = 0;   // the mask is not used here
-            det_step<RNA, true>(r.d, 0, u0 + m, c1, e2[m] > thr_long, rec, unused, [&](int pos) { if (rec) io.peak(pos); }, io);
+            det_step<RNA, true>(r.d, 0, u0 + m, c1, true, rec, unused, [&](int pos) { if (rec) io.peak(pos); }, io);
         }
     }
     for (int k = 0; k < w1; k++) r.t1c[k] = e1[U - w1 + k];
