@@ -168,6 +168,15 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 const int v[4] = {rv[g].x, rv[g].y, rv[g].z, rv[g].w};
+                float x[8];
+                walk::cvt8(v, off_first, unit_first, x);           // misc.c:28, two samples per instruction, no conversion unit
+                float xq[8];
+#pragma unroll
+                for (int m = 0; m < 8; m += 2) {
+                    const walk::F2 p = {x[m], x[m + 1]};
+                    const walk::F2 q = walk::f2sq(p);              // float squares (events.c:301)
+                    xq[m] = q.lo; xq[m + 1] = q.hi;
+                }
 #pragma unroll
                 for (int m = 0; m < 8; m++) {
                     if ((word >> (8 * g + m)) & 1u) {  // an event starts here: the running piece is complete
@@ -177,7 +186,9 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                         as = 0.0;
                         aq = 0.0;
                     }
-                    add_raw((m & 1) ? (v[m >> 1] >> 16) : (int)(int16_t)(v[m >> 1] & 0xffff), off_first, unit_first, as, aq);
+                    // widen_pos: exact for the positive pA of every read that keeps the fast path's results
+                    as = __dadd_rn(as, walk::widen_pos(x[m]));
+                    aq = __dadd_rn(aq, walk::widen_pos(xq[m]));
                 }
             }
             sm.S[slot] = as;
