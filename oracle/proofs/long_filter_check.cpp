@@ -54,7 +54,7 @@ static bool one_case(const int16_t* raw, int c0, double dig, double off, double 
     }
     const float off_f = (float)off;
     const LongK lk = long_consts<RNA>(c0, off_f, thr);
-    const bool cand = long_candidate(SL, long_var<w>(SL, QL), SR, long_var<w>(SR, QR), lk);
+    const bool cand = long_candidate(SR - SL, SL + SR, QL + QR, lk);   // the kernel's three running sums (exact integers)
     *cand_out = cand;
     *t_out = tref;
     return !(tref > thr) || cand;

@@ -246,8 +246,12 @@ SGW_HD void tstat_two(float A0, double L0, float B0, double V0, double B0sq, flo
     const F2 sc = fdivw2<W, W>(cv);                       // cv / w (float); shortcut valid for cv >= 1e-36
     const F2 half = {0.5f, 0.5f};
     const F2 sh = f2mul(sc, half);
+#if defined(WALK_X_NOTAIL)
+    t0 = fmul(fsub(B0, A0), sc.lo); t1 = fmul(fsub(B1, A1), sh.hi);
+#else
     t0 = tail(fsub(B0, A0), sc.lo, sh.lo, cv.lo, ok0);    // delta = mean2 - mean1
     t1 = tail(fsub(B1, A1), sc.hi, sh.hi, cv.hi, ok1);
+#endif
 }
 
 // ---- the reference's own operation sequence, from the raw samples (rare path) ---------------------------------------
@@ -364,6 +368,7 @@ SGW_HD void det_cold(WalkDet& d, int first_step) {  // both detectors start at `
 // ends at b and the chunk that starts there (the short detector; the long one has no state on the fast path);
 // word 6 of an END record carries l_start for the jobs of later chunks (not compared).
 struct Canon { int v[8]; };
+template <int RNA>
 SGW_HD Canon canon_of(const WalkDet& d, int b) {
     Canon c;
     (void)b;
@@ -454,19 +459,25 @@ SGW_HD void dual_step(DualDet& d, int u, float c1, float c2, const E& on_emit) {
 
 // ---- the long window on the fast path: a conservative test on exact integer sums -----------------------------------
 // z = raw - c0 (c0: an integer pivot of the chunk, |z| <= ZMAX so that every sum below is an exact integer in
-// float). For the windows L = [p - w, p), R = [p, p + w) of position p, w = w_long:
-//     S = sum z,  V = w * sum z^2 - S^2      (V / w^2 = the window's variance in raw units; pivot-free)
-//     the t-statistic of events.c:338-361 in exact arithmetic is  sqrt(w) * |S_R - S_L| / sqrt(V_L + V_R)
-// and the reference's rounded value t2(p) obeys (oracle/proofs/long_filter.md)
+// float). For the windows L = [p - w, p), R = [p, p + w) of position p, w = w_long, with S = sum z and
+// V = w * sum z^2 - S^2 per window (V / w^2: the window's variance in raw units; pivot-free), the t-statistic of
+// events.c:338-361 in exact arithmetic is sqrt(w) |S_R - S_L| / sqrt(V_L + V_R), and the reference's rounded value
+// t2(p) obeys (oracle/proofs/long_filter.md)
 //     t2(p) > thr   ==>   w (|S_R - S_L| + a)^2 (1 + 2^-12)  >=  thr^2 (V_L + V_R) - B,
-//     a = 8 u w M,  B = thr^2 48 u w^2 M^2,  u = 2^-24,  M >= max |raw + offset| over both windows.
-// long_candidate() evaluates the right-hand condition; a false result PROVES t2(p) <= thr.
+//     a = 8 u w M,  B = thr^2 64 u w^2 M^2,  u = 2^-24,  M >= max |raw + offset| over both windows.
+// The kernel keeps THREE running sums over the 2w samples around p, each updated with the samples that enter,
+// cross the middle and leave (exact integers: nothing drifts):
+//     dS = S_R - S_L,   T = S_L + S_R,   Q = sum z^2 over both windows,
+// and uses  V_L + V_R = w Q - (T^2 + dS^2) / 2:
+//     candidate  <=>  NOT( w (1 + 2^-12) (|dS| + a)^2 + thr^2 (T^2 + dS^2) / 2 + B  <  thr^2 w Q ).
+// long_candidate() evaluates that; a false result PROVES t2(p) <= thr.
 constexpr int ZMAX = 1023;
 struct LongK {
     float c0;      // pivot (integer valued)
     float ca;      // a
     float cw;      // w (1 + 2^-12)
-    float thr2;    // thr^2
+    float h2;      // thr^2 / 2
+    float t2w;     // thr^2 w
     float cB;      // B
     float thr;     // thr_long (9.0 for DNA and RNA; a context parameter so that tests can make the long detector fire)
 };
@@ -480,23 +491,19 @@ SGW_HD LongK long_consts(int c0, float off, float thr_long) {
     k.ca = fmul(fmul(8.0f * u * w, M), 1.0001f);
     k.cw = w * (1.0f + 0.000244140625f);
     k.thr = thr_long;
-    k.thr2 = fmul(thr_long, thr_long);
-    k.cB = fmul(fmul(fmul(k.thr2, 48.0f * u * w * w), fmul(M, M)), 1.0001f);
+    const float thr2 = fmul(thr_long, thr_long);
+    k.h2 = fmul(thr2, 0.5f);
+    k.t2w = fmul(thr2, w);
+    k.cB = fmul(fmul(fmul(thr2, 64.0f * u * w * w), fmul(M, M)), 1.0001f);
     return k;
 }
-SGW_HD bool long_candidate(float SL, float VL, float SR, float VR, const LongK& k) {
-    const float g = fadd(fabsf(fsub(SR, SL)), k.ca);
-    const float lhs = fmul(fmul(g, k.cw), g);
-    const float rhs = ffma(fadd(VL, VR), k.thr2, -k.cB);
+// dS = S_R - S_L, T = S_L + S_R, Q = sum of z^2 over both windows (exact integers)
+SGW_HD bool long_candidate(float dS, float T, float Q, const LongK& k) {
+    const float g = fadd(fabsf(dS), k.ca);
+    const float sq = ffma(T, T, fmul(dS, dS));
+    const float lhs = ffma(fmul(g, g), k.cw, ffma(sq, k.h2, k.cB));
+    const float rhs = fmul(Q, k.t2w);
     return !(lhs < rhs);  // (NaN / infinity anywhere: candidate)
-}
-// V = w * Q - S * S for exact integers S, Q in float: S*S = p + e exactly (e from the FMA), one rounding of the
-// result's own size at most (covered by the 2^-12 slack of the test)
-template <int W>
-SGW_HD float long_var(float S, float Q) {
-    const float p = fmul(S, S);
-    const float e = ffma(S, S, -p);
-    return fsub(ffma((float)W, Q, -p), e);
 }
 
 // a sample enters windows whose t-statistics are computed at most two blocks later
@@ -511,19 +518,21 @@ struct Rings {
     float A1[C::R1];               // left-window terms of the short window by window start
     double L1[C::R1];
     float T1c[C::w1];              // t1 of the last w1 positions of the previous block
-    // integer side (z = raw - pivot, exact in float)
-    F2 ZC[C::w1];                  // {z, z*z} of the last w1 samples of the previous block
-    F2 ZSc;                        // running {sum z, sum z*z} over the last w1 samples
-    F2 ZS[C::R1];                  // short-window sums by window start
-    float S2[C::R2], V2[C::R2];    // long-window S and V by window start
+    // integer side (z = raw - pivot, exact in float): the samples of the previous block, the last ZH2 ones of the
+    // block before it, and the three running sums of the long window pair (see long_candidate)
+    static constexpr int ZH2 = 2 * C::w2 - C::U;   // how far the 2w-sample history reaches into the block before the previous one
+    float Z1[C::U], Z2[ZH2];
+    float zdS, zT, zQ;
     SGW_HD void clear() {
 #pragma unroll
-        for (int k = 0; k < C::R1; k++) { P[k] = 0.0; PQ[k] = 0.0; A1[k] = 0.0f; L1[k] = 0.0; ZS[k].lo = 0.0f; ZS[k].hi = 0.0f; }
+        for (int k = 0; k < C::R1; k++) { P[k] = 0.0; PQ[k] = 0.0; A1[k] = 0.0f; L1[k] = 0.0; }
 #pragma unroll
-        for (int k = 0; k < C::w1; k++) { T1c[k] = 0.0f; ZC[k].lo = 0.0f; ZC[k].hi = 0.0f; }
+        for (int k = 0; k < C::w1; k++) T1c[k] = 0.0f;
 #pragma unroll
-        for (int k = 0; k < C::R2; k++) { S2[k] = 0.0f; V2[k] = 0.0f; }
-        ZSc.lo = 0.0f; ZSc.hi = 0.0f;
+        for (int k = 0; k < C::U; k++) Z1[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < ZH2; k++) Z2[k] = 0.0f;
+        zdS = 0.0f; zT = 0.0f; zQ = 0.0f;
     }
 };
 
@@ -538,7 +547,8 @@ SGW_HD void det_step(WalkDet& d, int m, int u, float c1, bool cand, bool rec, Pe
     acc.oldest = acc.oldest > over ? acc.oldest : over;
     // the short detector holds a peak above its threshold: the long detector is reset and masked up to
     // peak_pos + w_short (events.c:414-422) -- the current life ends before this step, a new one starts with it
-    bool hot = d.l_hot != 0;
+    // (straight-line selects: a rare branch per step measured 14 % slower than these few predicated instructions)
+    bool hot = d.l_hot;
     if (maskl & hot & rec) {                                 // rare: the life that ends here may have emitted
         if (DIRECT) io.job(d.l_start, u);
         else { acc.job_ls = d.l_start; acc.job_end = u; acc.jobs++; }   // (parked; a second one redoes the block)
@@ -617,18 +627,13 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
     acc.mk = 0u; acc.oldest = 0; acc.jobs = 0;
     const int u0 = tau0 - w2 + 1 + sh;                              // position of the block's first step
     float xq[U];                                                    // float squares (events.c:301), two per instruction
-    F2 zz[U];                                                       // {z, z*z}: exact integers
 #pragma unroll
     for (int m = 0; m < U; m += 2) {
         const F2 p = {x[m], x[m + 1]};
         const F2 q = f2sq(p);
         xq[m] = q.lo; xq[m + 1] = q.hi;
-        const F2 zp = {z[m], z[m + 1]};
-        const F2 zq = f2sq(zp);
-        zz[m].lo = zp.lo; zz[m].hi = zq.lo;
-        zz[m + 1].lo = zp.hi; zz[m + 1].hi = zq.hi;
     }
-    F2 zs = g.ZSc;
+    float zdS = g.zdS, zT = g.zT, zQ = g.zQ;
 #pragma unroll
     for (int m0 = 0; m0 < U; m0 += 2) {
         // ---- the short t-statistic of the two positions j1 = tau0 + m - w1 + 1, m = m0, m0 + 1 ----
@@ -670,26 +675,39 @@ SGW_HD void walk_block(Rings<RNA>& g, WalkDet& d, const float (&x)[Cfg<RNA>::U],
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int m = m0 + h;
-            const int s1 = (m - w1 + 1) & M1, s1l = (m - 2 * w1 + 1) & M1;
-            const int s2 = (m - 2 * w1 + 1) & M2;                   // slot of j2 = j1 - w1 (long window [j2, j2+w2))
-            const int s2l = (m - 2 * w1 + 1 - w2) & M2;             // slot of j2 - w2
-            const F2 zold = m >= w1 ? zz[m - w1 >= 0 ? m - w1 : 0] : g.ZC[m];
-            zs = f2add(zs, f2sub(zz[m], zold));                     // sums over [j1, j1+w1)
-            const F2 zl = f2add(g.ZS[s1l], zs);                     // long window = short(j2) + short(j1)
-            g.ZS[s1] = zs;
-            const float vr = long_var<w2>(zl.lo, zl.hi);
-            bool cand = long_candidate(g.S2[s2l], g.V2[s2l], zl.lo, vr, lk);
-            g.S2[s2] = zl.lo; g.V2[s2] = vr;
+            // the newest sample tau0 + m enters the right window, the one w2 back crosses into the left window,
+            // the one 2 w2 back leaves (static indices: this block, the previous one, the one before)
+            const float zn = z[m];
+            const float zm = m >= w2 ? z[m >= w2 ? m - w2 : 0] : g.Z1[m < w2 ? m + U - w2 : 0];
+            const float zo = m >= 2 * w2 - U ? g.Z1[m >= 2 * w2 - U ? m + U - 2 * w2 : 0] : g.Z2[m < 2 * w2 - U ? m : 0];
+#if defined(WALK_X_NOCAND)   // (timing experiments, tools/run_variants.sh: results are wrong with any WALK_X_* defined)
+            zT = fadd(zT, zn); (void)zm; (void)zo;
+            bool cand = false;
+#else
+            zT = fadd(zT, fsub(zn, zo));
+            zQ = fadd(zQ, fsub(fmul(zn, zn), fmul(zo, zo)));
+            zdS = fadd(fadd(zdS, fadd(zn, zo)), fmul(zm, -2.0f));
+            bool cand = long_candidate(zdS, zT, zQ, lk);
+#endif
             const int j2 = tau0 + m - w2 + 1;
             if (EDGE) cand = cand & (j2 >= w2) & (j2 + w2 <= n);    // t2 is 0 there (events.c:328-338)
             cand = cand | (zdirty > 0);
             const float c1 = m >= w1 ? t1v[m >= w1 ? m - w1 : 0] : g.T1c[m < w1 ? m : 0];  // t1(j2), computed w1 samples ago
+#if defined(WALK_X_NODET)
+            d.s_pv = fadd(d.s_pv, c1); d.l_hot = d.l_hot | cand;
+#elif defined(WALK_X_NOLIFE)
+            { bool mk_; int p2_; const int over_ = det_one<true, RNA>(d.s_pv, d.s_ps, m, u0 + m, c1, thr_short<RNA>(), acc, mk_, p2_, NoEmit());
+              acc.oldest = acc.oldest > over_ ? acc.oldest : over_; d.l_hot = d.l_hot | (cand & mk_); d.l_start += p2_ & 1; }
+#else
             if (!EDGE || (j2 >= 1 && j2 < n)) det_step<RNA, false>(d, m, u0 + m, c1, cand, rec, acc, NoEmit(), io);
+#endif
         }
     }
-    g.ZSc = zs;
+    g.zdS = zdS; g.zT = zT; g.zQ = zQ;
 #pragma unroll
-    for (int k = 0; k < w1; k++) g.ZC[k] = zz[U - w1 + k];
+    for (int k = 0; k < Rings<RNA>::ZH2; k++) g.Z2[k] = g.Z1[k + U - Rings<RNA>::ZH2];
+#pragma unroll
+    for (int k = 0; k < U; k++) g.Z1[k] = z[k];
 #if defined(WALK_TEST_REDO)  // host tests: take the rare path on every third block
     ok = ok & ((tau0 / U) % 3 != 0);
 #endif
@@ -898,7 +916,7 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
         const bool own = tau >= s0;
         if (tau == t_live) det_cold(d, t_live - C::LAG + sh);   // forget the steps taken on partly filled rings
         if (tau == s0) {
-            io.put_begin(canon_of(d, s0 - C::LAG + sh));
+            io.put_begin(canon_of<RNA>(d, s0 - C::LAG + sh));
             d.l_start = LS_PRED; d.l_hot = false;               // the running life began before this chunk's steps
         }
         const int tn = tau + U < s1 ? tau + U : tau;  // (the last block is simply loaded again)
@@ -918,7 +936,7 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
         zdirty = zdirty > 0 ? zdirty - 1 : 0;
     }
     if (d.l_hot) io.job(d.l_start, LS_CONT);
-    io.put_end(canon_of(d, s1 - C::LAG + sh));
+    io.put_end(canon_of<RNA>(d, s1 - C::LAG + sh));
     const int rmin0 = s16_lo(vmin), rmin1 = s16_hi(vmin);
     const int rmax0 = s16_lo(vmax), rmax1 = s16_hi(vmax);
     io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1, bc.can_low ? bc.low_t : -32769);
@@ -966,7 +984,7 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
         const bool own = tau >= s0;
         if (last && tau == t_live) det_cold(d, t_live - C::LAG + sh);
         if (last && tau == s0) {
-            io.put_begin(canon_of(d, s0 - C::LAG + sh));
+            io.put_begin(canon_of<RNA>(d, s0 - C::LAG + sh));
             d.l_start = LS_PRED; d.l_hot = false;
         }
         if (tau >= INNER_MIN && tau + U <= n) {
@@ -1022,7 +1040,7 @@ SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W
         if (d.l_hot) io.job(d.l_start, n + sh);      // the life ends with the read
     } else {
         if (d.l_hot) io.job(d.l_start, LS_CONT);
-        io.put_end(canon_of(d, s1 - C::LAG + sh));
+        io.put_end(canon_of<RNA>(d, s1 - C::LAG + sh));
     }
     if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)
     if (rmin <= rmax) io.witness(rmin, rmax, low_t);
