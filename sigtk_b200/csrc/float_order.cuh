@@ -35,29 +35,24 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
             bool ok = true;
             if (lane >= tile && lane < ntiles) {
                 const float* row = A + lane * SB_STRIDE;
-                // A tie rounds to even: after the first tie of the run the parity is 0 whatever came in, so the two
-                // summaries differ only by the carry of that first tie (c and 1 - c). One chain (incoming S even)
-                // plus that difference.
-                int inc0 = 0, dif = 0;
-                uint32_t par = 0u;
-                bool seen = false;
+                // The summary of a run = what it adds to S for an even and for an odd incoming S. Scaled by 2^(23-e)
+                // the accumulator is an integer-valued float in [2^23, 2^24), where one ulp is 1: the hardware's own
+                // float addition IS the recurrence (round to nearest, ties to even), so the run is simply added up
+                // twice, from the smallest even and the smallest odd accumulator of the binade. Both stay below 2^24
+                // (checked at the end: the sums only grow), or the tile is handed to the value-by-value path.
+                float acc0 = 8388608.0f, acc1 = 8388609.0f;
+                uint32_t sign = 0u;
 #pragma unroll 8
                 for (int k = 0; k < 32; k++) {
                     const float v = row[k];
                     const float x = __fmul_rn(v, scale);          // exact: a power of two
-                    ok = ok && ((__float_as_uint(v) >> 31) == 0u) && (x < 16777216.0f);
-                    const int a = __float2int_rd(x);
-                    const float f = __fsub_rn(x, (float)a);       // exact
-                    const bool tie = f == 0.5f;
-                    const uint32_t up = f > 0.5f ? 1u : 0u;
-                    const uint32_t t = par + (uint32_t)a;
-                    const uint32_t c = tie ? (t & 1u) : up;
-                    if (tie && !seen) { dif = 1 - 2 * (int)c; seen = true; }
-                    inc0 += a + (int)c;
-                    par = (t + c) & 1u;
+                    sign |= __float_as_uint(v);
+                    acc0 = __fadd_rn(acc0, x);
+                    acc1 = __fadd_rn(acc1, x);
                 }
-                u0 = (uint32_t)inc0;
-                u1 = (uint32_t)(inc0 + dif);
+                ok = ((sign >> 31) == 0u) && (acc0 < 16777216.0f) && (acc1 < 16777216.0f);  // (NaN / infinity: not ok)
+                u0 = __float_as_uint(acc0) - 0x4b000000u;         // mantissa integers: exact differences
+                u1 = __float_as_uint(acc1) - 0x4b000001u;
             }
             // the summaries compose (the parity after a tile is the parity of S + its increment): an inclusive scan
             // over the lanes gives the increment from tile `tile` through every tile for either incoming parity.
