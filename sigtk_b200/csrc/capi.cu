@@ -196,7 +196,35 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
     CU(cudaMemsetAsync(sc.counters, 0, 4 * sizeof(unsigned long long), st));
     StageMarks marks(ctx, st);
     if (b.n_reads == 0 || b.span == 0) {
-        CU(cudaMemsetAsync(o.ev_off, 0, ((size_t)b.n_reads + 1) * sizeof(uint64_t), st));
+        // nothing but empty records: every per-read output gets its defined value for an empty record (no event,
+        // zero statistics / entropies / segments, "record not longer than the window" for prefix) instead of whatever
+        // the previous batch left in the buffers
+        const size_t nr = b.n_reads;
+        CU(cudaMemsetAsync(o.ev_off, 0, (nr + 1) * sizeof(uint64_t), st));
+        if (nr && (want & SGPU_WANT_STAT)) CU(cudaMemsetAsync(o.stat, 0, nr * 6 * sizeof(float), st));
+        if (nr && (want & SGPU_WANT_ENT)) {
+            if (!o.ent) CU(dev_alloc(&o.ent, (uint64_t)ctx->max_reads * 3));
+            CU(cudaMemsetAsync(o.ent, 0, nr * 3 * sizeof(double), st));
+        }
+        if (nr && (want & SGPU_WANT_JNN)) {
+            if (!o.jnn_cnt) {
+                CU(dev_alloc(&o.jnn_cnt, ctx->max_reads));
+                CU(dev_alloc(&o.jnn_seg, 2 * jnn_seg_capacity(ctx->max_samples, ctx->max_reads)));
+            }
+            CU(cudaMemsetAsync(o.jnn_cnt, 0, nr * sizeof(uint32_t), st));
+        }
+        if (nr && (want & SGPU_WANT_PREFIX)) {
+            if (!o.prefix_pos) {
+                CU(dev_alloc(&o.prefix_pos, (uint64_t)ctx->max_reads * 4));
+                CU(dev_alloc(&o.prefix_stat, (uint64_t)ctx->max_reads * 6));
+            }
+            CU(cudaMemsetAsync(o.prefix_pos, 0xff, nr * 4 * sizeof(int32_t), st));   // (-1, -1, -1, -1)
+            CU(cudaMemsetAsync(o.prefix_stat, 0, nr * 6 * sizeof(float), st));
+        }
+        if (nr && (want & SGPU_WANT_EVENTS)) {
+            CU(cudaMemsetAsync(d_seq, 0, nr * sizeof(uint32_t), st));
+            CU(cudaMemsetAsync(d_fix, 0, nr * sizeof(uint32_t), st));
+        }
         ctx->last_launches = 0;
         return SGPU_OK;
     }

@@ -114,7 +114,10 @@ __global__ void __launch_bounds__(256) stat_median_kernel(DevBatch b, float* __r
     for (uint32_t r = blockIdx.x; r < b.n_reads; r += gridDim.x) {
         const int16_t* __restrict__ raw = b.samples + b.read_off[r];
         const uint32_t n = b.read_len[r];
-        if (n == 0) continue;
+        if (n == 0) {  // an empty record: defined values instead of the previous batch's
+            if (threadIdx.x == 0) { out[(size_t)r * 6 + 4] = 0.0f; out[(size_t)r * 6 + 5] = 0.0f; }
+            continue;
+        }
         const uint32_t rank = (uint32_t)((int)n / 2);  // ks_ksmall(n, copy, n/2), stat.h:60,70
         const int med_r = select_rank_i16<true>(raw, n, rank, hist, part, sh);
         const float off = b.offset[r], unit = b.unit[r];

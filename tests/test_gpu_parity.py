@@ -543,3 +543,18 @@ def test_two_million_sample_reads(ctx, orc, rna_flag):
     res = ctx.run(reads, rna=rna_flag, want=sg.WANT_EVENTS | sg.WANT_STAT)
     check_against_oracle(orc, res, reads, rna_flag, want=sg.WANT_EVENTS | sg.WANT_STAT)
     assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0
+
+
+def test_empty_records_get_defined_values(ctx):
+    """a batch of nothing but empty records after a batch with data, and an empty record inside a batch: no stale
+    values from the previous batch in any per-read output"""
+    reads = synth.make_reads(3, mean=5000.0, seed=90)
+    ctx.run(reads, rna=0, want=ALL | sg.WANT_ENT | sg.WANT_JNN | sg.WANT_PREFIX)
+    empty = (np.zeros(0, np.int16), 8192.0, 3.0, 1402.882324)
+    res = ctx.run([empty, empty], rna=0, want=ALL | sg.WANT_ENT | sg.WANT_JNN | sg.WANT_PREFIX)
+    assert np.array_equal(res.ev_off, np.zeros(3, np.uint64)) and res.events(0).n == 0
+    assert not res.stat[:, 4:].any() and not res.ent.any() and all(len(j) == 0 for j in res.jnn)
+    assert np.array_equal(res.prefix_pos, -np.ones((2, 4), np.int32))
+    res = ctx.run([reads[0], empty, reads[1]], rna=0, want=sg.WANT_EVENTS | sg.WANT_STAT)
+    assert res.events(1).n == 0 and res.stat[1, 4] == 0.0 and res.stat[1, 5] == 0.0
+    assert res.events(0).n > 1 and res.events(2).n > 1
