@@ -177,39 +177,74 @@ def copy_only_ceiling(torch, dev, h2d_bytes: int, d2h_bytes: int, steps: int, di
     return float(t.item())
 
 
+def _mix_t(torch, x):
+    """splitmix64 finaliser on int64 tensors (two's-complement wrap-around = uint64 arithmetic; logical shifts by masking)"""
+    def c(v):
+        return v - (1 << 64) if v >= (1 << 63) else v
+    x = x ^ ((x >> 30) & ((1 << 34) - 1))
+    x = x * c(synth._M1)
+    x = x ^ ((x >> 27) & ((1 << 37) - 1))
+    x = x * c(synth._M2)
+    x = x ^ ((x >> 31) & ((1 << 33) - 1))
+    return x
+
+
 def device_batch(torch, dev, lens: np.ndarray, first_index: int, seed: int, p_change: float = 0.1):
-    """One batch of synthetic reads generated on the device (signal model of sigtk_b200/synth.py).
+    """One batch of the counter-based synthetic set generated on the device: read k of the batch is read
+    first_index + k of the named set, bit-identical to sigtk_b200.synth.make_read_cb (same integer hashes, same exactly
+    rounded float64 operations; tests/test_synth.py) whatever the device, rank or batch boundaries.
     -> dict(samples i16[span], read_off i64[n+1], read_len i32[n], offset f32[n], unit f32[n], span, n_samples)"""
+    def c(v):
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
     n = len(lens)
     al = (lens + 7) // 8 * 8
     off = np.zeros(n + 1, dtype=np.int64)
     off[1:] = np.cumsum(al)
     span = int(off[-1])
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(seed)
-    samples = torch.empty(span, dtype=torch.int16, device=dev)
-    offsets = ((first_index + np.arange(n)) % 53).astype(np.float32)
-    scale = np.float32(synth.DIGITISATION / synth.RANGE)
-    CH = 1 << 25
+    samples = torch.zeros(span, dtype=torch.int16, device=dev)
+    index = first_index + np.arange(n, dtype=np.int64)
+    offsets = (index % 53).astype(np.float32)
+    keys = synth.read_key(seed, index).view(np.int64)
+    scale = synth.DIGITISATION / synth.RANGE
+    thr = int(p_change * (1 << 24))
+    CH = 1 << 24
     r0 = 0
     while r0 < n:  # groups of whole reads of about CH samples
         r1 = int(np.searchsorted(off, off[r0] + CH, side="right"))
         r1 = min(max(r1 - 1, r0 + 1), n)
         a, b = int(off[r0]), int(off[r1])
         m = b - a
-        change = torch.rand(m, device=dev, generator=gen) < p_change
-        change[0] = True
-        seg = torch.cumsum(change.to(torch.int32), 0, dtype=torch.int32) - 1
-        nlev = int(seg[-1].item()) + 1
-        levels = 60.0 + 60.0 * torch.rand(nlev, device=dev, generator=gen)
-        pa = levels[seg.long()]
-        del seg, change
-        pa += 2.0 * torch.randn(m, device=dev, generator=gen)
-        o = torch.repeat_interleave(torch.from_numpy(offsets[r0:r1]).to(dev),
-                                    torch.from_numpy(al[r0:r1]).to(dev), output_size=m)
-        raw = torch.round(pa * float(scale) - o).clamp_(-32768, 32767)
-        samples[a:b] = raw.to(torch.int16)
-        del pa, o, raw
+        reps = torch.from_numpy(al[r0:r1]).to(dev)
+        key = torch.repeat_interleave(torch.from_numpy(keys[r0:r1]).to(dev), reps, output_size=m)
+        rstart = torch.repeat_interleave(torch.from_numpy(off[r0:r1] - a).to(dev), reps, output_size=m)
+        pos = torch.arange(m, dtype=torch.int64, device=dev)
+        i = pos - rstart                                      # sample index inside its read (padding included)
+
+        def h(ii, stream):
+            return _mix_t(torch, key ^ (ii * c(synth._K_SAMPLE) + c(stream * synth._K_STREAM)))
+
+        change = ((h(i, 1) >> 40) & ((1 << 24) - 1)) < thr
+        change |= i == 0
+        start = torch.cummax(torch.where(change, pos, torch.full_like(pos, -1)), 0).values - rstart
+        del change
+        u = ((h(start, 2) >> 11) & ((1 << 53) - 1)).to(torch.float64) * (1.0 / 9007199254740992.0)
+        pa = 60.0 + 60.0 * u
+        del u, start
+        tot = torch.zeros(m, dtype=torch.int64, device=dev)
+        for s in (3, 4, 5):
+            hh = h(i, s)
+            for k in range(4):
+                tot += (hh >> (16 * k)) & 0xFFFF
+            del hh
+        pa += (tot - 393210).to(torch.float64) * (2.0 / 65536.0)
+        del tot
+        o = torch.repeat_interleave(torch.from_numpy(offsets[r0:r1].astype(np.float64)).to(dev), reps, output_size=m)
+        raw = torch.round(pa * scale - o).clamp_(-32768, 32767).to(torch.int16)
+        ln = torch.repeat_interleave(torch.from_numpy(lens[r0:r1]).to(dev), reps, output_size=m)
+        raw[i >= ln] = 0                                      # the padding up to the next multiple of 8 samples
+        samples[a:b] = raw
+        del pa, o, raw, key, rstart, pos, i, ln
         r0 = r1
     unit = (np.float32(synth.RANGE) / np.float32(synth.DIGITISATION)).astype(np.float32)
     return {
@@ -344,7 +379,7 @@ def run_reference(args):
     pool = []
     for j in range(3):  # three distinct samples, cycled
         base = j * reads_per_step
-        pool.append([synth.make_read(base + i, int(lens[base + i])) for i in range(reads_per_step)])
+        pool.append([synth.make_read_cb(base + i, int(lens[base + i])) for i in range(reads_per_step)])
     for w in range(args.warmup):
         cpu_time_reads(chk, pool[w % 3], threads)
     t_tot, s_tot, e_tot = 0.0, 0, 0
@@ -408,8 +443,7 @@ def run_ours(args):
         # step j works on the next world*B reads of the set, split into contiguous read ranges balanced by samples
         g0 = (j * world * B) % (N_SET - world * B)
         lo, hi = shard_ranges(lens_all[g0:g0 + world * B], world)[rank]
-        pool.append(device_batch(torch, dev, lens_all[g0 + lo:g0 + hi], g0 + lo, synth.SEED + 7919 * (j * world + rank),
-                                 p_change))
+        pool.append(device_batch(torch, dev, lens_all[g0 + lo:g0 + hi], g0 + lo, synth.SEED, p_change))
     torch.cuda.synchronize()
     max_span = max(p["span"] for p in pool)
     max_reads = max(p["n_reads"] for p in pool)

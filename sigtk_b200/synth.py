@@ -40,6 +40,62 @@ def make_read(index: int, length: int, seed: int = SEED, level_lo: float = 60.0,
     return raw, DIGITISATION, offset, RANGE
 
 
+# ---- the counter-based generator of the named benchmark set ----------------------------------------------------------
+# Every sample is a pure function of (seed, read index, sample index): any rank, GPU or CPU regenerates any read of
+# the 1,000,000-read set bit for bit ("counter-based ... so any GPU/CPU regenerates any read").
+# Only integer arithmetic and exactly rounded float64 operations are used -- no libm call whose last bit could differ
+# between numpy and CUDA: the N(0, 2 pA) noise is the sum of twelve 16-bit uniforms (Irwin-Hall: mean 0, standard
+# deviation 2 pA, support +-12 pA), the level changes and levels come from 64-bit hashes.
+# bench.py's device generator (torch, int64 with wrap-around) is the same arithmetic: tests/test_synth.py.
+_M1, _M2, _M3 = 0xBF58476D1CE4E5B9, 0x94D049BB133111EB, 0x9E3779B97F4A7C15
+_K_SAMPLE, _K_STREAM = 0xD1B54A32D192ED03, 0x8CB92BA72F3D8DD7
+_U64 = (1 << 64) - 1
+
+
+def _mix_np(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser on uint64 (wrap-around arithmetic)"""
+    x = x.astype(np.uint64, copy=True)
+    x ^= x >> np.uint64(30)
+    x *= np.uint64(_M1)
+    x ^= x >> np.uint64(27)
+    x *= np.uint64(_M2)
+    x ^= x >> np.uint64(31)
+    return x
+
+
+def read_key(seed: int, index) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        return _mix_np(np.uint64((seed * _M3) & _U64) + np.asarray(index, dtype=np.uint64))
+
+
+def _hash_np(key, i: np.ndarray, stream: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        return _mix_np(key ^ (i.astype(np.uint64) * np.uint64(_K_SAMPLE) + np.uint64((stream * _K_STREAM) & _U64)))
+
+
+def make_read_cb(index: int, length: int, seed: int = SEED, level_lo: float = 60.0, level_hi: float = 120.0,
+                 p_change: float = 0.1, noise: float = 2.0):
+    """One read of the counter-based set: (raw int16[length], digitisation, offset, range)."""
+    with np.errstate(over="ignore"):
+        key = read_key(seed, index)
+        i = np.arange(length, dtype=np.uint64)
+        change = (_hash_np(key, i, 1) >> np.uint64(40)) < np.uint64(int(p_change * (1 << 24)))
+        if length:
+            change[0] = True
+        start = np.maximum.accumulate(np.where(change, i.astype(np.int64), -1))
+        u = (_hash_np(key, start.astype(np.uint64), 2) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+        level = level_lo + (level_hi - level_lo) * u
+        tot = np.zeros(length, dtype=np.int64)
+        for s in (3, 4, 5):
+            h = _hash_np(key, i, s)
+            for k in range(4):
+                tot += ((h >> np.uint64(16 * k)) & np.uint64(0xFFFF)).astype(np.int64)
+        pa = level + (tot - 393210).astype(np.float64) * (noise / 65536.0)
+    offset = float(index % 53)
+    raw = np.rint(pa * (DIGITISATION / RANGE) - offset)
+    return np.clip(raw, -32768, 32767).astype(np.int16), DIGITISATION, offset, RANGE
+
+
 def make_reads(n_reads: int, mean: float = 40000.0, sigma: float = 0.6, seed: int = SEED, lo: int = 2000,
                hi: int = 4_000_000, rna: bool = False):
     """A list of reads with lognormal lengths. RNA-like reads dwell ~4x longer per level."""
