@@ -6,7 +6,7 @@ import sys
 from collections import defaultdict
 
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
-ours = ("ent_kernel", "jnn_walk", "walk_chunks", "verify_chunks", "chunk_count", "emit_events", "count_tile_bits", "scan_counts",
+ours = ("ent_kernel", "jnn_walk", "walk_chunks", "long_jobs", "prefix_", "verify_chunks", "chunk_count", "emit_events", "count_tile_bits", "scan_counts",
         "read_event_offsets", "init_reads", "build_seq_list", "gen_", "sum_fixups", "pa_kernel", "stat_", "svb_")
 agg = defaultdict(list)
 for r in rows:
