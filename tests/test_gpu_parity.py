@@ -558,3 +558,18 @@ def test_empty_records_get_defined_values(ctx):
     res = ctx.run([reads[0], empty, reads[1]], rna=0, want=sg.WANT_EVENTS | sg.WANT_STAT)
     assert res.events(1).n == 0 and res.stat[1, 4] == 0.0 and res.stat[1, 5] == 0.0
     assert res.events(0).n > 1 and res.events(2).n > 1
+
+
+def test_rna_reads_up_to_270k_samples(ctx, orc):
+    """BASELINE configs[1] is the reference's RNA file (absent from the checkout: a missing large blob); its golden
+    output test/event_rna.exp lists 100 reads of 14,509..269,194 samples. Twenty seeded RNA-like reads over that range
+    of lengths (long dwells, the RNA detector parameters), every boundary / mean / stdv / stat bit-exact."""
+    rng = np.random.default_rng(2024)
+    lens = np.concatenate([[14509, 269194, 200001, 65536, 131072 + 5], rng.integers(14509, 269194, 15)])
+    reads = [synth.make_read(5000 + k, int(n), seed=31, p_change=0.025, noise=float(rng.choice([1.0, 2.0, 3.0])))
+             for k, n in enumerate(lens)]
+    for lo in range(0, len(reads), 5):   # (the test context holds 8 M samples per batch)
+        part = reads[lo:lo + 5]
+        res = ctx.run(part, rna=1, want=sg.WANT_EVENTS | sg.WANT_STAT)
+        check_against_oracle(orc, res, part, 1, want=sg.WANT_EVENTS | sg.WANT_STAT)
+        assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0
