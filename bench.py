@@ -534,6 +534,8 @@ def run_ours(args):
         ul = [device_batch(torch, dev, np.full(160, 2_000_000, dtype=np.int64), 0, synth.SEED + 11, 0.1)]
         others["ultralong"] = dict(short_run(torch, sg, local, ul, 0, want),
                                    workload=WORKLOADS["ultralong"].format(mode=args.mode) + " (BASELINE configs[4])")
+        st = short_run(torch, sg, local, ul, 0, sg.WANT_STAT)   # `sigtk stat` on the same reads: one CTA per read
+        others["ultralong"]["stat"] = {k: st[k] for k in ("value", "unit", "ms_per_step", "stage_ms_per_step")}
         del ul
         torch.cuda.empty_cache()
         rn = [device_batch(torch, dev, lens_all[:8192], 0, synth.SEED + 13, 0.025)]

@@ -214,6 +214,8 @@ int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
 #define SGPU_PARAM_PORE      4 /* 0: R9 (JNNV2_RNA_R9_ADAPTOR), 1: RNA004 (JNNV2_RNA_RNA004_ADAPTOR), jnn.h:88-102: the
                                   host picks it from the BLOW5 header like pore_detect (misc.c:74-101); used by
                                   SGPU_WANT_PREFIX only (not a test parameter) */
+#define SGPU_PARAM_STAT_CTA_MIN 5 /* stat / jnn moments: reads of at least this many samples are added up by a CTA
+                                  (several warps per read), shorter ones by one warp; 0 = every read by a CTA */
 int  sgpu_set_param(sgpu_ctx_t *ctx, int key, double value);
 
 /* Device time of every kernel group of the last run, measured with CUDA events on the stream the kernels were

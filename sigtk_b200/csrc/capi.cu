@@ -237,8 +237,8 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
         if (!events || force_generic) marks.done("pa", launch_pa(b, o.pa, ctx->sm_count, st));
     }
     if (want & SGPU_WANT_STAT) {
-        marks.done("stat_moments", launch_stat_moments(b, o.stat, ctx->sm_count, st));
-        marks.done("stat_median", launch_stat_median(b, o.stat, ctx->sm_count, st));
+        marks.done("stat_moments", launch_stat_moments(b, o.stat, ctx->sc.tune_stat_cta_min, ctx->sm_count, st));
+        marks.done("stat_median", launch_stat_median(b, o.stat, ctx->sc.tune_stat_cta_min, ctx->sm_count, st));
     }
     if (want & SGPU_WANT_ENT) {
         if (!o.ent) CU(dev_alloc(&o.ent, (uint64_t)ctx->max_reads * 3));
@@ -255,7 +255,7 @@ int run_pipeline(sgpu_ctx* ctx, const DevBatch& b, uint32_t want, DevOut& o, uin
             CU(dev_alloc(&o.jnn_seg, 2 * jnn_seg_capacity(ctx->max_samples, ctx->max_reads)));
         }
         if (!ctx->jnn_mom) CU(dev_alloc(&ctx->jnn_mom, (uint64_t)ctx->max_reads * 2));
-        marks.done("jnn_moments", launch_jnn_moments(b, ctx->jnn_mom, ctx->sm_count, st));
+        marks.done("jnn_moments", launch_jnn_moments(b, ctx->jnn_mom, ctx->sc.tune_stat_cta_min, ctx->sm_count, st));
         marks.done("jnn_walk", launch_jnn(b, ctx->jnn_mom, o.jnn_cnt, o.jnn_seg, ctx->sm_count, st));
     }
     if (want & SGPU_WANT_PREFIX) {
@@ -390,6 +390,7 @@ int sgpu_create(sgpu_ctx_t** out, int device, uint64_t max_samples, uint32_t max
     CUC(dev_alloc(&sc.jobs, (uint64_t)sc.job_cap * 4));
     CUC(dev_alloc(&sc.job_count, 1));
     sc.tune_chunk_len = 0; sc.tune_warmup = 0; sc.tune_thr_long = 9.0f;  // events.c:46,53: threshold of the long detector
+    sc.tune_stat_cta_min = STAT_CTA_MIN_DEFAULT;
     CUC(dev_alloc(&sc.tile_cnt, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_read0, sc.max_tiles));
     CUC(dev_alloc(&sc.tile_base, (uint64_t)sc.max_tiles + 1));
@@ -775,6 +776,10 @@ int sgpu_set_param(sgpu_ctx_t* ctx, int key, double value) {
         case SGPU_PARAM_PORE:
             if (value != 0 && value != 1) return SGPU_E_INVAL;
             ctx->pore_rna004 = (int)value;
+            return SGPU_OK;
+        case SGPU_PARAM_STAT_CTA_MIN:
+            if (value < 0 || value > 4294967295.0) return SGPU_E_INVAL;
+            sc.tune_stat_cta_min = (uint32_t)value;
             return SGPU_OK;
         case SGPU_PARAM_THR_LONG:
             if (!(value > 0 && value < 1e6)) return SGPU_E_INVAL;

@@ -19,53 +19,63 @@ namespace sgpu {
 constexpr int SB = 1024;            // values per superblock
 constexpr int SB_STRIDE = 33;       // shared-memory row stride of a 32-value tile (conflict-free both ways)
 
-__device__ __forceinline__ float chain_superblock(const float* __restrict__ A, int ntiles, float s, int lane,
-                                                  int* __restrict__ sums, bool first) {
+// one lane, one tile of 32 values (row), the accumulator's binade given as scale = 2^(23-e): the increment of the
+// mantissa integer S for an even (u0) and for an odd (u1) incoming S; false when the tile cannot be summarised.
+// Scaled by 2^(23-e) the accumulator is an integer-valued float in [2^23, 2^24), where one ulp is 1: the hardware's own
+// float addition IS the recurrence (round to nearest, ties to even), so the run is simply added up twice, from the
+// smallest even and the smallest odd accumulator of the binade. Both stay below 2^24 (checked at the end: the sums
+// only grow), or the tile is handed to the value-by-value path.
+__device__ __forceinline__ bool tile_summary(const float* __restrict__ row, float scale, uint32_t& u0, uint32_t& u1) {
+    float acc0 = 8388608.0f, acc1 = 8388609.0f;
+    uint32_t sign = 0u;
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) {
+        const float v = row[k];
+        const float x = __fmul_rn(v, scale);          // exact: a power of two
+        sign |= __float_as_uint(v);
+        acc0 = __fadd_rn(acc0, x);
+        acc1 = __fadd_rn(acc1, x);
+    }
+    u0 = __float_as_uint(acc0) - 0x4b000000u;         // mantissa integers: exact differences
+    u1 = __float_as_uint(acc1) - 0x4b000001u;
+    return ((sign >> 31) == 0u) && (acc0 < 16777216.0f) && (acc1 < 16777216.0f);  // (NaN / infinity: not ok)
+}
+
+// the summaries compose (the parity after a tile is the parity of S + its increment): an inclusive scan over the
+// lanes gives the increment from the first summarised tile through every tile for either incoming parity.
+// (32-bit wrap-around can only happen after the first tile that ends the binade, which is all that is used.)
+__device__ __forceinline__ void compose_summaries(uint32_t& u0, uint32_t& u1, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t b0 = __shfl_up_sync(0xffffffffu, u0, d), b1 = __shfl_up_sync(0xffffffffu, u1, d);
+        if (lane >= d) {
+            const uint32_t n0 = b0 + ((b0 & 1u) ? u1 : u0);
+            const uint32_t n1 = b1 + ((b1 & 1u) ? u0 : u1);
+            u0 = n0; u1 = n1;
+        }
+    }
+}
+
+__device__ __forceinline__ bool summable(float s) {   // an accumulator whose binade can be worked in
+    const int e = (int)((__float_as_uint(s) >> 23) & 0xffu) - 127;
+    return s > 0.0f && e > -100 && e < 100;
+}
+
+__device__ __forceinline__ float chain_superblock(const float* __restrict__ A, int ntiles, float s, int lane, bool first) {
     int tile = 0;
     while (tile < ntiles) {  // (uniform across the warp)
         const uint32_t sb = __float_as_uint(s);
         const int e = (int)((sb >> 23) & 0xffu) - 127;
-        const bool s_ok = !first && s > 0.0f && e > -100 && e < 100;  // the first superblock starts from 0: binades fly by
+        const bool s_ok = !first && summable(s);  // the first superblock starts from 0: binades fly by
         int fail = tile;  // first tile that has to be added value by value
         uint32_t S = (sb & 0x7fffffu) | 0x800000u;
         if (s_ok) {
             const float scale = __uint_as_float((uint32_t)(127 + 23 - e) << 23);
-            // every lane summarises one tile: the increment of S for an even (u0) and for an odd (u1) incoming S
+            // every lane summarises one tile
             uint32_t u0 = 0u, u1 = 0u;  // lanes outside [tile, ntiles) are the identity
             bool ok = true;
-            if (lane >= tile && lane < ntiles) {
-                const float* row = A + lane * SB_STRIDE;
-                // The summary of a run = what it adds to S for an even and for an odd incoming S. Scaled by 2^(23-e)
-                // the accumulator is an integer-valued float in [2^23, 2^24), where one ulp is 1: the hardware's own
-                // float addition IS the recurrence (round to nearest, ties to even), so the run is simply added up
-                // twice, from the smallest even and the smallest odd accumulator of the binade. Both stay below 2^24
-                // (checked at the end: the sums only grow), or the tile is handed to the value-by-value path.
-                float acc0 = 8388608.0f, acc1 = 8388609.0f;
-                uint32_t sign = 0u;
-#pragma unroll 8
-                for (int k = 0; k < 32; k++) {
-                    const float v = row[k];
-                    const float x = __fmul_rn(v, scale);          // exact: a power of two
-                    sign |= __float_as_uint(v);
-                    acc0 = __fadd_rn(acc0, x);
-                    acc1 = __fadd_rn(acc1, x);
-                }
-                ok = ((sign >> 31) == 0u) && (acc0 < 16777216.0f) && (acc1 < 16777216.0f);  // (NaN / infinity: not ok)
-                u0 = __float_as_uint(acc0) - 0x4b000000u;         // mantissa integers: exact differences
-                u1 = __float_as_uint(acc1) - 0x4b000001u;
-            }
-            // the summaries compose (the parity after a tile is the parity of S + its increment): an inclusive scan
-            // over the lanes gives the increment from tile `tile` through every tile for either incoming parity.
-            // (32-bit wrap-around can only happen after the first tile that ends the binade, which is all we need.)
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t b0 = __shfl_up_sync(0xffffffffu, u0, d), b1 = __shfl_up_sync(0xffffffffu, u1, d);
-                if (lane >= d) {
-                    const uint32_t n0 = b0 + ((b0 & 1u) ? u1 : u0);
-                    const uint32_t n1 = b1 + ((b1 & 1u) ? u0 : u1);
-                    u0 = n0; u1 = n1;
-                }
-            }
+            if (lane >= tile && lane < ntiles) ok = tile_summary(A + lane * SB_STRIDE, scale, u0, u1);
+            compose_summaries(u0, u1, lane);
             const uint32_t S_after = S + ((S & 1u) ? u1 : u0);
             const uint32_t bad = __ballot_sync(0xffffffffu, !ok || S_after >= 0x1000000u);
             fail = bad ? __ffs(bad) - 1 : ntiles;  // the first tile that has to be added value by value
@@ -88,9 +98,26 @@ __device__ __forceinline__ float chain_superblock(const float* __restrict__ A, i
     return s;
 }
 
+// The summary of a whole superblock in the binade of `s` (summable(s) holds): what its tiles add to S for an even
+// (U0) and an odd (U1) incoming S -- valid as long as S stays below 2^24 to the superblock's end (the values are
+// non-negative, so S only grows: the caller checks the end). Superblocks summarised in the same binade compose like
+// tiles do: several warps take consecutive superblocks of one long read (stat_moments_cta_kernel).
+__device__ __forceinline__ bool summarise_superblock(const float* __restrict__ A, int ntiles, float s, int lane,
+                                                     uint32_t& U0, uint32_t& U1) {
+    const int e = (int)((__float_as_uint(s) >> 23) & 0xffu) - 127;
+    const float scale = __uint_as_float((uint32_t)(127 + 23 - e) << 23);
+    uint32_t u0 = 0u, u1 = 0u;
+    bool ok = true;
+    if (lane < ntiles) ok = tile_summary(A + lane * SB_STRIDE, scale, u0, u1);
+    compose_summaries(u0, u1, lane);
+    U0 = __shfl_sync(0xffffffffu, u0, 31);   // lanes past the last tile are the identity
+    U1 = __shfl_sync(0xffffffffu, u1, 31);
+    return __ballot_sync(0xffffffffu, !ok) == 0u;
+}
+
 
 constexpr int MED_BINS = 4096;
-// element of rank `rank` (0-based, ascending) of the int16 samples raw[0..n); all threads of the CTA call it.
+// element of rank `rank` (0-based, ascending) of the int16 samples raw[0..n); all threads of the CTA (256 or more) call it.
 // ALIGNED: raw is 16-byte aligned (a read's first sample: 128-bit loads); otherwise any sub-range of a read.
 // Two levels over the order-preserving key raw + 32768: the upper 12 bits (4096 bins: the ~1,000 ADC units a signal
 // spans spread over ~60 bins, so the shared-memory atomics of a warp rarely meet; with 256 bins they met on 2-4 bins),
@@ -103,13 +130,23 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
     for (int k = threadIdx.x; k < MED_BINS; k += blockDim.x) hist[k] = 0;
     __syncthreads();
     if (ALIGNED) {
-        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
-            const uint4 q = __ldg(src + w);
-            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+        // four 128-bit loads in flight per thread (a CTA's bandwidth is its bytes in flight over the load latency)
+        for (uint32_t w0 = threadIdx.x; w0 < n_words; w0 += 4u * blockDim.x) {
+            uint4 q[4];
 #pragma unroll
-            for (int h = 0; h < 8; h++) {
-                const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
-                if (w * 8u + h < n) atomicAdd(&hist[key >> 4], 1u);
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = w0 + (uint32_t)k * blockDim.x;
+                q[k] = w < n_words ? __ldg(src + w) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = w0 + (uint32_t)k * blockDim.x;
+                const uint32_t wd[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+                for (int h = 0; h < 8; h++) {
+                    const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
+                    if (w < n_words && w * 8u + h < n) atomicAdd(&hist[key >> 4], 1u);
+                }
             }
         }
     } else {
@@ -117,7 +154,7 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
             atomicAdd(&hist[(uint32_t)((int)__ldg(raw + i) + 32768) >> 4], 1u);
     }
     __syncthreads();
-    {   // 256 threads x 16 bins, then one thread over the 256 partial sums and the 16 bins of the group
+    if (threadIdx.x < 256) {   // 256 threads x 16 bins, then one thread over the 256 partial sums and the 16 bins of the group
         uint32_t sum = 0;
         for (int k = 0; k < MED_BINS / 256; k++) sum += hist[threadIdx.x * (MED_BINS / 256) + k];
         part[threadIdx.x] = sum;
@@ -144,13 +181,22 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
     if (threadIdx.x < 16) part[threadIdx.x] = 0;
     __syncthreads();
     if (ALIGNED) {
-        for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
-            const uint4 q = __ldg(src + w);
-            const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+        for (uint32_t w0 = threadIdx.x; w0 < n_words; w0 += 4u * blockDim.x) {
+            uint4 q[4];
 #pragma unroll
-            for (int h = 0; h < 8; h++) {
-                const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
-                if ((key >> 4) == hi && w * 8u + h < n) atomicAdd(&part[key & 15u], 1u);
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = w0 + (uint32_t)k * blockDim.x;
+                q[k] = w < n_words ? __ldg(src + w) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = w0 + (uint32_t)k * blockDim.x;
+                const uint32_t wd[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+#pragma unroll
+                for (int h = 0; h < 8; h++) {
+                    const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
+                    if ((key >> 4) == hi && w < n_words && w * 8u + h < n) atomicAdd(&part[key & 15u], 1u);
+                }
             }
         }
     } else {

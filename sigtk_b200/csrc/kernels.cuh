@@ -41,6 +41,7 @@ struct Scratch {
     // development / test parameters (sgpu_set_param): 0 = automatic
     uint32_t tune_chunk_len, tune_warmup;
     float tune_thr_long;             // the long detector's threshold (9.0)
+    uint32_t tune_stat_cta_min;      // reads of at least this many samples get a CTA in the moments kernels (stat.cu)
     uint32_t max_tiles;
     // per read
     uint32_t* wit_min; uint32_t* wit_max;  // exact-sum witness: min nonzero |pA| / max |pA| bit patterns
@@ -104,9 +105,10 @@ uint32_t svbzd_blocks_of(uint64_t n);
 int launch_svbzd_decode(const SvbBatch& s, SvbScratch& w, Scratch& sc, int16_t* samples, int sm_count, cudaStream_t st);
 
 // stat.cu
-int launch_stat_moments(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st);
-int launch_stat_median(const DevBatch& b, float* stat6, int sm_count, cudaStream_t st);
-int launch_jnn_moments(const DevBatch& b, float* moments2, int sm_count, cudaStream_t st);
+constexpr uint32_t STAT_CTA_MIN_DEFAULT = 131072u;
+int launch_stat_moments(const DevBatch& b, float* stat6, uint32_t cta_min, int sm_count, cudaStream_t st);
+int launch_stat_median(const DevBatch& b, float* stat6, uint32_t cta_min, int sm_count, cudaStream_t st);
+int launch_jnn_moments(const DevBatch& b, float* moments2, uint32_t cta_min, int sm_count, cudaStream_t st);
 
 // jnn.cu (`sigtk jnn`: band from the clamped signal's mean / stdv, counter machine per read -> (start, end) pairs)
 uint64_t jnn_seg_capacity(uint64_t max_samples, uint32_t max_reads);

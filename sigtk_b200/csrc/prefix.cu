@@ -34,7 +34,7 @@ constexpr int A_MERGE = 200;      // seg_dist
 __device__ __forceinline__ int clamp_raw(int v) { return min(max(v, 0), 1200); }   // rm_outlier, jnn.c:58-75
 
 // mean and standard deviation (float, sample order) of the pA of raw[a .. a + len)
-__device__ void range_moments(const int16_t* __restrict__ raw, int a, int len, float off, float unit, float* add, int* sums,
+__device__ void range_moments(const int16_t* __restrict__ raw, int a, int len, float off, float unit, float* add,
                               int lane, float* mean_out, float* stdv_out) {
     const float nf = (float)len;
     float mean = 0.0f;
@@ -53,7 +53,7 @@ __device__ void range_moments(const int16_t* __restrict__ raw, int a, int len, f
                 add[q * SB_STRIDE + lane] = v;
             }
             __syncwarp();
-            acc = chain_superblock(add, (min(SB, len - t0) + 31) >> 5, acc, lane, sums, t0 == 0);
+            acc = chain_superblock(add, (min(SB, len - t0) + 31) >> 5, acc, lane, t0 == 0);
         }
         if (pass == 0) { mean = __fdiv_rn(acc, nf); *mean_out = mean; }
         else *stdv_out = __fsqrt_rn(__fdiv_rn(acc, nf));
@@ -84,10 +84,8 @@ __device__ __forceinline__ void close_run(RunState& s, int lo) {
 __global__ void __launch_bounds__(128, 4) prefix_walk_kernel(DevBatch b, float std_scale, int lo_thresh,
                                                             int32_t* __restrict__ pos4, float* __restrict__ st6) {
     __shared__ float add_all[4][32 * SB_STRIDE];
-    __shared__ int sums_all[4][96];
     float* add = add_all[threadIdx.x >> 5];
     int* dbuf = reinterpret_cast<int*>(add);
-    int* sums = sums_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = warp; r < b.n_reads; r += n_warps) {
@@ -150,7 +148,7 @@ __global__ void __launch_bounds__(128, 4) prefix_walk_kernel(DevBatch b, float s
                     __syncwarp();
                     const int ntiles = (min(SB, nt - t0) + 31) >> 5;
                     if (pass < 2) {
-                        acc = chain_superblock(add, ntiles, acc, lane, sums, t0 == 0);
+                        acc = chain_superblock(add, ntiles, acc, lane, t0 == 0);
                     } else {
                         // the run logic, every lane the same (uniform): tile after tile, transition after transition
                         for (int tl = 0; tl < ntiles && !rs.chosen; tl++) {
@@ -185,7 +183,7 @@ __global__ void __launch_bounds__(128, 4) prefix_walk_kernel(DevBatch b, float s
             ax = 0; ay = 0;
             if (rs.chosen) { ax = rs.cx + PW / 2 - 1; ay = rs.cy + PW / 2 - 1; }
             if (ay > 0) {
-                range_moments(raw, ax, ay - ax, off, unit, add, sums, lane, &st[0], &st[1]);
+                range_moments(raw, ax, ay - ax, off, unit, add, lane, &st[0], &st[1]);
                 if (b.rna) {
                     // ---- poly-A: the counter machine of jnn_core over one bit per sample (in the band or not) ----
                     const float top = __fadd_rn(__fadd_rn(st[0], 30.0f), 20.0f), bot = __fsub_rn(__fadd_rn(st[0], 30.0f), 20.0f);
@@ -236,7 +234,7 @@ __global__ void __launch_bounds__(128, 4) prefix_walk_kernel(DevBatch b, float s
                         }
                     }
                     if (n_seg > 0) { px = sx0; py = sy0; }
-                    if (py > 0) range_moments(raw, ay + px, py - px, off, unit, add, sums, lane, &st[3], &st[4]);
+                    if (py > 0) range_moments(raw, ay + px, py - px, off, unit, add, lane, &st[3], &st[4]);
                 }
             }
         }

@@ -41,7 +41,7 @@ def test_python_mirror_matches_the_header():
     assert fields == [f[0] for f in _lib.Result._fields_]
     fields = re.findall(r"\*?\s*(\w+);", re.search(r"typedef struct \{([^}]*)\} sgpu_counters_t;", body).group(1))
     assert fields == [f[0] for f in _lib.Counters._fields_]
-    for name in ("CHUNK_LEN", "WARMUP", "THR_LONG"):
+    for name in ("CHUNK_LEN", "WARMUP", "THR_LONG", "PORE", "STAT_CTA_MIN"):
         assert getattr(_lib, "PARAM_" + name) == defs["SGPU_PARAM_" + name]
 
 

@@ -573,3 +573,27 @@ def test_rna_reads_up_to_270k_samples(ctx, orc):
         res = ctx.run(part, rna=1, want=sg.WANT_EVENTS | sg.WANT_STAT)
         check_against_oracle(orc, res, part, 1, want=sg.WANT_EVENTS | sg.WANT_STAT)
         assert int(res.seq_order.sum()) == 0 and int(res.fixups.sum()) == 0
+
+
+@pytest.mark.parametrize("cta_min", [0, 5000, 1 << 31])
+def test_stat_moments_by_warp_and_by_cta(ctx, orc, cta_min):
+    """stat.cu adds a read's floats up in the reference's order (stat.h:17-44) with one warp per read or, for long
+    reads, one CTA per read (several warps summarise consecutive superblocks in the accumulator's binade). Both
+    kernels on the same reads -- tiny ones, lengths around the superblock (1,024) and round (8,192) sizes, negative
+    samples (the value-by-value path), a constant read, zeros -- give the oracle's bits."""
+    rng = np.random.default_rng(77)
+    lens = [1, 2, 31, 32, 33, 1023, 1024, 1025, 8191, 8192, 8193, 16385, 40000, 100001, 3000, 262144 + 7]
+    reads = [synth.make_read(300 + k, n, seed=5) for k, n in enumerate(lens)]
+    neg = synth.make_read(900, 30000, seed=5)
+    reads.append(((neg[0].astype(np.int32) - 520).astype(np.int16), neg[1], 13.0, neg[3]))       # samples of both signs
+    reads.append((np.full(20000, 487, np.int16), 8192.0, 4.0, 1402.882324))                      # stdv exactly 0
+    reads.append((np.zeros(9000, np.int16), 8192.0, 0.0, 1402.882324))                           # sums stay 0
+    reads.append(((rng.integers(-32768, 32767, 50000)).astype(np.int16), 2048.0, -200.0, 748.58))  # full range
+    ctx.set_param(_sl.PARAM_STAT_CTA_MIN, cta_min)
+    try:
+        res = ctx.run(reads, rna=0, want=sg.WANT_STAT | sg.WANT_JNN)
+    finally:
+        ctx.set_param(_sl.PARAM_STAT_CTA_MIN, 131072)
+    for r, rd in enumerate(reads):
+        assert np.array_equal(bits(res.stat[r]), bits(orc.stat(*rd))), f"read {r} (n={len(rd[0])}): stat differs"
+        assert np.array_equal(res.jnn[r], orc.jnn(rd[0], 0)), f"read {r} (n={len(rd[0])}): jnn differs"
