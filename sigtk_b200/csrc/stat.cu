@@ -22,9 +22,9 @@ namespace sgpu {
 
 // the addends of one superblock (samples t0 .. t0+1023 of the read, 4 x 128-bit words per lane: lane L holds the
 // words q*32 + L) into the warp's shared rows: tile j/32, column j%32
-template <bool JNN>
-__device__ __forceinline__ void fill_addends(const uint4 (&cur)[4], int t0, int n, int lane, int pass, float mean_r,
-                                             float mean_p, float off, float unit, float (*add)[32 * SB_STRIDE]) {
+template <bool JNN, bool FULL>
+__device__ __forceinline__ void fill_addends_(const uint4 (&cur)[4], int t0, int n, int lane, int pass, float mean_r,
+                                              float mean_p, float off, float unit, float (*add)[32 * SB_STRIDE]) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const uint32_t wd[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
@@ -33,7 +33,7 @@ __device__ __forceinline__ void fill_addends(const uint4 (&cur)[4], int t0, int 
             const int j = q * 256 + lane * 8 + h;
             const int i = t0 + j;
             float ar = 0.0f, ap = 0.0f;
-            if (i < n) {
+            if (FULL || i < n) {
                 const int16_t v = (int16_t)(wd[h >> 1] >> ((h & 1) * 16));
                 if (JNN) {
                     ar = (float)min(max((int)v, 0), 1200);
@@ -52,6 +52,13 @@ __device__ __forceinline__ void fill_addends(const uint4 (&cur)[4], int t0, int 
             if (!JNN) add[JNN ? 0 : 1][at] = ap;
         }
     }
+}
+
+template <bool JNN>
+__device__ __forceinline__ void fill_addends(const uint4 (&cur)[4], int t0, int n, int lane, int pass, float mean_r,
+                                             float mean_p, float off, float unit, float (*add)[32 * SB_STRIDE]) {
+    if (t0 + SB <= n) fill_addends_<JNN, true>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);  // (no per-sample bound)
+    else fill_addends_<JNN, false>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);
 }
 
 template <bool JNN>
