@@ -122,6 +122,40 @@ constexpr int MED_BINS = 4096;
 // Two levels over the order-preserving key raw + 32768: the upper 12 bits (4096 bins: the ~1,000 ADC units a signal
 // spans spread over ~60 bins, so the shared-memory atomics of a warp rarely meet; with 256 bins they met on 2-4 bins),
 // then the lower 4 bits among the samples of the selected bin. 128-bit loads (the read starts 16-byte aligned).
+// one 128-bit word (8 samples, `cnt` of them inside the read) into the level-1 histogram: two keys per register,
+// key = raw + 32768 = raw ^ 0x8000 as 16 bits, bin = key >> 4
+__device__ __forceinline__ void med_count_word(const uint4& q, uint32_t cnt, uint32_t* hist) {
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+    if (cnt >= 8u) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t x = wd[j] ^ 0x80008000u;
+            atomicAdd(&hist[(x >> 4) & 0xfffu], 1u);
+            atomicAdd(&hist[x >> 20], 1u);
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+            const uint32_t key = ((wd[h >> 1] >> ((h & 1) * 16)) & 0xffffu) ^ 0x8000u;
+            if ((uint32_t)h < cnt) atomicAdd(&hist[key >> 4], 1u);
+        }
+    }
+}
+// level 2: the low 4 bits of the samples whose upper 12 bits equal those of `pattern` (both halves hold the bin's
+// first raw value). A register with no matching half -- nearly all of them -- is dismissed by one zero-halfword test.
+__device__ __forceinline__ void med_match_word(const uint4& q, uint32_t cnt, uint32_t pattern, uint32_t* part) {
+    const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t x = wd[j] ^ pattern;
+        const uint32_t m = x & 0xfff0fff0u;
+        if (((m - 0x00010001u) & ~m & 0x80008000u) != 0u) {   // some halfword of m may be zero (exact test below)
+            if ((m & 0xffffu) == 0u && (uint32_t)(2 * j) < cnt) atomicAdd(&part[x & 15u], 1u);
+            if ((m >> 16) == 0u && (uint32_t)(2 * j + 1) < cnt) atomicAdd(&part[(x >> 16) & 15u], 1u);
+        }
+    }
+}
+
 template <bool ALIGNED>
 __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint32_t rank, uint32_t* hist,
                                uint32_t* part, uint32_t* sh) {
@@ -141,12 +175,7 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t w = w0 + (uint32_t)k * blockDim.x;
-                const uint32_t wd[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
-#pragma unroll
-                for (int h = 0; h < 8; h++) {
-                    const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
-                    if (w < n_words && w * 8u + h < n) atomicAdd(&hist[key >> 4], 1u);
-                }
+                if (w < n_words) med_count_word(q[k], n - w * 8u, hist);
             }
         }
     } else {
@@ -154,25 +183,40 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
             atomicAdd(&hist[(uint32_t)((int)__ldg(raw + i) + 32768) >> 4], 1u);
     }
     __syncthreads();
-    if (threadIdx.x < 256) {   // 256 threads x 16 bins, then one thread over the 256 partial sums and the 16 bins of the group
+    if (threadIdx.x < 256) {   // 256 threads x 16 bins
         uint32_t sum = 0;
         for (int k = 0; k < MED_BINS / 256; k++) sum += hist[threadIdx.x * (MED_BINS / 256) + k];
         part[threadIdx.x] = sum;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t seen = 0, g = 0;
-        for (; g < 256; g++) {
-            if (seen + part[g] > rank) break;
-            seen += part[g];
+    if (threadIdx.x < 32) {
+        // the first warp finds the bin of the rank: every lane adds up 8 of the 256 partial sums, a shuffle scan
+        // places the rank in one lane's group, and that lane walks its 8 partial sums and then the 16 bins
+        const int lane = threadIdx.x;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) mine += part[lane * 8 + k];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        uint32_t k = g * (MED_BINS / 256);
-        for (;; k++) {
-            if (seen + hist[k] > rank) break;
-            seen += hist[k];
+        const uint32_t owner = __ballot_sync(0xffffffffu, incl > rank);   // (rank < n: never empty)
+        if (lane == __ffs(owner) - 1) {
+            uint32_t seen = incl - mine, g = (uint32_t)lane * 8u;
+            for (;; g++) {
+                if (seen + part[g] > rank) break;
+                seen += part[g];
+            }
+            uint32_t k = g * (MED_BINS / 256);
+            for (;; k++) {
+                if (seen + hist[k] > rank) break;
+                seen += hist[k];
+            }
+            sh[0] = k;
+            sh[1] = rank - seen;
         }
-        sh[0] = k;
-        sh[1] = rank - seen;
     }
     __syncthreads();
     const uint32_t hi = sh[0], rank2 = sh[1];
@@ -181,6 +225,8 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
     if (threadIdx.x < 16) part[threadIdx.x] = 0;
     __syncthreads();
     if (ALIGNED) {
+        const uint32_t first = ((hi << 4) ^ 0x8000u) & 0xffffu;   // the bin's first raw value (16-bit pattern)
+        const uint32_t pattern = first | (first << 16);
         for (uint32_t w0 = threadIdx.x; w0 < n_words; w0 += 4u * blockDim.x) {
             uint4 q[4];
 #pragma unroll
@@ -191,12 +237,7 @@ __device__ int select_rank_i16(const int16_t* __restrict__ raw, uint32_t n, uint
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t w = w0 + (uint32_t)k * blockDim.x;
-                const uint32_t wd[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
-#pragma unroll
-                for (int h = 0; h < 8; h++) {
-                    const uint32_t key = (uint32_t)((int)(int16_t)(wd[h >> 1] >> ((h & 1) * 16)) + 32768);
-                    if ((key >> 4) == hi && w < n_words && w * 8u + h < n) atomicAdd(&part[key & 15u], 1u);
-                }
+                if (w < n_words) med_match_word(q[k], n - w * 8u, pattern, part);
             }
         }
     } else {
