@@ -85,6 +85,15 @@ __global__ void __launch_bounds__(128) jnn_walk_kernel(DevBatch b, const float* 
     const JnnParams P = jnn_params(b.rna);
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    // the state map of every 8-sample pattern: a full word's map is the composition of its four bytes' maps (three
+    // compositions, no data-dependent loop; the stepping form above costs a loop per entry state)
+    __shared__ uint32_t byte_map[256];
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+        uint32_t f = 0;
+        for (int s = 0; s <= JNN_CLOSED; s++) f |= (uint32_t)jnn_word_end((uint32_t)v, ~(uint32_t)v & 0xffu, 8, s) << (3 * s);
+        byte_map[v] = f;
+    }
+    __syncthreads();
     for (uint32_t r = warp; r < b.n_reads; r += n_warps) {
         const int16_t* __restrict__ raw = b.samples + b.read_off[r];
         const int n = (int)b.read_len[r];
@@ -138,8 +147,12 @@ __global__ void __launch_bounds__(128) jnn_walk_kernel(DevBatch b, const float* 
             const uint32_t zeros = ~in & valid;
             // 1. the word as a map of states, and the state at its start
             uint32_t f = 0;
-#pragma unroll
-            for (int s = 0; s <= JNN_CLOSED; s++) f |= (uint32_t)jnn_word_end(in, zeros, m, s) << (3 * s);
+            if (m == 32) {
+                f = jnn_compose(jnn_compose(byte_map[in & 0xffu], byte_map[(in >> 8) & 0xffu]),
+                                jnn_compose(byte_map[(in >> 16) & 0xffu], byte_map[in >> 24]));
+            } else {   // the last words of a read
+                for (int s = 0; s <= JNN_CLOSED; s++) f |= (uint32_t)jnn_word_end(in, zeros, m, s) << (3 * s);
+            }
             uint32_t incl = f;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {

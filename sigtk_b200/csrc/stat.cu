@@ -22,7 +22,7 @@ namespace sgpu {
 
 // the addends of one superblock (samples t0 .. t0+1023 of the read, 4 x 128-bit words per lane: lane L holds the
 // words q*32 + L) into the warp's shared rows: tile j/32, column j%32
-template <bool JNN, bool FULL>
+template <bool JNN, bool FULL, int PASS>
 __device__ __forceinline__ void fill_addends_(const uint4 (&cur)[4], int t0, int n, int lane, int pass, float mean_r,
                                               float mean_p, float off, float unit, float (*add)[32 * SB_STRIDE]) {
 #pragma unroll
@@ -41,7 +41,7 @@ __device__ __forceinline__ void fill_addends_(const uint4 (&cur)[4], int t0, int
                     ar = (float)v;
                     ap = pa_of(v, off, unit);
                 }
-                if (pass) {
+                if (PASS) {
                     const float dr = __fsub_rn(ar, mean_r), dp = __fsub_rn(ap, mean_p);
                     ar = __fmul_rn(dr, dr);
                     ap = __fmul_rn(dp, dp);
@@ -57,8 +57,13 @@ __device__ __forceinline__ void fill_addends_(const uint4 (&cur)[4], int t0, int
 template <bool JNN>
 __device__ __forceinline__ void fill_addends(const uint4 (&cur)[4], int t0, int n, int lane, int pass, float mean_r,
                                              float mean_p, float off, float unit, float (*add)[32 * SB_STRIDE]) {
-    if (t0 + SB <= n) fill_addends_<JNN, true>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);  // (no per-sample bound)
-    else fill_addends_<JNN, false>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);
+    if (t0 + SB <= n) {  // (no per-sample bound)
+        if (pass) fill_addends_<JNN, true, 1>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);
+        else fill_addends_<JNN, true, 0>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);
+    } else {
+        if (pass) fill_addends_<JNN, false, 1>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);
+        else fill_addends_<JNN, false, 0>(cur, t0, n, lane, pass, mean_r, mean_p, off, unit, add);
+    }
 }
 
 template <bool JNN>
@@ -244,7 +249,7 @@ __device__ __forceinline__ void moments_by_cta(const DevBatch& b, float* __restr
 
 // The first `cta_blocks` CTAs take the long reads (they start first), the others the short ones, a warp each.
 template <bool JNN>
-__global__ void __launch_bounds__(CW * 32, 2) stat_moments_kernel(DevBatch b, float* __restrict__ out, uint32_t cta_min,
+__global__ void __launch_bounds__(CW * 32, 3) stat_moments_kernel(DevBatch b, float* __restrict__ out, uint32_t cta_min,
                                                                   uint32_t cta_blocks) {
     extern __shared__ float moments_add[];           // [CW][channels][32 * SB_STRIDE]: every warp's addends of one superblock
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
