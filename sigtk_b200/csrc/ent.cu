@@ -19,9 +19,9 @@
 
 namespace sgpu {
 
-constexpr int ENT_WIN = 8192;      // bins per shared-memory window
+constexpr int ENT_WIN = 4096;      // bins per shared-memory window
 constexpr int ENT_THREADS = 256;
-constexpr int ENT_CTAS_PER_SM = 3; // 66 KB of shared memory per CTA
+constexpr int ENT_CTAS_PER_SM = 4; // 35 KB of shared memory per CTA
 
 __device__ __forceinline__ uint32_t zigzag16(int32_t cur, int32_t prev) {
     const int32_t d = cur - prev;                             // ent.c:62
@@ -101,32 +101,58 @@ ent_kernel(DevBatch b, uint32_t* __restrict__ ovf_all, double* __restrict__ out)
         uint32_t rmin = 0xffffu, rmax = 0u, dmin = 0xffffu, dmax = 0u;
         bool rovf = false, dovf = false;
         const uint32_t nd = n - 1;  // deltas counted (ent.c:131)
-        // 8 samples per thread and step: one 128-bit load + the sample before it
-        for (uint32_t i0 = (uint32_t)tid * 8; i0 < n; i0 += ENT_THREADS * 8) {
-            int16_t v[8];
+        // 8 samples per thread and step: one 128-bit load + the sample before it; the next step's are in flight
+        // while this one is counted
+        auto load8 = [&](uint32_t i0, uint4& q, int32_t& prev) {
             if (i0 + 8 <= n) {
-                *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(raw + i0));
+                q = __ldg(reinterpret_cast<const uint4*>(raw + i0));
             } else {
-                for (int j = 0; j < 8; j++) v[j] = (i0 + j < n) ? raw[i0 + j] : (int16_t)0;
+                int16_t t[8];
+                for (int j = 0; j < 8; j++) t[j] = (i0 + j < n) ? raw[i0 + j] : (int16_t)0;
+                q = *reinterpret_cast<uint4*>(t);
             }
-            int32_t prev = i0 ? (int32_t)raw[i0 - 1] : 0;  // ent.c:124: prev starts at 0
+            prev = i0 ? (int32_t)raw[i0 - 1] : 0;  // ent.c:124: prev starts at 0
+        };
+        auto count1 = [&](int32_t val, int32_t prev, bool with_delta) {
+            const uint32_t key = (uint32_t)val & 0xffffu;
+            rmin = min(rmin, key); rmax = max(rmax, key);
+            const uint32_t d = (key - rbase) & 0xffffu;
+            if (d < ENT_WIN) atomicAdd(&s.raw[d], 1u);
+            else { atomicAdd(&ovf_raw[key], 1u); rovf = true; }
+            if (with_delta) {
+                const uint32_t z = zigzag16(val, prev);
+                dmin = min(dmin, z); dmax = max(dmax, z);
+                if (z < ENT_WIN) atomicAdd(&s.dlt[z], 1u);
+                else { atomicAdd(&ovf_dlt[z], 1u); dovf = true; }
+            }
+        };
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = make_uint4(0, 0, 0, 0);
+        int32_t prev_c = 0, prev_n = 0;
+        if ((uint32_t)tid * 8 < n) load8((uint32_t)tid * 8, cur, prev_c);
+        for (uint32_t i0 = (uint32_t)tid * 8; i0 < n; i0 += ENT_THREADS * 8) {
+            const uint32_t i1 = i0 + ENT_THREADS * 8;
+            if (i1 < n) load8(i1, nxt, prev_n);
+            const uint32_t wd[4] = {cur.x, cur.y, cur.z, cur.w};
+            int32_t prev = prev_c;
+            if (i0 + 8 <= nd) {   // every sample of the step has a delta (all but the read's last sample do)
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t i = i0 + j;
-                if (i >= n) break;
-                const uint32_t key = (uint16_t)v[j];
-                rmin = min(rmin, key); rmax = max(rmax, key);
-                const uint32_t d = (key - rbase) & 0xffffu;
-                if (d < ENT_WIN) atomicAdd(&s.raw[d], 1u);
-                else { atomicAdd(&ovf_raw[key], 1u); rovf = true; }
-                if (i < nd) {
-                    const uint32_t z = zigzag16((int32_t)v[j], prev);
-                    dmin = min(dmin, z); dmax = max(dmax, z);
-                    if (z < ENT_WIN) atomicAdd(&s.dlt[z], 1u);
-                    else { atomicAdd(&ovf_dlt[z], 1u); dovf = true; }
+                for (int j = 0; j < 8; j++) {
+                    const int32_t val = (int32_t)(int16_t)(wd[j >> 1] >> ((j & 1) * 16));
+                    count1(val, prev, true);
+                    prev = val;
                 }
-                prev = (int32_t)v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t i = i0 + j;
+                    if (i >= n) break;
+                    const int32_t val = (int32_t)(int16_t)(wd[j >> 1] >> ((j & 1) * 16));
+                    count1(val, prev, i < nd);
+                    prev = val;
+                }
             }
+            cur = nxt;
+            prev_c = prev_n;
         }
         // CTA-wide key ranges
         for (int o = 16; o; o >>= 1) {
