@@ -507,11 +507,12 @@ def run_ours(args):
     all_samples, all_events, all_reads = (float(x) for x in tot.tolist())
     value = all_samples / (ms_max * 1e-3) / 1e9
 
-    # ---- the siblings of the event path (`sigtk pa`, `sigtk stat`, `sigtk ent`, `sigtk jnn`), device resident, on the first batch ----------------
+    # ---- the siblings of the event path (`sigtk pa`, `sigtk stat`, `sigtk ent`, `sigtk jnn`, `sigtk prefix`), device resident, on the first batch ----------------
     siblings = {}
     if not args.no_siblings:
         p0 = pool[0]
-        for name, w_ in (("pa", sg.WANT_PA), ("stat", sg.WANT_STAT), ("ent", sg.WANT_ENT), ("jnn", sg.WANT_JNN)):
+        for name, w_ in (("pa", sg.WANT_PA), ("stat", sg.WANT_STAT), ("ent", sg.WANT_ENT), ("jnn", sg.WANT_JNN),
+                         ("prefix", sg.WANT_PREFIX)):
             tot_ms = 0.0
             for k in range(4):
                 ctx.run_device(p0["samples"].data_ptr(), p0["read_off"].data_ptr(), p0["read_len"].data_ptr(),

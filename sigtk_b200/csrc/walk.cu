@@ -220,11 +220,57 @@ struct JobIo {
     }
 };
 
+// long_job() (walk_core.cuh) with a WARP per life: the lanes form the exact t-statistics of 32 consecutive positions at
+// once (each from its own two windows: the double divisions and the square root of events.c:338-361 are a chain of
+// ~2,500 cycles per position when one thread steps alone), then every lane steps the detector over the 32 values in
+// order. Same operations, same order per position; what is emitted is ORed into the bitmap by lane 0.
+// Used for the RNA parameters, whose lives are few and long (windows of 14 and 28 samples, a life per ~50,000
+// samples); the DNA batches hold ~30 short lives per 100,000 samples and keep one thread per life.
+template <int RNA>
+__device__ void long_job_warp(const JobIo& io, int n, int sh, float off, float unit, int L, int k, int l_start, int end,
+                              float thr_long, int lane) {
+    using C = Cfg<RNA>;
+    constexpr int w1 = C::w1, w2 = C::w2;
+    for (int kk = k - 1; l_start == LS_PRED && kk >= 0; kk--) l_start = io.end_lstart(kk);
+    if (l_start == LS_PRED) return;
+    const int stop = n + sh;
+    const int own_end = end == LS_CONT ? (k + 1) * L - C::LAG + sh : (end < stop ? end : stop);
+    float pv = FLT_MAX; int ps = PS_NONE;
+    PeakAcc unused; unused.mk = 0u; unused.oldest = 0;
+    bool b2; int p2;
+    auto t_at = [&](int u, int w) -> float {
+        const int i = u - sh;
+        return (i >= w && i + w <= n) ? tstat_exact(io, i, w, n, off, unit) : 0.0f;
+    };
+    auto emit = [&](int pos) { if (lane == 0) io.peak(pos); };
+    for (int base = l_start; base < own_end; base += 32) {
+        const float t = base + lane < own_end ? t_at(base + lane, w2) : 0.0f;
+        const int cnt = min(32, own_end - base);
+        for (int q = 0; q < cnt; q++)
+            det_one<false, RNA>(pv, ps, 0, base + q, __shfl_sync(0xffffffffu, t, q), thr_long, unused, b2, p2, emit);
+    }
+    if (end != LS_CONT) return;
+    float spv; int sps;
+    io.end_short(k, &spv, &sps);
+    for (int base = own_end; base < stop; base += 32) {   // (l_start <= own_end: the life was alive at the chunk's last owned step)
+        const bool in = base + lane < stop;
+        const float t1 = in ? t_at(base + lane, w1) : 0.0f, t2 = in ? t_at(base + lane, w2) : 0.0f;
+        const int cnt = min(32, stop - base);
+        for (int q = 0; q < cnt; q++) {
+            det_one<true, RNA>(spv, sps, 0, base + q, __shfl_sync(0xffffffffu, t1, q), thr_short<RNA>(), unused, b2, p2, NoEmit());
+            if (b2) return;              // reset: the life ended before the long detector's step here
+            det_one<false, RNA>(pv, ps, 0, base + q, __shfl_sync(0xffffffffu, t2, q), thr_long, unused, b2, p2, emit);
+        }
+    }
+}
+
 template <int RNA>
 __global__ void __launch_bounds__(128) long_jobs_kernel(const WalkParams p) {
     const uint32_t nj = min(*p.job_count, p.job_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) p.counters[3] = nj;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nj; j += gridDim.x * blockDim.x) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t j = RNA ? tid >> 5 : tid; j < nj; j += RNA ? nt >> 5 : nt) {
         const int4 job = p.jobs[j];
         const uint32_t r = (uint32_t)job.x;
         const uint64_t base = p.b.read_off[r];
@@ -235,7 +281,8 @@ __global__ void __launch_bounds__(128) long_jobs_kernel(const WalkParams p) {
         io.st_end = p.st_end;
         io.sid_first = 2ull * r; io.sid_last = 2ull * r + 1; io.sid_int0 = 2ull * p.b.n_reads + p.ibase[r];
         io.nch = (int)n_chunks((uint32_t)n, (uint32_t)p.L);
-        long_job<RNA>(io, n, (int)(base & 31u), p.b.offset[r], p.b.unit[r], p.L, job.y, job.z, job.w, p.thr_long);
+        if (RNA) long_job_warp<RNA>(io, n, (int)(base & 31u), p.b.offset[r], p.b.unit[r], p.L, job.y, job.z, job.w, p.thr_long, lane);
+        else long_job<RNA>(io, n, (int)(base & 31u), p.b.offset[r], p.b.unit[r], p.L, job.y, job.z, job.w, p.thr_long);
     }
 }
 
@@ -343,7 +390,7 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
 // the lives of the long detector that may emit (a few per 100,000 samples), replayed exactly
 int launch_long_jobs(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int sm_count, cudaStream_t st) {
     const WalkParams p = walk_params(b, sc, nullptr, seq_flag, sm_count);
-    if (b.rna) long_jobs_kernel<1><<<sm_count * 4, 128, 0, st>>>(p);
+    if (b.rna) long_jobs_kernel<1><<<sm_count * 16, 128, 0, st>>>(p);  // (a warp per life)
     else long_jobs_kernel<0><<<sm_count * 4, 128, 0, st>>>(p);
     return 1;
 }

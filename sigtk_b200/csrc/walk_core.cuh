@@ -1066,12 +1066,18 @@ SGW_HD void long_job(Jo& io, int n, int sh, float off, float unit, int L, int k,
     float pv = FLT_MAX; int ps = PS_NONE;
     PeakAcc unused; unused.mk = 0u; unused.oldest = 0;
     bool b2; int p2;
-    auto t_at = [&](int u, int w) -> float {
-        const int i = u - sh;
-        return (i >= w && i + w <= n) ? tstat_exact(io, i, w, n, off, unit) : 0.0f;
-    };
+    // (one thread per life: the statistics of four consecutive steps are formed before the detector takes them, so
+    //  that their dependent chains overlap -- the longest life of a batch is the kernel's duration)
     SlidingT<Jo> slide;
     int u = l_start;
+    for (; u + 4 <= own_end; u += 4) {
+        float t[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) t[q] = slide.next(io, u + q - sh, w2, n, off, unit);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            det_one<false, RNA>(pv, ps, 0, u + q, t[q], thr_long, unused, b2, p2, [&](int pos) { io.peak(pos); });
+    }
     for (; u < own_end; u++)
         det_one<false, RNA>(pv, ps, 0, u, slide.next(io, u - sh, w2, n, off, unit), thr_long, unused, b2, p2,
                             [&](int pos) { io.peak(pos); });
@@ -1079,10 +1085,13 @@ SGW_HD void long_job(Jo& io, int n, int sh, float off, float unit, int L, int k,
     float spv; int sps;
     io.end_short(k, &spv, &sps);
     u = own_end;                     // (l_start <= own_end: the life was alive at the chunk's last owned step)
+    SlidingT<Jo> slide1;             // the short window from here on, the long one goes on sliding
     for (; u < stop; u++) {
-        det_one<true, RNA>(spv, sps, 0, u, t_at(u, w1), thr_short<RNA>(), unused, b2, p2, NoEmit());
+        const float t1 = slide1.next(io, u - sh, w1, n, off, unit);
+        const float t2 = slide.next(io, u - sh, w2, n, off, unit);
+        det_one<true, RNA>(spv, sps, 0, u, t1, thr_short<RNA>(), unused, b2, p2, NoEmit());
         if (b2) return;              // reset: the life ended before the long detector's step at u
-        det_one<false, RNA>(pv, ps, 0, u, t_at(u, w2), thr_long, unused, b2, p2, [&](int pos) { io.peak(pos); });
+        det_one<false, RNA>(pv, ps, 0, u, t2, thr_long, unused, b2, p2, [&](int pos) { io.peak(pos); });
     }
 }
 
