@@ -449,6 +449,10 @@ def run_ours(args):
     max_reads = max(p["n_reads"] for p in pool)
     ctx = sg.Context(device=local, max_samples=max_span, max_reads=max_reads,
                      flags=sg.F_NO_HOST_SLOTS | sg.F_STAGE_TIMERS)
+    if args.chunk_len:      # development: SGPU_PARAM_CHUNK_LEN / _WARMUP (never change results; 0 = automatic)
+        ctx.set_param(sg._lib.PARAM_CHUNK_LEN, args.chunk_len)
+    if args.detector_warmup:
+        ctx.set_param(sg._lib.PARAM_WARMUP, args.detector_warmup)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step(p):
@@ -744,6 +748,8 @@ def main():
     ap.add_argument("--no-svbzd", action="store_true", help="skip the compressed-input (svb-zd) measurements")
     ap.add_argument("--no-siblings", action="store_true", help="skip the pa / stat / ent kernel timings")
     ap.add_argument("--no-others", action="store_true", help="skip the ultralong / rna40k / real sub-lines")
+    ap.add_argument("--chunk-len", type=int, default=0, help="development: samples per detector chunk (0 = automatic)")
+    ap.add_argument("--detector-warmup", type=int, default=0, help="development: detector warm-up in samples (0 = default)")
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3:

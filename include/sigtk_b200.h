@@ -208,7 +208,7 @@ int  sgpu_counters(sgpu_ctx_t *ctx, sgpu_counters_t *out);
 /* Development / test parameters of a context (take effect from the next run; nothing reads the environment).
  * They never change results -- except SGPU_PARAM_THR_LONG, which replaces the reference's constant 9.0
  * (events.c:46,53) so that tests can make the long detector emit. */
-#define SGPU_PARAM_CHUNK_LEN 1 /* samples per detector chunk (power of two >= 128 DNA / 512 RNA); 0 = automatic */
+#define SGPU_PARAM_CHUNK_LEN 1 /* samples per detector chunk (multiple of 32, >= 128 DNA / 512 RNA); 0 = automatic */
 #define SGPU_PARAM_WARMUP    2 /* detector warm-up in samples (multiple of 8 DNA / 16 RNA, <= default); 0 = default */
 #define SGPU_PARAM_THR_LONG  3 /* threshold of the long detector */
 #define SGPU_PARAM_PORE      4 /* 0: R9 (JNNV2_RNA_R9_ADAPTOR), 1: RNA004 (JNNV2_RNA_RNA004_ADAPTOR), jnn.h:88-102: the

@@ -30,16 +30,18 @@ namespace {
 
 using namespace walk;
 
-// launch shape (measured, tools/run_variants.sh): 64-thread blocks, 6 per SM (168 registers, almost no spills, 3 warps
-// per scheduler) runs 2 % faster than 128 x 4 (128 registers, 4 warps per scheduler); 96 / 80 registers are slower
+// launch shape (measured, tools/run_variants.sh; profiles/r02_variants_occupancy.txt, r02_variants_nt.txt, r02_variants_rna.txt):
+// 128-thread blocks, 3 per SM for DNA (168 registers, almost no spills, 3 warps per scheduler) and 2 per SM for RNA
+// (254 registers, 2 warps per scheduler). 64 x 6 / 64 x 4: 1 % (DNA) and 4 % (RNA) slower; 4 warps per scheduler
+// means 128 registers and spills: 2-8 % slower (DNA), 168 registers for RNA: 12 % slower.
 #ifndef WALK_NT
-#define WALK_NT 64
+#define WALK_NT 128
 #endif
 #ifndef WALK_MINB
-#define WALK_MINB 6
+#define WALK_MINB 3
 #endif
 #ifndef WALK_MINB_RNA
-#define WALK_MINB_RNA 1
+#define WALK_MINB_RNA 2
 #endif
 constexpr int WNT = WALK_NT;  // threads per block of walk_chunks_kernel
 
@@ -338,6 +340,9 @@ static inline int grid_cap(uint64_t work, int block, int max_blocks) {
 
 // chunk length for a batch: as long as possible (the warm-up is amortised over it) while the batch still yields
 // a few waves of chunks. `forced` != 0: the context's development parameter SGPU_PARAM_CHUNK_LEN.
+// (measured on the 653 M-sample DNA batch, profiles/r02_chunk_sweep.txt: 480 ... 1120 samples within 1 % of each other,
+//  powers of two or not; 2048: +4.5 %, 4096: +13 % -- the reads' first and last chunks, which take the bounds-checked
+//  blocks, grow with the chunk, and fewer waves of blocks even out worse)
 uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced) {
     const uint32_t lmin = rna ? 512u : 128u;
     // (measured: for DNA one wave of resident threads is enough, the warm-up is what longer chunks save;
@@ -345,7 +350,7 @@ uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced) {
     const uint64_t want_chunks = (uint64_t)sm_count * (rna ? 2048ull : 384ull);
     uint32_t L = rna ? 4096u : 1024u;
     while (L > lmin && span / L < want_chunks) L >>= 1;
-    if (forced >= lmin && (forced & (forced - 1)) == 0u) L = forced;
+    if (forced >= lmin && forced % 32u == 0u) L = forced;
     return L;
 }
 uint32_t walk_warmup(int rna, uint32_t forced) {

@@ -474,7 +474,7 @@ def test_fuzz_adversarial_reads(ctx, orc, rna_flag, chunk_len, seed):
 
 
 # ---- round 2: the long detector's lives (not stepped by the walker, replayed as jobs) ----------------------------
-@pytest.mark.parametrize("rna_flag,chunk_len", [(0, 128), (0, 1024), (1, 512), (1, 4096)])
+@pytest.mark.parametrize("rna_flag,chunk_len", [(0, 128), (0, 1024), (0, 480), (1, 512), (1, 4096), (1, 736)])
 @pytest.mark.parametrize("thr", [0.3, 1.0, 2.5])
 def test_long_detector_lives_are_replayed(ctx, orc, rna_flag, chunk_len, thr):
     """with the reference's threshold (9.0) the long detector never emits on these reads; lowered through the
