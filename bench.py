@@ -432,7 +432,9 @@ def run_ours(args):
         lens_all = np.full(N_SET, 2_000_000, dtype=np.int64)
         B = min(B, 320)
     else:
-        lens_all = synth.read_lengths(N_SET)
+        lens_all = synth.read_lengths(N_SET, sigma=args.len_sigma) if args.len_sigma else synth.read_lengths(N_SET)
+    if args.fixed_len:                  # development: every read the same length
+        lens_all = np.full(N_SET, args.fixed_len, dtype=np.int64)
     pool_n = max(1, min(args.pool, args.steps + args.warmup))
     from sigtk_b200.shard import shard_ranges
     pool = []
@@ -748,6 +750,8 @@ def main():
     ap.add_argument("--no-svbzd", action="store_true", help="skip the compressed-input (svb-zd) measurements")
     ap.add_argument("--no-siblings", action="store_true", help="skip the pa / stat / ent kernel timings")
     ap.add_argument("--no-others", action="store_true", help="skip the ultralong / rna40k / real sub-lines")
+    ap.add_argument("--fixed-len", type=int, default=0, help="development: every read of the set has this many samples")
+    ap.add_argument("--len-sigma", type=float, default=0.0, help="development: sigma of the lognormal read lengths (default 0.6)")
     ap.add_argument("--chunk-len", type=int, default=0, help="development: samples per detector chunk (0 = automatic)")
     ap.add_argument("--detector-warmup", type=int, default=0, help="development: detector warm-up in samples (0 = default)")
     ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank to its GPU's NUMA node")

@@ -82,12 +82,15 @@ struct DevIo {
     uint32_t job_cap;
     uint32_t* __restrict__ seq_flag;
     int read, chunk;
+    unsigned lanes;              // the lanes of the warp that walk edge chunks together (walk_edge_dev)
 
     __device__ __forceinline__ void load8(int t, int (&v)[4]) const {
         const int4 w = __ldg(reinterpret_cast<const int4*>(sp + t));
         v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
     }
     __device__ __forceinline__ bool want_pa() const { return pa != nullptr; }
+    // largest v among the lanes of the warp that walk edge chunks together (`lanes`: their ballot): walk_edge
+    __device__ __forceinline__ int warp_max(int v) const { return __reduce_max_sync(lanes, v); }
     __device__ __forceinline__ void store_pa8(int t, const float* x) const {
         float4* dst = reinterpret_cast<float4*>(pa + t);
         __stcs(dst, make_float4(x[0], x[1], x[2], x[3]));      // streaming: nothing on the device reads pA back
@@ -161,10 +164,11 @@ __device__ __forceinline__ DevIo make_io(const WalkParams& p, uint32_t r, uint64
 }
 
 template <int RNA>
-__device__ __noinline__ void walk_edge_dev(const WalkParams& p, uint32_t r, int last) {
+__device__ __noinline__ void walk_edge_dev(const WalkParams& p, uint32_t r, int last, unsigned lanes) {
     int sh;
     const int n = (int)p.b.read_len[r];
     DevIo io = make_io(p, r, 2ull * r + (uint64_t)last, last ? (int)n_chunks((uint32_t)n, (uint32_t)p.L) - 1 : 0, &sh);
+    io.lanes = lanes;
     walk_edge<RNA>(io, n, io.off, io.unit, sh, p.L, p.W, last, p.thr_long);
 }
 
@@ -181,10 +185,15 @@ __device__ __forceinline__ uint32_t find_chunk_read(const uint64_t* __restrict__
 template <int RNA>
 __global__ void __launch_bounds__(WNT, RNA ? WALK_MINB_RNA : WALK_MINB) walk_chunks_kernel(const WalkParams p) {
     if (blockIdx.x < p.edge_blocks) {
-        // first chunks of all reads, then last chunks: the lanes of a warp walk chunks of the same kind
+        // first chunks of all reads, then (from a warp boundary) their last chunks: the lanes of a warp walk chunks of
+        // the same kind and meet between the phases of walk_edge
+        const uint32_t per_kind = (p.b.n_reads + 31u) & ~31u;
         const uint64_t e = (uint64_t)blockIdx.x * WNT + threadIdx.x;
-        if (e < p.b.n_reads) walk_edge_dev<RNA>(p, (uint32_t)e, 0);
-        else if (e < 2ull * p.b.n_reads) walk_edge_dev<RNA>(p, (uint32_t)(e - p.b.n_reads), 1);
+        const int last = e >= per_kind;
+        const uint64_t r = last ? e - per_kind : e;
+        const bool have = r < p.b.n_reads && e < 2ull * per_kind;
+        const unsigned lanes = __ballot_sync(0xffffffffu, have);
+        if (have) walk_edge_dev<RNA>(p, (uint32_t)r, last, lanes);
         return;
     }
     const uint64_t i = (uint64_t)(blockIdx.x - p.edge_blocks) * WNT + threadIdx.x;
@@ -371,7 +380,7 @@ static WalkParams walk_params(const DevBatch& b, Scratch& sc, float* pa_out, uin
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
     p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max; p.tile_read0 = sc.tile_read0;
-    p.edge_blocks = (uint32_t)((2ull * b.n_reads + WNT - 1) / WNT);
+    p.edge_blocks = (uint32_t)((2ull * ((b.n_reads + 31u) & ~31u) + WNT - 1) / WNT);   // (first and last chunks: whole warps each)
     p.thr_long = sc.tune_thr_long;
     p.jobs = reinterpret_cast<int4*>(sc.jobs); p.job_count = sc.job_count; p.job_cap = sc.job_cap; p.seq_flag = seq_flag;
     p.counters = sc.counters;

@@ -942,108 +942,191 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
     io.witness(rmin0 < rmin1 ? rmin0 : rmin1, rmax0 > rmax1 ? rmax0 : rmax1, bc.can_low ? bc.low_t : -32769);
 }
 
-// first chunk (last == 0) or last chunk (last == 1; only when the read has >= 2 chunks) of a read: bounds-checked
+// first chunk (last == 0) or last chunk (last == 1; only when the read has >= 2 chunks) of a read.
+// Only the blocks at either end of the read need bounds checks (samples or windows outside the read); the blocks in
+// between are the interior chunks' unchecked code. The chunk is walked in three phases -- checked head, unchecked
+// middle, checked tail -- each a function of its own (not inlined on the device: one loop holding both block variants
+// spilled ~100 registers and ran its blocks twice as slowly as an interior chunk; the phases pass the walk's state
+// through EdgeCtx, three calls per chunk).
+#if defined(__CUDACC__)
+#define SGW_PHASE __host__ __device__ __noinline__
+#else
+#define SGW_PHASE inline
+#endif
+template <int RNA>
+struct EdgeCtx {
+    Rings<RNA> g;
+    WalkDet d;
+    int rmin, rmax, dirty, zdirty;
+    int n, sh, s0, s1, t_live, last, low_t, c0;
+    float off, unit;
+    bool pa;
+    LongK lk;
+    BlockCvt bc;
+};
+// what every block of an edge chunk does before its samples
+template <int RNA, class Io>
+SGW_HD void edge_block_begin(Io& io, EdgeCtx<RNA>& e, int tau) {
+    using C = Cfg<RNA>;
+    if (e.last && tau == e.t_live) det_cold(e.d, e.t_live - C::LAG + e.sh);
+    if (e.last && tau == e.s0) {
+        io.put_begin(canon_of<RNA>(e.d, e.s0 - C::LAG + e.sh));
+        e.d.l_start = LS_PRED; e.d.l_hot = false;
+    }
+}
+// blocks [tau_from, tau_to) whose samples and windows all lie inside the read: the interior chunks' code
+template <int RNA, class Io>
+SGW_PHASE void edge_inner(Io& io, EdgeCtx<RNA>& ec, int tau_from, int tau_to) {
+    using C = Cfg<RNA>;
+    constexpr int U = C::U;
+    // every lane of the warp takes as many turns as the lane with the most blocks and sits out the ones it has no
+    // block for: the lanes leave the loop, and the function, together
+    const int turns = io.warp_max(tau_to > tau_from ? (tau_to - tau_from) / U : 0);
+    EdgeCtx<RNA> e = ec;                              // (registers for the duration of the phase)
+    float x[U], z[U];
+    int vn[U / 8][4];                                 // the next block's samples, loaded one block ahead
+    if (tau_from < tau_to) {
+#pragma unroll
+        for (int h = 0; h < U / 8; h++) io.load8(tau_from + 8 * h, vn[h]);
+    }
+    int tau = tau_from;
+#pragma unroll 1
+    for (int turn = 0; turn < turns; turn++, tau += U) {
+        if (tau >= tau_to) continue;
+        const bool own = tau >= e.s0;
+        edge_block_begin<RNA>(io, e, tau);
+        const int tn = tau + U < tau_to ? tau + U : tau;   // (the last block is simply loaded again)
+        uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;
+#pragma unroll
+        for (int h = 0; h < U / 8; h++) {
+            int v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = vn[h][q];
+            io.load8(tn + 8 * h, vn[h]);
+            cvt_group(io, e.bc, e.lk, v, tau + 8 * h, own, e.off, e.unit, x + 8 * h, z + 8 * h, bmin, bmax, e.dirty);
+        }
+        if (own) {  // (an owned inner block lies inside [s0, s1): s1 is n or a multiple of U)
+            const int b0 = s16_lo(bmin), b1 = s16_hi(bmin), c0x = s16_lo(bmax), c1x = s16_hi(bmax);
+            e.rmin = b0 < e.rmin ? b0 : e.rmin; e.rmin = b1 < e.rmin ? b1 : e.rmin;
+            e.rmax = c0x > e.rmax ? c0x : e.rmax; e.rmax = c1x > e.rmax ? c1x : e.rmax;
+        }
+        clamp_far<U>(e.bc, bmin, bmax, z, e.zdirty);
+        walk_block<RNA, false>(e.g, e.d, x, z, tau, e.n, e.sh, own, tau >= e.t_live, tau >= e.t_live - U, e.dirty, e.zdirty,
+                               e.off, e.unit, e.lk, io);
+        e.dirty = e.dirty > 0 ? e.dirty - 1 : 0;
+        e.zdirty = e.zdirty > 0 ? e.zdirty - 1 : 0;
+    }
+    ec = e;
+}
+// blocks [tau_from, tau_to) at either end of the read: every sample and window is checked against the read's bounds
+template <int RNA, class Io>
+SGW_PHASE void edge_checked(Io& io, EdgeCtx<RNA>& ec, int tau_from, int tau_to) {
+    using C = Cfg<RNA>;
+    constexpr int U = C::U;
+    const int turns = io.warp_max(tau_to > tau_from ? (tau_to - tau_from) / U : 0);   // (see edge_inner)
+    EdgeCtx<RNA> e = ec;
+    float x[U], z[U];
+    const int n = e.n, c0 = e.c0, low_t = e.low_t;
+    int tau = tau_from;
+#pragma unroll 1
+    for (int turn = 0; turn < turns; turn++, tau += U) {
+        if (tau >= tau_to) continue;
+        const bool own = tau >= e.s0;
+        edge_block_begin<RNA>(io, e, tau);
+#pragma unroll
+        for (int h = 0; h < U / 8; h++) {
+            const int t8 = tau + 8 * h;
+            int v[4] = {0, 0, 0, 0};
+            if (t8 < n) io.load8(t8, v);  // t8 < n: inside the read's padded span
+            float y[8], zy[8];
+            cvt8(v, e.off, e.unit, e.lk.c0, y, zy);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const bool in = t8 + q < n;
+                const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
+                const bool low = in & (raw <= low_t);   // rare: handed to the block as 0, its windows are dirty
+                x[8 * h + q] = (in & !low) ? y[q] : 0.0f;
+                const bool zbad = in & ((raw - c0 > ZMAX) | (c0 - raw > ZMAX));  // rare: enters the integer sums clamped
+                z[8 * h + q] = !in ? 0.0f : !zbad ? zy[q] : raw > c0 ? (float)(ZMAX + 1) : -(float)(ZMAX + 1);
+                if (zbad) e.zdirty = DIRTY_BLOCKS;
+                if (low) {
+                    e.dirty = DIRTY_BLOCKS;
+                    const uint32_t a = f_bits(y[q]) & 0x7fffffffu;
+                    io.low_samples(t8 + q, a != 0u ? a : 0xffffffffu, a);
+                }
+                if (own && in && t8 + q < e.s1) {
+                    e.rmin = raw < e.rmin ? raw : e.rmin;
+                    e.rmax = raw > e.rmax ? raw : e.rmax;
+                    if (e.pa) io.store_pa1(t8 + q, y[q]);
+                }
+            }
+        }
+        walk_block<RNA, true>(e.g, e.d, x, z, tau, n, e.sh, own, tau >= e.t_live, tau >= e.t_live - U, e.dirty, e.zdirty,
+                              e.off, e.unit, e.lk, io);
+        e.dirty = e.dirty > 0 ? e.dirty - 1 : 0;
+        e.zdirty = e.zdirty > 0 ? e.zdirty - 1 : 0;
+    }
+    ec = e;
+}
+
+// The lanes of a warp walk the first (or the last) chunks of 32 different reads and spend different numbers of blocks
+// in the middle phase. Every phase therefore runs io.warp_max(blocks) turns in every lane (a lane without a block sits
+// the turn out), so that the lanes leave each phase together: lanes that returned from the middle phase one after the
+// other ran their checked tails on their own, two lanes active -- 8 times the instructions of the converged tail.
+// For that, no lane leaves walk_edge() early: a read without this chunk walks empty phases.
 template <int RNA, class Io>
 SGW_HD void walk_edge(Io& io, int n, float off, float unit, int sh, int L, int W, int last, float thr_long) {
     using C = Cfg<RNA>;
     constexpr int U = C::U;
     const uint32_t nch = n_chunks((uint32_t)n, (uint32_t)L);
-    if (nch == 0u || (last && nch < 2u)) return;
+    const bool none = nch == 0u || (last && nch < 2u);   // the read has no such chunk
     // owned samples [s0, s1); owned detector steps [s0 - LAG, s1 - LAG), all remaining steps for the read's last chunk
-    const int s0 = last ? (int)(nch - 1u) * L : 0;
+    EdgeCtx<RNA> e;
+    e.n = n; e.sh = sh; e.off = off; e.unit = unit; e.last = last;
+    e.s0 = last ? (int)(nch - 1u) * L : 0;
     const bool to_end = last || nch == 1u;
-    const int s1 = to_end ? n : L;
-    const int t_live = last ? s0 - W : 0;            // >= 2U for a last chunk because L >= W + 2U
-    const int step_end = to_end ? n : s1 - C::LAG;   // owned blocks: until every owned step has been taken
-    Rings<RNA> g;
-    g.clear();
-    WalkDet d;
-    det_cold(d, sh + 1);  // first chunk: the reference's initial state, masked_to = 0: position 0 is skipped (events.c:516-536, 387)
-    float x[U], z[U];
-    int rmin = 32767, rmax = -32768;
+    e.s1 = to_end ? n : L;
+    e.t_live = last ? e.s0 - W : 0;                  // >= 2U for a last chunk because L >= W + 2U
+    const int step_end = to_end ? n : e.s1 - C::LAG; // owned blocks: until every owned step has been taken
+    e.g.clear();
+    det_cold(e.d, sh + 1);  // first chunk: the reference's initial state, masked_to = 0: position 0 is skipped (events.c:516-536, 387)
+    e.rmin = 32767; e.rmax = -32768;
     bool can_low;
     const int low_t0 = low_threshold(off, &can_low);
-    const int low_t = can_low ? low_t0 : -32769;
-    int dirty = 0, zdirty = 0;
-    const bool pa = io.want_pa();
-    const int t_first = last ? t_live - C::FILL * U : 0;
-    int c0;
-    {
+    e.low_t = can_low ? low_t0 : -32769;
+    e.dirty = 0; e.zdirty = 0;
+    e.pa = io.want_pa();
+    const int t_first = last ? e.t_live - C::FILL * U : 0;
+    e.c0 = 0;
+    if (!none) {
         int v0[4] = {0, 0, 0, 0};
         io.load8(t_first, v0);                        // t_first < n: inside the read's padded span
         const int a = s16_lo((uint32_t)v0[0]), b = t_first + 1 < n ? s16_hi((uint32_t)v0[0]) : a;
-        c0 = pivot_of(a, b, t_first + 2 < n ? s16_lo((uint32_t)v0[1]) : a);
+        e.c0 = pivot_of(a, b, t_first + 2 < n ? s16_lo((uint32_t)v0[1]) : a);
     }
-    const LongK lk = long_consts<RNA>(c0, off, thr_long);
-    const BlockCvt bc = block_cvt(off, c0, pa);
-    // blocks whose samples and windows all lie inside the read take the unchecked code of the interior chunks
-    // (reads of a few thousand samples are mostly edge chunks); only the first and the last blocks are bounds-checked
+    e.lk = long_consts<RNA>(e.c0, off, thr_long);
+    e.bc = block_cvt(off, e.c0, e.pa);
+    // blocks tau = t_first, t_first + U, ... while tau - LAG < step_end (all multiples of U); a block is an inner one
+    // when INNER_MIN <= tau and tau + U <= n: checked head, unchecked middle, checked tail
     constexpr int INNER_MIN = (2 * C::w2 - 1 + U - 1) / U * U;
-#pragma unroll 1
-    for (int tau = t_first; tau - C::LAG < step_end; tau += U) {
-        const bool own = tau >= s0;
-        if (last && tau == t_live) det_cold(d, t_live - C::LAG + sh);
-        if (last && tau == s0) {
-            io.put_begin(canon_of<RNA>(d, s0 - C::LAG + sh));
-            d.l_start = LS_PRED; d.l_hot = false;
-        }
-        if (tau >= INNER_MIN && tau + U <= n) {
-            uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;
-#pragma unroll
-            for (int h = 0; h < U / 8; h++) {
-                int v[4];
-                io.load8(tau + 8 * h, v);
-                cvt_group(io, bc, lk, v, tau + 8 * h, own, off, unit, x + 8 * h, z + 8 * h, bmin, bmax, dirty);
-            }
-            if (own) {  // (an owned inner block lies inside [s0, s1): s1 is n or a multiple of U)
-                const int b0 = s16_lo(bmin), b1 = s16_hi(bmin), c0x = s16_lo(bmax), c1x = s16_hi(bmax);
-                rmin = b0 < rmin ? b0 : rmin; rmin = b1 < rmin ? b1 : rmin;
-                rmax = c0x > rmax ? c0x : rmax; rmax = c1x > rmax ? c1x : rmax;
-            }
-            clamp_far<U>(bc, bmin, bmax, z, zdirty);
-            walk_block<RNA, false>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
-        } else {
-#pragma unroll
-            for (int h = 0; h < U / 8; h++) {
-                const int t8 = tau + 8 * h;
-                int v[4] = {0, 0, 0, 0};
-                if (t8 < n) io.load8(t8, v);  // t8 < n: inside the read's padded span
-                float y[8], zy[8];
-                cvt8(v, off, unit, lk.c0, y, zy);
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const bool in = t8 + q < n;
-                    const int raw = (q & 1) ? (v[q >> 1] >> 16) : (int)(int16_t)(v[q >> 1] & 0xffff);
-                    const bool low = in & (raw <= low_t);   // rare: handed to the block as 0, its windows are dirty
-                    x[8 * h + q] = (in & !low) ? y[q] : 0.0f;
-                    const bool zbad = in & ((raw - c0 > ZMAX) | (c0 - raw > ZMAX));  // rare: enters the integer sums clamped
-                    z[8 * h + q] = !in ? 0.0f : !zbad ? zy[q] : raw > c0 ? (float)(ZMAX + 1) : -(float)(ZMAX + 1);
-                    if (zbad) zdirty = DIRTY_BLOCKS;
-                    if (low) {
-                        dirty = DIRTY_BLOCKS;
-                        const uint32_t a = f_bits(y[q]) & 0x7fffffffu;
-                        io.low_samples(t8 + q, a != 0u ? a : 0xffffffffu, a);
-                    }
-                    if (own && in && t8 + q < s1) {
-                        rmin = raw < rmin ? raw : rmin;
-                        rmax = raw > rmax ? raw : rmax;
-                        if (pa) io.store_pa1(t8 + q, y[q]);
-                    }
-                }
-            }
-            walk_block<RNA, true>(g, d, x, z, tau, n, sh, own, tau >= t_live, tau >= t_live - U, dirty, zdirty, off, unit, lk, io);
-        }
-        dirty = dirty > 0 ? dirty - 1 : 0;
-        zdirty = zdirty > 0 ? zdirty - 1 : 0;
-    }
+    const int tau_end = none ? t_first : (step_end + C::LAG + U - 1) / U * U;
+    int in0 = t_first > INNER_MIN ? t_first : INNER_MIN;
+    in0 = in0 < tau_end ? in0 : tau_end;
+    int in1 = n / U * U;
+    in1 = in1 < tau_end ? in1 : tau_end;
+    in1 = in1 > in0 ? in1 : in0;
+    edge_checked<RNA>(io, e, t_first, in0);
+    edge_inner<RNA>(io, e, in0, in1);
+    edge_checked<RNA>(io, e, in1, tau_end);
+    if (none) return;
     if (to_end) {
-        if (d.l_hot) io.job(d.l_start, n + sh);      // the life ends with the read
+        if (e.d.l_hot) io.job(e.d.l_start, n + sh);  // the life ends with the read
     } else {
-        if (d.l_hot) io.job(d.l_start, LS_CONT);
-        io.put_end(canon_of<RNA>(d, s1 - C::LAG + sh));
+        if (e.d.l_hot) io.job(e.d.l_start, LS_CONT);
+        io.put_end(canon_of<RNA>(e.d, e.s1 - C::LAG + sh));
     }
     if (!last) io.peak(sh);  // event 0 starts at the read's first sample (events.c:490-497)
-    if (rmin <= rmax) io.witness(rmin, rmax, low_t);
+    if (e.rmin <= e.rmax) io.witness(e.rmin, e.rmax, e.low_t);
 }
 
 // ---- a life of the long detector, replayed with the reference's own operations --------------------------------------
