@@ -349,9 +349,9 @@ static inline int grid_cap(uint64_t work, int block, int max_blocks) {
 
 // chunk length for a batch: as long as possible (the warm-up is amortised over it) while the batch still yields
 // a few waves of chunks. `forced` != 0: the context's development parameter SGPU_PARAM_CHUNK_LEN.
-// (measured on the 653 M-sample DNA batch, profiles/r02_chunk_sweep.txt: 480 ... 1120 samples within 1 % of each other,
-//  powers of two or not; 2048: +4.5 %, 4096: +13 % -- the reads' first and last chunks, which take the bounds-checked
-//  blocks, grow with the chunk, and fewer waves of blocks even out worse)
+// (measured on the 653 M-sample batches, profiles/r02_chunk_sweep.txt, last section: DNA 512 ... 1536 samples within
+//  1 % of each other, powers of two or not, 2048: +3 %, 4096: +5 %; RNA 2048 best, 1024: +10 %, 4096: +2 % -- the
+//  reads' first and last chunks grow with the chunk, and fewer waves of blocks even out worse)
 uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced) {
     const uint32_t lmin = rna ? 512u : 128u;
     // (measured: for DNA one wave of resident threads is enough, the warm-up is what longer chunks save;

@@ -11,6 +11,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"walk|long_jo
 ncu --set full --clock-control none --import-source on -k regex:walk_chunks -s 3 -c 1 -f -o gpurun_out/${R}_walk_chunks python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --no-siblings --no-others --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:emit_events -s 3 -c 1 -f -o gpurun_out/${R}_emit_events python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --no-siblings --no-others --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:stat_moments -s 1 -c 1 -f -o gpurun_out/${R}_stat_moments python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --no-others --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stat_median -s 1 -c 1 -f -o gpurun_out/${R}_stat_median python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --no-others --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:jnn_walk -s 1 -c 1 -f -o gpurun_out/${R}_jnn_walk python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --no-others --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ent_kernel -s 1 -c 1 -f -o gpurun_out/${R}_ent_kernel python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --no-others --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:long_jobs -s 3 -c 1 -f -o gpurun_out/${R}_long_jobs python bench.py --steps 1 --warmup 3 --no-cpu --no-svbzd --no-siblings --no-others --reads-per-step 4096 --e2e-reads 64 > /dev/null 2>&1
 python tools/cli_bench.py --reads 8000 --modes event-c,event,stat,pa,jnn,ent,prefix 2>gpurun_out/cli_bench_err.log | tee gpurun_out/${R}_cli_bench.jsonl | cut -c1-200
-python tools/stat_time.py 2>&1 | tail -3 | tee gpurun_out/${R}_stat_pa_time.jsonl
+python tools/stat_time.py 2>&1 | tee gpurun_out/${R}_stat_cta_sweep.jsonl | tail -3
+python tools/rna_jobs_time.py 2>&1 | tee gpurun_out/${R}_rna_jobs_time.jsonl
