@@ -71,7 +71,7 @@ int launch_walk(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_fla
 int launch_long_jobs(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int sm_count, cudaStream_t st);
 int launch_verify_chunks(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count, cudaStream_t st);
 uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads);
-uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced);
+uint32_t walk_chunk_len(uint64_t span, uint32_t n_reads, int rna, int sm_count, uint32_t forced);
 uint32_t walk_warmup(int rna, uint32_t forced);
 uint32_t walk_job_capacity(uint64_t max_samples);
 int launch_build_seq_list(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int force_all, int sm_count,

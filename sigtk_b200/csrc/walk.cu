@@ -352,13 +352,20 @@ static inline int grid_cap(uint64_t work, int block, int max_blocks) {
 // (measured on the 653 M-sample batches, profiles/r02_chunk_sweep.txt, last section: DNA 512 ... 1536 samples within
 //  1 % of each other, powers of two or not, 2048: +3 %, 4096: +5 %; RNA 2048 best, 1024: +10 %, 4096: +2 % -- the
 //  reads' first and last chunks grow with the chunk, and fewer waves of blocks even out worse)
-uint32_t walk_chunk_len(uint64_t span, int rna, int sm_count, uint32_t forced) {
+uint32_t walk_chunk_len(uint64_t span, uint32_t n_reads, int rna, int sm_count, uint32_t forced) {
     const uint32_t lmin = rna ? 512u : 128u;
     // (measured: for DNA one wave of resident threads is enough, the warm-up is what longer chunks save;
     //  the RNA instantiation does better with four times as many)
     const uint64_t want_chunks = (uint64_t)sm_count * (rna ? 2048ull : 384ull);
     uint32_t L = rna ? 4096u : 1024u;
     while (L > lmin && span / L < want_chunks) L >>= 1;
+    // short reads: a read's first and last chunks cost more than the ones in between (and the lanes of a warp wait
+    // for the longest last chunk), so a read should be a dozen chunks or more (the reference's 100 real reads, 4,700
+    // samples on average: 384 samples per chunk 9 % faster than 1,024)
+    if (n_reads) {
+        const uint64_t per_read = span / n_reads / 12u / 128u * 128u;
+        if (per_read < L) L = per_read > lmin ? (uint32_t)per_read : lmin;
+    }
     if (forced >= lmin && forced % 32u == 0u) L = forced;
     return L;
 }
@@ -376,7 +383,7 @@ uint64_t walk_state_slots(uint64_t max_samples, uint32_t max_reads) { return 2ul
 uint32_t walk_job_capacity(uint64_t max_samples) { return (uint32_t)(max_samples / 64u + 4096u); }  // (16 B each)
 
 static WalkParams walk_params(const DevBatch& b, Scratch& sc, float* pa_out, uint32_t* seq_flag, int sm_count) {
-    const uint32_t L = walk_chunk_len(b.span, b.rna, sm_count, sc.tune_chunk_len), W = walk_warmup(b.rna, sc.tune_warmup);
+    const uint32_t L = walk_chunk_len(b.span, b.n_reads, b.rna, sm_count, sc.tune_chunk_len), W = walk_warmup(b.rna, sc.tune_warmup);
     WalkParams p;
     p.b = b; p.L = (int)L; p.W = (int)W; p.ibase = sc.wk_ibase; p.pa = pa_out; p.bitmap = sc.bitmap;
     p.st_begin = sc.wk_begin; p.st_end = sc.wk_end; p.wit_min = sc.wit_min; p.wit_max = sc.wit_max; p.tile_read0 = sc.tile_read0;
@@ -410,7 +417,7 @@ int launch_long_jobs(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, int sm_
 }
 
 int launch_verify_chunks(const DevBatch& b, Scratch& sc, uint32_t* seq_flag, uint32_t* fixups, int sm_count, cudaStream_t st) {
-    const uint32_t L = walk_chunk_len(b.span, b.rna, sm_count, sc.tune_chunk_len);
+    const uint32_t L = walk_chunk_len(b.span, b.n_reads, b.rna, sm_count, sc.tune_chunk_len);
     const uint64_t max_interior = b.span / L;
     verify_chunks_kernel<<<grid_cap(max_interior + b.n_reads, 256, sm_count * 8), 256, 0, st>>>(
         b, L, sc.wk_ibase, sc.wk_begin, sc.wk_end, seq_flag, fixups);
