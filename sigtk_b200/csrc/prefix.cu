@@ -32,6 +32,10 @@ constexpr int A_TOLERATED = 30;   // error
 constexpr int A_MERGE = 200;      // seg_dist
 
 __device__ __forceinline__ int clamp_raw(int v) { return min(max(v, 0), 1200); }   // rm_outlier, jnn.c:58-75
+__device__ __forceinline__ uint32_t clamp2(uint32_t two) {                          // the same on two packed int16
+    return __vmins2(__vmaxs2(two, 0u), 1200u * 0x10001u);
+}
+static_assert(PW % 8 == 0, "the two ranges of a window difference are loaded with the same alignment");
 
 // mean and standard deviation (float, sample order) of the pA of raw[a .. a + len)
 __device__ void range_moments(const int16_t* __restrict__ raw, int a, int len, float off, float unit, float* add,
@@ -99,7 +103,12 @@ __global__ void __launch_bounds__(128, 4) prefix_walk_kernel(DevBatch b, float s
             const float ntf = (float)nt;
             // the first window's sum (exact integer)
             int s_first = 0;
-            for (int i = lane; i < PW; i += 32) s_first += clamp_raw((int)__ldg(raw + i));
+            for (int w = lane; w < PW / 8; w += 32) {   // 128-bit loads (a read starts 16-byte aligned)
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(raw) + w);
+                const uint32_t c4[4] = {clamp2(q.x), clamp2(q.y), clamp2(q.z), clamp2(q.w)};
+#pragma unroll
+                for (int h = 0; h < 4; h++) s_first += (int)(c4[h] & 0xffffu) + (int)(c4[h] >> 16);
+            }
             for (int o = 16; o; o >>= 1) s_first += __shfl_xor_sync(0xffffffffu, s_first, o);
             float mn = 0.0f, floor_ = 0.0f;
             RunState rs = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -108,13 +117,33 @@ __global__ void __launch_bounds__(128, 4) prefix_walk_kernel(DevBatch b, float s
                 int s_base = s_first;
                 for (int t0 = 0; t0 < nt; t0 += SB) {
                     __syncwarp();
-                    // d[i] = c[i + PW] - c[i]: the window sum moves by d[i] from position i to i + 1
-#pragma unroll 4
-                    for (int q = 0; q < 32; q++) {
-                        const int i = t0 + q * 32 + lane;
-                        int d = 0;
-                        if (i < nt) d = clamp_raw((int)__ldg(raw + i + PW)) - clamp_raw((int)__ldg(raw + i));
-                        dbuf[q * SB_STRIDE + lane] = d;
+                    // d[i] = c[i + PW] - c[i]: the window sum moves by d[i] from position i to i + 1.
+                    // Lane L takes the 128-bit words q * 32 + L of both ranges (PW is a multiple of 8: they are
+                    // aligned alike; eight loads in flight per lane), two samples per clamp / subtraction
+                    {
+                        const uint4* __restrict__ lo = reinterpret_cast<const uint4*>(raw + t0);
+                        const uint4* __restrict__ hi = reinterpret_cast<const uint4*>(raw + t0 + PW);
+                        uint4 a[4], c[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int wq = q * 32 + lane;
+                            const bool in = t0 + wq * 8 < nt;   // (the word's first position; the read is padded to 8 samples)
+                            a[q] = in ? __ldg(lo + wq) : make_uint4(0, 0, 0, 0);
+                            c[q] = in ? __ldg(hi + wq) : make_uint4(0, 0, 0, 0);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t av[4] = {a[q].x, a[q].y, a[q].z, a[q].w}, cv[4] = {c[q].x, c[q].y, c[q].z, c[q].w};
+#pragma unroll
+                            for (int h = 0; h < 4; h++) {
+                                const uint32_t d2 = __vsub2(clamp2(cv[h]), clamp2(av[h]));   // two differences in [-1200, 1200]
+                                const int j = q * 256 + lane * 8 + 2 * h;                     // position in the superblock
+                                const int i = t0 + j;
+                                const int d0 = (int)(int16_t)(d2 & 0xffffu), d1 = (int)d2 >> 16;
+                                dbuf[(j >> 5) * SB_STRIDE + (j & 31)] = i < nt ? d0 : 0;
+                                dbuf[(j >> 5) * SB_STRIDE + (j & 31) + 1] = i + 1 < nt ? d1 : 0;
+                            }
+                        }
                     }
                     __syncwarp();
                     // lane L owns tile L: its 32 consecutive positions
@@ -136,7 +165,12 @@ __global__ void __launch_bounds__(128, 4) prefix_walk_kernel(DevBatch b, float s
                         const int d = row[k];
                         float v = 0.0f;
                         if (i < nt) {
-                            const float t = __fdiv_rn((float)s, (float)PW);   // rolling_window, jnn.c:41,46
+                            // rolling_window, jnn.c:41,46: (float)s / 2000, by the reciprocal and one residual
+                            // correction (equal to the IEEE quotient for every integer s <= 2^24:
+                            // oracle/proofs/div_window_check.c)
+                            const float sf = (float)s;
+                            const float q0 = __fmul_rn(sf, 1.0f / (float)PW);
+                            const float t = __fmaf_rn(__fmaf_rn(-(float)PW, q0, sf), 1.0f / (float)PW, q0);
                             if (pass == 0) v = t;
                             else if (pass == 1) { const float dv = __fsub_rn(t, mn); v = __fmul_rn(dv, dv); }
                             else { below |= (t < floor_ ? 1u : 0u) << k; above |= (t > floor_ ? 1u : 0u) << k; }

@@ -275,3 +275,17 @@ def test_long_filter_checker_finds_no_violation(tmp_path):
     import json
     d = json.loads(out)
     assert d["violations"] == 0 and d["t_above_threshold"] > 500000
+
+
+def test_window_division_shortcut_is_exact(tmp_path):
+    """oracle/proofs/div_window_check.c: `sigtk prefix` divides the rolling-window sum by 2000 for every position; the
+    CUDA path uses the reciprocal with one residual correction, which must equal the IEEE quotient for every value the
+    (exact integer) sum can take -- checked for every integer up to 2^24."""
+    import json
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(os.path.dirname(here), "oracle", "proofs", "div_window_check.c")
+    exe = str(tmp_path / "div_window_check")
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=off", src, "-o", exe, "-lm"])
+    out = json.loads(subprocess.check_output([exe]).decode())
+    assert out["mismatches"] == 0 and out["values"] == (1 << 24) + 1
