@@ -89,6 +89,13 @@ struct DevIo {
         v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
     }
     __device__ __forceinline__ bool want_pa() const { return pa != nullptr; }
+    // the line that holds sample t on its way into L1 (a thread walks its chunk 16 bytes at a time, a 128-byte line of
+    // its own per 8 blocks: asked for a few blocks ahead, the load that crosses into a new line finds it there)
+    __device__ __forceinline__ void prefetch(int t) const {
+#if !defined(WALK_NO_PREFETCH)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + t));
+#endif
+    }
     // largest v among the lanes of the warp that walk edge chunks together (`lanes`: their ballot): walk_edge
     __device__ __forceinline__ int warp_max(int v) const { return __reduce_max_sync(lanes, v); }
     __device__ __forceinline__ void store_pa8(int t, const float* x) const {

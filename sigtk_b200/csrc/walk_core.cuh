@@ -888,6 +888,12 @@ SGW_HD void clamp_far(const BlockCvt& k, uint32_t bmin, uint32_t bmax, float* z,
     }
 }
 
+// how many blocks ahead of its loads a chunk asks for its samples' cache line (io.prefetch; measured on the bench
+// batch, profiles/r02_variants_pf.txt: none 3.77 ms, 2-4 blocks 3.71, 8-16 blocks 3.62, 32 blocks 3.66)
+#if !defined(WALK_PF_BLOCKS)
+#define WALK_PF_BLOCKS 12
+#endif
+
 // interior chunk k (1 <= k <= nch-2) of a read: every access is inside the read, no bounds checks.
 // ONE loop (one copy of the block code in the instruction cache) runs the two ring-fill blocks, the detector
 // warm-up and the owned samples.
@@ -920,6 +926,7 @@ SGW_HD void walk_interior(Io& io, int n, float off, float unit, int sh, int L, i
             d.l_start = LS_PRED; d.l_hot = false;               // the running life began before this chunk's steps
         }
         const int tn = tau + U < s1 ? tau + U : tau;  // (the last block is simply loaded again)
+        io.prefetch(tau + WALK_PF_BLOCKS * U < s1 ? tau + WALK_PF_BLOCKS * U : tau);
         uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;  // packed extremes of this block's samples
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {
@@ -996,6 +1003,7 @@ SGW_PHASE void edge_inner(Io& io, EdgeCtx<RNA>& ec, int tau_from, int tau_to) {
         const bool own = tau >= e.s0;
         edge_block_begin<RNA>(io, e, tau);
         const int tn = tau + U < tau_to ? tau + U : tau;   // (the last block is simply loaded again)
+        io.prefetch(tau + WALK_PF_BLOCKS * U < tau_to ? tau + WALK_PF_BLOCKS * U : tau);
         uint32_t bmin = 0x7fff7fffu, bmax = 0x80008000u;
 #pragma unroll
         for (int h = 0; h < U / 8; h++) {

@@ -25,6 +25,7 @@ struct HostIo {
     void load8(int t, int (&v)[4]) const { memcpy(v, sp + t, 16); }
     bool want_pa() const { return pa != nullptr; }
     int warp_max(int v) const { return v; }
+    void prefetch(int) const {}
     void store_pa8(int t, const float* x) const { memcpy(pa + t, x, 32); }
     void store_pa1(int t, float x) const { pa[t] = x; }
     void peak(int pos) const { bm[pos >> 5] |= 1u << (pos & 31); }
