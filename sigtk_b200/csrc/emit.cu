@@ -161,6 +161,14 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
         // (a tile with LOW samples takes the general path: its sums need real conversions)
         const bool one_read = rs_first <= flat0 && flat0 + EWT <= rend_first && total <= (uint32_t)EFAST && !tile_low;
         if (one_read) {
+            // the tile's last event runs on past the tile: the next tile's bitmap words and the first 32 samples behind
+            // the tile are asked for now, one per lane, and used after step 2 (when one lane looked for the event's end
+            // and added its samples on its own, the other 31 waited on its loads at the end of every tile)
+            const uint64_t w_next = (wt + 1) * 32 + (uint64_t)lane;
+            const bool w_valid = w_next < n_words && (long long)(w_next << 5) < rend_first;
+            const uint32_t next_bits = w_valid ? bitmap[w_next] : 0u;
+            const long long i_behind = flat0 + EWT + lane;
+            const int raw_behind = i_behind < rend_first ? (int)__ldg(b.samples + i_behind) : 0;
             // ---- fast path, step 2: the pieces of this lane's 32 samples ----------------------------------------------
             int slot = EFAST + lane;             // where the running piece goes: first the head of this word
             int next = (int)(incl - own);        // index of this word's first event
@@ -210,6 +218,31 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
             }
             __syncwarp();
             const int last_word = 31 - __clz(nz);
+            // where the tile's last event ends (the next start, at most the read's end), and what it has beyond its
+            // own piece: the heads of the empty words behind it and the samples past the tile -- by the whole warp
+            long long e_tail;
+            {
+                const uint32_t m = __ballot_sync(0xffffffffu, next_bits != 0u);
+                const uint32_t all_valid = __ballot_sync(0xffffffffu, w_valid);
+                if (m) {
+                    const int l0 = __ffs(m) - 1;
+                    const uint32_t bits0 = __shfl_sync(0xffffffffu, next_bits, l0);
+                    e_tail = (long long)(((wt + 1) * 32 + (uint64_t)l0) << 5) + __ffs(bits0) - 1;
+                    if (e_tail > rend_first) e_tail = rend_first;
+                } else if (all_valid == 0xffffffffu) {
+                    e_tail = next_start(bitmap, (wt + 2) * 32, n_words, rend_first);   // (an event of more than 1,024 samples)
+                } else {
+                    e_tail = rend_first;
+                }
+            }
+            double tail_s = lane > last_word ? sm.S[EFAST + lane] : 0.0, tail_q = lane > last_word ? sm.Q[EFAST + lane] : 0.0;
+            if (i_behind < e_tail) add_raw_any(raw_behind, off_first, unit_first, tail_s, tail_q, true);
+            for (long long i = i_behind + 32; i < e_tail; i += 32) add_raw_any((int)__ldg(b.samples + i), off_first, unit_first, tail_s, tail_q, true);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {   // (exact sums: any order)
+                tail_s = __dadd_rn(tail_s, __shfl_xor_sync(0xffffffffu, tail_s, o));
+                tail_q = __dadd_rn(tail_q, __shfl_xor_sync(0xffffffffu, tail_q, o));
+            }
             // ---- step 3: events in order ---------------------------------------------------------------------------------
             for (uint32_t j0 = 0; j0 < total; j0 += 32) {
                 const uint32_t j = j0 + lane;
@@ -220,12 +253,9 @@ __global__ void __launch_bounds__(EWARPS * 32, EMIT_MINB) emit_events_kernel(Dev
                 if (j + 1 < total) {
                     e = flat0 + sm.list[j + 1];
                 } else {  // the last event of the tile: the empty words after it, then past the tile
-                    for (int l2 = last_word + 1; l2 < 32; l2++) {
-                        es = __dadd_rn(es, sm.S[EFAST + l2]);
-                        eq = __dadd_rn(eq, sm.Q[EFAST + l2]);
-                    }
-                    e = next_start(bitmap, (wt + 1) * 32, n_words, rend_first);
-                    for (long long i = flat0 + EWT; i < e; i++) add_raw_any((int)__ldg(b.samples + i), off_first, unit_first, es, eq, true);
+                    es = __dadd_rn(es, tail_s);
+                    eq = __dadd_rn(eq, tail_q);
+                    e = e_tail;
                 }
                 const uint64_t k = kbase + j;
                 if (k >= ev_cap) { atomicExch(status, SGPU_DEV_E_EVCAP); continue; }
