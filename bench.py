@@ -319,12 +319,14 @@ def short_run(torch, sg, local, batches, rna, want, steps=3, warmup=3):
     for k in range(steps):
         p = batches[(warmup + k) % len(batches)]
         step(p)
-        for name, ms, _ in ctx.stage_times():
-            stage_ms[name] = stage_ms.get(name, 0.0) + ms
         ns += p["n_samples"]
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
+    for k in range(steps):               # per-kernel times: the same steps again (see main)
+        step(batches[(warmup + k) % len(batches)])
+        for name, ms_, _ in ctx.stage_times():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms_
     c = ctx.counters()
     ctx.close()
     last = batches[(warmup + steps - 1) % len(batches)]
